@@ -1,0 +1,212 @@
+/* psph.h — C ABI of the B200-native Plume-SPH particle hot path.
+ *
+ * The reference (Plume-SPH, C++/MPI, CPU only) has no plugin/FFI interface: its seam is
+ * the set of free functions its driver calls once per time step
+ * (/root/reference/src/plume/particler.h:22-357, src/multiproc/multiproc.h:39-110, call
+ * sites in src/plume/main.cc:217-486 for 3-D and :676-751 for 1-D).  Each entry point
+ * below replaces one of those calls; the citation on each says which.  The reference
+ * driver keeps ownership of input parsing, atmosphere/eruption set-up, domain growth and
+ * output; the particle table lives on the GPU between calls (INTEGRATION.md shows the
+ * binding a maintainer adds to main.cc).
+ *
+ * Conventions (mirroring the reference's): one host thread per context; a context is not
+ * thread-safe; every call is asynchronous on the context's CUDA stream unless it returns
+ * data to the host; return value <0 = API/CUDA/NCCL failure (fatal, the driver should
+ * MPI_Abort as main.cc:247-249 does), 0 = ok, >0 = number of particles that violated an
+ * invariant the reference assert()s on (e.g. rho <= 0, mom_engr_update.cc:148,228).
+ *
+ * No torch types, no C++ types: plain pointers and sizes only.
+ */
+#ifndef PSPH_H
+#define PSPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSPH_ABI_VERSION 1
+
+/* bc_type values (src/datstr/particle.h:137-145) */
+#define PSPH_BC_ERUPT 0
+#define PSPH_BC_PRESSURE 1
+#define PSPH_BC_WALL 2
+#define PSPH_BC_NOSAVE_REAL 99
+#define PSPH_BC_REAL 100
+
+/* bucket types (src/plume/constant.h:120-124) */
+#define PSPH_CELL_BRIEF 0
+#define PSPH_CELL_UNDERGROUND 10
+#define PSPH_CELL_MIXED 11
+#define PSPH_CELL_OVERGROUND 12
+#define PSPH_CELL_PRESS_BC 13
+
+/* Compile-time choices of the reference (src/plume/options.h, constant.h, parameters.h),
+ * turned into one run-time record.  psph_config_default_3d()/_1d() fill in the reference's
+ * defaults; SURVEY.md Appendix E lists which option set each BASELINE config needs. */
+typedef struct psph_config
+{
+  int abi_version;           /* PSPH_ABI_VERSION */
+  int dim;                   /* CODE_DIMENSION: 1 or 3 (config.h) */
+
+  /* options.h */
+  int use_gsph;              /* USE_GSPH: 0 artificial-viscosity SPH, 1 Godunov SPH */
+  int riemann_solver;        /* RIEMANN_SOLVER: 0 Roe, 1 HLLC */
+  int have_turbulence_lans;  /* HAVE_TURBULENCE_LANS: 0 | 1 */
+  int have_energy_smooth;    /* HAVE_ENERGY_SMOOTH: 0 | 1 */
+  int pghost_contribute_des; /* PGHOST_CONTRIBUTE_DES: 0 | 1 | 2 (particle.h:570-580) */
+  int fluid_compressibility; /* FLUID_COMPRESSIBILITY: 0 ideal-gas mixture, 1 Tait */
+  int adaptive_sml;          /* ADAPTIVE_SML: 0 | 1 */
+  int sml_update_int;        /* SML_UPDATE_INT (constant.h:189); 1-D driver calls every step */
+
+  /* constant.h */
+  double cutoff;             /* CUTOFF   = 3 */
+  double cutoff2;            /* CUTOFF2  = 8 (3-D) / 12 (1-D) */
+  double neigh_radius;       /* 4.25, neighs.cc:84 */
+  double msfrc_thresh;       /* MSFRC_THRESH = 1e-6 */
+  double epsilon_half;       /* EPSILON_HALF = 0.4 */
+  double prandtl_num;        /* PRANDTL_NUM = 0.85 */
+  double heat_trans_scale_ratio; /* HEAT_TRANS_SCALE_RATIO = 1 */
+  double e_smooth_ratio;     /* E_SMOOTH_RATIO = 4 */
+  double tiny;               /* TINY = 1e-8 (Bucket::determine_escape) */
+
+  /* parameters.h */
+  double alf, beta, ata;     /* artificial viscosity alf_P, beta_P, ata_P */
+  double g;                  /* g_P (0 when ATMOSPHERE_TYPE==2) */
+  double cfl;                /* CFL_P */
+  double eta_smooth;         /* eta_smooth_P */
+  double c_smooth;           /* C_smooth_P = 2 */
+  double thresh;             /* thresh_P = 1e-5 */
+  int num_loop;              /* num_loop_P */
+  int pad0;
+  double ng0, Cvs, Cvg, Cva, Rg, Ra, rhoa0, pa0; /* EOS constants (particle.cc:528-604) */
+  double erupt_top;          /* Ll_P[2]: erupt ghost turns real at z >= this (update_pos.cc:137) */
+  double smlen_real;         /* matprops->smoothing_length, given to a particle that turns real */
+
+  /* background mesh (src/preproc/preprocess.cc:99-179, dataread.cc:380-387):
+   * cell (i,j,k) spans [ (mindom[d]+i*del)/len_scale , (mindom[d]+(i+1)*del)/len_scale ).
+   * 1-D: one cell holding everything (ncell = {1,1,1}); the reference keeps no mesh there. */
+  double mindom[3];
+  double del;
+  double len_scale;
+  int ncell[3];
+
+  /* particle-table iteration order (src/datstr/thashtab.cc:204-222): hash table size and
+   * the key range it was built with.  Only used by psph_download(order=REFERENCE). */
+  int ptable_size;           /* 4 000 000 (dataread.cc:254) / 10 000 (:506) */
+
+  /* placement */
+  int device;                /* CUDA device ordinal */
+  int rank, nranks;          /* key-range slab owner / number of slabs */
+  int pad1;
+} psph_config;
+
+/* One particle, host side (array of structs).  Field-for-field the reference's
+ * ParticlePack (src/multiproc/pack_data.h:31-77) plus the EOS outputs that the reference
+ * recomputes on unpack (pack_data.cc:459) — carried here so an upload is loss-free. */
+typedef struct psph_particle
+{
+  uint32_t key[3];           /* TKey: birth Hilbert key + add_step (thashtab.h:18-85) */
+  int32_t bc_type, phase_num, involved, guest;
+  int32_t myprocess;
+  double mass, smlen, mass_frac;
+  double pressure, gamma, sound_speed, temperature, specific_heat_p;
+  double phase_density[2];
+  double coords[3], vel[3], smoothed_v[3];
+  double rho, engr, smoothed_e;
+  double grad[15];           /* d_rho,d_u,d_v,d_w,d_p (GSPH only) */
+} psph_particle;
+
+/* Per-cell attributes the driver owns (Bucket, src/datstr/bucket.h:212-300). */
+typedef struct psph_cell_attr
+{
+  int32_t type;              /* PSPH_CELL_* */
+  int32_t has_involved;      /* Bucket::get_has_involved() != 0 */
+  int32_t active;
+  int32_t bucket_index[6];   /* bucket.cc:434-452 */
+  int32_t pad;
+  double bnd[6];
+} psph_cell_attr;
+
+typedef struct psph_ctx psph_ctx;
+
+enum { PSPH_ORDER_DEVICE = 0, PSPH_ORDER_REFERENCE = 1 };
+
+/* column ids for psph_column() (device pointers, SoA) */
+enum {
+  PSPH_COL_X = 0, PSPH_COL_Y, PSPH_COL_Z, PSPH_COL_VX, PSPH_COL_VY, PSPH_COL_VZ,
+  PSPH_COL_SVX, PSPH_COL_SVY, PSPH_COL_SVZ, PSPH_COL_RHO, PSPH_COL_E, PSPH_COL_MASS,
+  PSPH_COL_H, PSPH_COL_KS, PSPH_COL_P, PSPH_COL_GAMMA, PSPH_COL_C, PSPH_COL_T, PSPH_COL_CP,
+  PSPH_COL_COUNT
+};
+
+void psph_config_default_3d(psph_config *cfg);   /* options.h:452-837, parameters.h:881-1046 */
+void psph_config_default_1d(psph_config *cfg);   /* options.h:18-409,  parameters.h:1228-1450 */
+
+/* after Read_Grid (main.cc:104) */
+int psph_create(const psph_config *cfg, psph_ctx **out);
+void psph_destroy(psph_ctx *ctx);
+const char *psph_last_error(const psph_ctx *ctx);
+
+/* Bucket attributes: after Read_Grid and whenever the driver changes them
+ * (adapt_domain.cc, mesh_update.cc).  attr == NULL: every cell OVERGROUND, involved, active. */
+int psph_set_cells(psph_ctx *ctx, const psph_cell_attr *attr, size_t ncells);
+
+/* after initialisation (main.cc:199) / after add_new_erupt (:417) / ghost regeneration (:271-283) */
+int psph_upload(psph_ctx *ctx, const psph_particle *rows, size_t n);
+int psph_append(psph_ctx *ctx, const psph_particle *rows, size_t n);
+/* before write_output (main.cc:474); order REFERENCE = THashTable iteration order */
+int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, size_t *n, int order);
+size_t psph_num_particles(const psph_ctx *ctx);
+/* device-resident SoA column (valid until the next call that reorders particles) */
+int psph_column(psph_ctx *ctx, int col, double **dptr);
+/* Upload directly from device SoA columns (bench / device-side generators): cols[PSPH_COL_*],
+ * bc/phase int32 device arrays; keys are assigned from the row index. */
+int psph_upload_device_soa(psph_ctx *ctx, const double *const *cols, const int32_t *bc,
+                           const int32_t *phase, size_t n);
+
+/* timestep(), main.cc:220 — returns the unclipped CFL dt; TimeProps::incrtime stays on host */
+int psph_timestep(psph_ctx *ctx, double *dt);
+/* after incrtime (main.cc:231): dt actually used, step counter, TimeProps::iferupt() */
+int psph_set_dt(psph_ctx *ctx, double dt, int step, int erupting);
+
+int psph_search_neighs(psph_ctx *ctx);       /* search_neighs_consth, main.cc:318 */
+int psph_adaptive_sml(psph_ctx *ctx);        /* adaptive_sml,         main.cc:322 */
+int psph_calc_gradients(psph_ctx *ctx);      /* calc_gradients,       main.cc:343 */
+int psph_mom_engr_update(psph_ctx *ctx);     /* mom_engr_update,      main.cc:358 */
+int psph_smooth_density(psph_ctx *ctx);      /* smooth_density,       main.cc:378 */
+int psph_smooth_velocity(psph_ctx *ctx);     /* smooth_velocity,      main.cc:392 */
+int psph_update_pos(psph_ctx *ctx);          /* update_pos,           main.cc:405 */
+int psph_rebin(psph_ctx *ctx, int *lost);    /* update_particles_in_bucket, main.cc:408 */
+
+/* The whole per-step hot path in one call, in the reference's order (main.cc:217-408):
+ * timestep -> [clip on host via cb] -> search -> [adaptive_sml] -> [gradients] -> mom/energy
+ * -> density -> [velocity filter] -> positions -> re-bin.  dt_max caps the CFL dt (output/end
+ * time clipping of properties.h:71-82); *dt_used returns the dt applied. */
+int psph_step(psph_ctx *ctx, double dt_max, int erupting, double *dt_used, int *lost);
+/* Same, nsteps times with no host round trip in between (dt stays on the device). */
+int psph_run(psph_ctx *ctx, int nsteps, int erupting);
+
+/* move_data (main.cc:326..471) / repartition (:440-464); no-ops for nranks == 1
+ * (move_data.cc:53-54).  nccl_unique_id: 128 bytes from ncclGetUniqueId on rank 0. */
+int psph_comm_init(psph_ctx *ctx, const void *nccl_unique_id, size_t id_bytes);
+int psph_exchange_ghosts(psph_ctx *ctx);
+int psph_repartition(psph_ctx *ctx);
+
+/* test-only: neighbour lists exactly as search_neighs_consth builds them (neighs.cc:37-211),
+ * as CSR over rows of the REFERENCE-order download.  Two-call protocol: idx == NULL returns
+ * the total count in *nnz. */
+int psph_emit_neighbours(psph_ctx *ctx, int64_t *offsets, int32_t *idx, size_t idx_cap, size_t *nnz);
+
+/* instrumentation: kernels launched since the last call (bench.py gpu_launches), and the
+ * device time of the last launch of a named kernel family measured with CUDA events */
+int64_t psph_launch_count(psph_ctx *ctx, int reset);
+int psph_sync(psph_ctx *ctx);
+void *psph_stream(psph_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSPH_H */

@@ -1,0 +1,614 @@
+/* psph_oracle.c — CPU restatement of the Plume-SPH per-timestep hot path.
+ * TEST INFRASTRUCTURE ONLY — see psph_oracle.h for the rules and the parity pins.
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared (no FMA contraction, so that sums match
+ * the -O2 x86-64 build of the reference bit for bit). */
+#include "psph_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define D3(a, i, k) ((a)[3 * (i) + (k)])
+
+static int need_neigh(const psph_oracle_state *st, int64_t i)
+{ /* particle.h:555-558 */
+  return (st->bc[i] == 100 || st->bc[i] == 99) && !st->guest[i];
+}
+static int is_real(const psph_oracle_state *st, int64_t i)
+{ /* particle.h:612-615 */
+  return st->bc[i] == 100 || st->bc[i] == 99;
+}
+static int contr_dens(const psph_config *c, const psph_oracle_state *st, int64_t j)
+{ /* particle.h:570-580 */
+  int b = st->bc[j];
+  if (c->pghost_contribute_des == 1) return b == 100 || b == 99 || b == 1;
+  if (c->pghost_contribute_des == 2) return b == 100 || b == 99 || b == 1 || b == 0;
+  return b == 100 || b == 99;
+}
+static int contr_vel_smooth(const psph_oracle_state *st, int64_t j)
+{ /* particle.h:587-590 */
+  int b = st->bc[j];
+  return b == 100 || b == 99 || b == 2;
+}
+
+static int in_support(int dim, const double *dx, double h)
+{ /* sph_header.h:49-60 */
+  for (int i = 0; i < dim; i++)
+    if (fabs(dx[i]) > h) return 0;
+  return 1;
+}
+
+double psph_oracle_weight(int dim, const double *s, double h, double cutoff)
+{ /* sph_lib.cc:207-230 */
+  const double t1 = 0.564189583547756;
+  for (int i = 0; i < dim; i++)
+    if (fabs(s[i]) > cutoff) return 0;
+  double norm = 1, expt = 0;
+  for (int i = 0; i < dim; i++) {
+    norm *= t1 / h;
+    expt += s[i] * s[i];
+  }
+  return norm * exp(-expt);
+}
+
+double psph_oracle_d_weight(int dim, const double *s, double h, double cutoff, int dir)
+{ /* sph_lib.cc:240-253 */
+  for (int i = 0; i < dim; i++)
+    if (fabs(s[i]) > cutoff) return 0;
+  double tmp = -2 * s[dir] / h;
+  return tmp * psph_oracle_weight(dim, s, h, cutoff);
+}
+
+void psph_oracle_eos(const psph_config *c, psph_oracle_state *st, int64_t i)
+{ /* Particle::update_second_var, particle.cc:528-604 */
+  double desm = st->rho[i];
+  double ks = st->ks[i];
+  double na = 1 - ks;
+  double engr = st->e[i];
+  double ng = c->ng0 * ks;
+  double ns = ks - ng;
+  double Cvm = ns * c->Cvs + ng * c->Cvg + na * c->Cva;
+  if (c->fluid_compressibility == 0) {
+    double Rm = ng * c->Rg + na * c->Ra;
+    double Rmg = Rm / (ng + na);
+    st->gamma[i] = 1 + Rm / Cvm;
+    double desmg = desm * (na + ng);
+    st->p[i] = Rmg * desmg * engr / Cvm;
+    st->c[i] = pow(st->gamma[i] * st->p[i] / desmg, 0.5);
+  } else {
+    double gama = 7.0;
+    double B = c->rhoa0 * st->c[i] * st->c[i] / gama; /* previous sound speed */
+    st->p[i] = B * (pow(desm / c->rhoa0, gama) - 1) + c->pa0;
+    st->c[i] = pow(gama * (st->p[i] + B - c->pa0) / desm, 0.5);
+  }
+  st->rho_ph[2 * i + 0] = st->rho[i] * na;
+  st->rho_ph[2 * i + 1] = st->rho[i] * ks;
+  st->T[i] = engr / Cvm;
+  if (c->have_turbulence_lans != 0) st->Cp[i] = Cvm;
+}
+
+/* ---------------- background mesh ---------------- */
+static int64_t ncells_of(const psph_config *c) { return (int64_t) c->ncell[0] * c->ncell[1] * c->ncell[2]; }
+static int64_t cell_lin(const psph_config *c, int i, int j, int k)
+{ return ((int64_t) i * c->ncell[1] + j) * c->ncell[2] + k; } /* x-major, z-minor as preprocess.cc:169-181 */
+static double cell_min(const psph_config *c, int d, int i) { return (c->mindom[d] + i * c->del) / c->len_scale; }
+static double cell_max(const psph_config *c, int d, int i) { return (c->mindom[d] + (i + 1) * c->del) / c->len_scale; }
+
+static int cell_index_1(const psph_config *c, int d, double x)
+{ /* membership is [mincrd, maxcrd) against the stored bounds, update_pos.cc:257-271 */
+  int i = (int) floor((x * c->len_scale - c->mindom[d]) / c->del);
+  if (i < 0) i = 0;
+  if (i > c->ncell[d] - 1) i = c->ncell[d] - 1;
+  while (i > 0 && x < cell_min(c, d, i)) i--;
+  while (i < c->ncell[d] - 1 && x >= cell_max(c, d, i)) i++;
+  return i;
+}
+
+int psph_oracle_bin(const psph_config *c, psph_oracle_state *st)
+{
+  int64_t nc = ncells_of(c);
+  int32_t *cell = (int32_t *) malloc(sizeof(int32_t) * (st->n ? st->n : 1));
+  memset(st->cell_off, 0, sizeof(int64_t) * (nc + 1));
+  for (int64_t p = 0; p < st->n; p++) {
+    int idx[3] = { 0, 0, 0 };
+    if (c->dim == 3)
+      for (int d = 0; d < 3; d++) idx[d] = cell_index_1(c, d, D3(st->x, p, d));
+    cell[p] = (int32_t) cell_lin(c, idx[0], idx[1], idx[2]);
+    st->cell_off[cell[p] + 1]++;
+  }
+  for (int64_t q = 0; q < nc; q++) st->cell_off[q + 1] += st->cell_off[q];
+  int64_t *fill = (int64_t *) malloc(sizeof(int64_t) * nc);
+  memcpy(fill, st->cell_off, sizeof(int64_t) * nc);
+  for (int64_t p = 0; p < st->n; p++) st->cell_rows[fill[cell[p]]++] = (int32_t) p;
+  free(fill);
+  free(cell);
+  return 0;
+}
+
+/* ---------------- neighbour search ---------------- */
+void psph_oracle_free_lists(psph_oracle_state *st)
+{
+  free(st->nb_off); st->nb_off = NULL;
+  free(st->nb_idx); st->nb_idx = NULL;
+}
+
+int psph_oracle_search(const psph_config *c, psph_oracle_state *st)
+{ /* search_neighs_consth, neighs.cc:37-211 */
+  int64_t nc = ncells_of(c);
+  psph_oracle_free_lists(st);
+  /* lists are stored per row; rows that get no list keep an empty one */
+  int64_t *cnt = (int64_t *) calloc(st->n + 1, sizeof(int64_t));
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) {
+      st->nb_off = (int64_t *) malloc(sizeof(int64_t) * (st->n + 1));
+      st->nb_off[0] = 0;
+      for (int64_t p = 0; p < st->n; p++) st->nb_off[p + 1] = st->nb_off[p] + cnt[p];
+      st->nb_idx = (int32_t *) malloc(sizeof(int32_t) * (st->nb_off[st->n] ? st->nb_off[st->n] : 1));
+    }
+    for (int ci = 0; ci < c->ncell[0]; ci++)
+      for (int cj = 0; cj < c->ncell[1]; cj++)
+        for (int ck = 0; ck < c->ncell[2]; ck++) {
+          int64_t cl = cell_lin(c, ci, cj, ck);
+          int64_t b0 = st->cell_off[cl], b1 = st->cell_off[cl + 1];
+          if (b1 == b0) continue; /* :65 plist empty */
+          int has_ghost = 0; /* :69 */
+          for (int64_t q = b0; q < b1; q++) {
+            int b = st->bc[st->cell_rows[q]];
+            if (b == 0 || b == 1 || b == 2) has_ghost = 1;
+          }
+          for (int64_t q = b0; q < b1; q++) {
+            int64_t i = st->cell_rows[q];
+            if (st->guest[i]) continue; /* guest buckets are skipped (:65); single-rank: none */
+            if (!c->use_gsph && has_ghost && st->bc[i] != 100) continue; /* :76-79 */
+            double hi = c->neigh_radius * st->h[i]; /* :84 */
+            int64_t w = pass ? st->nb_off[i] : 0, m = 0;
+            /* all particles of the own bucket, no distance test (:88-92) */
+            for (int64_t r = b0; r < b1; r++) {
+              if (pass) st->nb_idx[w + m] = st->cell_rows[r];
+              m++;
+            }
+            /* 26 neighbouring buckets in table order x-major/z-minor (preprocess.cc:288-314) */
+            for (int di = -1; di <= 1; di++)
+              for (int dj = -1; dj <= 1; dj++)
+                for (int dk = -1; dk <= 1; dk++) {
+                  if (!di && !dj && !dk) continue;
+                  int ni = ci + di, nj = cj + dj, nk = ck + dk;
+                  if (ni < 0 || nj < 0 || nk < 0 || ni >= c->ncell[0] || nj >= c->ncell[1] || nk >= c->ncell[2])
+                    continue;
+                  int64_t nl = cell_lin(c, ni, nj, nk);
+                  for (int64_t r = st->cell_off[nl]; r < st->cell_off[nl + 1]; r++) {
+                    int64_t j = st->cell_rows[r];
+                    double ds[3];
+                    for (int k = 0; k < c->dim; k++) ds[k] = D3(st->x, i, k) - D3(st->x, j, k);
+                    if (in_support(c->dim, ds, hi)) { /* :130 */
+                      if (pass) st->nb_idx[w + m] = (int32_t) j;
+                      m++;
+                    }
+                  }
+                }
+            if (!pass) cnt[i] = m;
+          }
+        }
+  }
+  free(cnt);
+  return 0;
+}
+
+/* ---------------- timestep ---------------- */
+double psph_oracle_timestep(const psph_config *c, const psph_oracle_state *st)
+{ /* timestep.cc:95-135 (3-D), :140-183 (1-D) */
+  double dt = 1.0E+10;
+  for (int64_t i = 0; i < st->n; i++)
+    if (need_neigh(st, i)) {
+      double temp = st->h[i] / st->c[i];
+      if (temp < dt) dt = temp;
+    }
+  return c->cfl * dt;
+}
+
+/* ---------------- adaptive smoothing length ---------------- */
+int psph_oracle_adaptive_sml(const psph_config *c, psph_oracle_state *st)
+{ /* neighs.cc:479-693, ADAPTIVE_SML==1 branch */
+  for (int64_t i = 0; i < st->n; i++) {
+    if (!need_neigh(st, i)) continue;
+    for (int loop = 0; loop < c->num_loop; loop++) {
+      double H_old = st->h[i];
+      double H_star = H_old * c->c_smooth;
+      double supp = c->cutoff2 * H_star;
+      double rho_star = 0.;
+      for (int64_t q = st->nb_off[i]; q < st->nb_off[i + 1]; q++) {
+        int64_t j = st->nb_idx[q];
+        if (!contr_dens(c, st, j)) continue;
+        double dx[3], si[3];
+        for (int k = 0; k < c->dim; k++) {
+          dx[k] = D3(st->x, i, k) - D3(st->x, j, k);
+          si[k] = dx[k] / H_star;
+        }
+        if (in_support(c->dim, dx, supp))
+          rho_star += psph_oracle_weight(c->dim, si, H_star, c->cutoff) * st->mass[j];
+      }
+      double H_new;
+      if (c->dim == 3) H_new = c->eta_smooth * cbrt(st->mass[i] / rho_star);
+      else H_new = c->eta_smooth * (st->mass[i] / rho_star);
+      st->h[i] = H_new; /* put_smlen: RATIO_SML_DX == 1 (constant.h:190) */
+      double err = fabs((H_new - H_old) / H_old);
+      if (err < c->thresh) break;
+    }
+  }
+  return 0;
+}
+
+/* ---------------- smooth_density ---------------- */
+int psph_oracle_smooth_density(const psph_config *c, psph_oracle_state *st)
+{ /* density_massfrac.cc:25-359 with DENSITY_UPDATE_SPH==11, DENSITY_UPDATE_SML==11 */
+  int bad = 0;
+  double *nrho = (double *) malloc(sizeof(double) * st->n);
+  double *nks = (double *) malloc(sizeof(double) * st->n);
+  double *ne = (double *) malloc(sizeof(double) * st->n);
+  for (int64_t i = 0; i < st->n; i++) {
+    if (!need_neigh(st, i)) continue;
+    double supp = c->cutoff2 * st->h[i]; /* :93 */
+    double tmprho[2] = { 0., 0. };
+    double wnorm_e = 0.0, engr = 0.0;
+    for (int64_t q = st->nb_off[i]; q < st->nb_off[i + 1]; q++) {
+      int64_t j = st->nb_idx[q];
+      if (!contr_dens(c, st, j)) continue; /* :135 */
+      double mj = st->mass[j], rhoj = st->rho[j];
+      int ph = st->phase[j];
+      if (ph < 1 || ph > 2) continue;
+      double ds[3], s[3], s_e[3];
+      for (int k = 0; k < c->dim; k++) ds[k] = D3(st->x, i, k) - D3(st->x, j, k);
+      if (!in_support(c->dim, ds, supp)) continue; /* :151 */
+      double hi = 0.5 * (st->h[i] + st->h[j]); /* :155 */
+      for (int k = 0; k < c->dim; k++) s[k] = ds[k] / hi;
+      if (c->have_energy_smooth == 1) { /* :163-168 */
+        for (int k = 0; k < c->dim; k++) s_e[k] = c->e_smooth_ratio * ds[k] / hi;
+        double wm_e = psph_oracle_weight(c->dim, s_e, hi / c->e_smooth_ratio, c->cutoff) * mj;
+        wnorm_e += wm_e / rhoj;
+        engr += wm_e * st->e[j] / rhoj;
+      }
+      double wght = psph_oracle_weight(c->dim, s, hi, c->cutoff);
+      double wm = wght * mj;
+      tmprho[ph - 1] += wm;
+    }
+    if (c->have_energy_smooth == 1) {
+      if (!(wnorm_e > 0)) bad++;
+      engr = engr / wnorm_e; /* :230 */
+      ne[i] = engr;
+    }
+    double density = 0.0, phaserho[2];
+    for (int ph = 0; ph < 2; ph++) { /* :268-273 */
+      phaserho[ph] = tmprho[ph];
+      density += phaserho[ph];
+    }
+    double mssfrc = phaserho[1] / density; /* :285 */
+    if (!(density > 0)) bad++;
+    nrho[i] = density;
+    nks[i] = mssfrc;
+  }
+  /* second pass, :337-352 */
+  for (int64_t i = 0; i < st->n; i++)
+    if (need_neigh(st, i)) {
+      st->ks[i] = nks[i];
+      if (st->ks[i] >= c->msfrc_thresh && st->involved[i] != 2) st->involved[i] = 2;
+      st->rho[i] = nrho[i];
+      if (c->have_energy_smooth == 1) st->e[i] = ne[i];
+      psph_oracle_eos(c, st, i);
+    }
+  free(nrho); free(nks); free(ne);
+  return bad;
+}
+
+/* ---------------- mom_engr_update (SPH) ---------------- */
+static double art_vis(const psph_config *c, double rhoab, double sndspdab, const double *rab, const double *vab,
+                      double rsqab, double h)
+{ /* sph_lib.cc:402-424 */
+  double vrab = 0., vis = 0.;
+  for (int k = 0; k < c->dim; k++) vrab += rab[k] * vab[k];
+  double miuab = h * vrab / (rsqab + c->ata * h * h);
+  if (vrab > 0) vis = 0.;
+  else if (vrab < 0) vis = (c->beta * miuab - c->alf * sndspdab) * miuab / rhoab;
+  return vis;
+}
+
+static double sph_epsilon_heat_conductivity(const psph_config *c, double Cp_ab, const double *ds, const double *vab,
+                                            double hab, double cab)
+{ /* sph_lib.cc:1399-1439 */
+  double dotvv = 0., dotvr = 0., dotrr = 0., kab;
+  for (int i = 0; i < c->dim; i++) dotvr += fabs(vab[i] * ds[i]);
+  if (dotvr == 0.) return 0.;
+  for (int i = 0; i < c->dim; i++) dotrr += ds[i] * ds[i];
+  for (int i = 0; i < c->dim; i++) dotvv += vab[i] * vab[i];
+  if (c->dim == 3) kab = 10.0 * c->epsilon_half * Cp_ab * dotrr * dotvv / (c->prandtl_num * dotvr);
+  else kab = 0.0;
+  return kab / (hab * cab);
+}
+
+static double compute_F(int dim, const double *dwdx, const double *dx)
+{ /* sph_lib.cc:257-281 */
+  double r_sq = 0., W_r = 0.;
+  for (int i = 0; i < dim; i++) W_r += dwdx[i] * dx[i];
+  if (W_r == 0) return 0.0;
+  for (int i = 0; i < dim; i++) r_sq += dx[i] * dx[i];
+  return W_r / r_sq;
+}
+
+static int mom_engr_sph(const psph_config *c, psph_oracle_state *st, double dt)
+{ /* mom_engr_update.cc:30-439, ME_UPDATE_SML==2, MOMENTUM_DISCRETIZE==0 */
+  int bad = 0;
+  int dim = c->dim, lans = c->have_turbulence_lans != 0;
+  double *nv = (double *) malloc(sizeof(double) * 3 * st->n);
+  double *ne = (double *) malloc(sizeof(double) * st->n);
+  double gravity_last = -c->g;
+  for (int64_t i = 0; i < st->n; i++) {
+    if (!need_neigh(st, i)) continue;
+    double hi = st->h[i], supp = c->cutoff2 * hi;
+    double pressi = st->p[i], tempi = st->T[i], Cp_i = st->Cp[i];
+    if (!(st->rho[i] > 0)) bad++;
+    double Vi = 1.0 / st->rho[i];
+    double pvsqi = pressi * Vi * Vi;
+    double veli[3], rhs_v[3] = { 0, 0, 0 }, rhs_e = 0;
+    for (int k = 0; k < dim; k++) veli[k] = lans ? D3(st->sv, i, k) : D3(st->v, i, k);
+    for (int64_t q = st->nb_off[i]; q < st->nb_off[i + 1]; q++) {
+      int64_t j = st->nb_idx[q];
+      if (j == i) continue; /* :201 */
+      double dist_sq = 0, dx[3], si[3], s_heati[3];
+      double h = 0.5 * (hi + st->h[j]);
+      for (int k = 0; k < dim; k++) {
+        dx[k] = D3(st->x, i, k) - D3(st->x, j, k);
+        si[k] = dx[k] / h;
+        dist_sq += dx[k] * dx[k];
+      }
+      if (!in_support(dim, dx, supp)) continue;
+      double mj = st->mass[j], pressj = st->p[j];
+      if (!(st->rho[j] > 0)) bad++;
+      double Vj = 1.0 / st->rho[j];
+      double velij[3];
+      for (int k = 0; k < dim; k++) velij[k] = veli[k] - (lans ? D3(st->sv, j, k) : D3(st->v, j, k));
+      double rhoab = 0.5 * (st->rho[i] + st->rho[j]);
+      double sndspdab = 0.5 * (st->c[i] + st->c[j]);
+      double vis = art_vis(c, rhoab, sndspdab, dx, velij, dist_sq, h);
+      if (lans) { /* SPH_epsilon_mom, sph_lib.cc:1331-1338 */
+        double dotv = 0.;
+        for (int k = 0; k < dim; k++) dotv += velij[k] * velij[k];
+        vis -= c->epsilon_half * dotv * Vj;
+      }
+      double mpvsqij = mj * (pressj * Vj * Vj + pvsqi + vis);
+      double dwdxi[3], dwdx_heati[3];
+      for (int k = 0; k < dim; k++) s_heati[k] = si[k] * c->heat_trans_scale_ratio;
+      for (int k = 0; k < dim; k++) {
+        dwdxi[k] = psph_oracle_d_weight(dim, si, h, c->cutoff, k);
+        dwdx_heati[k] = psph_oracle_d_weight(dim, s_heati, h / c->heat_trans_scale_ratio, c->cutoff, k);
+      }
+      double heat_tran = 0.;
+      if (lans) { /* :307-314 */
+        double Cp_ij = 0.5 * (st->Cp[j] + Cp_i);
+        double hab = 0.5 * (hi + st->h[j]);
+        double kij = sph_epsilon_heat_conductivity(c, Cp_ij, dx, velij, hab, sndspdab);
+        double Fij = compute_F(dim, dwdx_heati, dx);
+        heat_tran = mj * Vj * Vi * kij * (tempi - st->T[j]) * Fij;
+      }
+      for (int k = 0; k < dim; k++) rhs_v[k] -= mpvsqij * dwdxi[k];
+      double deltae = 0.;
+      for (int k = 0; k < dim; k++) deltae += 0.5 * (mpvsqij * dwdxi[k]) * velij[k];
+      rhs_e += (deltae + heat_tran);
+    }
+    double unew[3];
+    for (int k = 0; k < dim; k++) unew[k] = D3(st->v, i, k) + dt * rhs_v[k];
+    unew[dim - 1] += dt * gravity_last; /* :350 */
+    for (int k = 0; k < dim; k++) D3(nv, i, k) = unew[k];
+    ne[i] = st->e[i] + dt * (rhs_e + veli[dim - 1] * gravity_last); /* :354 */
+  }
+  for (int64_t i = 0; i < st->n; i++)
+    if (need_neigh(st, i)) { /* :412-418 */
+      for (int k = 0; k < dim; k++) D3(st->v, i, k) = D3(nv, i, k);
+      st->e[i] = ne[i];
+      psph_oracle_eos(c, st, i);
+    }
+  free(nv); free(ne);
+  return bad;
+}
+
+int psph_oracle_mom_engr_update(const psph_config *c, psph_oracle_state *st, double dt)
+{
+  if (c->use_gsph) return -1; /* GSPH variant: oracle/psph_oracle_gsph.c (pending) */
+  return mom_engr_sph(c, st, dt);
+}
+
+int psph_oracle_calc_gradients(const psph_config *c, psph_oracle_state *st)
+{
+  (void) c; (void) st;
+  return -1;
+}
+
+/* ---------------- smooth_velocity ---------------- */
+int psph_oracle_smooth_velocity(const psph_config *c, psph_oracle_state *st)
+{ /* smooth_velocity.cc:25-165, HAVE_TURBULENCE_LANS==1 */
+  int bad = 0, dim = c->dim;
+  for (int64_t i = 0; i < st->n; i++) {
+    if (!need_neigh(st, i)) continue;
+    double hi = st->h[i], supp = c->cutoff2 * hi;
+    double temp_dv[3] = { 0, 0, 0 }, wnorm = 0.;
+    for (int64_t q = st->nb_off[i]; q < st->nb_off[i + 1]; q++) {
+      int64_t j = st->nb_idx[q];
+      if (!contr_vel_smooth(st, j)) continue;
+      double ds[3], s[3];
+      for (int k = 0; k < dim; k++) ds[k] = D3(st->x, i, k) - D3(st->x, j, k);
+      if (!in_support(dim, ds, supp)) continue;
+      for (int k = 0; k < dim; k++) s[k] = ds[k] / hi;
+      double wght = psph_oracle_weight(dim, s, hi, c->cutoff);
+      double mvw = wght * st->mass[j] / st->rho[j];
+      for (int k = 0; k < dim; k++) temp_dv[k] += mvw * (D3(st->v, j, k) - D3(st->v, i, k));
+      wnorm += mvw;
+    }
+    if (!(wnorm > 0)) bad++;
+    for (int k = 0; k < dim; k++) temp_dv[k] /= wnorm;
+    for (int k = 0; k < dim; k++) D3(st->sv, i, k) = D3(st->v, i, k) + temp_dv[k];
+  }
+  return bad;
+}
+
+/* ---------------- update_pos ---------------- */
+int psph_oracle_update_pos(const psph_config *c, psph_oracle_state *st, double dt, int erupting)
+{ /* update_pos.cc:35-168 */
+  int dim = c->dim, lans = c->have_turbulence_lans != 0;
+  for (int64_t i = 0; i < st->n; i++) {
+    if (st->removed && st->removed[i]) continue;
+    if (is_real(st, i)) {
+      for (int k = 0; k < dim; k++)
+        D3(st->x, i, k) = D3(st->x, i, k) + dt * (lans ? D3(st->sv, i, k) : D3(st->v, i, k));
+    } else if (st->bc[i] == 0 && erupting) {
+      for (int k = 0; k < dim; k++) D3(st->x, i, k) = D3(st->x, i, k) + dt * D3(st->v, i, k);
+      if (dim == 3 && D3(st->x, i, 2) >= c->erupt_top) { /* :134-142 */
+        st->bc[i] = 100;
+        st->h[i] = c->smlen_real;
+        st->involved[i] = 2;
+      }
+    }
+  }
+  return 0;
+}
+
+/* ---------------- update_particles_in_bucket ---------------- */
+static int determine_escape(const psph_config *c, const psph_cell_attr *a, const double *pos)
+{ /* Bucket::determine_escape, bucket.cc:434-452 */
+  for (int i = 0; i < c->dim; i++) {
+    if (a->bucket_index[i * 2] == -1) {
+      if ((pos[i] - a->bnd[i * 2]) < -c->tiny) return 1;
+    } else if (a->bucket_index[i * 2 + 1] == 1) {
+      if ((pos[i] - a->bnd[i * 2 + 1]) > c->tiny) return 1;
+    }
+  }
+  return 0;
+}
+
+typedef struct { int32_t *v; int64_t n, cap; } ivec;
+static void ivec_push(ivec *a, int32_t x)
+{
+  if (a->n == a->cap) { a->cap = a->cap ? 2 * a->cap : 8; a->v = (int32_t *) realloc(a->v, sizeof(int32_t) * a->cap); }
+  a->v[a->n++] = x;
+}
+
+int psph_oracle_rebin(const psph_config *c, psph_oracle_state *st, int *lost)
+{ /* update_particles_in_bucket, update_pos.cc:172-462, single rank (no guests).
+   * new plist of a bucket = [arrivals from buckets visited earlier] ++ [its ghosts, old order]
+   * ++ [its staying real/erupt particles, old order] ++ [arrivals from buckets visited later]
+   * (add_particle appends to new_plist, bucket.h:642-645; put_new_plist appends too, :305-308). */
+  if (c->dim != 3) return 0;
+  int64_t nc = ncells_of(c);
+  ivec *np = (ivec *) calloc(nc, sizeof(ivec));
+  int nlost = 0;
+  for (int64_t oi = 0; oi < nc; oi++) {
+    int64_t cl = st->cell_order ? st->cell_order[oi] : oi;
+    const psph_cell_attr *a = st->cell_attr ? &st->cell_attr[cl] : NULL;
+    if (a && (a->type == PSPH_CELL_BRIEF || !a->active)) continue;
+    int ck = (int) (cl % c->ncell[2]), cj = (int) ((cl / c->ncell[2]) % c->ncell[1]);
+    int ci = (int) (cl / ((int64_t) c->ncell[2] * c->ncell[1]));
+    int idx[3] = { ci, cj, ck };
+    ivec ghosts = { 0, 0, 0 }, realp = { 0, 0, 0 };
+    for (int64_t q = st->cell_off[cl]; q < st->cell_off[cl + 1]; q++) {
+      int32_t p = st->cell_rows[q];
+      if (!(is_real(st, p) || st->bc[p] == 0)) { ivec_push(&ghosts, p); continue; }
+      double pos[3];
+      for (int k = 0; k < 3; k++) pos[k] = D3(st->x, p, k);
+      if (is_real(st, p) && a && a->type == PSPH_CELL_MIXED && determine_escape(c, a, pos)) {
+        st->removed[p] = 1; nlost++; continue;
+      }
+      int left = 0, nidx[3];
+      for (int k = 0; k < 3; k++) { /* :257-271 */
+        nidx[k] = idx[k];
+        if (pos[k] < cell_min(c, k, idx[k])) { nidx[k] = idx[k] - 1; left = 1; }
+        else if (pos[k] >= cell_max(c, k, idx[k])) { nidx[k] = idx[k] + 1; left = 1; }
+      }
+      if (!left) { ivec_push(&realp, p); continue; }
+      int inside = 1;
+      for (int k = 0; k < 3; k++) if (nidx[k] < 0 || nidx[k] >= c->ncell[k]) inside = 0;
+      if (!inside) { st->removed[p] = 1; nlost++; continue; }
+      int64_t nl = cell_lin(c, nidx[0], nidx[1], nidx[2]);
+      const psph_cell_attr *na = st->cell_attr ? &st->cell_attr[nl] : NULL;
+      if (na && !na->has_involved) { st->removed[p] = 1; nlost++; continue; } /* :300-304 */
+      ivec_push(&np[nl], p);
+    }
+    for (int64_t q = 0; q < ghosts.n; q++) ivec_push(&np[cl], ghosts.v[q]);
+    for (int64_t q = 0; q < realp.n; q++) ivec_push(&np[cl], realp.v[q]);
+    free(ghosts.v); free(realp.v);
+  }
+  /* second loop (:405-447): PRESS_BC buckets and inactive buckets keep their old plist */
+  int64_t *noff = (int64_t *) malloc(sizeof(int64_t) * (nc + 1));
+  int32_t *nrows = (int32_t *) malloc(sizeof(int32_t) * (st->n ? st->n : 1));
+  noff[0] = 0;
+  for (int64_t cl = 0; cl < nc; cl++) {
+    const psph_cell_attr *a = st->cell_attr ? &st->cell_attr[cl] : NULL;
+    int keep_old = a && (a->type == PSPH_CELL_BRIEF || !a->active || a->type == PSPH_CELL_PRESS_BC);
+    int64_t w = noff[cl];
+    if (keep_old) {
+      for (int64_t q = st->cell_off[cl]; q < st->cell_off[cl + 1]; q++)
+        if (!st->removed[st->cell_rows[q]]) nrows[w++] = st->cell_rows[q];
+    } else
+      for (int64_t q = 0; q < np[cl].n; q++) nrows[w++] = np[cl].v[q];
+    noff[cl + 1] = w;
+    free(np[cl].v);
+  }
+  memcpy(st->cell_off, noff, sizeof(int64_t) * (nc + 1));
+  memcpy(st->cell_rows, nrows, sizeof(int32_t) * noff[nc]);
+  free(noff); free(nrows); free(np);
+  if (lost) *lost = nlost;
+  return 0;
+}
+
+/* ---------------- THashTable iteration order ---------------- */
+typedef struct { int64_t slot; uint32_t k[3]; int64_t row; } ord_t;
+static int ord_cmp(const void *a, const void *b)
+{
+  const ord_t *x = (const ord_t *) a, *y = (const ord_t *) b;
+  if (x->slot != y->slot) return x->slot < y->slot ? -1 : 1;
+  for (int i = 0; i < 3; i++)
+    if (x->k[i] != y->k[i]) return x->k[i] < y->k[i] ? -1 : 1;
+  return 0;
+}
+void psph_oracle_table_order(const psph_config *c, const uint32_t *key, int64_t n, int64_t *perm)
+{ /* thashtab.cc:204-222 (hash), :86-134 (sorted chains), :246-262 (iteration) */
+  ord_t *o = (ord_t *) malloc(sizeof(ord_t) * (n ? n : 1));
+  double umax = (double) 0xffffffffu;
+  int S02 = c->ptable_size / 10, S01 = c->ptable_size - S02;
+  for (int64_t i = 0; i < n; i++) {
+    if (c->dim == 1) o[i].slot = key[3 * i];
+    else o[i].slot = (int) ((double) key[3 * i] / umax * S01) + (int) ((double) key[3 * i + 1] / umax * S02);
+    for (int k = 0; k < 3; k++) o[i].k[k] = key[3 * i + k];
+    o[i].row = i;
+  }
+  qsort(o, n, sizeof(ord_t), ord_cmp);
+  for (int64_t i = 0; i < n; i++) perm[i] = o[i].row;
+  free(o);
+}
+
+/* ---------------- Hilbert key ---------------- */
+void psph_oracle_hsfc3d(const double coord[3], uint32_t key[2])
+{ /* HSFC3d + hsfc3d, hilbert.c:156-271,289-303 (Zoltan's 3-D Hilbert curve), restated as a
+   * 63-bit index walk: 21 levels, per level the octant is Gray-decoded under the current axis
+   * permutation/reflection, then the frame is rotated by a per-octant rule.  The reference
+   * stores level i, bit n at bit offset 3i+n of a 2-word key, i.e. the 63-bit index shifted
+   * right by one (its last bit falls off the end of the 2-word key). */
+  static const unsigned char gray_inv[8] = { 0, 1, 3, 2, 7, 6, 4, 5 };
+  /* new axis slot a takes old slot src[c][a], reflected if flip[c][a] */
+  static const unsigned char src[8][3] = { {2,1,0}, {0,2,1}, {0,1,2}, {2,0,1}, {2,0,1}, {0,1,2}, {0,2,1}, {2,1,0} };
+  static const unsigned char flip[8][3] = { {0,0,0}, {0,0,0}, {0,0,0}, {1,1,0}, {0,1,1}, {0,0,0}, {0,1,1}, {1,0,1} };
+  const uint32_t imax = 0xffffffffu;
+  uint32_t cc[3];
+  for (int d = 0; d < 3; d++) {
+    double v = (coord[d] <= 0) ? 0 : imax * coord[d];
+    cc[d] = (uint32_t) ((imax < v) ? imax : v);
+  }
+  unsigned char ax[3] = { 0, 2, 4 }; /* (dimension << 1) | reflect */
+  uint64_t H = 0;
+  for (int i = 1; i <= 21; i++) {
+    unsigned s = 32 - i, g = 0;
+    for (int a = 0; a < 3; a++) g |= (((cc[ax[a] >> 1] >> s) ^ ax[a]) & 1u) << a;
+    unsigned oct = gray_inv[g];
+    H = (H << 3) | oct;
+    unsigned char old[3] = { ax[0], ax[1], ax[2] };
+    for (int a = 0; a < 3; a++) ax[a] = old[src[oct][a]] ^ flip[oct][a];
+  }
+  uint64_t K = H >> 1;
+  key[0] = (uint32_t) (K >> 32);
+  key[1] = (uint32_t) (K & 0xffffffffu);
+}

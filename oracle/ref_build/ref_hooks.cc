@@ -1,0 +1,382 @@
+/* Stage hooks around the UNMODIFIED reference driver.
+ *
+ * This translation unit textually includes /root/reference/src/plume/main.cc
+ * after #define-renaming the stage calls it makes (timestep, search_neighs_consth,
+ * adaptive_sml, calc_gradients, mom_engr_update, smooth_density, smooth_velocity,
+ * update_pos, update_particles_in_bucket, add_new_erupt, apply_bcond) to the
+ * psphhook_* wrappers below. Every wrapper calls the reference's own function
+ * (compiled from /root/reference/src, untouched) and, when PSPH_DUMP_DIR is set,
+ * writes the particle table before/after it. So: reference loop, reference
+ * numerics, extra dumps. Nothing here is product code (see oracle/README.md).
+ *
+ * Environment:
+ *   PSPH_DUMP_DIR     directory for dumps (unset -> no dumps)
+ *   PSPH_DUMP_STEPS   "a-b" inclusive step range to dump (default 1-1); step 0 = state
+ *                     at the first timestep() call, i.e. after initialisation
+ *   PSPH_DUMP_NEIGH   1 -> also dump neighbour lists after search_neighs_consth
+ *   PSPH_MAX_STEPS    stop the run (exit 0) once this many steps completed
+ *   PSPH_STAGE_TIMES  1 -> print accumulated wall time per stage at exit
+ *
+ * Dump file "<dir>/s<step>_<stage>_<pre|post>.bin":
+ *   i32 magic 0x50535048, i32 dim, i32 gsph, i64 n, f64 time, f64 dt, then n rows
+ *   of DumpRow in THashTable iteration order (thashtab.cc:246-262).
+ * Neighbour file "<dir>/s<step>_neigh.bin": i64 n, i64 offsets[n+1], i32 idx[...]
+ *   (indices into the dump rows of the same step).
+ * Bucket file "<dir>/s<step>_<stage>_buckets.bin": i64 nb, then per non-brief bucket:
+ *   u32 key[2], f64 mincrd[3], f64 maxcrd[3], i32 type, has_involved, active, guest, np,
+ *   i32 rows[np] (plist order).
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <string>
+#include <vector>
+#include <list>
+#include <iostream>
+using namespace std;
+
+#include <mpi.h>
+#include <hashtab.h>
+#include <thashtab.h>
+#include <bucket.h>
+#include <particle.h>
+#include <properties.h>
+#include <bnd_image.h>
+#include <bgmesh.h>
+#include <multiproc.h>
+#include <particler.h>
+#include "constant.h"
+#include "parameters.h"
+#include "sph_header.h"
+
+#ifndef USE_GSPH
+#define USE_GSPH 0
+#endif
+
+struct DumpRow
+{
+  unsigned key[3];
+  int bc_type, phase, involved, guest;
+  int pad;
+  double mass, smlen, mass_frac, pressure, gamma, sound_speed, temperature, specific_heat_p;
+  double phase_density[2];
+  double coord[3], vel[3], smoothed_v[3];
+  double rho, engr, smoothed_e;
+  double grad[15]; /* d_rho, d_u, d_v, d_w, d_p (GSPH builds; else 0) */
+};
+
+namespace {
+int g_step = 0;
+int g_lo = 1, g_hi = 1;
+const char *g_dir = NULL;
+bool g_neigh = false, g_times = false;
+int g_max_steps = -1;
+double g_time = 0, g_dt = 0;
+map<string, double> g_stage_time;
+double g_loop_t0 = 0;
+
+double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+void print_times()
+{
+  if (!g_times) return;
+  double tot = now() - g_loop_t0;
+  fprintf(stderr, "PSPH_STAGE_TIMES steps=%d loop_wall=%.6f\n", g_step, tot);
+  for (map<string, double>::iterator it = g_stage_time.begin(); it != g_stage_time.end(); ++it)
+    fprintf(stderr, "PSPH_STAGE %s %.6f\n", it->first.c_str(), it->second);
+}
+
+void init_once()
+{
+  static bool done = false;
+  if (done) return;
+  done = true;
+  g_dir = getenv("PSPH_DUMP_DIR");
+  if (const char *s = getenv("PSPH_DUMP_STEPS")) {
+    if (sscanf(s, "%d-%d", &g_lo, &g_hi) < 2) g_hi = g_lo;
+  }
+  g_neigh = getenv("PSPH_DUMP_NEIGH") && atoi(getenv("PSPH_DUMP_NEIGH"));
+  g_times = getenv("PSPH_STAGE_TIMES") && atoi(getenv("PSPH_STAGE_TIMES"));
+  if (const char *s = getenv("PSPH_MAX_STEPS")) g_max_steps = atoi(s);
+  atexit(print_times);
+}
+
+bool dumping() { return g_dir && g_step >= g_lo && g_step <= g_hi; }
+
+struct KeyLess { bool operator()(const TKey &a, const TKey &b) const { return a < b; } };
+
+void fill_row(Particle *p, DumpRow *r)
+{
+  memset(r, 0, sizeof(*r));
+  TKey k = p->getKey();
+  for (int i = 0; i < TKEYLENGTH; i++) r->key[i] = k.key[i];
+  r->bc_type = p->get_bc_type();
+  r->phase = p->which_phase();
+  r->involved = p->get_involved();
+  r->guest = p->is_guest() ? 1 : 0;
+  r->mass = p->get_mass();
+  r->smlen = p->get_smlen();
+  r->mass_frac = p->get_mass_frac();
+  r->pressure = p->get_pressure();
+  r->gamma = p->get_gamma();
+  r->sound_speed = p->get_sound_speed();
+  r->temperature = p->get_temperature();
+  r->specific_heat_p = p->get_specific_heat_p();
+  r->phase_density[0] = *(p->get_phase_density());
+  r->phase_density[1] = *(p->get_phase_density() + 1);
+  for (int i = 0; i < DIMENSION; i++) {
+    r->coord[i] = *(p->get_coords() + i);
+    r->vel[i] = *(p->get_vel() + i);
+    r->smoothed_v[i] = *(p->get_smoothed_velocity() + i);
+  }
+  r->rho = p->get_density();
+  r->engr = p->get_energy();
+  r->smoothed_e = p->get_smoothed_energy();
+#if (USE_GSPH == 1 || USE_GSPH == 2)
+  for (int i = 0; i < DIMENSION; i++) {
+    r->grad[0 + i] = *(p->get_density_derivative() + i);
+    r->grad[3 + i] = *(p->get_velocity_u_derivative() + i);
+    r->grad[6 + i] = *(p->get_velocity_v_derivative() + i);
+    r->grad[9 + i] = *(p->get_velocity_w_derivative() + i);
+    r->grad[12 + i] = *(p->get_pressure_derivative() + i);
+  }
+#endif
+}
+
+void dump_table(THashTable *P, const char *stage, const char *when, bool with_neigh = false)
+{
+  if (!dumping()) return;
+  char fn[512];
+  snprintf(fn, sizeof fn, "%s/s%04d_%s_%s.bin", g_dir, g_step, stage, when);
+  FILE *f = fopen(fn, "wb");
+  if (!f) { perror(fn); exit(1); }
+  vector<DumpRow> rows;
+  vector<Particle *> ptrs;
+  THTIterator itr(P);
+  Particle *p;
+  while ((p = (Particle *) itr.next())) { DumpRow r; fill_row(p, &r); rows.push_back(r); ptrs.push_back(p); }
+  int magic = 0x50535048, dim = DIMENSION, gsph = USE_GSPH;
+  long long n = rows.size();
+  fwrite(&magic, 4, 1, f); fwrite(&dim, 4, 1, f); fwrite(&gsph, 4, 1, f);
+  fwrite(&n, 8, 1, f); fwrite(&g_time, 8, 1, f); fwrite(&g_dt, 8, 1, f);
+  if (n) fwrite(&rows[0], sizeof(DumpRow), n, f);
+  fclose(f);
+  if (with_neigh) {
+    map<TKey, int, KeyLess> idx;
+    for (long long i = 0; i < n; i++) idx[ptrs[i]->getKey()] = (int) i;
+    vector<long long> off(n + 1, 0);
+    vector<int> ids;
+    for (long long i = 0; i < n; i++) {
+      vector<TKey> nb = ptrs[i]->get_neighs();
+      for (size_t j = 0; j < nb.size(); j++) {
+        map<TKey, int, KeyLess>::iterator it = idx.find(nb[j]);
+        ids.push_back(it == idx.end() ? -1 : it->second);
+      }
+      off[i + 1] = (long long) ids.size();
+    }
+    snprintf(fn, sizeof fn, "%s/s%04d_neigh.bin", g_dir, g_step);
+    f = fopen(fn, "wb");
+    fwrite(&n, 8, 1, f); fwrite(&off[0], 8, n + 1, f);
+    if (!ids.empty()) fwrite(&ids[0], 4, ids.size(), f);
+    fclose(f);
+  }
+}
+
+#if CODE_DIMENSION == 3
+void dump_buckets(THashTable *P, HashTable *BG, const char *stage)
+{
+  if (!dumping()) return;
+  map<TKey, int, KeyLess> idx;
+  {
+    THTIterator itr(P);
+    Particle *p; int i = 0;
+    while ((p = (Particle *) itr.next())) idx[p->getKey()] = i++;
+  }
+  char fn[512];
+  snprintf(fn, sizeof fn, "%s/s%04d_%s_buckets.bin", g_dir, g_step, stage);
+  FILE *f = fopen(fn, "wb");
+  long long nb = 0;
+  fwrite(&nb, 8, 1, f);
+  HTIterator it(BG);
+  void *t;
+  while ((t = it.next())) {
+    BriefBucket *bb = (BriefBucket *) t;
+    if (bb->check_brief()) continue;
+    Bucket *b = (Bucket *) t;
+    Key k = b->getKey();
+    fwrite(k.key, 4, 2, f);
+    fwrite(b->get_mincrd(), 8, 3, f);
+    fwrite(b->get_maxcrd(), 8, 3, f);
+    vector<TKey> pl = b->get_plist();
+    int v[5] = { b->get_bucket_type(), (int) b->get_has_involved(), (int) b->is_active(), (int) b->is_guest(), (int) pl.size() };
+    fwrite(v, 4, 5, f);
+    for (size_t j = 0; j < pl.size(); j++) {
+      map<TKey, int, KeyLess>::iterator q = idx.find(pl[j]);
+      int r = q == idx.end() ? -1 : q->second;
+      fwrite(&r, 4, 1, f);
+    }
+    nb++;
+  }
+  fseek(f, 0, SEEK_SET);
+  fwrite(&nb, 8, 1, f);
+  fclose(f);
+}
+#endif
+
+struct StageTimer
+{
+  const char *name; double t0;
+  StageTimer(const char *n) : name(n), t0(now()) {}
+  ~StageTimer() { g_stage_time[name] += now() - t0; }
+};
+
+void begin_step(THashTable *P, double dt_unclipped)
+{
+  init_once();
+  if (g_step == 0) g_loop_t0 = now();
+  if (g_max_steps >= 0 && g_step >= g_max_steps) {
+    /* state after the last completed step */
+    g_lo = g_hi = g_step; /* always dump the final state when dumping is on */
+    dump_table(P, "final", "post");
+    exit(0);
+  }
+  (void) dt_unclipped;
+}
+}
+
+/* ---- wrappers: same signatures as the reference prototypes (particler.h:22-357) ---- */
+#if CODE_DIMENSION == 1
+double psphhook_timestep(THashTable *P, TimeProps *tp)
+{
+  init_once();
+  begin_step(P, 0);
+  if (g_step == 0) { int lo = g_lo, hi = g_hi; g_lo = g_hi = 0; dump_table(P, "init", "post"); g_lo = lo; g_hi = hi; }
+  double dt;
+  { StageTimer st("timestep"); dt = timestep(P, tp); }
+  g_step++;
+  /* incrtime() runs next in main.cc and may clip dt (properties.h:71-82); mirror it for the header */
+  double d = dt;
+  if (tp->time + d > tp->ndtimeoutput) d = tp->ndtimeoutput - tp->time;
+  if (tp->time + d > tp->ndmax_time) d = tp->ndmax_time - tp->time;
+  g_dt = d; g_time = tp->time + d;
+  dump_table(P, "timestep", "post");
+  return dt;
+}
+#else
+double psphhook_timestep(HashTable *BG, THashTable *P, TimeProps *tp)
+{
+  init_once();
+  begin_step(P, 0);
+  if (g_step == 0) {
+    int lo = g_lo, hi = g_hi; g_lo = g_hi = 0;
+    dump_table(P, "init", "post"); dump_buckets(P, BG, "init");
+    g_lo = lo; g_hi = hi;
+  }
+  double dt;
+  { StageTimer st("timestep"); dt = timestep(BG, P, tp); }
+  g_step++;
+  double d = dt;
+  if (tp->time + d > tp->ndtimeoutput) d = tp->ndtimeoutput - tp->time;
+  if (tp->time + d > tp->ndmax_time) d = tp->ndmax_time - tp->time;
+  g_dt = d; g_time = tp->time + d;
+  dump_table(P, "timestep", "post");
+  dump_buckets(P, BG, "timestep");
+  return dt;
+}
+
+int psphhook_search_neighs_consth(int myid, THashTable *P, HashTable *BG)
+{
+  init_once();
+  if (g_step == 0) return search_neighs_consth(myid, P, BG); /* call during initialisation */
+  int r;
+  { StageTimer st("search_neighs_consth"); r = search_neighs_consth(myid, P, BG); }
+  dump_table(P, "search", "post", g_neigh);
+  return r;
+}
+
+void psphhook_update_particles_in_bucket(int myid, THashTable *P, HashTable *BG, int *lost)
+{
+  { StageTimer st("update_particles_in_bucket"); update_particles_in_bucket(myid, P, BG, lost); }
+  dump_table(P, "rebin", "post");
+  dump_buckets(P, BG, "rebin");
+}
+
+#ifndef SIMULATE_ASH
+void psphhook_add_new_erupt(int myid, THashTable *P, HashTable *BG, TimeProps *tp, MatProps *mp, SimProps *sp, double dt)
+{
+  { StageTimer st("add_new_erupt"); add_new_erupt(myid, P, BG, tp, mp, sp, dt); }
+  dump_table(P, "erupt", "post");
+  dump_buckets(P, BG, "erupt");
+}
+#endif
+
+int psphhook_apply_bcond(int myid, THashTable *P, HashTable *BG, MatProps *mp, list<BndImage> &img)
+{
+  init_once();
+  if (g_step == 0) return apply_bcond(myid, P, BG, mp, img);
+  int r;
+  { StageTimer st("apply_bcond"); r = apply_bcond(myid, P, BG, mp, img); }
+  dump_table(P, "bcond", "post");
+  return r;
+}
+#endif
+
+void psphhook_adaptive_sml(int myid, THashTable *P)
+{
+  init_once();
+  if (g_step == 0) { adaptive_sml(myid, P); return; }
+  { StageTimer st("adaptive_sml"); adaptive_sml(myid, P); }
+  dump_table(P, "sml", "post");
+}
+
+#if (USE_GSPH == 1 || USE_GSPH == 2)
+void calc_gradients(THashTable *P_table);
+void psphhook_calc_gradients(THashTable *P)
+{
+  { StageTimer st("calc_gradients"); calc_gradients(P); }
+  dump_table(P, "grad", "post");
+}
+#endif
+
+int psphhook_mom_engr_update(int myid, THashTable *P, TimeProps *tp, SimProps *sp)
+{
+  dump_table(P, "mom", "pre");
+  int r;
+  { StageTimer st("mom_engr_update"); r = mom_engr_update(myid, P, tp, sp); }
+  dump_table(P, "mom", "post");
+  return r;
+}
+
+void psphhook_smooth_density(THashTable *P)
+{
+  { StageTimer st("smooth_density"); smooth_density(P); }
+  dump_table(P, "dens", "post");
+}
+
+void psphhook_smooth_velocity(THashTable *P)
+{
+  { StageTimer st("smooth_velocity"); smooth_velocity(P); }
+  dump_table(P, "svel", "post");
+}
+
+void psphhook_update_pos(THashTable *P, TimeProps *tp, MatProps *mp)
+{
+  { StageTimer st("update_pos"); update_pos(P, tp, mp); }
+  dump_table(P, "pos", "post");
+}
+
+/* ---- the unmodified reference driver, with its stage calls renamed ---- */
+#define timestep psphhook_timestep
+#define search_neighs_consth psphhook_search_neighs_consth
+#define adaptive_sml psphhook_adaptive_sml
+#define calc_gradients psphhook_calc_gradients
+#define mom_engr_update psphhook_mom_engr_update
+#define smooth_density psphhook_smooth_density
+#define smooth_velocity psphhook_smooth_velocity
+#define update_pos psphhook_update_pos
+#define update_particles_in_bucket psphhook_update_particles_in_bucket
+#define add_new_erupt psphhook_add_new_erupt
+#define apply_bcond psphhook_apply_bcond
+#include PSPH_REF_MAIN_CC

@@ -1,0 +1,4 @@
+#define CODE_DIMENSION 3
+#define HAVE_MPI_H 1
+#define HAVE_HDF5_H 1
+#define MULTI_PROC /**/

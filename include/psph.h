@@ -196,13 +196,29 @@ int psph_exchange_ghosts(psph_ctx *ctx);
 int psph_repartition(psph_ctx *ctx);
 
 /* test-only: neighbour lists exactly as search_neighs_consth builds them (neighs.cc:37-211),
- * as CSR over rows of the REFERENCE-order download.  Two-call protocol: idx == NULL returns
- * the total count in *nnz. */
+ * as CSR over device rows: offsets[n+1], idx = device row numbers, both in the row order that
+ * psph_download(order = PSPH_ORDER_DEVICE) returns right afterwards (map through the keys).
+ * Order inside one list is unspecified.  Two-call protocol: idx == NULL only fills offsets
+ * and *nnz. */
 int psph_emit_neighbours(psph_ctx *ctx, int64_t *offsets, int32_t *idx, size_t idx_cap, size_t *nnz);
 
-/* instrumentation: kernels launched since the last call (bench.py gpu_launches), and the
- * device time of the last launch of a named kernel family measured with CUDA events */
+/* Invariant violations the reference assert()s on (rho <= 0, empty normalisation sums),
+ * counted on the device since the last reset; synchronises the stream. */
+int psph_errors(psph_ctx *ctx, int reset);
+
+/* diagnostic: linear background-cell index (x-major, z-minor) of every row, in the row order
+ * psph_download(order = PSPH_ORDER_DEVICE) returns right afterwards; replaces walking the
+ * Bucket plists (bucket.h:255-321) in the tests of update_particles_in_bucket. */
+int psph_cell_of_rows(psph_ctx *ctx, int32_t *cells, size_t cap);
+
+/* instrumentation: kernels launched since the last call (bench.py gpu_launches); with
+ * psph_set_timing(on) every stage call is bracketed by CUDA events on the context stream
+ * (and synchronised) and psph_stage_ms returns the accumulated device time of a stage:
+ * 0 timestep, 1 search, 2 adaptive_sml, 3 gradients, 4 mom_engr, 5 density, 6 velocity,
+ * 7 update_pos, 8 rebin. */
 int64_t psph_launch_count(psph_ctx *ctx, int reset);
+int psph_set_timing(psph_ctx *ctx, int on);
+double psph_stage_ms(psph_ctx *ctx, int stage, int reset);
 int psph_sync(psph_ctx *ctx);
 void *psph_stream(psph_ctx *ctx);
 

@@ -258,6 +258,8 @@ class OracleState:
             attr[lin]["type"] = b["type"]
             attr[lin]["has_involved"] = b["has_involved"]
             attr[lin]["active"] = b["active"]
+            attr[lin]["bucket_index"] = b["bucket_index"]
+            attr[lin]["bnd"] = b["bnd"]
             order.append(lin)
             lists[lin] = b["rows"]
         # HTIterator only visits existing buckets; append the rest so every cell is listed once

@@ -158,7 +158,10 @@ int psph_oracle_search(const psph_config *c, psph_oracle_state *st)
           for (int64_t q = b0; q < b1; q++) {
             int64_t i = st->cell_rows[q];
             if (st->guest[i]) continue; /* guest buckets are skipped (:65); single-rank: none */
-            if (!c->use_gsph && has_ghost && st->bc[i] != 100) continue; /* :76-79 */
+            if (c->dim == 1) { /* no search in 1-D: every need_neigh particle lists all particles in
+                                * creation order, add_air.cc:470-479 */
+              if (!need_neigh(st, i)) continue;
+            } else if (!c->use_gsph && has_ghost && st->bc[i] != 100) continue; /* :76-79 */
             double hi = c->neigh_radius * st->h[i]; /* :84 */
             int64_t w = pass ? st->nb_off[i] : 0, m = 0;
             /* all particles of the own bucket, no distance test (:88-92) */

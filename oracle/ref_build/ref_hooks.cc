@@ -24,7 +24,7 @@
  *   (indices into the dump rows of the same step).
  * Bucket file "<dir>/s<step>_<stage>_buckets.bin": i64 nb, then per non-brief bucket:
  *   u32 key[2], f64 mincrd[3], f64 maxcrd[3], i32 type, has_involved, active, guest, np,
- *   i32 rows[np] (plist order).
+ *   i32 bucket_index[6], f64 bnd[6], i32 rows[np] (plist order).
  */
 #include <cstdio>
 #include <cstdlib>
@@ -212,6 +212,8 @@ void dump_buckets(THashTable *P, HashTable *BG, const char *stage)
     vector<TKey> pl = b->get_plist();
     int v[5] = { b->get_bucket_type(), (int) b->get_has_involved(), (int) b->is_active(), (int) b->is_guest(), (int) pl.size() };
     fwrite(v, 4, 5, f);
+    fwrite(b->get_bucket_index(), 4, 6, f);
+    fwrite(b->get_bnd(), 8, 6, f);
     for (size_t j = 0; j < pl.size(); j++) {
       map<TKey, int, KeyLess>::iterator q = idx.find(pl[j]);
       int r = q == idx.end() ? -1 : q->second;

@@ -41,7 +41,7 @@ def read_neigh(path):
 
 
 def read_buckets(path):
-    """-> list of dicts (key, mincrd, maxcrd, type, has_involved, active, guest, rows)."""
+    """-> list of dicts (key, mincrd, maxcrd, type, has_involved, active, guest, bucket_index, bnd, rows)."""
     out = []
     with open(path, "rb") as f:
         nb, = struct.unpack("<q", f.read(8))
@@ -50,9 +50,11 @@ def read_buckets(path):
             mn = struct.unpack("<ddd", f.read(24))
             mx = struct.unpack("<ddd", f.read(24))
             typ, inv, act, guest, npart = struct.unpack("<iiiii", f.read(20))
+            bidx = struct.unpack("<6i", f.read(24))
+            bnd = struct.unpack("<6d", f.read(48))
             rows = np.fromfile(f, dtype="<i4", count=npart)
             out.append(dict(key=key, mincrd=mn, maxcrd=mx, type=typ, has_involved=inv,
-                            active=act, guest=guest, rows=rows))
+                            active=act, guest=guest, bucket_index=bidx, bnd=bnd, rows=rows))
     return out
 
 

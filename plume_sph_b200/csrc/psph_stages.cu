@@ -1,0 +1,574 @@
+// psph_stages.cu — the per-time-step stages of the SPH (artificial-viscosity) path:
+// timestep, adaptive_sml, mom_engr_update, smooth_density, smooth_velocity, update_pos and the
+// fused step driver.  Every stage cites the reference code it replaces; the C ABI is
+// include/psph.h.  Pair sums run on the warp gather of psph_gather.cuh.
+#include "psph_gather.cuh"
+#include <cstring>
+
+// =========================================================================================
+// timestep  (src/plume/timestep.cc:95-135 3-D, :140-183 1-D): dt = CFL * min_i h_i / c_i over
+// need_neigh particles.  TimeProps::incrtime (properties.h:71-82) clips dt on the host; the
+// clip arrives here as dt_max.
+// =========================================================================================
+__global__ void k_timestep_reset(StepState *ss) { ss->min_hc_bits = (unsigned long long) __double_as_longlong(1.0E+10); }
+
+__global__ void k_timestep(Tab V, StepState *ss)
+{
+  const int n = ss->n;
+  double m = 1.0E+10;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+    if (dev_need_neigh(V.i[I_BC][p], V.i[I_GUEST][p])) {
+      double t = V.d[D_H][p] / V.d[D_C][p];
+      if (t < m) m = t;
+    }
+  for (int o = 16; o; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // positive doubles order like their bit patterns
+  if ((threadIdx.x & 31) == 0 && m < 1.0E+10) atomicMin(&ss->min_hc_bits, (unsigned long long) __double_as_longlong(m));
+}
+
+__global__ void k_timestep_finish(KParams K, StepState *ss, double *dt_cfl_out)
+{
+  double dt = K.cfl * __longlong_as_double((long long) ss->min_hc_bits);
+  if (dt_cfl_out) *dt_cfl_out = dt;
+  ss->dt = fmin(dt, ss->dt_max);
+}
+
+// =========================================================================================
+// stage records (32-byte rows read by the pair loops with 128-bit loads)
+// =========================================================================================
+__global__ void k_refresh_geo(DevView V, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double h = 0.0;
+  if (p < ss->n) {
+    h = V.t.d[D_H][p];
+    V.geo[p] = make_double4(V.t.d[D_X][p], V.t.d[D_Y][p], V.t.d[D_Z][p], h);
+  }
+  for (int o = 16; o; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
+  if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
+}
+__global__ void k_hmax_reset(StepState *ss) { ss->hmax_bits = 0ull; }
+__global__ void k_hmax_finish(StepState *ss) { ss->hmax = __longlong_as_double((long long) ss->hmax_bits); }
+
+// mom_engr_update: rec0 = {m, p*V*V, V, rho}  rec1 = {c, Cp, T, -}  rec2 = {u_x, u_y, u_z, -}
+// with V = 1/rho and u = smoothed velocity when HAVE_TURBULENCE_LANS != 0 (mom_engr_update.cc:170-176)
+__global__ void k_pack_mom(DevView V, KParams K, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n) return;
+  double rho = V.t.d[D_RHO][p], Vj = 1.0 / rho;
+  V.rec[0][p] = make_double4(V.t.d[D_MASS][p], V.t.d[D_P][p] * Vj * Vj, Vj, rho);
+  V.rec[1][p] = make_double4(V.t.d[D_C][p], V.t.d[D_CP][p], V.t.d[D_T][p], 0.0);
+  const int u = K.lans ? D_SVX : D_VX;
+  V.rec[2][p] = make_double4(V.t.d[u][p], V.t.d[u + 1][p], V.t.d[u + 2][p], 0.0);
+}
+// smooth_density: rec0 = {m, m/rho, m*e/rho, -}
+__global__ void k_pack_dens(DevView V, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n) return;
+  double m = V.t.d[D_MASS][p], mv = m / V.t.d[D_RHO][p];
+  V.rec[0][p] = make_double4(m, mv, mv * V.t.d[D_E][p], 0.0);
+}
+// smooth_velocity: rec0 = {m/rho, v_x, v_y, v_z}
+__global__ void k_pack_vel(DevView V, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n) return;
+  V.rec[0][p] = make_double4(V.t.d[D_MASS][p] / V.t.d[D_RHO][p], V.t.d[D_VX][p], V.t.d[D_VY][p], V.t.d[D_VZ][p]);
+}
+
+// =========================================================================================
+// smooth_density  (src/plume/density_massfrac.cc:25-359; DENSITY_UPDATE_SPH 11, DENSITY_UPDATE_SML 11)
+// =========================================================================================
+template <int DIM>
+struct DensStage
+{
+  struct I { double h, supp; };
+  struct A { double rho1, rho2, wn, en; };
+  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *, int i, I &s)
+  {
+    if (!(V.flags[i] & F_NEED)) return false;
+    s.h = V.t.d[D_H][i];
+    s.supp = K.cutoff2 * s.h; // :93
+    return true;
+  }
+  static __device__ __forceinline__ double reach(const KParams &K, const I &s, double hmax)
+  { return fmin(K.cutoff * 0.5 * (s.h + hmax), s.supp); }
+  static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.rho1 = a.rho2 = a.wn = a.en = 0.0; }
+  static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
+                                              double dz, double hj, int fj, int j)
+  {
+    if ((fj & (F_CDENS | F_PHOK)) != (F_CDENS | F_PHOK)) return;   // :135, :141
+    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;           // :151
+    const double h = 0.5 * (s.h + hj);                              // :155
+    if (outside_kernel<DIM>(dx, dy, dz, h, K.cutoff)) return;       // weight() == 0
+    const double r2 = dx * dx + dy * dy + dz * dz, invh = 1.0 / h;
+    const double4 rj = ld_rec(V.rec[0], j);
+    const double w = dev_weight_in<DIM>(r2, invh);
+    if (fj & F_PH2) a.rho2 += w * rj.x; else a.rho1 += w * rj.x;
+    if (K.energy_smooth == 1) {                                     // :163-168, kernel of width h/E_SMOOTH_RATIO
+      const double q = K.e_ratio;
+      if (!outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) {
+        const double we = dev_weight_in<DIM>(r2, q * invh);
+        a.wn += we * rj.y;
+        a.en += we * rj.z;
+      }
+    }
+  }
+  static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *ss, int i, I &, A &a, int, int lane)
+  {
+    const double r1 = warp_sum(a.rho1), r2 = warp_sum(a.rho2), wn = warp_sum(a.wn), en = warp_sum(a.en);
+    if (lane == 0) {
+      const double rho = r1 + r2;                                   // :268-273
+      V.scr[0][i] = rho;
+      V.scr[1][i] = r2 / rho;                                       // :285
+      int bad = !(rho > 0);
+      if (K.energy_smooth == 1) { V.scr[2][i] = en / wn; bad += !(wn > 0); } // :230
+      if (bad) atomicAdd(&ss->bad, bad);
+    }
+    return false;
+  }
+};
+
+// second pass of smooth_density (:337-352): commit, flag involved, equation of state
+__global__ void k_commit_dens(DevView V, KParams K, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n || !(V.flags[p] & F_NEED)) return;
+  const double ks = V.scr[1][p], rho = V.scr[0][p];
+  V.t.d[D_KS][p] = ks;
+  if (ks >= K.msfrc_thresh && V.t.i[I_INVOLVED][p] != 2) V.t.i[I_INVOLVED][p] = 2;
+  V.t.d[D_RHO][p] = rho;
+  double e = V.t.d[D_E][p];
+  if (K.energy_smooth == 1) { e = V.scr[2][p]; V.t.d[D_E][p] = e; }
+  EosOut o = dev_eos(K, rho, ks, e, V.t.d[D_C][p], V.t.d[D_CP][p], V.t.d[D_GAMMA][p]);
+  V.t.d[D_P][p] = o.p; V.t.d[D_GAMMA][p] = o.gamma; V.t.d[D_C][p] = o.c; V.t.d[D_T][p] = o.T; V.t.d[D_CP][p] = o.Cp;
+  V.t.d[D_RPH0][p] = o.rph0; V.t.d[D_RPH1][p] = o.rph1;
+}
+
+// =========================================================================================
+// mom_engr_update, SPH variant  (src/plume/mom_engr_update.cc:30-439; ME_UPDATE_SML 2,
+// MOMENTUM_DISCRETIZE 0; art_vis sph_lib.cc:402-424; SPH-epsilon terms :1331-1439; compute_F :257-281)
+// =========================================================================================
+template <int DIM>
+struct MomStage
+{
+  struct I { int i; double h, supp, rho, Vi, pvsq, c, T, Cp, u[3]; };
+  struct A { double rv[3], re; };
+  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *ss, int i, I &s)
+  {
+    if (!(V.flags[i] & F_NEED)) return false;
+    s.i = i;
+    s.h = V.t.d[D_H][i];
+    s.supp = K.cutoff2 * s.h;
+    s.rho = V.t.d[D_RHO][i];
+    s.Vi = 1.0 / s.rho;
+    s.pvsq = V.t.d[D_P][i] * s.Vi * s.Vi;
+    s.c = V.t.d[D_C][i]; s.T = V.t.d[D_T][i]; s.Cp = V.t.d[D_CP][i];
+    const int u = K.lans ? D_SVX : D_VX;
+    s.u[0] = V.t.d[u][i]; s.u[1] = V.t.d[u + 1][i]; s.u[2] = V.t.d[u + 2][i];
+    return true;
+  }
+  static __device__ __forceinline__ double reach(const KParams &K, const I &s, double hmax)
+  { return fmin(K.cutoff * 0.5 * (s.h + hmax), s.supp); }
+  static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.rv[0] = a.rv[1] = a.rv[2] = a.re = 0.0; }
+  static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
+                                              double dz, double hj, int, int j)
+  {
+    if (j == s.i) return;                                           // :201
+    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;
+    const double h = 0.5 * (s.h + hj);
+    if (outside_kernel<DIM>(dx, dy, dz, h, K.cutoff)) return;       // d_weight() == 0 for every term
+    const double r2 = dx * dx + dy * dy + dz * dz, invh = 1.0 / h;
+    const double4 r0 = ld_rec(V.rec[0], j), r1 = ld_rec(V.rec[1], j), uj = ld_rec(V.rec[2], j);
+    const double w = dev_weight_in<DIM>(r2, invh);
+    const double g = -2.0 * invh * invh * w;                        // dW/dx_k = g * dx_k
+    const double vx = s.u[0] - uj.x, vy = s.u[1] - uj.y, vz = s.u[2] - uj.z;
+    const double vr = dx * vx + dy * vy + dz * vz, vv = vx * vx + vy * vy + vz * vz;
+    const double cab = 0.5 * (s.c + r1.x);
+    double vis = 0.0;                                               // art_vis
+    if (vr < 0) {
+      const double miu = h * vr / (r2 + K.ata * h * h);
+      vis = (K.beta * miu - K.alf * cab) * miu / (0.5 * (s.rho + r0.w));
+    }
+    if (K.lans) vis -= K.epsilon_half * vv * r0.z;                  // SPH_epsilon_mom
+    const double mpv = r0.x * (r0.y + s.pvsq + vis);
+    double heat = 0.0;
+    if (K.lans && DIM == 3) {                                       // :307-314
+      const double avr = fabs(vx * dx) + fabs(vy * dy) + fabs(vz * dz);
+      if (avr != 0. && r2 > 0.) {
+        const double kij = 10.0 * K.epsilon_half * (0.5 * (r1.y + s.Cp)) * r2 * vv / (K.prandtl * avr) / (h * cab);
+        heat = r0.x * r0.z * s.Vi * kij * (s.T - r1.z) * g;         // F_ij = (gradW . dx) / r2 = g
+      }
+    }
+    const double mg = mpv * g;
+    a.rv[0] -= mg * dx;
+    if (DIM == 3) { a.rv[1] -= mg * dy; a.rv[2] -= mg * dz; }
+    a.re += 0.5 * mg * vr + heat;
+  }
+  static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *ss, int i, I &s, A &a, int, int lane)
+  {
+    const double r0 = warp_sum(a.rv[0]), r1 = DIM == 3 ? warp_sum(a.rv[1]) : 0.0, r2 = DIM == 3 ? warp_sum(a.rv[2]) : 0.0;
+    const double re = warp_sum(a.re);
+    if (lane == 0) {
+      const double dt = ss->dt, grav = -K.g;
+      double un[3] = { V.t.d[D_VX][i] + dt * r0, V.t.d[D_VY][i] + dt * r1, V.t.d[D_VZ][i] + dt * r2 };
+      un[DIM - 1] += dt * grav;                                     // :350
+      V.scr[0][i] = un[0]; V.scr[1][i] = un[1]; V.scr[2][i] = un[2];
+      V.scr[3][i] = V.t.d[D_E][i] + dt * (re + s.u[DIM - 1] * grav); // :354
+      if (!(s.rho > 0)) atomicAdd(&ss->bad, 1);
+    }
+    return false;
+  }
+};
+
+// second pass of mom_engr_update (:412-418): commit + equation of state
+__global__ void k_commit_mom(DevView V, KParams K, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n || !(V.flags[p] & F_NEED)) return;
+  V.t.d[D_VX][p] = V.scr[0][p];
+  if (K.dim == 3) { V.t.d[D_VY][p] = V.scr[1][p]; V.t.d[D_VZ][p] = V.scr[2][p]; }
+  const double e = V.scr[3][p];
+  V.t.d[D_E][p] = e;
+  EosOut o = dev_eos(K, V.t.d[D_RHO][p], V.t.d[D_KS][p], e, V.t.d[D_C][p], V.t.d[D_CP][p], V.t.d[D_GAMMA][p]);
+  V.t.d[D_P][p] = o.p; V.t.d[D_GAMMA][p] = o.gamma; V.t.d[D_C][p] = o.c; V.t.d[D_T][p] = o.T; V.t.d[D_CP][p] = o.Cp;
+  V.t.d[D_RPH0][p] = o.rph0; V.t.d[D_RPH1][p] = o.rph1;
+}
+
+// =========================================================================================
+// smooth_velocity  (src/plume/smooth_velocity.cc:25-165, HAVE_TURBULENCE_LANS == 1)
+// =========================================================================================
+template <int DIM>
+struct VelStage
+{
+  struct I { double h, invh, supp, v[3]; };
+  struct A { double dv[3], wn; };
+  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *, int i, I &s)
+  {
+    if (!(V.flags[i] & F_NEED)) return false;
+    s.h = V.t.d[D_H][i]; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
+    s.v[0] = V.t.d[D_VX][i]; s.v[1] = V.t.d[D_VY][i]; s.v[2] = V.t.d[D_VZ][i];
+    return true;
+  }
+  static __device__ __forceinline__ double reach(const KParams &K, const I &s, double) { return K.cutoff * s.h; }
+  static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.dv[0] = a.dv[1] = a.dv[2] = a.wn = 0.0; }
+  static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
+                                              double dz, double, int fj, int j)
+  {
+    if (!(fj & F_CVEL)) return;
+    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;
+    if (outside_kernel<DIM>(dx, dy, dz, s.h, K.cutoff)) return;
+    const double4 rj = ld_rec(V.rec[0], j);
+    const double mvw = dev_weight_in<DIM>(dx * dx + dy * dy + dz * dz, s.invh) * rj.x;
+    a.dv[0] += mvw * (rj.y - s.v[0]);
+    if (DIM == 3) { a.dv[1] += mvw * (rj.z - s.v[1]); a.dv[2] += mvw * (rj.w - s.v[2]); }
+    a.wn += mvw;
+  }
+  static __device__ __forceinline__ bool end(const DevView &V, const KParams &, StepState *ss, int i, I &s, A &a, int, int lane)
+  {
+    const double d0 = warp_sum(a.dv[0]), d1 = DIM == 3 ? warp_sum(a.dv[1]) : 0.0, d2 = DIM == 3 ? warp_sum(a.dv[2]) : 0.0;
+    const double wn = warp_sum(a.wn);
+    if (lane == 0) {
+      if (!(wn > 0)) atomicAdd(&ss->bad, 1);
+      V.t.d[D_SVX][i] = s.v[0] + d0 / wn;
+      if (DIM == 3) { V.t.d[D_SVY][i] = s.v[1] + d1 / wn; V.t.d[D_SVZ][i] = s.v[2] + d2 / wn; }
+    }
+    return false;
+  }
+};
+
+// =========================================================================================
+// adaptive_sml  (src/plume/neighs.cc:479-693, ADAPTIVE_SML == 1): up to num_loop_P fixed-point
+// sweeps h <- eta * (m / rho*)^(1/D), rho* = sum_j m_j W(dx / 2h, 2h).  Reads only x_j, m_j of
+// the neighbours, so the in-place update of h_i is order independent.
+// =========================================================================================
+template <int DIM>
+struct SmlStage
+{
+  struct I { double h, hs, invhs, supp, m; };
+  struct A { double rho; };
+  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *, int i, I &s)
+  {
+    if (!(V.flags[i] & F_NEED)) return false;
+    s.h = V.t.d[D_H][i]; s.m = V.t.d[D_MASS][i];
+    return true;
+  }
+  static __device__ __forceinline__ double reach(const KParams &K, const I &s, double) { return K.cutoff * s.hs; }
+  static __device__ __forceinline__ void begin(const KParams &K, I &s, A &a, int)
+  {
+    s.hs = s.h * K.c_smooth; s.invhs = 1.0 / s.hs; s.supp = K.cutoff2 * s.hs;
+    a.rho = 0.0;
+  }
+  static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
+                                              double dz, double, int fj, int j)
+  {
+    if (!(fj & F_CDENS)) return;
+    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;
+    if (outside_kernel<DIM>(dx, dy, dz, s.hs, K.cutoff)) return;
+    a.rho += dev_weight_in<DIM>(dx * dx + dy * dy + dz * dz, s.invhs) * __ldg(&V.t.d[D_MASS][j]);
+  }
+  static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *, int i, I &s, A &a, int pass, int lane)
+  {
+    const double rho = warp_sum(a.rho);
+    const double hn = DIM == 3 ? K.eta_smooth * cbrt(s.m / rho) : K.eta_smooth * (s.m / rho);
+    const double err = fabs((hn - s.h) / s.h);
+    s.h = hn;
+    const bool again = !(err < K.thresh) && pass + 1 < K.num_loop;
+    if (!again && lane == 0) V.t.d[D_H][i] = hn;
+    return again;
+  }
+};
+
+// =========================================================================================
+// update_pos  (src/plume/update_pos.cc:35-168)
+// =========================================================================================
+__global__ void k_update_pos(Tab V, KParams K, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n) return;
+  const double dt = ss->dt;
+  const int bc = V.i[I_BC][p];
+  if (dev_is_real(bc)) {
+    const int u = K.lans ? D_SVX : D_VX;
+    for (int k = 0; k < K.dim; k++) V.d[D_X + k][p] = V.d[D_X + k][p] + dt * V.d[u + k][p];
+  } else if (bc == 0 && ss->erupting) {
+    for (int k = 0; k < K.dim; k++) V.d[D_X + k][p] = V.d[D_X + k][p] + dt * V.d[D_VX + k][p];
+    if (K.dim == 3 && V.d[D_Z][p] >= K.erupt_top) {                 // :134-142
+      V.i[I_BC][p] = 100;
+      V.d[D_H][p] = K.smlen_real;
+      V.i[I_INVOLVED][p] = 2;
+    }
+  }
+}
+
+// =========================================================================================
+// host side of the stages
+// =========================================================================================
+#define GRID(n) (unsigned) (((n) + 255) / 256), 256, 0, ctx->stream
+
+struct StageTimer
+{
+  psph_ctx *ctx; int id;
+  StageTimer(psph_ctx *c, int i) : ctx(c), id(i) { if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream); }
+  ~StageTimer()
+  {
+    if (!ctx->timing) return;
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stage_ms[id] += ms;
+  }
+};
+
+static int ensure_list(psph_ctx *ctx)
+{
+  if (ctx->list_valid) return 0;
+  return psph_build_cell_list(ctx);
+}
+
+static int refresh_geo(psph_ctx *ctx)
+{
+  k_hmax_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  if (ctx->n > 0) { k_refresh_geo<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
+  k_hmax_finish<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int psph_timestep(psph_ctx *ctx, double *dt)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  StageTimer tm(ctx, ST_TIMESTEP);
+  k_timestep_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  if (ctx->n > 0) {
+    int grid = std::min((ctx->n + 255) / 256, ctx->sms * 8);
+    k_timestep<<<grid, 256, 0, ctx->stream>>>(ctx->cur.t, ctx->d_ss);
+    PSPH_LAUNCH_CHECK();
+  }
+  // the unclipped CFL dt goes through the pinned mirror's dt field
+  k_timestep_finish<<<1, 1, 0, ctx->stream>>>(ctx->kp, ctx->d_ss, nullptr);
+  PSPH_LAUNCH_CHECK();
+  if (dt) {
+    PSPH_CUDA(cudaMemcpyAsync(ctx->h_ss, ctx->d_ss, sizeof(StepState), cudaMemcpyDeviceToHost, ctx->stream));
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    *dt = ctx->kp.cfl * __builtin_bit_cast(double, ctx->h_ss->min_hc_bits);
+  }
+  return 0;
+}
+
+extern "C" int psph_set_dt(psph_ctx *ctx, double dt, int step, int erupting)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->step = step;
+  struct { double dt; } v = { dt };
+  PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->dt, &v.dt, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int iv[2] = { erupting, step };
+  PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->erupting, iv, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int psph_search_neighs(psph_ctx *ctx)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  StageTimer tm(ctx, ST_SEARCH);
+  if (ctx->cfg.dim == 1 && ctx->list_valid) return refresh_geo(ctx); // 1-D: no mesh, no search (main.cc:676-751)
+  return psph_build_cell_list(ctx);
+}
+
+extern "C" int psph_adaptive_sml(psph_ctx *ctx)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  StageTimer tm(ctx, ST_SML);
+  if (ensure_list(ctx)) return -1;
+  if (ctx->n == 0) return 0;
+  if (launch_gather<SmlStage>(ctx)) return -1;
+  return refresh_geo(ctx);
+}
+
+extern "C" int psph_mom_engr_update(psph_ctx *ctx)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (ctx->cfg.use_gsph) return psph_gsph_mom_engr(ctx);
+  StageTimer tm(ctx, ST_MOM);
+  if (ensure_list(ctx)) return -1;
+  if (ctx->n == 0) return 0;
+  k_pack_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  if (launch_gather<MomStage>(ctx)) return -1;
+  k_commit_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int psph_smooth_density(psph_ctx *ctx)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  StageTimer tm(ctx, ST_DENS);
+  if (ensure_list(ctx)) return -1;
+  if (ctx->n == 0) return 0;
+  k_pack_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  if (launch_gather<DensStage>(ctx)) return -1;
+  k_commit_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int psph_smooth_velocity(psph_ctx *ctx)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  StageTimer tm(ctx, ST_VEL);
+  if (ensure_list(ctx)) return -1;
+  if (ctx->n == 0) return 0;
+  k_pack_vel<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  return launch_gather<VelStage>(ctx);
+}
+
+extern "C" int psph_update_pos(psph_ctx *ctx)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  StageTimer tm(ctx, ST_POS);
+  if (ctx->n == 0) return 0;
+  k_update_pos<<<GRID(ctx->n)>>>(ctx->cur.t, ctx->kp, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int psph_rebin(psph_ctx *ctx, int *lost)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  {
+    StageTimer tm(ctx, ST_REBIN);
+    if (psph_rebin_rows(ctx)) return -1;
+  }
+  if (lost) {
+    PSPH_CUDA(cudaMemcpyAsync(ctx->h_ss, ctx->d_ss, sizeof(StepState), cudaMemcpyDeviceToHost, ctx->stream));
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    *lost = ctx->h_ss->lost;
+  }
+  return 0;
+}
+
+// one step in the reference's order (main.cc:217-408 3-D; :676-751 1-D), no host round trip
+static int step_async(psph_ctx *ctx)
+{
+  const psph_config &c = ctx->cfg;
+  ctx->step++;
+  if (psph_timestep(ctx, nullptr)) return -1;
+  if (psph_search_neighs(ctx)) return -1;
+  if (c.adaptive_sml && (c.dim == 1 || ctx->step % c.sml_update_int == 0))
+    if (psph_adaptive_sml(ctx)) return -1;
+  if (c.use_gsph && psph_calc_gradients(ctx)) return -1;
+  if (psph_mom_engr_update(ctx)) return -1;
+  if (psph_smooth_density(ctx)) return -1;
+  if (c.have_turbulence_lans && psph_smooth_velocity(ctx)) return -1;
+  if (psph_update_pos(ctx)) return -1;
+  if (psph_rebin(ctx, nullptr)) return -1;
+  return 0;
+}
+
+static int set_step_inputs(psph_ctx *ctx, double dt_max, int erupting)
+{
+  double v = dt_max;
+  PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->dt_max, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int e = erupting;
+  PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->erupting, &e, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream)); // v, e are stack variables
+  return 0;
+}
+
+extern "C" int psph_errors(psph_ctx *ctx, int reset)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  PSPH_CUDA(cudaMemcpyAsync(ctx->h_ss, ctx->d_ss, sizeof(StepState), cudaMemcpyDeviceToHost, ctx->stream));
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  int bad = ctx->h_ss->bad;
+  ctx->n = ctx->list_valid ? ctx->h_ss->n : ctx->n;
+  if (reset && bad) {
+    PSPH_CUDA(cudaMemsetAsync(&ctx->d_ss->bad, 0, sizeof(int), ctx->stream));
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return bad;
+}
+
+extern "C" int psph_step(psph_ctx *ctx, double dt_max, int erupting, double *dt_used, int *lost)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (set_step_inputs(ctx, dt_max > 0 ? dt_max : 1.0e300, erupting)) return -1;
+  if (step_async(ctx)) return -1;
+  int bad = psph_errors(ctx, 1);
+  if (bad < 0) return bad;
+  if (dt_used) *dt_used = ctx->h_ss->dt;
+  if (lost) *lost = ctx->h_ss->lost;
+  return bad;
+}
+
+extern "C" int psph_run(psph_ctx *ctx, int nsteps, int erupting)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (set_step_inputs(ctx, 1.0e300, erupting)) return -1;
+  for (int s = 0; s < nsteps; s++)
+    if (step_async(ctx)) return -1;
+  return 0;
+}
+
+extern "C" int psph_set_timing(psph_ctx *ctx, int on)
+{
+  ctx->timing = on;
+  memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
+  return 0;
+}
+extern "C" double psph_stage_ms(psph_ctx *ctx, int stage, int reset)
+{
+  if (stage < 0 || stage >= ST_COUNT) return -1.0;
+  double v = ctx->stage_ms[stage];
+  if (reset) ctx->stage_ms[stage] = 0;
+  return v;
+}

@@ -1,0 +1,177 @@
+"""Solver — the reference's per-time-step stage API on the GPU.
+
+Method names and order follow the free functions the reference driver calls
+(/root/reference/src/plume/particler.h:22-357, call sites src/plume/main.cc:217-486 for 3-D
+and :676-751 for 1-D); each forwards to one entry point of include/psph.h.  Error
+behaviour mirrors the reference: a negative return (API/CUDA failure) raises, a positive
+count of invariant violations is returned like mom_engr_update()'s ``ierr``.
+"""
+import ctypes as C
+import numpy as np
+from . import lib as _l
+
+ORDER_DEVICE, ORDER_REFERENCE = 0, 1
+STAGES = ("timestep", "search", "adaptive_sml", "gradients", "mom_engr", "density", "velocity", "update_pos", "rebin")
+
+
+class Solver:
+    def __init__(self, cfg):
+        self.L = _l.load()
+        self.cfg = cfg.copy()
+        h = C.c_void_p()
+        rc = self.L.psph_create(C.byref(self.cfg), C.byref(h))
+        if rc != 0 or not h:
+            raise _l.PsphError(f"psph_create failed ({rc}): "
+                               + ("no CUDA device — this library has no CPU fallback" if rc == -3 else "bad config"))
+        self.h = h
+
+    # -- life cycle ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.psph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise _l.PsphError(f"{what} failed ({rc}): {self.L.psph_last_error(self.h).decode()}")
+        return rc
+
+    # -- data ------------------------------------------------------------------------
+    def set_cells(self, attr):
+        if attr is None:
+            return self._ck(self.L.psph_set_cells(self.h, None, 0), "psph_set_cells")
+        attr = np.ascontiguousarray(attr, dtype=_l.CELL_ATTR_DTYPE)
+        return self._ck(self.L.psph_set_cells(self.h, attr.ctypes.data, attr.size), "psph_set_cells")
+
+    def upload(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=_l.PARTICLE_DTYPE)
+        return self._ck(self.L.psph_upload(self.h, rows.ctypes.data, rows.size), "psph_upload")
+
+    def append(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=_l.PARTICLE_DTYPE)
+        return self._ck(self.L.psph_append(self.h, rows.ctypes.data, rows.size), "psph_append")
+
+    def download(self, order=ORDER_REFERENCE, out=None):
+        n = C.c_size_t(0)
+        self._ck(self.L.psph_download(self.h, None, 0, C.byref(n), order), "psph_download")
+        if out is None:
+            out = np.zeros(n.value, _l.PARTICLE_DTYPE)
+        self._ck(self.L.psph_download(self.h, out.ctypes.data, out.size, C.byref(n), order), "psph_download")
+        return out[:n.value]
+
+    def upload_device_soa(self, cols, bc=None, phase=None, n=0):
+        """cols: list of PSPH_COL_COUNT device pointers (ints); bc/phase: device pointers or None."""
+        arr = (C.c_void_p * len(cols))(*cols)
+        return self._ck(self.L.psph_upload_device_soa(self.h, arr, bc, phase, n), "psph_upload_device_soa")
+
+    @property
+    def n(self):
+        return int(self.L.psph_num_particles(self.h))
+
+    def neighbours(self):
+        """(offsets, idx, rows): CSR neighbour lists over device rows + the rows in that order."""
+        n = self.n
+        nnz = C.c_size_t(0)
+        off = np.zeros(n + 1, np.int64)
+        self._ck(self.L.psph_emit_neighbours(self.h, off.ctypes.data, None, 0, C.byref(nnz)), "psph_emit_neighbours")
+        n = self.n
+        off = off[:n + 1]
+        idx = np.zeros(max(nnz.value, 1), np.int32)
+        self._ck(self.L.psph_emit_neighbours(self.h, off.ctypes.data, idx.ctypes.data, idx.size, C.byref(nnz)),
+                 "psph_emit_neighbours")
+        rows = self.download(ORDER_DEVICE)
+        return off, idx[:nnz.value], rows
+
+    def cells(self):
+        """(cells, rows): background-cell index of every row + the rows, both in device order"""
+        n = C.c_size_t(0)
+        self._ck(self.L.psph_download(self.h, None, 0, C.byref(n), ORDER_DEVICE), "psph_download")
+        cells = np.zeros(max(n.value, 1), np.int32)
+        self._ck(self.L.psph_cell_of_rows(self.h, cells.ctypes.data, cells.size), "psph_cell_of_rows")
+        return cells[:n.value], self.download(ORDER_DEVICE)
+
+    # -- stages (reference names) ------------------------------------------------------
+    def timestep(self):
+        dt = C.c_double(0)
+        self._ck(self.L.psph_timestep(self.h, C.byref(dt)), "psph_timestep")
+        return dt.value
+
+    def set_dt(self, dt, step=0, erupting=1):
+        return self._ck(self.L.psph_set_dt(self.h, dt, step, int(erupting)), "psph_set_dt")
+
+    def search_neighs_consth(self):
+        return self._ck(self.L.psph_search_neighs(self.h), "psph_search_neighs")
+
+    def adaptive_sml(self):
+        return self._ck(self.L.psph_adaptive_sml(self.h), "psph_adaptive_sml")
+
+    def calc_gradients(self):
+        return self._ck(self.L.psph_calc_gradients(self.h), "psph_calc_gradients")
+
+    def mom_engr_update(self):
+        return self._ck(self.L.psph_mom_engr_update(self.h), "psph_mom_engr_update")
+
+    def smooth_density(self):
+        return self._ck(self.L.psph_smooth_density(self.h), "psph_smooth_density")
+
+    def smooth_velocity(self):
+        return self._ck(self.L.psph_smooth_velocity(self.h), "psph_smooth_velocity")
+
+    def update_pos(self):
+        return self._ck(self.L.psph_update_pos(self.h), "psph_update_pos")
+
+    def update_particles_in_bucket(self):
+        lost = C.c_int(0)
+        self._ck(self.L.psph_rebin(self.h, C.byref(lost)), "psph_rebin")
+        return lost.value
+
+    def errors(self, reset=True):
+        return self._ck(self.L.psph_errors(self.h, int(reset)), "psph_errors")
+
+    # -- fused drivers -----------------------------------------------------------------
+    def step(self, dt_max=0.0, erupting=1):
+        """One full time step in the reference's order; returns (dt_used, lost, ierr)."""
+        dt, lost = C.c_double(0), C.c_int(0)
+        rc = self._ck(self.L.psph_step(self.h, dt_max, int(erupting), C.byref(dt), C.byref(lost)), "psph_step")
+        return dt.value, lost.value, rc
+
+    def run(self, nsteps, erupting=1):
+        return self._ck(self.L.psph_run(self.h, nsteps, int(erupting)), "psph_run")
+
+    def sync(self):
+        return self._ck(self.L.psph_sync(self.h), "psph_sync")
+
+    # -- instrumentation -----------------------------------------------------------------
+    def launch_count(self, reset=True):
+        return int(self.L.psph_launch_count(self.h, int(reset)))
+
+    def set_timing(self, on=True):
+        self.L.psph_set_timing(self.h, int(on))
+
+    def stage_ms(self, reset=False):
+        return {name: float(self.L.psph_stage_ms(self.h, i, int(reset))) for i, name in enumerate(STAGES)}
+
+    def stream(self):
+        return self.L.psph_stream(self.h)
+
+    def column(self, col):
+        p = C.c_void_p()
+        self._ck(self.L.psph_column(self.h, col, C.byref(p)), "psph_column")
+        return p.value
+
+    # -- multi-GPU ---------------------------------------------------------------------
+    def comm_init(self, unique_id):
+        buf = (C.c_char * len(unique_id)).from_buffer_copy(unique_id)
+        return self._ck(self.L.psph_comm_init(self.h, buf, len(unique_id)), "psph_comm_init")
+
+    def exchange_ghosts(self):
+        return self._ck(self.L.psph_exchange_ghosts(self.h), "psph_exchange_ghosts")
+
+    def repartition(self):
+        return self._ck(self.L.psph_repartition(self.h), "psph_repartition")

@@ -1,0 +1,147 @@
+"""Shared helpers of the test-suite: golden fixtures, conversions between the reference dump
+rows (oracle/refio.py), the oracle state (oracle/oracle_py.py) and the product's host rows
+(plume_sph_b200.PARTICLE_DTYPE), and tolerances.
+
+The oracle is the CHECKER here; the thing under test in the -m gpu tests is always the CUDA
+library reached through the C ABI (plume_sph_b200.Solver -> libpsph.so).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+import oracle_py as op
+import refio
+import plume_sph_b200 as psph
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# FP64 tolerance of a field after ONE stage, relative to the field's max magnitude: the CUDA
+# path sums in a different order (lane-strided partial sums + shuffle tree instead of the
+# reference's list order), contracts a*b+c into FMAs, uses 1/h once per pair instead of three
+# divisions and CUDA's exp() instead of glibc's.  Each is a few ulp per term.
+RTOL_STAGE = 2e-13
+# after ~100 steps: the per-stage differences add up (and are amplified by the shock)
+RTOL_MID = 1e-10
+# after hundreds of steps the reference algorithm's own discrete decisions (adaptive_sml's
+# `err < thresh` exit, pairs crossing the kernel cutoff) turn a 1e-16 difference into ~1e-6:
+# measured on the reference restatement itself in test_reference_algorithm_is_sensitive
+RTOL_LONG = 5e-5
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def to_product_cfg(ocfg):
+    c = psph.PsphConfig()
+    assert C.sizeof(c) == C.sizeof(ocfg)
+    C.memmove(C.byref(c), C.byref(ocfg), C.sizeof(c))
+    return c
+
+
+def to_oracle_cfg(pcfg):
+    c = op.Config()
+    assert C.sizeof(c) == C.sizeof(pcfg)
+    C.memmove(C.byref(c), C.byref(pcfg), C.sizeof(c))
+    return c
+
+
+def dump_to_particles(rows):
+    """reference dump rows (refio.DUMP_ROW) -> psph_particle rows"""
+    p = np.zeros(len(rows), psph.PARTICLE_DTYPE)
+    p["key"] = rows["key"]
+    p["bc_type"] = rows["bc_type"]
+    p["phase_num"] = rows["phase"]
+    p["involved"] = rows["involved"]
+    p["guest"] = rows["guest"]
+    for a, b in (("mass", "mass"), ("smlen", "smlen"), ("mass_frac", "mass_frac"), ("pressure", "pressure"),
+                 ("gamma", "gamma"), ("sound_speed", "sound_speed"), ("temperature", "temperature"),
+                 ("specific_heat_p", "specific_heat_p"), ("phase_density", "phase_density"), ("coords", "coord"),
+                 ("vel", "vel"), ("smoothed_v", "smoothed_v"), ("rho", "rho"), ("engr", "engr"),
+                 ("smoothed_e", "smoothed_e"), ("grad", "grad")):
+        p[a] = rows[b]
+    return p
+
+
+# product row field -> oracle state array name
+P2O = dict(mass="mass", smlen="h", mass_frac="ks", pressure="p", gamma="gamma", sound_speed="c", temperature="T",
+           specific_heat_p="Cp", phase_density="rho_ph", coords="x", vel="v", smoothed_v="sv", rho="rho", engr="e",
+           smoothed_e="se", grad="grad", key="key", bc_type="bc", phase_num="phase", involved="involved", guest="guest")
+# reference dump field -> product row field
+D2P = dict(mass="mass", smlen="smlen", mass_frac="mass_frac", pressure="pressure", gamma="gamma",
+           sound_speed="sound_speed", temperature="temperature", specific_heat_p="specific_heat_p",
+           phase_density="phase_density", coord="coords", vel="vel", smoothed_v="smoothed_v", rho="rho", engr="engr",
+           smoothed_e="smoothed_e", grad="grad", bc_type="bc_type", phase="phase_num", involved="involved")
+
+
+def particles_to_oracle(cfg, rows):
+    s = op.OracleState(cfg, len(rows))
+    for pf, of in P2O.items():
+        s.a[of][...] = rows[pf]
+    return s
+
+
+def oracle_to_particles(s):
+    p = np.zeros(s.n, psph.PARTICLE_DTYPE)
+    for pf, of in P2O.items():
+        p[pf] = s.a[of]
+    return p
+
+
+def cell_attrs(cfg, z, tag="b0"):
+    """psph_cell_attr array for the whole mesh from a golden bucket dump (absent = BRIEF)."""
+    n1, n2 = int(cfg.ncell[1]), int(cfg.ncell[2])
+    ncells = int(cfg.ncell[0]) * n1 * n2
+    attr = np.zeros(ncells, psph.CELL_ATTR_DTYPE)
+    mn = z[tag + "_mincrd"]
+    lin = np.zeros(len(mn), np.int64)
+    for b in range(len(mn)):
+        idx = [int(round((mn[b][d] * cfg.len_scale - cfg.mindom[d]) / cfg.delta)) for d in range(3)]
+        lin[b] = (idx[0] * n1 + idx[1]) * n2 + idx[2]
+    a = z[tag + "_attr"]
+    attr["type"][lin] = a[:, 0]
+    attr["has_involved"][lin] = a[:, 1]
+    attr["active"][lin] = a[:, 2]
+    attr["bucket_index"][lin] = z[tag + "_bindex"]
+    attr["bnd"][lin] = z[tag + "_bnd"]
+    return attr, lin
+
+
+def oracle_state_3d(cfg, z, tag="b0"):
+    """Oracle state from a golden 3-D fixture: rows of `pre`, plists and attributes of the buckets."""
+    s = op.OracleState.from_dump(cfg, z["pre"])
+    attr, lin = cell_attrs(cfg, z, tag)
+    off, rows = z[tag + "_off"], z[tag + "_rows"]
+    order = list(lin)
+    seen = set(order)
+    order += [c for c in range(s.ncells) if c not in seen]
+    s.cell_order = np.asarray(order, np.int32)
+    s.cell_attr = attr.view(op.CELL_ATTR_DTYPE) if attr.dtype != op.CELL_ATTR_DTYPE else attr
+    counts = np.zeros(s.ncells, np.int64)
+    counts[lin] = np.diff(off)
+    s.cell_off[:] = 0
+    s.cell_off[1:] = np.cumsum(counts)
+    for b, c in enumerate(lin):
+        s.cell_rows[s.cell_off[c]:s.cell_off[c] + counts[c]] = rows[off[b]:off[b + 1]]
+    s._bind()
+    return s
+
+
+def relerr(a, b):
+    """max |a-b| relative to max |b| (per field, as the tolerance is stated)"""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    return float(np.abs(a - b).max() / scale) if b.size else 0.0
+
+
+def key_index(rows):
+    """dict key-tuple -> row index"""
+    k = rows["key"]
+    return {(int(a), int(b), int(c)): i for i, (a, b, c) in enumerate(k)}
+
+
+def match_rows(rows, ref_rows):
+    """permutation p with rows[p[i]].key == ref_rows[i].key"""
+    idx = key_index(rows)
+    return np.asarray([idx[(int(a), int(b), int(c))] for a, b, c in ref_rows["key"]], np.int64)

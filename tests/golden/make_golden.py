@@ -1,0 +1,160 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures of tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+The reference (Plume-SPH) has no tests or golden vectors of its own, so the
+pins are outputs of the reference itself: oracle/_ref/<variant>/particler_hooked is the
+reference's own main.cc + stage functions compiled from /root/reference/src in place
+(recipe: oracle/ref_build/build_ref.py); the hooks only dump the particle table around each
+stage call.  This script runs those binaries on the reference's own input files
+(/root/reference/bin/simulation_*.data) and stores what the tests need as compressed .npz.
+
+Run in the build container only (needs /root/reference and oracle/_ref):
+    python oracle/ref_build/build_ref.py && python tests/golden/make_golden.py
+The fixtures are committed; nothing at test time reads /root/reference.
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import refio  # noqa: E402
+
+REF = os.environ.get("PSPH_REFERENCE", "/root/reference")
+REFBIN = os.path.join(ROOT, "oracle", "_ref")
+
+NMID = 100
+
+STAGE_FIELDS = {
+    "sml": ["smlen"],
+    "grad": ["grad"],
+    "mom": ["vel", "engr", "pressure", "sound_speed", "temperature", "specific_heat_p", "gamma", "phase_density"],
+    "dens": ["rho", "mass_frac", "engr", "pressure", "sound_speed", "temperature", "involved", "gamma"],
+    "svel": ["smoothed_v"],
+    "pos": ["coord", "bc_type", "smlen", "involved"],
+}
+
+
+def run_ref(variant, workdir, env):
+    exe = os.path.join(REFBIN, variant, "particler_hooked")
+    e = dict(os.environ)
+    e.update({k: str(v) for k, v in env.items()})
+    with open(os.path.join(workdir, "out.log"), "w") as f:
+        subprocess.run([exe], cwd=workdir, env=e, stdout=f, stderr=subprocess.STDOUT, check=False)
+
+
+def stage_dumps(dump, step, stages):
+    out = {}
+    for st in stages:
+        fn = os.path.join(dump, "s%04d_%s_post.bin" % (step, st))
+        if not os.path.exists(fn):
+            continue
+        _, rows = refio.read_dump(fn)
+        for f in STAGE_FIELDS[st]:
+            out["s%d_%s_%s" % (step, st, f)] = rows[f]
+    return out
+
+
+def golden_1d(name, variant, simdata, nfinal):
+    with tempfile.TemporaryDirectory() as wd:
+        shutil.copy(os.path.join(REF, "bin", "scale.data"), wd)
+        shutil.copy(os.path.join(REF, "bin", simdata), os.path.join(wd, "simulation.data"))
+        dump = os.path.join(wd, "dump")
+        os.makedirs(dump)
+        run_ref(variant, wd, dict(PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="1-3", PSPH_MAX_STEPS=nfinal))
+        h0, init = refio.read_dump(os.path.join(dump, "s0000_init_post.bin"))
+        out = dict(init=init)
+        dts = []
+        for step in (1, 2, 3):
+            h, _ = refio.read_dump(os.path.join(dump, "s%04d_timestep_post.bin" % step))
+            dts.append(h["dt"])
+            out.update(stage_dumps(dump, step, ["sml", "grad", "mom", "dens", "pos"]))
+        hf, fin = refio.read_dump(os.path.join(dump, "s%04d_final_post.bin" % nfinal))
+        # state after NMID steps (before rounding differences can flip one of the algorithm's
+        # discrete decisions, see tests/test_oracle_vs_ref.py::test_reference_algorithm_is_sensitive)
+        dump2 = os.path.join(wd, "dump2")
+        os.makedirs(dump2)
+        run_ref(variant, wd, dict(PSPH_DUMP_DIR=dump2, PSPH_DUMP_STEPS="0-0", PSPH_MAX_STEPS=NMID))
+        hm, mid = refio.read_dump(os.path.join(dump2, "s%04d_final_post.bin" % NMID))
+        out["mid"] = mid
+        out["mid_time"] = np.asarray([hm["time"]])
+        out["mid_steps"] = np.asarray([NMID])
+        sim = [ln.split(":", 1)[1].strip() for ln in open(os.path.join(wd, "simulation.data")) if ":" in ln]
+        out["t_end"] = np.asarray([float(np.float32(float(sim[0])))])   # dataread.cc parses with stof
+        out["t_out"] = np.asarray([float(np.float32(float(sim[2])))])
+        out["dt"] = np.asarray(dts)
+        out["final"] = fin
+        out["final_time"] = np.asarray([hf["time"]])
+        out["final_steps"] = np.asarray([nfinal])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "n =", len(init), "final time", hf["time"], "->", os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
+
+
+def golden_3d(name, variant, edits, list_stride=4):
+    """Small 3-D plume: the reference's default case (bin/simulation.data, Eyjafjallajokull
+    parameters, Meteo sounding) with a smaller initial domain; state around every stage of step 1."""
+    with tempfile.TemporaryDirectory() as top:
+        wd = os.path.join(top, "run")
+        os.makedirs(wd)
+        shutil.copytree(os.path.join(REF, "Meteo_data"), os.path.join(top, "Meteo_data"))
+        shutil.copy(os.path.join(REF, "bin", "scale.data"), wd)
+        txt = open(os.path.join(REF, "bin", "simulation.data")).read()
+        for a, b in edits:
+            assert a in txt, a
+            txt = txt.replace(a, b)
+        open(os.path.join(wd, "simulation.data"), "w").write(txt)
+        smlen = [l for l in txt.splitlines() if l.startswith("smoothing length")][0].split(":")[1]
+        subprocess.run([os.path.join(REFBIN, variant, "preprocess"), "1", smlen, "0"], cwd=wd, check=True,
+                       stdout=subprocess.DEVNULL)
+        dump = os.path.join(wd, "dump")
+        os.makedirs(dump)
+        run_ref(variant, wd, dict(PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="1-1", PSPH_DUMP_NEIGH=1, PSPH_MAX_STEPS=1))
+        h, pre = refio.read_dump(os.path.join(dump, "s0001_timestep_post.bin"))
+        out = dict(pre=pre, dt=np.asarray([h["dt"]]))
+        out.update(stage_dumps(dump, 1, ["grad", "mom", "dens", "svel", "pos"]))
+        # buckets: attributes + plists (rows of `pre`) before the step and after the re-bin
+        for tag, fn in (("b0", "s0001_timestep_buckets.bin"), ("b1", "s0001_rebin_buckets.bin")):
+            bk = refio.read_buckets(os.path.join(dump, fn))
+            out[tag + "_mincrd"] = np.asarray([b["mincrd"] for b in bk])
+            out[tag + "_key"] = np.asarray([b["key"] for b in bk], np.uint32)
+            out[tag + "_attr"] = np.asarray([[b["type"], b["has_involved"], b["active"], b["guest"]] for b in bk], np.int32)
+            out[tag + "_bindex"] = np.asarray([b["bucket_index"] for b in bk], np.int32)
+            out[tag + "_bnd"] = np.asarray([b["bnd"] for b in bk], np.float64)
+            out[tag + "_off"] = np.cumsum([0] + [len(b["rows"]) for b in bk]).astype(np.int64)
+            out[tag + "_rows"] = np.concatenate([b["rows"] for b in bk]).astype(np.int32)
+        # neighbour lists of every list_stride-th listed particle
+        off, idx = refio.read_neigh(os.path.join(dump, "s0001_neigh.bin"))
+        listed = np.nonzero(np.diff(off) > 0)[0]
+        out["nlisted"] = np.asarray([len(listed)])
+        out["list_counts"] = np.diff(off).astype(np.int32)
+        sel = listed[::list_stride]
+        out["list_rows"] = sel.astype(np.int32)
+        out["list_off"] = np.cumsum([0] + [off[i + 1] - off[i] for i in sel]).astype(np.int64)
+        out["list_idx"] = np.concatenate([np.sort(idx[off[i]:off[i + 1]]) for i in sel]).astype(np.int32)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "n =", len(pre), "listed", len(listed), "->", os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
+
+
+SMALL_3D = [("initial domain:-2000", "initial domain:-350"), ("initial domain:2000", "initial domain:350"),
+            ("initial domain:2700", "initial domain:2400")]
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["sod_sph", "sod_gsph", "sod0_gsph", "shu_sph", "shu_gsph", "blast_gsph",
+                             "plume3d_small", "plume3d_small_gsph"]
+    table = {
+        "sod_sph": lambda: golden_1d("sod_sph", "1d_sod_sph", "simulation_1D_shocktube_Sod.data", 1000),
+        "sod_gsph": lambda: golden_1d("sod_gsph", "1d_sod_gsph", "simulation_1D_shocktube_Sod.data", 1000),
+        "sod0_gsph": lambda: golden_1d("sod0_gsph", "1d_sod0_gsph", "simulation_1D_shocktube_Sod_GSPH.data", 300),
+        "shu_sph": lambda: golden_1d("shu_sph", "1d_shu_sph", "simulation_1D_shocktube_shu-Osher.data", 200),
+        "shu_gsph": lambda: golden_1d("shu_gsph", "1d_shu_gsph", "simulation_1D_shocktube_shu-Osher.data", 200),
+        # (the reference's own plain-SPH build aborts on the strong blast at step 4: assert c>0, timestep.cc:167)
+        "blast_gsph": lambda: golden_1d("blast_gsph", "1d_blast_gsph", "simulation_1D_shocktube_Strong-Blast.data", 300),
+        "plume3d_small": lambda: golden_3d("plume3d_small", "3d_plume", SMALL_3D),
+        "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D),
+    }
+    for w in which:
+        table[w]()

@@ -1,0 +1,114 @@
+"""-m gpu: CUDA path (through the C ABI) against the reference's own dumps of the 3-D plume
+case (tests/golden/plume3d_small.npz, produced by the unmodified reference — see
+tests/golden/make_golden.py): every stage of time step 1.
+
+Bars: neighbour lists, particle ordering, re-binning, flags: bit-exact.  Fields: relative
+tolerance RTOL_STAGE (tests/common.py) per stage, stated against the field's max magnitude.
+"""
+import numpy as np
+import pytest
+
+import oracle_py as op
+from common import (golden, to_product_cfg, dump_to_particles, cell_attrs, relerr, match_rows, RTOL_STAGE, D2P)
+import plume_sph_b200 as psph
+from plume_sph_b200.solver import ORDER_REFERENCE, ORDER_DEVICE
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def case():
+    z = golden("plume3d_small")
+    ocfg = op.config_3d()
+    cfg = to_product_cfg(ocfg)
+    s = psph.Solver(cfg)
+    attr, _ = cell_attrs(ocfg, z)
+    s.set_cells(attr)
+    s.upload(dump_to_particles(z["pre"]))
+    yield z, ocfg, s
+    s.close()
+
+
+def check_stage(s, z, stage, fields, exact=()):
+    out = s.download(ORDER_REFERENCE)
+    pre = z["pre"]
+    assert np.array_equal(out["key"], pre["key"])
+    worst = {}
+    for f in fields:
+        ref = z["s1_%s_%s" % (stage, f)]
+        got = out[D2P[f]]
+        if f in exact:
+            assert np.array_equal(got, ref), (stage, f)
+        else:
+            worst[f] = relerr(got, ref)
+            assert worst[f] <= RTOL_STAGE, (stage, f, worst[f])
+    return worst
+
+
+def test_step1_all_stages(case):
+    z, ocfg, s = case
+    pre = z["pre"]
+    # (1) particle ordering: the REFERENCE-order download reproduces THashTable iteration order
+    out = s.download(ORDER_REFERENCE)
+    assert np.array_equal(out["key"], pre["key"])
+    assert np.array_equal(out["coords"], pre["coord"])
+    # timestep: CFL dt, bit-exact (a min of exact quotients)
+    dt = s.timestep()
+    assert dt == float(z["dt"][0])
+    s.set_dt(dt, 1, 1)
+    # (2) neighbour search: list lengths of every particle + full sets of the sampled ones
+    s.search_neighs_consth()
+    off, idx, rows = s.neighbours()
+    dev2ref = match_rows(pre, rows)            # device row -> row of `pre`
+    counts = np.zeros(len(pre), np.int64)
+    counts[dev2ref] = np.diff(off)
+    assert np.array_equal(counts, z["list_counts"])
+    ref2dev = np.zeros(len(pre), np.int64)
+    ref2dev[dev2ref] = np.arange(len(pre))
+    loff, lidx = z["list_off"], z["list_idx"]
+    for q, r in enumerate(z["list_rows"]):
+        d = ref2dev[r]
+        mine = np.sort(dev2ref[idx[off[d]:off[d + 1]]])
+        assert np.array_equal(mine, lidx[loff[q]:loff[q + 1]]), r
+    # (3) the summation stages
+    s.mom_engr_update()
+    check_stage(s, z, "mom", ["vel", "engr", "pressure", "sound_speed", "temperature", "specific_heat_p", "gamma",
+                              "phase_density"])
+    s.smooth_density()
+    check_stage(s, z, "dens", ["rho", "mass_frac", "engr", "pressure", "sound_speed", "temperature", "involved"],
+                exact=("involved",))
+    s.smooth_velocity()
+    check_stage(s, z, "svel", ["smoothed_v"])
+    # (4) integrator + re-bin
+    s.update_pos()
+    check_stage(s, z, "pos", ["coord", "bc_type", "smlen", "involved"], exact=("bc_type", "smlen", "involved"))
+    lost = s.update_particles_in_bucket()
+    assert lost == 0
+    assert s.errors() == 0
+    cells, rows = s.cells()
+    dev2ref = match_rows(pre, rows)
+    got = np.zeros(len(pre), np.int64)
+    got[dev2ref] = cells
+    attr, lin = cell_attrs(ocfg, z, "b1")
+    want = np.full(len(pre), -1, np.int64)
+    boff, brows = z["b1_off"], z["b1_rows"]
+    for b, c in enumerate(lin):
+        want[brows[boff[b]:boff[b + 1]]] = c
+    assert np.array_equal(got, want)
+
+
+def test_fused_step_equals_staged(case):
+    """psph_step (no host round trip between stages) == the staged calls above"""
+    z, ocfg, s = case
+    staged = s.download(ORDER_REFERENCE)
+    cfg = to_product_cfg(ocfg)
+    s2 = psph.Solver(cfg)
+    attr, _ = cell_attrs(ocfg, z)
+    s2.set_cells(attr)
+    s2.upload(dump_to_particles(z["pre"]))
+    dt, lost, ierr = s2.step(0.0, 1)
+    assert dt == float(z["dt"][0]) and lost == 0 and ierr == 0
+    fused = s2.download(ORDER_REFERENCE)
+    for f in ("coords", "vel", "smoothed_v", "rho", "engr", "mass_frac", "pressure", "smlen", "bc_type"):
+        assert np.array_equal(fused[f], staged[f]), f
+    s2.close()

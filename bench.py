@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py — particle-updates/s of the Plume-SPH per-time-step hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n EDGE] [--impl b200|reference]
+
+Workload (BASELINE.json config 4): the synthetic 3-D particle cube, 3-D SPH
+defaults (artificial-viscosity SPH + LANS velocity filter + energy smoothing, ideal-gas
+mixture EOS, g = 0): EDGE^3 real particles on a jittered unit lattice (h = 1), a central
+sphere of erupted material, one bucket-thick (8 h) shell of static pressure ghosts.
+One "step" = one full time step of the hot path in the reference's order
+(main.cc:217-408): timestep -> neighbour search (cell-list build) -> mom_engr_update ->
+smooth_density -> smooth_velocity -> update_pos -> update_particles_in_bucket.
+`value` = real particles advanced per second, whole job, inputs resident in HBM; `e2e` =
+the same through the C ABI with HOST rows: psph_upload (pinned host AoS -> device SoA) +
+psph_step + psph_download every step.
+
+--impl reference: the UNMODIFIED reference compiled in oracle/_ref (its own 3-D plume case,
+small initial domain) timed on the host cores; see oracle/ref_build/ref_run.py.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT,):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "particle-updates/sec (3D plume)"
+UNIT = "particle-updates/s"
+# algorithmic bytes per real-particle-update of each pair gather
+ALG_BYTES = {"gather_mom_engr": 228, "gather_density": 148, "gather_velocity": 100}
+ALG_BYTES_STEP = 1184
+
+
+def measured_peaks():
+    try:
+        j = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(j["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# device-side generator of the synthetic cube (same shape as plume_sph_b200.cases.cube, which
+# builds host rows for the tests)
+# ------------------------------------------------------------------------------------------
+def cube_columns(torch, cfg, n, dev, seed=20260101, smlen=1.0, lo=None, hi=None):
+    """SoA columns (PSPH_COL_* order) + bc/phase of the block of lattice sites [lo, hi) of the
+    (n + 16)^3 cube-with-shell; default = everything."""
+    from plume_sph_b200 import cases
+    g = 8
+    lo = lo if lo is not None else (-g, -g, -g)
+    hi = hi if hi is not None else (n + g, n + g, n + g)
+    ax = [torch.arange(lo[k], hi[k], device=dev, dtype=torch.float64) for k in range(3)]
+    I, J, K = torch.meshgrid(ax[0], ax[1], ax[2], indexing="ij")
+    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
+    N = I.numel()
+    real = (I >= 0) & (I < n) & (J >= 0) & (J < n) & (K >= 0) & (K < n)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed + 7919 * (lo[0] + g))
+    jit = (torch.rand((3, N), device=dev, dtype=torch.float64, generator=gen) * 2 - 1) * (0.1 * smlen)
+    pos = [(c + 0.5) * smlen + torch.where(real, jit[k], torch.zeros_like(c)) for k, c in enumerate((I, J, K))]
+    ctr = 0.5 * n * smlen
+    r2 = (pos[0] - ctr) ** 2 + (pos[1] - ctr) ** 2 + (pos[2] - ctr) ** 2
+    ph2 = real & (r2 < (n * smlen / 8.0) ** 2)
+    ks = ph2.to(torch.float64)
+    rho = torch.full((N,), cases.RHO0, device=dev, dtype=torch.float64)
+    e_air = cases.P0 / (0.4 * cases.RHO0)
+    ng = cfg.ng0
+    cvm2 = (1 - ng) * cfg.Cvs + ng * cfg.Cvg
+    p_air = cfg.Ra * cases.RHO0 * e_air / cfg.Cva
+    e = torch.where(ph2, torch.full_like(rho, p_air * cvm2 / (cfg.Rg * ng * cases.RHO0)), torch.full_like(rho, e_air))
+    # Particle::update_second_var (particle.cc:528-604), ideal-gas mixture
+    na, ngk = 1 - ks, ng * ks
+    ns = ks - ngk
+    Cvm = ns * cfg.Cvs + ngk * cfg.Cvg + na * cfg.Cva
+    Rm = ngk * cfg.Rg + na * cfg.Ra
+    gamma = 1 + Rm / Cvm
+    desmg = rho * (na + ngk)
+    p = (Rm / (ngk + na)) * desmg * e / Cvm
+    c = torch.sqrt(gamma * p / desmg)
+    c_air = float((cfg.Ra / cfg.Cva + 1) * p_air / cases.RHO0) ** 0.5
+    vj = (torch.rand((3, N), device=dev, dtype=torch.float64, generator=gen) * 2 - 1) * (0.05 * c_air)
+    vel = [torch.where(real, vj[k], torch.zeros_like(rho)) for k in range(3)]
+    mass = torch.full_like(rho, cases.RHO0 * smlen ** 3)
+    h = torch.full_like(rho, smlen)
+    cols = pos + vel + [v.clone() for v in vel] + [rho, e, mass, h, ks, p, gamma, c, e / Cvm, Cvm]
+    bc = torch.where(real, 100, 1).to(torch.int32)
+    phase = torch.where(ph2, 2, 1).to(torch.int32)
+    return [x.contiguous() for x in cols], bc.contiguous(), phase.contiguous(), int(real.sum().item())
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import plume_sph_b200 as psph
+    from plume_sph_b200 import cases
+    from plume_sph_b200.solver import ORDER_DEVICE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    cfg = cases.cube_config(n)
+    cfg.device = local
+    cfg.rank, cfg.nranks = rank, world
+    from plume_sph_b200.slabs import setup_cube_ranks  # slab decomposition across ranks (no-op for 1 rank)
+    s, n_real_local, n_rows_local = setup_cube_ranks(torch, dist, psph, cfg, n, dev, rank, world, cube_columns)
+
+    stream = torch.cuda.ExternalStream(s.stream(), device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        s.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        s.run(1, erupting=0)
+    barrier()
+    s.launch_count(reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        s.run(1, erupting=0)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = s.launch_count(reset=True)
+    clk = clocks.stop() if rank == 0 else None
+    bad = s.errors()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    cnt = torch.tensor([float(n_real_local), float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    n_real = int(cnt[0].item())
+    value = n_real * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel device times (separate pass, events around every kernel; not the timed region)
+    s.set_timing(True)
+    ksteps = max(1, min(2, args.steps))
+    for _ in range(ksteps):
+        s.run(1, erupting=0)
+    s.sync()
+    kms = s.kernel_ms()
+    sms = s.stage_ms()
+    s.set_timing(False)
+    peak, peak_src = measured_peaks()
+    dom = max(ALG_BYTES, key=lambda k: kms[k][0])
+    dom_ms = kms[dom][0] / max(kms[dom][1], 1)
+    achieved = ALG_BYTES[dom] * n_real_local / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_gather<%s>" % dom, "achieved": round(achieved, 2), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None,
+                "alg_bytes_per_update": ALG_BYTES[dom], "updates_per_launch": n_real_local,
+                "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
+                "note": "FP64 pair loop: compute-bound (SURVEY.md §8d), HBM fraction is low by construction; "
+                        "see profiles/ for the FP64 pipe utilisation",
+                "step_hbm": {"alg_bytes_per_update": ALG_BYTES_STEP,
+                             "achieved_GBps": round(ALG_BYTES_STEP * n_real / (ms / args.steps * 1e-3) / 1e9, 2)},
+                "stage_ms_per_step": {k: round(v / ksteps, 4) for k, v in sms.items() if v > 0},
+                "kernel_ms_per_launch": {k: round(v[0] / max(v[1], 1), 4) for k, v in kms.items() if v[1] > 0}}
+
+    # ---- end to end through the C ABI with host rows (pinned): upload + step + download per step
+    e2e = None
+    if not args.no_e2e:
+        host = s.host_rows(n_rows_local + 1024)
+        out = s.download(ORDER_DEVICE, out=host)
+        nrow = len(out)
+        ke = max(1, min(args.steps, 3))
+        import ctypes as C
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            s._ck(s.L.psph_upload(s.h, host.ctypes.data, nrow), "psph_upload")
+            s.step(0.0, 0)
+            got = C.c_size_t(0)
+            s._ck(s.L.psph_download(s.h, host.ctypes.data, host.size, C.byref(got), ORDER_DEVICE), "psph_download")
+            nrow = got.value
+        barrier()
+        te = time.perf_counter() - t0
+        tt = torch.tensor([te], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+        rowb = psph.PARTICLE_DTYPE.itemsize
+        e2e = {"value": round(n_real * ke / te, 1), "unit": UNIT, "h2d_bytes_per_step": nrow * rowb,
+               "d2h_bytes_per_step": nrow * rowb, "steps": ke,
+               "what": "psph_upload(host AoS rows, pinned) + psph_step + psph_download(host AoS rows) every step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_port(args.cpu_n)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+                "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic 3-D particle cube, %d^3 real + 8h pressure-ghost shell, "
+                                       "3-D SPH defaults (art. viscosity + LANS + energy smoothing), g=0" % n,
+                           "real_particles": n_real, "rows_rank0": n_rows_local, "edge": n,
+                           "l2": "inputs (%.1f GB of SoA columns) far larger than the 126 MB L2" %
+                                 (n_rows_local * 700 / 1e9),
+                           "parallelism": "key-range slabs x%d" % world if world > 1 else "1 GPU"},
+                "roofline": roofline, "gpu_launches": int(cnt[1].item()), "clocks": clk, "e2e": e2e,
+                "invariant_violations": bad}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_port(n):
+    """oracle/psph_oracle.c (scalar C restatement of the reference algorithm, 1 thread) on an
+    n^3 sample of the same synthetic cube: one full step."""
+    sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    from plume_sph_b200 import cases
+    from common import to_oracle_cfg, particles_to_oracle
+    cfg, rows = cases.cube(n, seed=1)
+    o = particles_to_oracle(to_oracle_cfg(cfg), rows)
+    nreal = int((rows["bc_type"] == 100).sum())
+    o.bin()
+    t0 = time.perf_counter()
+    dt = o.timestep()
+    o.search()
+    o.mom_engr_update(dt)
+    o.smooth_density()
+    o.smooth_velocity()
+    o.update_pos(dt, 0)
+    o.rebin()
+    t = time.perf_counter() - t0
+    return {"value": round(nreal / t, 1), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d^3 real-particle sample of the same synthetic cube (%d rows with ghost shell), 1 step, "
+                      "oracle/psph_oracle.c, 1 thread, %.1f s" % (n, len(rows), t)}
+
+
+def run_reference(args):
+    """The unmodified reference (oracle/_ref/3d_plume, compiled from /root/reference/src in place)
+    on its own 3-D dusty-gas plume case with a small initial domain, 1 rank per replica, as many
+    replicas side by side as there are host cores (no MPI in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_build"))
+    import ref_run
+    ncpu = os.cpu_count() or 1
+    if ref_run.have_inputs():
+        reps = max(1, min(ncpu, args.ref_replicas if args.ref_replicas > 0 else ncpu))
+        steps, warm = max(1, args.steps), 0  # CPU code: no warm-up effect; every step is timed
+        steps = min(steps, 2)
+        r = ref_run.time_plume3d(steps, warm, replicas=reps, edits=ref_run.MEDIUM)
+        path = ("timestep", "search_neighs_consth", "adaptive_sml", "mom_engr_update", "smooth_density",
+                "smooth_velocity", "update_pos", "update_particles_in_bucket")
+        t_loop = max(r["seconds"])
+        # like for like: only the stages the B200 path replaces (apply_bcond / add_new_erupt stay with
+        # the reference driver); stage times are those of the last replica
+        t_path = sum(r["stages"].get(k, 0.0) for k in path)
+        frac = t_path / max(sum(r["stages"].values()), 1e-30)
+        value = r["updates"] * reps / (t_loop * frac)
+        sample = ("unmodified reference, its own 3-D plume case (bin/simulation.data, initial domain shrunk to "
+                  "+-1000 m: %d real / %d total particles), %d step(s), %d single-rank replicas side by side "
+                  "(no MPI in the image); hot-path stages only = %.0f%% of its loop (apply_bcond excluded); "
+                  "loop wall %.1f s" % (r["real"], r["total"], steps, reps, 100 * frac, t_loop))
+        kind, cores, ms = "reference", reps, t_loop * frac * 1e3 / steps
+    else:
+        cpu = cpu_baseline_port(args.cpu_n)
+        value, sample, kind, cores, ms = cpu["value"], cpu["sample"], "port", 1, None
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3-D dusty-gas plume hot path on host cores (bounded sample)"},
+            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=216, help="cube edge in particles per GPU^(1/3) (216 -> 1.0e7 real)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--strong", dest="weak", action="store_false", help="fixed total cube (default: weak, per-GPU cube)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=32)
+    ap.add_argument("--ref-replicas", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -219,6 +219,14 @@ int psph_cell_of_rows(psph_ctx *ctx, int32_t *cells, size_t cap);
 int64_t psph_launch_count(psph_ctx *ctx, int reset);
 int psph_set_timing(psph_ctx *ctx, int on);
 double psph_stage_ms(psph_ctx *ctx, int stage, int reset);
+/* per-kernel device time (CUDA events on the context stream, only while psph_set_timing is on):
+ * 0 gather mom_engr, 1 gather density, 2 gather velocity filter, 3 gather adaptive_sml,
+ * 4 gather gradients, 5 gather GSPH mom_engr, 6 radix sort, 7 column reorder */
+double psph_kernel_ms(psph_ctx *ctx, int kernel, int reset, int64_t *calls);
+/* pinned host memory for the rows passed to psph_upload / psph_append / psph_download
+ * (optional: any host pointer works, pinned ones copy at full PCIe rate) */
+void *psph_host_alloc(size_t bytes);
+void psph_host_free(void *p);
 int psph_sync(psph_ctx *ctx);
 void *psph_stream(psph_ctx *ctx);
 

@@ -75,7 +75,8 @@ bool g_neigh = false, g_times = false;
 int g_max_steps = -1;
 double g_time = 0, g_dt = 0;
 map<string, double> g_stage_time;
-double g_loop_t0 = 0;
+double g_loop_t0 = 0, g_excluded = 0;
+THashTable *g_P = NULL;
 
 double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
@@ -84,6 +85,13 @@ void print_times()
   if (!g_times) return;
   double tot = now() - g_loop_t0;
   fprintf(stderr, "PSPH_STAGE_TIMES steps=%d loop_wall=%.6f\n", g_step, tot);
+  if (g_P) { /* particles the loop advances: need_neigh() (particle.h:555-558) */
+    long long nreal = 0, ntot = 0;
+    THTIterator itr(g_P);
+    Particle *p;
+    while ((p = (Particle *) itr.next())) { ntot++; if (p->need_neigh()) nreal++; }
+    fprintf(stderr, "PSPH_PARTICLES real=%lld total=%lld\n", nreal, ntot);
+  }
   for (map<string, double>::iterator it = g_stage_time.begin(); it != g_stage_time.end(); ++it)
     fprintf(stderr, "PSPH_STAGE %s %.6f\n", it->first.c_str(), it->second);
 }
@@ -238,6 +246,16 @@ void begin_step(THashTable *P, double dt_unclipped)
 {
   init_once();
   if (g_step == 0) g_loop_t0 = now();
+  g_P = P;
+  if (g_times) { /* wall time at the start of step g_step+1 (time spent counting excluded) + particles it will advance */
+    double t = now();
+    long long nreal = 0, ntot = 0;
+    THTIterator itr(P);
+    Particle *q;
+    while ((q = (Particle *) itr.next())) { ntot++; if (q->need_neigh()) nreal++; }
+    fprintf(stderr, "PSPH_STEP %d %.6f real=%lld total=%lld\n", g_step, t - g_loop_t0 - g_excluded, nreal, ntot);
+    g_excluded += now() - t;
+  }
   if (g_max_steps >= 0 && g_step >= g_max_steps) {
     /* state after the last completed step */
     g_lo = g_hi = g_step; /* always dump the final state when dumping is on */

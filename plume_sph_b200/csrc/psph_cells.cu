@@ -134,15 +134,22 @@ int psph_build_cell_list(psph_ctx *ctx)
       PSPH_CUDA(cudaMalloc(&ctx->d_cub_tmp, need));
       ctx->cub_tmp_bytes = need;
     }
-    cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp, need, ctx->d_sortkey, ctx->d_sortkey_alt, ctx->d_perm,
-                                    ctx->d_perm_alt, n_cap, 0, end_bit, s);
+    {
+      KernelTimer kt(ctx, KN_SORT);
+      cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp, need, ctx->d_sortkey, ctx->d_sortkey_alt, ctx->d_perm,
+                                      ctx->d_perm_alt, n_cap, 0, end_bit, s);
+    }
+    ctx->launches += 1 + (end_bit + 7) / 8 * 2; // cub: histogram + (onesweep) one launch per 8-bit digit, approx.
     PSPH_CUDA(cudaGetLastError());
   }
   k_count_live<<<1, 1, 0, s>>>(ctx->d_sortkey_alt, n_cap, inf_key, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (n_cap > 0) {
     int nd = ctx->has_grad ? D_NCOL : D_GRAD0;
-    k_reorder<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur.t, ctx->alt, ctx->d_perm_alt, ctx->d_ss, nd);
+    {
+      KernelTimer kt(ctx, KN_REORDER);
+      k_reorder<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur.t, ctx->alt, ctx->d_perm_alt, ctx->d_ss, nd);
+    }
     PSPH_LAUNCH_CHECK();
     Tab t = ctx->cur.t; ctx->cur.t = ctx->alt; ctx->alt = t;
   }

@@ -186,6 +186,9 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
   PSPH_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   PSPH_CUDA(cudaEventCreate(&ctx->ev0));
   PSPH_CUDA(cudaEventCreate(&ctx->ev1));
+  PSPH_CUDA(cudaEventCreate(&ctx->kev0));
+  PSPH_CUDA(cudaEventCreate(&ctx->kev1));
+  memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms); memset(ctx->kernel_calls, 0, sizeof ctx->kernel_calls);
   PSPH_CUDA(cudaMalloc(&ctx->d_cell2rank, ctx->ncells * sizeof(int32_t)));
   PSPH_CUDA(cudaMalloc(&ctx->d_rank2cell, ctx->ncells * sizeof(int32_t)));
   PSPH_CUDA(cudaMalloc(&ctx->d_sub_start, (ctx->ncells * SUBS + 1) * sizeof(int32_t)));
@@ -225,6 +228,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   cudaFree(ctx->d_cub_tmp); cudaFree(ctx->d_ss); cudaFreeHost(ctx->h_ss);
   cudaFree(ctx->d_aos);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->kev0); cudaEventDestroy(ctx->kev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -232,6 +236,14 @@ extern "C" void psph_destroy(psph_ctx *ctx)
 extern "C" const char *psph_last_error(const psph_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" size_t psph_num_particles(const psph_ctx *ctx) { return ctx ? (size_t) ctx->n : 0; }
 extern "C" void *psph_stream(psph_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+// pinned host staging for psph_upload / psph_download buffers (plain malloc semantics otherwise)
+extern "C" void *psph_host_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void psph_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" int psph_sync(psph_ctx *ctx) { PSPH_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
 extern "C" int64_t psph_launch_count(psph_ctx *ctx, int reset)
 {

@@ -162,10 +162,11 @@ __global__ void __launch_bounds__(GT) k_gather(DevView V, GridView G, KParams K,
 static __global__ void k_reset_work(StepState *ss) { ss->work = 0; }
 
 template <int DIM, class S>
-int launch_gather_d(psph_ctx *ctx)
+int launch_gather_d(psph_ctx *ctx, int kid)
 {
   k_reset_work<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
   PSPH_LAUNCH_CHECK();
+  KernelTimer kt(ctx, kid);
   int nchunks = (ctx->n + CHUNK - 1) / CHUNK;
   int grid = min(max(nchunks, 1), ctx->sms * 8);
   k_gather<DIM, S><<<grid, GT, 0, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss);
@@ -173,8 +174,8 @@ int launch_gather_d(psph_ctx *ctx)
   return 0;
 }
 template <template <int> class S>
-int launch_gather(psph_ctx *ctx)
+int launch_gather(psph_ctx *ctx, int kid)
 {
-  if (ctx->cfg.dim == 3) return launch_gather_d<3, S<3> >(ctx);
-  return launch_gather_d<1, S<1> >(ctx);
+  if (ctx->cfg.dim == 3) return launch_gather_d<3, S<3> >(ctx, kid);
+  return launch_gather_d<1, S<1> >(ctx, kid);
 }

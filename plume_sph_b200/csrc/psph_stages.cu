@@ -427,7 +427,7 @@ extern "C" int psph_adaptive_sml(psph_ctx *ctx)
   StageTimer tm(ctx, ST_SML);
   if (ensure_list(ctx)) return -1;
   if (ctx->n == 0) return 0;
-  if (launch_gather<SmlStage>(ctx)) return -1;
+  if (launch_gather<SmlStage>(ctx, KN_GATHER_SML)) return -1;
   return refresh_geo(ctx);
 }
 
@@ -440,7 +440,7 @@ extern "C" int psph_mom_engr_update(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (launch_gather<MomStage>(ctx)) return -1;
+  if (launch_gather<MomStage>(ctx, KN_GATHER_MOM)) return -1;
   k_commit_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   return 0;
@@ -454,7 +454,7 @@ extern "C" int psph_smooth_density(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (launch_gather<DensStage>(ctx)) return -1;
+  if (launch_gather<DensStage>(ctx, KN_GATHER_DENS)) return -1;
   k_commit_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   return 0;
@@ -468,7 +468,7 @@ extern "C" int psph_smooth_velocity(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_vel<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  return launch_gather<VelStage>(ctx);
+  return launch_gather<VelStage>(ctx, KN_GATHER_VEL);
 }
 
 extern "C" int psph_update_pos(psph_ctx *ctx)
@@ -563,7 +563,17 @@ extern "C" int psph_set_timing(psph_ctx *ctx, int on)
 {
   ctx->timing = on;
   memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
+  memset(ctx->kernel_ms, 0, sizeof ctx->kernel_ms);
+  memset(ctx->kernel_calls, 0, sizeof ctx->kernel_calls);
   return 0;
+}
+extern "C" double psph_kernel_ms(psph_ctx *ctx, int kernel, int reset, int64_t *calls)
+{
+  if (kernel < 0 || kernel >= KN_COUNT) return -1.0;
+  double v = ctx->kernel_ms[kernel];
+  if (calls) *calls = ctx->kernel_calls[kernel];
+  if (reset) { ctx->kernel_ms[kernel] = 0; ctx->kernel_calls[kernel] = 0; }
+  return v;
 }
 extern "C" double psph_stage_ms(psph_ctx *ctx, int stage, int reset)
 {

@@ -114,6 +114,9 @@ API = {
     "psph_launch_count": (C.c_int64, [_VP, C.c_int]),
     "psph_set_timing": (C.c_int, [_VP, C.c_int]),
     "psph_stage_ms": (C.c_double, [_VP, C.c_int, C.c_int]),
+    "psph_kernel_ms": (C.c_double, [_VP, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    "psph_host_alloc": (_VP, [C.c_size_t]),
+    "psph_host_free": (None, [_VP]),
     "psph_sync": (C.c_int, [_VP]),
     "psph_stream": (_VP, [_VP]),
 }

@@ -11,6 +11,8 @@ import numpy as np
 from . import lib as _l
 
 ORDER_DEVICE, ORDER_REFERENCE = 0, 1
+KERNELS = ("gather_mom_engr", "gather_density", "gather_velocity", "gather_adaptive_sml", "gather_gradients",
+           "gather_gsph_mom_engr", "radix_sort", "reorder")
 STAGES = ("timestep", "search", "adaptive_sml", "gradients", "mom_engr", "density", "velocity", "update_pos", "rebin")
 
 
@@ -30,6 +32,9 @@ class Solver:
         if getattr(self, "h", None):
             self.L.psph_destroy(self.h)
             self.h = None
+        for p in getattr(self, "_pinned", []):
+            self.L.psph_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -48,6 +53,16 @@ class Solver:
             return self._ck(self.L.psph_set_cells(self.h, None, 0), "psph_set_cells")
         attr = np.ascontiguousarray(attr, dtype=_l.CELL_ATTR_DTYPE)
         return self._ck(self.L.psph_set_cells(self.h, attr.ctypes.data, attr.size), "psph_set_cells")
+
+    def host_rows(self, n):
+        """n psph_particle rows in pinned host memory (psph_host_alloc); freed with the solver"""
+        nbytes = max(int(n), 1) * _l.PARTICLE_DTYPE.itemsize
+        p = self.L.psph_host_alloc(nbytes)
+        if not p:
+            raise _l.PsphError("psph_host_alloc failed")
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        buf = (C.c_char * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=_l.PARTICLE_DTYPE, count=int(n))
 
     def upload(self, rows):
         rows = np.ascontiguousarray(rows, dtype=_l.PARTICLE_DTYPE)
@@ -156,6 +171,15 @@ class Solver:
 
     def stage_ms(self, reset=False):
         return {name: float(self.L.psph_stage_ms(self.h, i, int(reset))) for i, name in enumerate(STAGES)}
+
+    def kernel_ms(self, reset=False):
+        """{kernel: (device ms, launches)} of the individually timed kernels (timing on only)"""
+        out = {}
+        for i, name in enumerate(KERNELS):
+            c = C.c_int64(0)
+            ms = float(self.L.psph_kernel_ms(self.h, i, int(reset), C.byref(c)))
+            out[name] = (ms, int(c.value))
+        return out
 
     def stream(self):
         return self.L.psph_stream(self.h)

@@ -3,7 +3,7 @@
 // Replaces the reference's per-bucket particle lists (Bucket::particles, bucket.h:255-321,
 // maintained by update_particles_in_bucket, update_pos.cc:172-462) and the 27-bucket walk of
 // search_neighs_consth (neighs.cc:37-211): rows are radix-sorted by
-//   key = rank(cell) * 64 + subcell(cell, position)       (subcell = sx*16 + sy*4 + sz)
+//   key = rank(cell) * 512 + subcell(cell, position)      (subcell = sx*64 + sy*8 + sz)
 // (rank = position of the cell along the reference's bucket Hilbert curve), every column is
 // permuted into that order, and sub_start[key] gives the first row of every (cell, subcell).
 // Rows flagged removed by the re-bin (cell == -1) sort to the end and are dropped.
@@ -11,6 +11,8 @@
 // function of the input: results are reproducible run to run.
 #include "psph_internal.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 __global__ void k_make_keys(Tab V, GridView G, StepState *ss, int n_cap, uint32_t inf_key,
                             uint32_t *__restrict__ key, uint32_t *__restrict__ perm)
@@ -25,8 +27,8 @@ __global__ void k_make_keys(Tab V, GridView G, StepState *ss, int n_cap, uint32_
         uint32_t sub = 0;
         if (G.dim == 3) {
           int ck = cell % G.ncell[2], cj = (cell / G.ncell[2]) % G.ncell[1], ci = cell / (G.ncell[2] * G.ncell[1]);
-          sub = (uint32_t) (dev_sub_of(G, 0, ci, V.d[D_X][p]) * 16 + dev_sub_of(G, 1, cj, V.d[D_Y][p]) * 4 +
-                            dev_sub_of(G, 2, ck, V.d[D_Z][p]));
+          sub = (uint32_t) (dev_sub_of(G, 0, ci, V.d[D_X][p]) * (SUBDIV * SUBDIV) +
+                            dev_sub_of(G, 1, cj, V.d[D_Y][p]) * SUBDIV + dev_sub_of(G, 2, ck, V.d[D_Z][p]));
         }
         k = (uint32_t) G.cell2rank[cell] * (uint32_t) SUBS + sub;
         h = V.d[D_H][p];
@@ -40,7 +42,7 @@ __global__ void k_make_keys(Tab V, GridView G, StepState *ss, int n_cap, uint32_
   if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
 }
 
-__global__ void k_reset_list_scalars(StepState *ss) { ss->hmax_bits = 0ull; ss->n_need = 0; }
+__global__ void k_reset_list_scalars(StepState *ss) { ss->hmax_bits = 0ull; ss->n_need = 0; ss->n_grad = 0; }
 
 // after the sort: number of live rows = first row whose key is inf_key
 __global__ void k_count_live(const uint32_t *__restrict__ key, int n_cap, uint32_t inf_key, StepState *ss)
@@ -84,31 +86,70 @@ __global__ void k_ghost_cells(Tab V, const StepState *ss, uint8_t *__restrict__ 
   if (b == 0 || b == 1 || b == 2) has_ghost[V.i[I_CELL][p]] = 1;
 }
 
-// per-row flag word, geometry record, h at list-build time
-__global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss)
+// per-row flag word, geometry record, packed subcell coordinates, h at list-build time
+__global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss, int n_cap)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  bool need = false;
-  if (p < ss->n) {
-    int bc = V.t.i[I_BC][p], guest = V.t.i[I_GUEST][p], ph = V.t.i[I_PHASE][p];
-    int f = 0;
-    need = dev_need_neigh(bc, guest);
-    // SPH build, 3-D: in buckets that hold a ghost only bc_type==100 rows get a list (neighs.cc:76-79)
-    if (need && K.dim == 3 && !K.use_gsph && G.cell_has_ghost[V.t.i[I_CELL][p]] && bc != 100) need = false;
-    if (need) f |= F_NEED;
-    if (dev_contr_dens(K.pghost, bc)) f |= F_CDENS;
-    if (dev_contr_vel(bc)) f |= F_CVEL;
-    if (ph == 2) f |= F_PH2;
-    if (ph == 1 || ph == 2) f |= F_PHOK;
-    if (dev_is_real(bc)) f |= F_REAL;
-    if (!guest) f |= F_GRADROW;
-    V.flags[p] = f;
-    double h = V.t.d[D_H][p];
-    V.t.d[D_HLIST][p] = h;
-    V.geo[p] = make_double4(V.t.d[D_X][p], V.t.d[D_Y][p], V.t.d[D_Z][p], h);
+  if (p >= n_cap) return;
+  if (p >= ss->n) { V.flags[p] = 0; return; }
+  int bc = V.t.i[I_BC][p], guest = V.t.i[I_GUEST][p], ph = V.t.i[I_PHASE][p];
+  int f = 0;
+  bool need = dev_need_neigh(bc, guest);
+  // SPH build, 3-D: in buckets that hold a ghost only bc_type==100 rows get a list (neighs.cc:76-79)
+  if (need && K.dim == 3 && !K.use_gsph && G.cell_has_ghost[V.t.i[I_CELL][p]] && bc != 100) need = false;
+  if (need) f |= F_NEED;
+  if (dev_contr_dens(K.pghost, bc)) f |= F_CDENS;
+  if (dev_contr_vel(bc)) f |= F_CVEL;
+  if (ph == 2) f |= F_PH2;
+  if (ph == 1 || ph == 2) f |= F_PHOK;
+  if (dev_is_real(bc)) f |= F_REAL;
+  if (!guest) f |= F_GRADROW;
+  V.flags[p] = f;
+  const double x[3] = { V.t.d[D_X][p], V.t.d[D_Y][p], V.t.d[D_Z][p] };
+  double h = V.t.d[D_H][p];
+  V.t.d[D_HLIST][p] = h;
+  V.geo[p] = make_double4(x[0], x[1], x[2], h);
+  unsigned long long pk = 0;
+  if (G.dim == 3) {
+    // subcell of the row inside the bucket it is a member of (the same function the sort key uses),
+    // plus a flag for rows within 1e-6 subcells of a subcell face (their candidate box is widened by one)
+    const int cell = V.t.i[I_CELL][p];
+    const int ci[3] = { cell / (G.ncell[2] * G.ncell[1]), (cell / G.ncell[2]) % G.ncell[1], cell % G.ncell[2] };
+    unsigned long long near = 0;
+    for (int d = 0; d < 3; d++) {
+      const int sub = dev_sub_of(G, d, ci[d], x[d]);
+      const double q = (x[d] - cell_min_d(G, d, ci[d])) * G.inv_subw - sub;
+      if (!(q > 1e-6 && q < 1.0 - 1e-6)) near = 1;
+      pk |= (unsigned long long) (ci[d] * SUBDIV + sub) << (20 * d);
+    }
+    pk |= near << 60;
   }
-  unsigned m = __ballot_sync(0xffffffffu, need);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ss->n_need, __popc(m));
+  V.gsub[p] = pk;
+}
+
+struct FlagSet
+{
+  const int32_t *flags; int bit;
+  __device__ __forceinline__ bool operator()(int p) const { return (flags[p] & bit) != 0; }
+};
+
+// ascending list of the rows that carry `bit` -> idx, count -> *d_count (device)
+static int select_rows(psph_ctx *ctx, int n_cap, int bit, int32_t *idx, int *d_count)
+{
+  cub::CountingInputIterator<int> it(0);
+  FlagSet pred = { ctx->cur.flags, bit };
+  size_t need = 0;
+  cub::DeviceSelect::If(nullptr, need, it, idx, d_count, n_cap, pred, ctx->stream);
+  if (need > ctx->cub_tmp_bytes) {
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_cub_tmp);
+    PSPH_CUDA(cudaMalloc(&ctx->d_cub_tmp, need));
+    ctx->cub_tmp_bytes = need;
+  }
+  cub::DeviceSelect::If(ctx->d_cub_tmp, need, it, idx, d_count, n_cap, pred, ctx->stream);
+  ctx->launches += 2;
+  PSPH_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int psph_build_cell_list(psph_ctx *ctx)
@@ -130,6 +171,7 @@ int psph_build_cell_list(psph_ctx *ctx)
     cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->d_sortkey, ctx->d_sortkey_alt, ctx->d_perm, ctx->d_perm_alt,
                                     n_cap, 0, end_bit, s);
     if (need > ctx->cub_tmp_bytes) {
+      PSPH_CUDA(cudaStreamSynchronize(s));
       cudaFree(ctx->d_cub_tmp);
       PSPH_CUDA(cudaMalloc(&ctx->d_cub_tmp, need));
       ctx->cub_tmp_bytes = need;
@@ -159,8 +201,10 @@ int psph_build_cell_list(psph_ctx *ctx)
   if (n_cap > 0) {
     k_ghost_cells<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur.t, ctx->d_ss, ctx->d_cell_has_ghost);
     PSPH_LAUNCH_CHECK();
-    k_row_flags<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur, G, ctx->kp, ctx->d_ss);
+    k_row_flags<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur, G, ctx->kp, ctx->d_ss, n_cap);
     PSPH_LAUNCH_CHECK();
+    if (select_rows(ctx, n_cap, F_NEED, ctx->cur.need_idx, &ctx->d_ss->n_need)) return -1;
+    if (ctx->has_grad && select_rows(ctx, n_cap, F_GRADROW, ctx->cur.grad_idx, &ctx->d_ss->n_grad)) return -1;
   }
   ctx->list_valid = true;
   ctx->n_dirty = true;

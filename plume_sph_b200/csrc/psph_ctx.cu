@@ -138,6 +138,7 @@ GridView psph_grid_view(const psph_ctx *ctx)
   G.dim = ctx->cfg.dim;
   G.ncells = ctx->ncells;
   G.del = ctx->cfg.del; G.len_scale = ctx->cfg.len_scale;
+  G.inv_subw = 1.0 / (ctx->cfg.del / (ctx->cfg.len_scale * SUBDIV));
   G.cell2rank = ctx->d_cell2rank; G.rank2cell = ctx->d_rank2cell; G.sub_start = ctx->d_sub_start;
   G.cell_has_ghost = ctx->d_cell_has_ghost;
   G.attr = ctx->d_attr;
@@ -222,6 +223,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   for (int c = 0; c < NSCRATCH; c++) cudaFree(ctx->cur.scr[c]);
   for (int c = 0; c < NREC; c++) cudaFree(ctx->cur.rec[c]);
   cudaFree(ctx->cur.geo); cudaFree(ctx->cur.flags);
+  cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
   cudaFree(ctx->d_cell_has_ghost);
   cudaFree(ctx->d_sortkey); cudaFree(ctx->d_sortkey_alt); cudaFree(ctx->d_perm); cudaFree(ctx->d_perm_alt);
@@ -286,6 +288,9 @@ int psph_reserve(psph_ctx *ctx, size_t rows)
   for (int c = 0; c < NREC; c++) if (grow(ctx, ctx->cur.rec[c], 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.geo, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.flags, 0, ncap)) return -1;
+  if (grow(ctx, ctx->cur.gsub, 0, ncap)) return -1;
+  if (grow(ctx, ctx->cur.need_idx, 0, ncap)) return -1;
+  if (ctx->has_grad && grow(ctx, ctx->cur.grad_idx, 0, ncap)) return -1;
   if (grow(ctx, ctx->d_sortkey, 0, ncap)) return -1;
   if (grow(ctx, ctx->d_sortkey_alt, 0, ncap)) return -1;
   if (grow(ctx, ctx->d_perm, 0, ncap)) return -1;

@@ -62,20 +62,33 @@ __global__ void k_pack_mom(DevView V, KParams K, StepState *ss)
   const int u = K.lans ? D_SVX : D_VX;
   V.rec[2][p] = make_double4(V.t.d[u][p], V.t.d[u + 1][p], V.t.d[u + 2][p], 0.0);
 }
-// smooth_density: rec0 = {m, m/rho, m*e/rho, -}
+// smooth_density: rec0 = {m, m/rho, m*e/rho, phase_num == 2}
 __global__ void k_pack_dens(DevView V, StepState *ss)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ss->n) return;
   double m = V.t.d[D_MASS][p], mv = m / V.t.d[D_RHO][p];
-  V.rec[0][p] = make_double4(m, mv, mv * V.t.d[D_E][p], 0.0);
+  const int f = V.flags[p];
+  // contr_dens() false or phase outside {1,2} (density_massfrac.cc:135,141): the row adds exact zeros
+  if ((f & (F_CDENS | F_PHOK)) != (F_CDENS | F_PHOK)) { m = 0.0; mv = 0.0; }
+  V.rec[0][p] = make_double4(m, mv, mv * V.t.d[D_E][p], (f & F_PH2) ? 1.0 : 0.0);
 }
 // smooth_velocity: rec0 = {m/rho, v_x, v_y, v_z}
 __global__ void k_pack_vel(DevView V, StepState *ss)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ss->n) return;
-  V.rec[0][p] = make_double4(V.t.d[D_MASS][p] / V.t.d[D_RHO][p], V.t.d[D_VX][p], V.t.d[D_VY][p], V.t.d[D_VZ][p]);
+  // contr_vel_smooth() false (smooth_velocity.cc:100): zero weight
+  const double mv = (V.flags[p] & F_CVEL) ? V.t.d[D_MASS][p] / V.t.d[D_RHO][p] : 0.0;
+  V.rec[0][p] = make_double4(mv, V.t.d[D_VX][p], V.t.d[D_VY][p], V.t.d[D_VZ][p]);
+}
+
+// adaptive_sml: scr[7] = m_j (0 when contr_dens() is false, neighs.cc:556)
+__global__ void k_pack_sml(DevView V, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n) return;
+  V.scr[7][p] = (V.flags[p] & F_CDENS) ? V.t.d[D_MASS][p] : 0.0;
 }
 
 // =========================================================================================
@@ -84,29 +97,26 @@ __global__ void k_pack_vel(DevView V, StepState *ss)
 template <int DIM>
 struct DensStage
 {
-  struct I { double h, supp; };
+  static constexpr bool kSymH = true, kSkipSelf = false;
+  static constexpr int kRows = F_NEED;
+  struct I { double h, supp, hk; };
   struct A { double rho1, rho2, wn, en; };
-  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *, int i, I &s)
+  static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
   {
-    if (!(V.flags[i] & F_NEED)) return false;
     s.h = V.t.d[D_H][i];
     s.supp = K.cutoff2 * s.h; // :93
-    return true;
   }
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double hmax)
   { return fmin(K.cutoff * 0.5 * (s.h + hmax), s.supp); }
   static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.rho1 = a.rho2 = a.wn = a.en = 0.0; }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
-                                              double dz, double hj, int fj, int j)
+                                              double dz, double hj, int j)
   {
-    if ((fj & (F_CDENS | F_PHOK)) != (F_CDENS | F_PHOK)) return;   // :135, :141
-    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;           // :151
     const double h = 0.5 * (s.h + hj);                              // :155
-    if (outside_kernel<DIM>(dx, dy, dz, h, K.cutoff)) return;       // weight() == 0
     const double r2 = dx * dx + dy * dy + dz * dz, invh = 1.0 / h;
     const double4 rj = ld_rec(V.rec[0], j);
     const double w = dev_weight_in<DIM>(r2, invh);
-    if (fj & F_PH2) a.rho2 += w * rj.x; else a.rho1 += w * rj.x;
+    if (rj.w != 0.0) a.rho2 += w * rj.x; else a.rho1 += w * rj.x;   // phase of j
     if (K.energy_smooth == 1) {                                     // :163-168, kernel of width h/E_SMOOTH_RATIO
       const double q = K.e_ratio;
       if (!outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) {
@@ -154,11 +164,12 @@ __global__ void k_commit_dens(DevView V, KParams K, StepState *ss)
 template <int DIM>
 struct MomStage
 {
-  struct I { int i; double h, supp, rho, Vi, pvsq, c, T, Cp, u[3]; };
+  static constexpr bool kSymH = true, kSkipSelf = true;
+  static constexpr int kRows = F_NEED;
+  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3]; };
   struct A { double rv[3], re; };
-  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *ss, int i, I &s)
+  static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *ss, int i, I &s)
   {
-    if (!(V.flags[i] & F_NEED)) return false;
     s.i = i;
     s.h = V.t.d[D_H][i];
     s.supp = K.cutoff2 * s.h;
@@ -168,18 +179,14 @@ struct MomStage
     s.c = V.t.d[D_C][i]; s.T = V.t.d[D_T][i]; s.Cp = V.t.d[D_CP][i];
     const int u = K.lans ? D_SVX : D_VX;
     s.u[0] = V.t.d[u][i]; s.u[1] = V.t.d[u + 1][i]; s.u[2] = V.t.d[u + 2][i];
-    return true;
   }
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double hmax)
   { return fmin(K.cutoff * 0.5 * (s.h + hmax), s.supp); }
   static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.rv[0] = a.rv[1] = a.rv[2] = a.re = 0.0; }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
-                                              double dz, double hj, int, int j)
+                                              double dz, double hj, int j)
   {
-    if (j == s.i) return;                                           // :201
-    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;
     const double h = 0.5 * (s.h + hj);
-    if (outside_kernel<DIM>(dx, dy, dz, h, K.cutoff)) return;       // d_weight() == 0 for every term
     const double r2 = dx * dx + dy * dy + dz * dz, invh = 1.0 / h;
     const double4 r0 = ld_rec(V.rec[0], j), r1 = ld_rec(V.rec[1], j), uj = ld_rec(V.rec[2], j);
     const double w = dev_weight_in<DIM>(r2, invh);
@@ -243,23 +250,20 @@ __global__ void k_commit_mom(DevView V, KParams K, StepState *ss)
 template <int DIM>
 struct VelStage
 {
-  struct I { double h, invh, supp, v[3]; };
+  static constexpr bool kSymH = false, kSkipSelf = false;
+  static constexpr int kRows = F_NEED;
+  struct I { double h, invh, supp, hk, v[3]; };
   struct A { double dv[3], wn; };
-  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *, int i, I &s)
+  static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
   {
-    if (!(V.flags[i] & F_NEED)) return false;
-    s.h = V.t.d[D_H][i]; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
+    s.h = V.t.d[D_H][i]; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
     s.v[0] = V.t.d[D_VX][i]; s.v[1] = V.t.d[D_VY][i]; s.v[2] = V.t.d[D_VZ][i];
-    return true;
   }
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double) { return K.cutoff * s.h; }
   static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.dv[0] = a.dv[1] = a.dv[2] = a.wn = 0.0; }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
-                                              double dz, double, int fj, int j)
+                                              double dz, double, int j)
   {
-    if (!(fj & F_CVEL)) return;
-    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;
-    if (outside_kernel<DIM>(dx, dy, dz, s.h, K.cutoff)) return;
     const double4 rj = ld_rec(V.rec[0], j);
     const double mvw = dev_weight_in<DIM>(dx * dx + dy * dy + dz * dz, s.invh) * rj.x;
     a.dv[0] += mvw * (rj.y - s.v[0]);
@@ -287,27 +291,24 @@ struct VelStage
 template <int DIM>
 struct SmlStage
 {
-  struct I { double h, hs, invhs, supp, m; };
+  static constexpr bool kSymH = false, kSkipSelf = false;
+  static constexpr int kRows = F_NEED;
+  struct I { double h, hs, hk, invhs, supp, m; };
   struct A { double rho; };
-  static __device__ __forceinline__ bool init(const DevView &V, const KParams &K, StepState *, int i, I &s)
+  static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
   {
-    if (!(V.flags[i] & F_NEED)) return false;
     s.h = V.t.d[D_H][i]; s.m = V.t.d[D_MASS][i];
-    return true;
   }
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double) { return K.cutoff * s.hs; }
   static __device__ __forceinline__ void begin(const KParams &K, I &s, A &a, int)
   {
-    s.hs = s.h * K.c_smooth; s.invhs = 1.0 / s.hs; s.supp = K.cutoff2 * s.hs;
+    s.hs = s.h * K.c_smooth; s.hk = s.hs; s.invhs = 1.0 / s.hs; s.supp = K.cutoff2 * s.hs;
     a.rho = 0.0;
   }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
-                                              double dz, double, int fj, int j)
+                                              double dz, double, int j)
   {
-    if (!(fj & F_CDENS)) return;
-    if (!dev_in_support<DIM>(dx, dy, dz, s.supp)) return;
-    if (outside_kernel<DIM>(dx, dy, dz, s.hs, K.cutoff)) return;
-    a.rho += dev_weight_in<DIM>(dx * dx + dy * dy + dz * dz, s.invhs) * __ldg(&V.t.d[D_MASS][j]);
+    a.rho += dev_weight_in<DIM>(dx * dx + dy * dy + dz * dz, s.invhs) * __ldg(&V.scr[7][j]);
   }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *, int i, I &s, A &a, int pass, int lane)
   {
@@ -427,6 +428,8 @@ extern "C" int psph_adaptive_sml(psph_ctx *ctx)
   StageTimer tm(ctx, ST_SML);
   if (ensure_list(ctx)) return -1;
   if (ctx->n == 0) return 0;
+  k_pack_sml<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
   if (launch_gather<SmlStage>(ctx, KN_GATHER_SML)) return -1;
   return refresh_geo(ctx);
 }

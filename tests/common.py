@@ -16,16 +16,22 @@ import plume_sph_b200 as psph
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # FP64 tolerance of a field after ONE stage, relative to the field's max magnitude: the CUDA
-# path sums in a different order (lane-strided partial sums + shuffle tree instead of the
-# reference's list order), contracts a*b+c into FMAs, uses 1/h once per pair instead of three
-# divisions and CUDA's exp() instead of glibc's.  Each is a few ulp per term.
+# path sums in a different order (lane partial sums + shuffle tree instead of the reference's
+# list order), contracts a*b+c into FMAs, uses 1/h once per pair instead of three divisions
+# and CUDA's exp() instead of glibc's.  Each is a few ulp per term.
 RTOL_STAGE = 2e-13
-# after ~100 steps: the per-stage differences add up (and are amplified by the shock)
+# one whole time step started from identical states (lock-step checks along a long run)
+RTOL_STEP = 2e-12
+# after 30 steps: the per-stage differences only add up
 RTOL_MID = 1e-10
-# after hundreds of steps the reference algorithm's own discrete decisions (adaptive_sml's
-# `err < thresh` exit, pairs crossing the kernel cutoff) turn a 1e-16 difference into ~1e-6:
-# measured on the reference restatement itself in test_reference_algorithm_is_sensitive
-RTOL_LONG = 5e-5
+# Beyond ~50 steps the reference ALGORITHM itself is not reproducible to rounding: a 1e-16
+# relative perturbation of the initial energies grows to 1e-8 (velocity) by step 60 and to
+# 4e-4 by step 100 (tests/test_oracle_vs_ref.py::test_reference_algorithm_is_sensitive measures
+# this on the bit-exact restatement: adaptive_sml's `err < thresh` exit and pairs crossing the
+# kernel cutoff are discrete decisions).  End-state comparisons after hundreds of steps are
+# therefore stated per field against that measured sensitivity (x25 margin), and the tight
+# statement over long runs is the lock-step one (RTOL_STEP at every checked step).
+RTOL_LONG = {"coord": 5e-5, "smlen": 5e-4, "rho": 2e-3, "engr": 1e-3, "pressure": 2e-3, "vel": 2.5e-2}
 
 
 def golden(name):

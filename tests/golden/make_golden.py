@@ -27,7 +27,7 @@ import refio  # noqa: E402
 REF = os.environ.get("PSPH_REFERENCE", "/root/reference")
 REFBIN = os.path.join(ROOT, "oracle", "_ref")
 
-NMID = 100
+NMID = 30
 
 STAGE_FIELDS = {
     "sml": ["smlen"],

@@ -141,15 +141,19 @@ def z_steps():
 
 
 def test_reference_algorithm_is_sensitive():
-    """Why the long-run tolerance of the GPU tests (common.RTOL_LONG) is ~1e-5 and not 1e-12: the
-    reference ALGORITHM amplifies a 1e-16 relative perturbation of the initial energies to >1e-9
-    within a few hundred steps (discrete decisions: adaptive_sml's convergence exit, pairs crossing
-    the kernel cutoff).  Up to ~100 steps the same perturbation stays at rounding level."""
-    _, a, _ = run_sod(400)
-    _, b, _ = run_sod(400, perturb=1e-16)
-    d400 = np.abs(a.a["x"][:, 0] - b.a["x"][:, 0]).max() / np.abs(a.a["x"]).max()
-    _, a, _ = run_sod(100)
-    _, b, _ = run_sod(100, perturb=1e-16)
-    d100 = np.abs(a.a["x"][:, 0] - b.a["x"][:, 0]).max() / np.abs(a.a["x"]).max()
-    assert d100 < 1e-13
-    assert 1e-9 < d400 < 5e-5
+    """Why end-state tolerances of long GPU runs (common.RTOL_LONG) are 1e-5..1e-2 and not 1e-12: the
+    reference ALGORITHM amplifies a 1e-16 relative perturbation of the initial energies by many
+    orders of magnitude within ~60 steps (discrete decisions: adaptive_sml's convergence exit,
+    pairs crossing the kernel cutoff).  Up to 30 steps the same perturbation stays at rounding
+    level, which is where the tight end-state comparison (RTOL_MID) is made."""
+    def spread(nsteps):
+        _, a, _ = run_sod(nsteps)
+        _, b, _ = run_sod(nsteps, perturb=1e-16)
+        return {f: float(np.abs(a.a[f] - b.a[f]).max() / np.abs(a.a[f]).max()) for f in ("x", "v", "rho", "e", "h")}
+    d30, d100, d400 = spread(30), spread(100), spread(400)
+    assert max(d30.values()) < 1e-12, d30
+    assert d100["v"] > 1e-9, d100            # already far above rounding ...
+    assert d400["v"] > 1e-9, d400
+    from common import RTOL_LONG            # ... and inside the stated long-run tolerances
+    for f, k in (("x", "coord"), ("v", "vel"), ("rho", "rho"), ("e", "engr"), ("h", "smlen")):
+        assert d400[f] < RTOL_LONG[k] and d100[f] < RTOL_LONG[k], (f, d100[f], d400[f])

@@ -4,9 +4,10 @@
 // per bucket) that overlap the box x_i +- reach; for every (x, y) subcell column and every
 // bucket the column crosses, the z-run of subcells is ONE contiguous row range ("segment") of
 // the sorted table.  A warp works in two alternating phases:
-//   scan : eight segments at a time, four lanes per segment, two rows per lane (both loads in
-//          flight together): every lane loads the 32-byte {x,y,z,h} record of a candidate row with
-//          a single 256-bit load and applies the reference's own gates, bit for bit:
+//   scan : the row ranges are expanded (warp prefix sum) into a dense candidate list in shared
+//          memory; every lane takes two candidates at a time (both loads in flight together),
+//          loads the 32-byte {x,y,z,h} record of the row with a single 256-bit load and applies
+//          the reference's own gates, bit for bit:
 //            list gate   : j in i's bucket, or |dx_k| <= 4.25*h_i(list) for all k   (neighs.cc:84-92,130)
 //            stage gates : in_support(dx, CUTOFF2*h_i), kernel cutoff |dx_k/h| <= 3
 //                                                            (sph_header.h:49-60, sph_lib.cc:216-218)
@@ -27,16 +28,13 @@ constexpr int GT = GW * 32;    // threads per CTA
 constexpr int RPW = 16;        // consecutive list entries per warp and chunk
 constexpr int CHUNK = GW * RPW;// entries per CTA chunk (spatially compact: its candidates share L1)
 constexpr int QCAP = 128;      // queue slots per warp (power of two, >= 31 + 64)
-constexpr int SEGCAP = 128;    // segments resolved per batch
-constexpr int LPS = 4;         // lanes per segment in the scan phase (two rows per lane and iteration)
+constexpr int CANDCAP = 768;   // candidate rows expanded per batch
 constexpr unsigned FULL = 0xffffffffu;
 
 struct WarpScratch
 {
-  int seg_beg[SEGCAP];         // first row | own-bucket flag in bit 31
-  int seg_end[SEGCAP];
-  int qj[QCAP];
-  double qdx[QCAP], qdy[QCAP], qdz[QCAP], qh[QCAP];
+  int cand[CANDCAP];           // candidate row | own-bucket flag in bit 31
+  int qj[QCAP];                // rows that passed the gates, waiting for a pair round
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -83,6 +81,45 @@ __device__ __forceinline__ bool dev_in_support(double dx, double dy, double dz, 
   if (DIM == 3 && (fabs(dy) > supp || fabs(dz) > supp)) return false;
   return true;
 }
+// ---- branch-free FP64 helpers for the pair bodies ------------------------------------------
+// The pair loops are bound by dependent-instruction latency, not by the FP64 pipe: libdevice's
+// exp() and '/' each carry a slow-path branch that splits the pair body into basic blocks and
+// stops the scheduler from interleaving the independent chains.  These versions are straight
+// line code, valid for the argument ranges that occur here (normal, finite operands), and
+// accurate to <= 2 ulp — inside the FP64 tolerance the parity tests state.
+
+// 1/x for normal finite x: hardware seed + two Newton steps
+__device__ __forceinline__ double dev_rcp(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+// exp(x) for -700 < x <= 0 (the kernel exponent is >= -27): k = rint(x*log2 e), r = x - k ln 2,
+// degree-11 polynomial in Estrin form, scaled by 2^k through the exponent field
+__device__ __forceinline__ double dev_exp_neg(double x)
+{
+  const double kd0 = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(kd0);
+  const double kd = kd0 - 6755399441055744.0;
+  double r = fma(kd, -6.93147180559945286e-01, x);   // ln 2 split hi + lo
+  r = fma(kd, -2.31904681384629956e-17, r);
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double p01 = r + 1.0;
+  const double p23 = fma(r, 1.66666666666664770e-01, 5.00000000000001221e-01);
+  const double p45 = fma(r, 8.33333333345504315e-03, 4.16666666665197541e-02);
+  const double p67 = fma(r, 1.98412695891154973e-04, 1.38888889459163798e-03);
+  const double p89 = fma(r, 2.75575145458824386e-06, 2.48014910390991645e-05);
+  const double pab = fma(r, 2.50223225365029900e-08, 2.76309034881731077e-07);
+  const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
+  const double p = fma(r8, q2, fma(r4, q1, q0));
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
 // SPH kernel (sph_lib.cc:207-230) for a pair already known to be inside the cutoff:
 // w = (pi^-1/2 / h)^DIM * exp(-|dx|^2/h^2)
 template <int DIM>
@@ -90,13 +127,14 @@ __device__ __forceinline__ double dev_weight_in(double r2, double invh)
 {
   const double t = 0.564189583547756 * invh;
   const double norm = DIM == 3 ? t * t * t : t;
-  return norm * exp(-(r2 * invh * invh));
+  return norm * dev_exp_neg(-(r2 * invh * invh));
 }
 
 // Stage interface (static members):
 //   kSymH         pair smoothing length is 0.5*(h_i+h_j) (true) or S::I::hk (false)
 //   kSkipSelf     j == i is not a pair (mom_engr_update.cc:201)
 //   kRows         RowFlags bit of the rows the stage updates (selects the row list it walks)
+//   kMinBlocks    resident CTAs per SM the register allocation must allow
 //   struct I      per-row state, identical in every lane; members h, supp (= CUTOFF2*h_i), hk
 //   struct A      per-lane accumulators
 //   void  init(V,K,ss,i,I&)             load row i
@@ -107,7 +145,7 @@ __device__ __forceinline__ double dev_weight_in(double r2, double invh)
 // Rows that must not contribute to a stage's sums (contr_dens / contr_vel_smooth false) carry
 // zeros in the stage record, so the scan phase needs no flag word.
 template <int DIM, class S>
-__global__ void __launch_bounds__(GT) k_gather(DevView V, GridView G, KParams K, StepState *ss)
+__global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridView G, KParams K, StepState *ss)
 {
   __shared__ WarpScratch s_scr[GW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -135,30 +173,41 @@ __global__ void __launch_bounds__(GT) k_gather(DevView V, GridView G, KParams K,
         int qn = 0, qhead = 0; // queue state, identical in every lane
 
         // ---- scan phase, one candidate per lane: list gate (neighs.cc:88-92 own bucket, :130 others),
-        // in_support (sph_header.h:49-60) and kernel cutoff (sph_lib.cc:216-218) on t = max_k |dx_k|
-        auto consider = [&](bool live, bool own, int j, const double4 &gj) {
-          const double dx = gi.x - gj.x, dy = gi.y - gj.y, dz = gi.z - gj.z;
-          const double t = DIM == 3 ? fmax(fmax(fabs(dx), fabs(dy)), fabs(dz)) : fabs(dx);
-          bool ok = live && !(t > (own ? lim_own : lim_other)) && !(S::kSkipSelf && j == i);
+        // in_support (sph_header.h:49-60) and kernel cutoff |dx_k / h| <= 3 (sph_lib.cc:216-218).  The
+        // cutoff is decided without dividing unless a component sits within 2^-48 of the face.
+        auto consider = [&](bool live, int cj, const double4 &gj) {
+          const int j = cj & 0x7fffffff;
+          // |dx_k| as ordered bit patterns: non-negative doubles compare like unsigned integers, which keeps
+          // the three-way test off the FP64 pipe
+          const double dx = gi.x - gj.x, dy = DIM == 3 ? gi.y - gj.y : 0.0, dz = DIM == 3 ? gi.z - gj.z : 0.0;
+          const unsigned long long ax = (unsigned long long) __double_as_longlong(dx) & 0x7fffffffffffffffull,
+                                   ay = (unsigned long long) __double_as_longlong(dy) & 0x7fffffffffffffffull,
+                                   az = (unsigned long long) __double_as_longlong(dz) & 0x7fffffffffffffffull;
+          const double h = S::kSymH ? 0.5 * (st.h + gj.w) : st.hk;
+          const double b = K.cutoff * h;
+          const unsigned long long blo = (unsigned long long) __double_as_longlong(b * (1.0 - 0x1p-48));
+          bool ok = live && ax <= blo && ay <= blo && az <= blo;
+          if (live && !ok) { // outside, or within rounding of the cutoff face
+            const unsigned long long bhi = (unsigned long long) __double_as_longlong(b * (1.0 + 0x1p-48));
+            if (ax <= bhi && ay <= bhi && az <= bhi)
+              ok = !(fabs(dx / h) > K.cutoff || fabs(dy / h) > K.cutoff || fabs(dz / h) > K.cutoff);
+          }
           if (ok) {
-            const double h = S::kSymH ? 0.5 * (st.h + gj.w) : st.hk;
-            const double b = K.cutoff * h;
-            if (t > b * (1.0 - 0x1p-48)) ok = !(t > b * (1.0 + 0x1p-48)) && !(fabs(t / h) > K.cutoff);
+            const double lim = cj < 0 ? lim_own : lim_other;
+            if (b > lim) ok = !(fabs(dx) > lim || fabs(dy) > lim || fabs(dz) > lim);
+            if (S::kSkipSelf && j == i) ok = false;
           }
           const unsigned m = __ballot_sync(FULL, ok);
-          if (ok) {
-            const int s = (qhead + qn + __popc(m & lt)) & (QCAP - 1);
-            W.qj[s] = j; W.qdx[s] = dx; W.qdy[s] = dy; W.qdz[s] = dz; W.qh[s] = gj.w;
-          }
+          if (ok) W.qj[(qhead + qn + __popc(m & lt)) & (QCAP - 1)] = j;
           qn += __popc(m);
         };
 
         // ---- candidate enumeration state
         int j0 = 0;                                  // 1-D: next row
-        int gx0 = 0, gy0 = 0, gz0 = 0, gz1 = 0, ncolx = 0, ncoly = 0, ncol = 0, cz0 = 0, cz1 = 0, cpr = 32;
+        int gx0 = 0, gy0 = 0, gz0 = 0, gz1 = 0, ncoly = 1, ncol = 0, cz0 = 0, cz1 = 0;
         float inv_ncoly = 1.0f;
-        int col_base = 0, ns = 0, s0 = 0, j = 0, e = 0;
-        bool own = false;
+        int col_base = -32, cz = 0, c0 = 0, total = 0, beg = 0, len = 0, cellxy = 0, subxy = 0;
+        bool have = false, own = false;
         int cell_i = 0;
         if (DIM == 3) {
           cell_i = V.t.i[I_CELL][i];
@@ -168,10 +217,10 @@ __global__ void __launch_bounds__(GT) k_gather(DevView V, GridView G, KParams K,
           gx0 = max(sx - kR, 0); gy0 = max(sy - kR, 0); gz0 = max(sz - kR, 0);
           const int gx1 = min(sx + kR, G.ncell[0] * SUBDIV - 1), gy1 = min(sy + kR, G.ncell[1] * SUBDIV - 1);
           gz1 = min(sz + kR, G.ncell[2] * SUBDIV - 1);
-          ncolx = gx1 - gx0 + 1; ncoly = gy1 - gy0 + 1; ncol = ncolx * ncoly;
+          ncoly = gy1 - gy0 + 1; ncol = (gx1 - gx0 + 1) * ncoly;
           inv_ncoly = 1.0f / (float) ncoly;
           cz0 = gz0 / SUBDIV; cz1 = gz1 / SUBDIV;
-          cpr = min(32, SEGCAP / (cz1 - cz0 + 1));
+          cz = cz1;
         }
         // one scan iteration (up to 64 candidates); false when no candidate is left
         auto scan_next = [&]() -> bool {
@@ -179,64 +228,65 @@ __global__ void __launch_bounds__(GT) k_gather(DevView V, GridView G, KParams K,
             // the 1-D reference has no search: every particle lists every particle (add_air.cc:470-479)
             if (j0 >= n) return false;
             const int jj = min(j0 + lane, n - 1);
-            consider(j0 + lane < n, true, jj, ld_rec(V.geo, jj));
+            consider(j0 + lane < n, jj | 0x80000000, ld_rec(V.geo, jj));
             j0 += 32;
             return true;
           }
           for (;;) {
-            if (__any_sync(FULL, j < e)) {
-              const bool l0 = j < e, l1 = j + LPS < e;
-              const double4 g0 = ld_rec(V.geo, l0 ? j : i), g1 = ld_rec(V.geo, l1 ? j + LPS : i);
-              consider(l0, own, j, g0);
-              if (__any_sync(FULL, l1)) consider(l1, own, j + LPS, g1);
-              j += 2 * LPS;
+            if (c0 < total) { // two candidates per lane, both loads in flight
+              const int ca = c0 + lane, cb = ca + 32;
+              const bool la = ca < total, lb = cb < total;
+              const int ja = la ? W.cand[ca] : i, jb = lb ? W.cand[cb] : i;
+              const double4 ga = ld_rec(V.geo, ja & 0x7fffffff), gb = ld_rec(V.geo, jb & 0x7fffffff);
+              consider(la, ja, ga);
+              if (c0 + 32 < total) consider(lb, jb, gb);
+              c0 += 64;
               return true;
             }
-            if (s0 < ns) { // next group of 32/LPS segments
-              const int sidx = s0 + lane / LPS;
-              int b = 0;
-              e = 0;
-              if (sidx < ns) { b = W.seg_beg[sidx]; e = W.seg_end[sidx]; }
-              own = b < 0; b &= 0x7fffffff;
-              j = b + lane % LPS;
-              s0 += 32 / LPS;
-              continue;
-            }
-            if (col_base >= ncol) return false;
-            // resolve the z-runs of the next cpr (x, y) subcell columns to row ranges; keep the non-empty ones
-            __syncwarp();
-            const int col = col_base + lane;
-            const bool have = lane < cpr && col < ncol;
-            int cellxy = 0, subxy = 0;
-            if (have) {
-              const int ix = (int) (((float) col + 0.5f) * inv_ncoly), iy = col - ix * ncoly;
-              const int gx = gx0 + ix, gy = gy0 + iy;
-              cellxy = ((gx / SUBDIV) * G.ncell[1] + (gy / SUBDIV)) * G.ncell[2];
-              subxy = (gx % SUBDIV) * (SUBDIV * SUBDIV) + (gy % SUBDIV) * SUBDIV;
-            }
-            ns = 0;
-            for (int cz = cz0; cz <= cz1; cz++) {
-              int beg = 0, end = 0, o = 0;
+            if (total) { total = 0; c0 = 0; __syncwarp(); } // list consumed
+            // refill: expand row ranges into the candidate list until it is full or nothing is left
+            for (;;) {
+              if (__any_sync(FULL, len > 0)) {
+                const int quota = (CANDCAP - total) / 32;
+                if (quota == 0) break;
+                const int take = min(len, quota);
+                int off = take;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
+                const int sum = __shfl_sync(FULL, off, 31);
+                off += total - take;
+                const int tag = own ? 0x80000000 : 0;
+                for (int k = 0; k < take; k++) W.cand[off + k] = (beg + k) | tag;
+                beg += take; len -= take; total += sum;
+                continue;
+              }
+              if (cz < cz1) { // the z-run of every column of this round inside the next bucket along z
+                cz++;
+                beg = 0; len = 0; own = false;
+                if (have) {
+                  const int cell = cellxy + cz;
+                  const int zlo = (cz == cz0) ? (gz0 % SUBDIV) : 0, zhi = (cz == cz1) ? (gz1 % SUBDIV) : SUBDIV - 1;
+                  const int t = __ldg(&G.cell2rank[cell]) * SUBS + subxy;
+                  beg = __ldg(&G.sub_start[t + zlo]);
+                  len = __ldg(&G.sub_start[t + zhi + 1]) - beg;
+                  own = cell == cell_i;
+                }
+                continue;
+              }
+              col_base += 32; // next round of 32 (x, y) subcell columns
+              if (col_base >= ncol) break;
+              const int col = col_base + lane;
+              have = col < ncol;
               if (have) {
-                const int cell = cellxy + cz;
-                const int zlo = (cz == cz0) ? (gz0 % SUBDIV) : 0, zhi = (cz == cz1) ? (gz1 % SUBDIV) : SUBDIV - 1;
-                const int t = __ldg(&G.cell2rank[cell]) * SUBS + subxy;
-                beg = __ldg(&G.sub_start[t + zlo]);
-                end = __ldg(&G.sub_start[t + zhi + 1]);
-                o = cell == cell_i;
+                const int ix = (int) (((float) col + 0.5f) * inv_ncoly), iy = col - ix * ncoly;
+                const int gx = gx0 + ix, gy = gy0 + iy;
+                cellxy = ((gx / SUBDIV) * G.ncell[1] + (gy / SUBDIV)) * G.ncell[2];
+                subxy = (gx % SUBDIV) * (SUBDIV * SUBDIV) + (gy % SUBDIV) * SUBDIV;
               }
-              const bool ne = end > beg;
-              const unsigned m = __ballot_sync(FULL, ne);
-              if (ne) {
-                const int p = ns + __popc(m & lt);
-                W.seg_beg[p] = beg | (o << 31);
-                W.seg_end[p] = end;
-              }
-              ns += __popc(m);
+              cz = cz0 - 1;
             }
+            if (total == 0) return false;
             __syncwarp();
-            col_base += cpr;
-            s0 = 0; j = 0; e = 0;
           }
         };
 
@@ -246,8 +296,9 @@ __global__ void __launch_bounds__(GT) k_gather(DevView V, GridView G, KParams K,
             __syncwarp();
             const int c = min(32, qn);
             if (lane < c) {
-              const int s = (qhead + lane) & (QCAP - 1);
-              S::pair(V, K, st, acc, W.qdx[s], W.qdy[s], W.qdz[s], W.qh[s], W.qj[s]);
+              const int j = W.qj[(qhead + lane) & (QCAP - 1)];
+              const double4 gj = ld_rec(V.geo, j);
+              S::pair(V, K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, j);
             }
             qhead = (qhead + c) & (QCAP - 1);
             qn -= c;

@@ -98,7 +98,7 @@ template <int DIM>
 struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false;
-  static constexpr int kRows = F_NEED;
+  static constexpr int kRows = F_NEED, kMinBlocks = 3;
   struct I { double h, supp, hk; };
   struct A { double rho1, rho2, wn, en; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
@@ -113,10 +113,12 @@ struct DensStage
                                               double dz, double hj, int j)
   {
     const double h = 0.5 * (s.h + hj);                              // :155
-    const double r2 = dx * dx + dy * dy + dz * dz, invh = 1.0 / h;
+    const double r2 = dx * dx + dy * dy + dz * dz, invh = dev_rcp(h);
     const double4 rj = ld_rec(V.rec[0], j);
-    const double w = dev_weight_in<DIM>(r2, invh);
-    if (rj.w != 0.0) a.rho2 += w * rj.x; else a.rho1 += w * rj.x;   // phase of j
+    const double wm = dev_weight_in<DIM>(r2, invh) * rj.x;
+    const bool ph2 = rj.w != 0.0;                                   // phase of j
+    a.rho2 += ph2 ? wm : 0.0;
+    a.rho1 += ph2 ? 0.0 : wm;
     if (K.energy_smooth == 1) {                                     // :163-168, kernel of width h/E_SMOOTH_RATIO
       const double q = K.e_ratio;
       if (!outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) {
@@ -165,7 +167,7 @@ template <int DIM>
 struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true;
-  static constexpr int kRows = F_NEED;
+  static constexpr int kRows = F_NEED, kMinBlocks = 2;
   struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3]; };
   struct A { double rv[3], re; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *ss, int i, I &s)
@@ -187,27 +189,28 @@ struct MomStage
                                               double dz, double hj, int j)
   {
     const double h = 0.5 * (s.h + hj);
-    const double r2 = dx * dx + dy * dy + dz * dz, invh = 1.0 / h;
+    const double r2 = dx * dx + dy * dy + dz * dz, invh = dev_rcp(h);
     const double4 r0 = ld_rec(V.rec[0], j), r1 = ld_rec(V.rec[1], j), uj = ld_rec(V.rec[2], j);
     const double w = dev_weight_in<DIM>(r2, invh);
     const double g = -2.0 * invh * invh * w;                        // dW/dx_k = g * dx_k
     const double vx = s.u[0] - uj.x, vy = s.u[1] - uj.y, vz = s.u[2] - uj.z;
     const double vr = dx * vx + dy * vy + dz * vz, vv = vx * vx + vy * vy + vz * vz;
     const double cab = 0.5 * (s.c + r1.x);
-    double vis = 0.0;                                               // art_vis
-    if (vr < 0) {
-      const double miu = h * vr / (r2 + K.ata * h * h);
-      vis = (K.beta * miu - K.alf * cab) * miu / (0.5 * (s.rho + r0.w));
-    }
+    // art_vis (sph_lib.cc:402-424): miu = h vr / (r2 + ata h^2); (beta miu - alf cab) miu / rho_ab if vr < 0.
+    // One reciprocal serves both quotients; selected, not branched.
+    const double dA = r2 + K.ata * h * h, dB = s.rho + r0.w, rAB = dev_rcp(dA * dB);
+    const double miu = h * vr * dB * rAB;
+    double vis = (K.beta * miu - K.alf * cab) * miu * (2.0 * dA * rAB);
+    vis = vr < 0 ? vis : 0.0;
     if (K.lans) vis -= K.epsilon_half * vv * r0.z;                  // SPH_epsilon_mom
     const double mpv = r0.x * (r0.y + s.pvsq + vis);
     double heat = 0.0;
     if (K.lans && DIM == 3) {                                       // :307-314
       const double avr = fabs(vx * dx) + fabs(vy * dy) + fabs(vz * dz);
-      if (avr != 0. && r2 > 0.) {
-        const double kij = 10.0 * K.epsilon_half * (0.5 * (r1.y + s.Cp)) * r2 * vv / (K.prandtl * avr) / (h * cab);
-        heat = r0.x * r0.z * s.Vi * kij * (s.T - r1.z) * g;         // F_ij = (gradW . dx) / r2 = g
-      }
+      const bool on = avr != 0. && r2 > 0.;
+      // k_ij = 10 eps Cp_ab r2 vv / (Pr avr) / (h cab)   (sph_lib.cc:1399-1439); F_ij = (gradW . dx) / r2 = g
+      const double kij = 10.0 * K.epsilon_half * (0.5 * (r1.y + s.Cp)) * r2 * vv * dev_rcp(on ? K.prandtl * avr * h * cab : 1.0);
+      heat = on ? r0.x * r0.z * s.Vi * kij * (s.T - r1.z) * g : 0.0;
     }
     const double mg = mpv * g;
     a.rv[0] -= mg * dx;
@@ -251,7 +254,7 @@ template <int DIM>
 struct VelStage
 {
   static constexpr bool kSymH = false, kSkipSelf = false;
-  static constexpr int kRows = F_NEED;
+  static constexpr int kRows = F_NEED, kMinBlocks = 3;
   struct I { double h, invh, supp, hk, v[3]; };
   struct A { double dv[3], wn; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
@@ -292,7 +295,7 @@ template <int DIM>
 struct SmlStage
 {
   static constexpr bool kSymH = false, kSkipSelf = false;
-  static constexpr int kRows = F_NEED;
+  static constexpr int kRows = F_NEED, kMinBlocks = 3;
   struct I { double h, hs, hk, invhs, supp, m; };
   struct A { double rho; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)

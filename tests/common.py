@@ -22,8 +22,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL_STAGE = 2e-13
 # one whole time step started from identical states (lock-step checks along a long run)
 RTOL_STEP = 2e-12
-# after 30 steps: the per-stage differences only add up
-RTOL_MID = 1e-10
+# after 30 steps: the per-stage differences add up and are amplified ~1e3x by the shock
+# (the same test_reference_algorithm_is_sensitive run: 1e-16 in -> 8.5e-14 out at step 30)
+RTOL_MID = 2e-9
 # Beyond ~50 steps the reference ALGORITHM itself is not reproducible to rounding: a 1e-16
 # relative perturbation of the initial energies grows to 1e-8 (velocity) by step 60 and to
 # 4e-4 by step 100 (tests/test_oracle_vs_ref.py::test_reference_algorithm_is_sensitive measures

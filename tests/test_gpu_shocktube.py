@@ -33,7 +33,9 @@ def test_first_steps_stage_by_stage(name):
     for step in (1, 2, 3):
         dt = float(z["dt"][step - 1])
         cfl = s.timestep()
-        assert cfl >= dt and (cfl == dt or step > 1 or True)
+        # the CFL dt is a min of quotients of the current state: bit-exact at step 1, within the
+        # state's own rounding differences afterwards
+        assert (cfl == dt) if step == 1 else abs(cfl - dt) <= 1e-12 * dt
         s.set_dt(dt, step, 1)
         s.search_neighs_consth()
         seq = [("sml", s.adaptive_sml, ["smlen"])]

@@ -163,6 +163,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
+    if world > 1 and args.weak:   # weak scaling: the global cube holds world x the per-GPU cube
+        n = int(round(args.n * world ** (1.0 / 3.0)))
     cfg = cases.cube_config(n)
     cfg.device = local
     cfg.rank, cfg.nranks = rank, world
@@ -262,8 +264,8 @@ def run_b200(args):
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
                 "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic 3-D particle cube, %d^3 real + 8h pressure-ghost shell, "
-                                       "3-D SPH defaults (art. viscosity + LANS + energy smoothing), g=0" % n,
+                "config": {"workload": "synthetic 3-D particle cube, %d^3 real (%d^3 per GPU) + 8h pressure-ghost shell, "
+                                       "3-D SPH defaults (art. viscosity + LANS + energy smoothing), g=0" % (n, args.n),
                            "real_particles": n_real, "rows_rank0": n_rows_local, "edge": n,
                            "l2": "inputs (%.1f GB of SoA columns) far larger than the 126 MB L2" %
                                  (n_rows_local * 700 / 1e9),

@@ -160,6 +160,9 @@ int psph_append(psph_ctx *ctx, const psph_particle *rows, size_t n);
 /* before write_output (main.cc:474); order REFERENCE = THashTable iteration order */
 int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, size_t *n, int order);
 size_t psph_num_particles(const psph_ctx *ctx);
+/* rows the summation stages update on this rank (need_neigh, particle.h:555-558, and the list rule of
+ * neighs.cc:65-82); builds the cell list if needed and synchronises */
+int64_t psph_num_updated(psph_ctx *ctx);
 /* device-resident SoA column (valid until the next call that reorders particles) */
 int psph_column(psph_ctx *ctx, int col, double **dptr);
 /* Upload directly from device SoA columns (bench / device-side generators): cols[PSPH_COL_*],
@@ -190,10 +193,18 @@ int psph_step(psph_ctx *ctx, double dt_max, int erupting, double *dt_used, int *
 int psph_run(psph_ctx *ctx, int nsteps, int erupting);
 
 /* move_data (main.cc:326..471) / repartition (:440-464); no-ops for nranks == 1
- * (move_data.cc:53-54).  nccl_unique_id: 128 bytes from ncclGetUniqueId on rank 0. */
+ * (move_data.cc:53-54).  nccl_unique_id: 128 bytes from ncclGetUniqueId on rank 0, handed to every
+ * rank by the driver (MPI_Bcast in the reference driver, torch.distributed in bench.py).
+ * psph_exchange_ghosts sends what changed since the previous call: the columns a stage wrote, or
+ * -- after update_pos / re-bin / upload / append -- migrates rows to their new owner and mirrors
+ * the boundary cells anew. */
+int psph_comm_unique_id(void *out, size_t cap);   /* rank 0: ncclGetUniqueId; returns the id size (128) */
 int psph_comm_init(psph_ctx *ctx, const void *nccl_unique_id, size_t id_bytes);
 int psph_exchange_ghosts(psph_ctx *ctx);
 int psph_repartition(psph_ctx *ctx);
+/* slab boundaries in cell-rank units (cuts[0..nranks]); returns nranks */
+int psph_slab_cuts(psph_ctx *ctx, int *cuts, size_t cap);
+int64_t psph_comm_bytes_sent(psph_ctx *ctx, int reset);
 
 /* test-only: neighbour lists exactly as search_neighs_consth builds them (neighs.cc:37-211),
  * as CSR over device rows: offsets[n+1], idx = device row numbers, both in the row order that

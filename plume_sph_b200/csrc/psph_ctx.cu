@@ -315,7 +315,7 @@ extern "C" int psph_set_cells(psph_ctx *ctx, const psph_cell_attr *attr, size_t 
 // ---------------------------------------------------------------------------------------
 // AoS (host, reference ParticlePack-like rows) <-> SoA (device columns)
 // ---------------------------------------------------------------------------------------
-__global__ void k_aos_to_soa(const psph_particle *__restrict__ rows, int n, int base, Tab V, GridView G, int has_grad)
+__global__ void k_aos_to_soa(const psph_particle *__restrict__ rows, int n, int base, Tab V, GridView G, int has_grad, int rank)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -332,7 +332,7 @@ __global__ void k_aos_to_soa(const psph_particle *__restrict__ rows, int n, int 
   if (has_grad)
     for (int k = 0; k < 15; k++) V.d[D_GRAD0 + k][p] = r.grad[k];
   V.i[I_BC][p] = r.bc_type; V.i[I_PHASE][p] = r.phase_num; V.i[I_INVOLVED][p] = r.involved;
-  V.i[I_GUEST][p] = r.guest; V.i[I_MYPROC][p] = r.myprocess;
+  V.i[I_GUEST][p] = r.guest; V.i[I_MYPROC][p] = r.guest ? r.myprocess : rank;
   V.i[I_KEY0][p] = (int32_t) r.key[0]; V.i[I_KEY1][p] = (int32_t) r.key[1]; V.i[I_KEY2][p] = (int32_t) r.key[2];
   // bucket membership by position: [mincrd, maxcrd) against the mesh bounds exactly as the
   // reference stores them (dataread.cc:380-387; membership test update_pos.cc:257-271)
@@ -395,9 +395,10 @@ static int upload_at(psph_ctx *ctx, const psph_particle *rows, size_t n, size_t 
     if (ensure_aos(ctx, n)) return -1;
     PSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, rows, n * sizeof(psph_particle), cudaMemcpyHostToDevice, ctx->stream));
     k_aos_to_soa<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_aos, (int) n, (int) base, ctx->cur.t,
-                                                                         psph_grid_view(ctx), ctx->has_grad);
+                                                                         psph_grid_view(ctx), ctx->has_grad, ctx->cfg.rank);
     PSPH_LAUNCH_CHECK();
   }
+  psph_comm_mark(ctx, DIRTY_LAYOUT);
   ctx->n = (int) (base + n);
   ctx->h_ss->n = ctx->n;
   PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->n, &ctx->h_ss->n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -467,13 +468,13 @@ extern "C" int psph_column(psph_ctx *ctx, int col, double **dptr)
   return 0;
 }
 
-__global__ void k_fill_from_soa(Tab V, GridView G, int n, const int32_t *bc, const int32_t *phase)
+__global__ void k_fill_from_soa(Tab V, GridView G, int n, const int32_t *bc, const int32_t *phase, int rank)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   V.i[I_BC][p] = bc ? bc[p] : 100; V.i[I_PHASE][p] = phase ? phase[p] : 1;
-  V.i[I_INVOLVED][p] = 0; V.i[I_GUEST][p] = 0; V.i[I_MYPROC][p] = 0;
-  V.i[I_KEY0][p] = p; V.i[I_KEY1][p] = 0; V.i[I_KEY2][p] = 0;
+  V.i[I_INVOLVED][p] = 0; V.i[I_GUEST][p] = 0; V.i[I_MYPROC][p] = rank;
+  V.i[I_KEY0][p] = p; V.i[I_KEY1][p] = rank; V.i[I_KEY2][p] = 0;
   V.d[D_HLIST][p] = V.d[D_H][p]; V.d[D_SE][p] = V.d[D_E][p];
   double ks = V.d[D_KS][p], rho = V.d[D_RHO][p];
   V.d[D_RPH0][p] = rho * (1 - ks); V.d[D_RPH1][p] = rho * ks;
@@ -493,9 +494,10 @@ extern "C" int psph_upload_device_soa(psph_ctx *ctx, const double *const *cols, 
     PSPH_CUDA(cudaMemcpyAsync(ctx->cur.t.d[c], cols[c], n * sizeof(double), cudaMemcpyDefault, ctx->stream));
   }
   if (n) {
-    k_fill_from_soa<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), (int) n, bc, phase);
+    k_fill_from_soa<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), (int) n, bc, phase, ctx->cfg.rank);
     PSPH_LAUNCH_CHECK();
   }
+  psph_comm_mark(ctx, DIRTY_LAYOUT);
   ctx->n = (int) n; ctx->h_ss->n = ctx->n;
   PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->n, &ctx->h_ss->n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   PSPH_CUDA(cudaStreamSynchronize(ctx->stream));

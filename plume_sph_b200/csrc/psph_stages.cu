@@ -373,7 +373,7 @@ static int ensure_list(psph_ctx *ctx)
   return psph_build_cell_list(ctx);
 }
 
-static int refresh_geo(psph_ctx *ctx)
+int psph_refresh_geo(psph_ctx *ctx)
 {
   k_hmax_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
   PSPH_LAUNCH_CHECK();
@@ -394,6 +394,7 @@ extern "C" int psph_timestep(psph_ctx *ctx, double *dt)
     k_timestep<<<grid, 256, 0, ctx->stream>>>(ctx->cur.t, ctx->d_ss);
     PSPH_LAUNCH_CHECK();
   }
+  if (ctx->cfg.nranks > 1 && psph_comm_min_dt(ctx)) return -1;
   // the unclipped CFL dt goes through the pinned mirror's dt field
   k_timestep_finish<<<1, 1, 0, ctx->stream>>>(ctx->kp, ctx->d_ss, nullptr);
   PSPH_LAUNCH_CHECK();
@@ -421,7 +422,7 @@ extern "C" int psph_search_neighs(psph_ctx *ctx)
 {
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   StageTimer tm(ctx, ST_SEARCH);
-  if (ctx->cfg.dim == 1 && ctx->list_valid) return refresh_geo(ctx); // 1-D: no mesh, no search (main.cc:676-751)
+  if (ctx->cfg.dim == 1 && ctx->list_valid) return psph_refresh_geo(ctx); // 1-D: no mesh, no search (main.cc:676-751)
   return psph_build_cell_list(ctx);
 }
 
@@ -434,7 +435,8 @@ extern "C" int psph_adaptive_sml(psph_ctx *ctx)
   k_pack_sml<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_gather<SmlStage>(ctx, KN_GATHER_SML)) return -1;
-  return refresh_geo(ctx);
+  psph_comm_mark(ctx, DIRTY_H);
+  return psph_refresh_geo(ctx);
 }
 
 extern "C" int psph_mom_engr_update(psph_ctx *ctx)
@@ -449,6 +451,7 @@ extern "C" int psph_mom_engr_update(psph_ctx *ctx)
   if (launch_gather<MomStage>(ctx, KN_GATHER_MOM)) return -1;
   k_commit_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
+  psph_comm_mark(ctx, DIRTY_MOM);
   return 0;
 }
 
@@ -463,6 +466,7 @@ extern "C" int psph_smooth_density(psph_ctx *ctx)
   if (launch_gather<DensStage>(ctx, KN_GATHER_DENS)) return -1;
   k_commit_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
+  psph_comm_mark(ctx, DIRTY_DENS);
   return 0;
 }
 
@@ -474,6 +478,7 @@ extern "C" int psph_smooth_velocity(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_vel<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
+  psph_comm_mark(ctx, DIRTY_VEL);
   return launch_gather<VelStage>(ctx, KN_GATHER_VEL);
 }
 
@@ -484,6 +489,7 @@ extern "C" int psph_update_pos(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_update_pos<<<GRID(ctx->n)>>>(ctx->cur.t, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
+  psph_comm_mark(ctx, DIRTY_LAYOUT);
   return 0;
 }
 
@@ -506,17 +512,30 @@ extern "C" int psph_rebin(psph_ctx *ctx, int *lost)
 static int step_async(psph_ctx *ctx)
 {
   const psph_config &c = ctx->cfg;
+  const bool multi = c.nranks > 1;
   ctx->step++;
+  if (multi && psph_exchange_ghosts(ctx)) return -1;               // pending migration / ghost rebuild
   if (psph_timestep(ctx, nullptr)) return -1;
   if (psph_search_neighs(ctx)) return -1;
-  if (c.adaptive_sml && (c.dim == 1 || ctx->step % c.sml_update_int == 0))
+  if (c.adaptive_sml && (c.dim == 1 || ctx->step % c.sml_update_int == 0)) {
     if (psph_adaptive_sml(ctx)) return -1;
-  if (c.use_gsph && psph_calc_gradients(ctx)) return -1;
+    if (multi && psph_exchange_ghosts(ctx)) return -1;             // main.cc:326
+  }
+  if (c.use_gsph) {
+    if (psph_calc_gradients(ctx)) return -1;
+    if (multi && psph_exchange_ghosts(ctx)) return -1;             // main.cc:347
+  }
   if (psph_mom_engr_update(ctx)) return -1;
+  if (multi && psph_exchange_ghosts(ctx)) return -1;               // main.cc:374
   if (psph_smooth_density(ctx)) return -1;
-  if (c.have_turbulence_lans && psph_smooth_velocity(ctx)) return -1;
+  if (multi && psph_exchange_ghosts(ctx)) return -1;               // main.cc:387
+  if (c.have_turbulence_lans) {
+    if (psph_smooth_velocity(ctx)) return -1;
+    if (multi && psph_exchange_ghosts(ctx)) return -1;             // main.cc:395
+  }
   if (psph_update_pos(ctx)) return -1;
   if (psph_rebin(ctx, nullptr)) return -1;
+  if (multi && psph_exchange_ghosts(ctx)) return -1;               // main.cc:430
   return 0;
 }
 
@@ -542,6 +561,15 @@ extern "C" int psph_errors(psph_ctx *ctx, int reset)
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return bad;
+}
+
+// rows the gathers update (need_neigh and the list rule), exact after a list build; synchronises
+extern "C" int64_t psph_num_updated(psph_ctx *ctx)
+{
+  if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return -1;
+  ctx->n_dirty = true;
+  if (psph_sync_n(ctx)) return -1;
+  return ctx->h_ss->n_need;
 }
 
 extern "C" int psph_step(psph_ctx *ctx, double dt_max, int erupting, double *dt_used, int *lost)

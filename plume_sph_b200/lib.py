@@ -91,6 +91,7 @@ API = {
     "psph_append": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_download": (C.c_int, [_VP, _VP, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
     "psph_num_particles": (C.c_size_t, [_VP]),
+    "psph_num_updated": (C.c_int64, [_VP]),
     "psph_column": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     "psph_upload_device_soa": (C.c_int, [_VP, C.POINTER(_VP), _VP, _VP, C.c_size_t]),
     "psph_timestep": (C.c_int, [_VP, C.POINTER(C.c_double)]),
@@ -105,7 +106,10 @@ API = {
     "psph_rebin": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "psph_step": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "psph_run": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "psph_comm_unique_id": (C.c_int, [_VP, C.c_size_t]),
     "psph_comm_init": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "psph_slab_cuts": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "psph_comm_bytes_sent": (C.c_int64, [_VP, C.c_int]),
     "psph_exchange_ghosts": (C.c_int, [_VP]),
     "psph_repartition": (C.c_int, [_VP]),
     "psph_emit_neighbours": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -190,9 +190,30 @@ class Solver:
         return p.value
 
     # -- multi-GPU ---------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: the NCCL unique id (bytes) every rank passes to comm_init"""
+        buf = (C.c_char * 128)()
+        n = _l.load().psph_comm_unique_id(buf, 128)
+        if n <= 0:
+            raise _l.PsphError("psph_comm_unique_id failed (NCCL not available)")
+        return bytes(buf[:n])
+
     def comm_init(self, unique_id):
         buf = (C.c_char * len(unique_id)).from_buffer_copy(unique_id)
         return self._ck(self.L.psph_comm_init(self.h, buf, len(unique_id)), "psph_comm_init")
+
+    def slab_cuts(self):
+        cuts = (C.c_int * 64)()
+        p = self._ck(self.L.psph_slab_cuts(self.h, cuts, 64), "psph_slab_cuts")
+        return [int(cuts[k]) for k in range(p + 1)]
+
+    def comm_bytes_sent(self, reset=True):
+        return int(self.L.psph_comm_bytes_sent(self.h, int(reset)))
+
+    @property
+    def num_updated(self):
+        return int(self._ck(self.L.psph_num_updated(self.h), "psph_num_updated"))
 
     def exchange_ghosts(self):
         return self._ck(self.L.psph_exchange_ghosts(self.h), "psph_exchange_ghosts")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — particle-updates/s of the Plume-SPH per-time-step hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n EDGE] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--edge EDGE] [--impl b200|reference]
 
 Workload (BASELINE.json config 4): the synthetic 3-D particle cube, 3-D SPH
 defaults (artificial-viscosity SPH + LANS velocity filter + energy smoothing, ideal-gas
@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=216, help="cube edge in particles per GPU^(1/3) (216 -> 1.0e7 real)")
+    ap.add_argument("--edge", dest="n", type=int, default=216, help="cube edge in particles per GPU^(1/3) (216 -> 1.0e7 real)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--strong", dest="weak", action="store_false", help="fixed total cube (default: weak, per-GPU cube)")
     ap.add_argument("--no-e2e", action="store_true")

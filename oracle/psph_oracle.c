@@ -411,16 +411,239 @@ static int mom_engr_sph(const psph_config *c, psph_oracle_state *st, double dt)
   return bad;
 }
 
+/* ---------------- GSPH: Riemann solvers, mom_engr_update, calc_gradients ---------------- */
+/* Option set restated: RP_MASS_WEIGHTED 0, SWITCH_OFF_AV_FOR_EXPAN 0, GSPH_SPECIFIC_VOL_APP 0,
+ * MINI_DERIVATIVE_COND 4 (piecewise-constant Riemann states), SHEAR_VEL_APP 2, HLL_WAVE_SPEED_EVA 0,
+ * FLUID_COMPRESSIBILITY 0 — the 1-D defaults (options.h:141-262).  With MINI_DERIVATIVE_COND 4 the
+ * gradients do not enter the Riemann states (sph_lib.cc:2487-2493). */
+static void hllc_rp_solver(double dl, double dr, double pl, double pr, double ul, double ur, double gj, double gi,
+                           double *p_star, double *u_star)
+{ /* sph_lib.cc:1753-1908, USE_GSPH==1 branch */
+  double rdl = sqrt(dl), rdr = sqrt(dr);
+  double denominator = 1.0 / (rdl + rdr);
+  double ulr = (ul * rdl + ur * rdr) * denominator;
+  double plr = (pl * rdl + pr * rdr) * denominator;
+  double gammalr = (gj * rdl + gi * rdr) * denominator;
+  double dlr = (dl * rdl + dr * rdr) * denominator;
+  double clr = sqrt(gammalr * plr / dlr);
+  double vl = ul - ulr, vr = ur - ulr;
+  double cl = sqrt(gj * pl / dl), cr = sqrt(gi * pr / dr);
+  double Sl = fmin(vl - cl, -clr);
+  double Sr = fmax(vr + cr, clr);
+  double Sm = (dr * vr * (Sr - vr) - dl * vl * (Sl - vl) + pl - pr) / (dr * (Sr - vr) - dl * (Sl - vl));
+  double p_hat = dl * (vl - Sl) * (vl - Sm) + pl;
+  double Ml = dl * ul, Mr = dr * ur;
+  double el = pl / (dl * (gj - 1)), er = pr / (dr * (gi - 1));
+  double El = dl * (el + 0.5 * ul * ul), Er = dr * (er + 0.5 * ur * ur);
+  if (Sl > 0) { *p_star = pl; *u_star = ul; }
+  else if ((Sl <= 0) && (Sm > 0)) {
+    *p_star = Sm / (Sl - Sm) * ((Sl - vl) * Ml + (p_hat - pl)) + p_hat;
+    *u_star = (Sm / (Sl - Sm) * ((Sl - vl) * El + p_hat * Sm - pl * vl) + (Sm + ulr) * p_hat) / (*p_star);
+  } else if ((Sm <= 0) && (Sr > 0)) {
+    *p_star = Sm / (Sr - Sm) * ((Sr - vr) * Mr + (p_hat - pr)) + p_hat;
+    *u_star = (Sm / (Sr - Sm) * ((Sr - vr) * Er + p_hat * Sm - pr * vr) + (Sm + ulr) * p_hat) / (*p_star);
+  } else if (Sr <= 0) { *p_star = pr; *u_star = ur; }
+  else { *p_star = NAN; *u_star = NAN; }
+}
+
+static void roe_rp_solver(double dl, double dr, double pl, double pr, double ul, double ur, double gj, double gi,
+                          double *p_star, double *u_star)
+{ /* sph_lib.cc:1694-1749 */
+  double rdl = sqrt(dl), rdr = sqrt(dr);
+  double denominator = 1.0 / (rdl + rdr);
+  double plr = (pl * rdl + pr * rdr) * denominator;
+  double gammalr = (gj * rdl + gi * rdr) * denominator;
+  double dlr = (dl * rdl + dr * rdr) * denominator;
+  double clr = sqrt(gammalr * plr / dlr);
+  clr = dlr * clr;
+  double ulr = (ul * rdl + ur * rdr) * denominator;
+  *p_star = plr - 0.5 * clr * (ur - ul);
+  *u_star = ulr - 0.5 * (pr - pl) / clr;
+}
+
+static void riemann_solver(const psph_config *c, double rhoi, double rhoj, const double *vi, const double *vj, double pi,
+                           double pj, const double *xi, const double *xj, double gi, double gj, double *p_star,
+                           double *v_star)
+{ /* sph_lib.cc:2247-2600 with the option set above */
+  int dim = c->dim;
+  double dx[3], e[3], dist = 0.0;
+  for (int i = 0; i < dim; i++) dx[i] = xi[i] - xj[i];
+  for (int i = 0; i < dim; i++) dist += dx[i] * dx[i];
+  dist = sqrt(dist);
+  for (int i = 0; i < dim; i++) e[i] = dx[i] / dist; /* Compute_eij, :1624-1631 */
+  double ui = 0.0, uj = 0.0;
+  for (int i = 0; i < dim; i++) { ui += vi[i] * e[i]; uj += vj[i] * e[i]; }
+  /* MINI_DERIVATIVE_COND == 4 */
+  double dr = rhoi, ur = ui, pr = pi, dl = rhoj, ul = uj, pl = pj;
+  double u_star;
+  if (c->riemann_solver == 0) roe_rp_solver(dl, dr, pl, pr, ul, ur, gj, gi, p_star, &u_star);
+  else hllc_rp_solver(dl, dr, pl, pr, ul, ur, gj, gi, p_star, &u_star);
+  /* SHEAR_VEL_APP == 2 */
+  double rdl = sqrt(dl), rdr = sqrt(dr);
+  double denominator = 1.0 / (rdl + rdr);
+  double ulr = (ul * rdl + ur * rdr) * denominator;
+  for (int i = 0; i < dim; i++) {
+    double vlr = (vj[i] * rdl + vi[i] * rdr) * denominator;
+    v_star[i] = e[i] * u_star + vlr - ulr * e[i];
+  }
+}
+
+static int mom_engr_gsph(const psph_config *c, psph_oracle_state *st, double dt)
+{ /* mom_engr_update.cc:443-1145, ME_UPDATE_SML==2 */
+  int bad = 0;
+  int dim = c->dim, lans = c->have_turbulence_lans != 0;
+  double *nv = (double *) malloc(sizeof(double) * 3 * st->n);
+  double *ne = (double *) malloc(sizeof(double) * st->n);
+  double gravity[3] = { 0, 0, 0 };
+  gravity[dim - 1] = -c->g;
+  for (int64_t i = 0; i < st->n; i++) {
+    if (!need_neigh(st, i)) continue;
+    double xi[3], hi = st->h[i], supp = c->cutoff2 * hi;
+    for (int k = 0; k < dim; k++) xi[k] = D3(st->x, i, k);
+    double pressi = st->p[i], tempi = st->T[i], Cp_i = st->Cp[i], sndspdi = st->c[i], gammai = st->gamma[i];
+    if (!(st->rho[i] > 0)) bad++;
+    double Vi = 1.0 / st->rho[i];
+    double veli[3], rhs_v[3] = { 0, 0, 0 }, rhs_e = 0;
+    for (int k = 0; k < dim; k++) veli[k] = lans ? D3(st->sv, i, k) : D3(st->v, i, k);
+    for (int pass = 0; pass < 2; pass++) {
+      for (int64_t q = st->nb_off[i]; q < st->nb_off[i + 1]; q++) {
+        int64_t j = st->nb_idx[q];
+        if (j == i) continue;
+        double dx[3], xj[3], si[3], dwdxi[3], vsqdwi[3], vsqdwj[3], velj[3], velij[3];
+        for (int k = 0; k < dim; k++) { xj[k] = D3(st->x, j, k); dx[k] = xi[k] - xj[k]; }
+        if (!in_support(dim, dx, supp)) continue;
+        if (!(st->rho[j] > 0)) bad++;
+        double Vj = 1.0 / st->rho[j];
+        double mj = st->mass[j], pressj = st->p[j], hj = st->h[j], sndspdj = st->c[j], gammaj = st->gamma[j];
+        double hij = 0.5 * (hi + hj);
+        for (int k = 0; k < dim; k++) si[k] = dx[k] / hij;
+        for (int k = 0; k < dim; k++) dwdxi[k] = psph_oracle_d_weight(dim, si, hij, c->cutoff, k);
+        double max_dw = 0.0;
+        for (int k = 0; k < dim; k++) {
+          vsqdwi[k] = Vi * Vi * dwdxi[k];
+          vsqdwj[k] = Vj * Vj * dwdxi[k];
+          if (fabs(vsqdwi[k]) > max_dw) max_dw = fabs(vsqdwi[k]);
+        }
+        if (!(max_dw > 0)) continue;
+        for (int k = 0; k < dim; k++) velj[k] = lans ? D3(st->sv, j, k) : D3(st->v, j, k);
+        double p_star, v_star[3];
+        riemann_solver(c, st->rho[i], st->rho[j], veli, velj, pressi, pressj, xi, xj, gammai, gammaj, &p_star, v_star);
+        double turb_stress = 0.0;
+        for (int k = 0; k < dim; k++) velij[k] = veli[k] - velj[k];
+        if (lans) { /* SPH_epsilon_mom, sph_lib.cc:1331-1338 */
+          double dotv = 0.;
+          for (int k = 0; k < dim; k++) dotv += velij[k] * velij[k];
+          turb_stress = c->epsilon_half * dotv * Vj;
+        }
+        if (pass == 0) {
+          for (int k = 0; k < dim; k++) rhs_v[k] -= mj * (p_star * (vsqdwi[k] + vsqdwj[k]) - turb_stress * dwdxi[k]);
+        } else {
+          double x_dot_star[3];
+          for (int k = 0; k < dim; k++) x_dot_star[k] = veli[k] + 0.5 * dt * (rhs_v[k] + gravity[k]);
+          double heat_tran = 0.;
+          if (lans) {
+            double sndspdab = 0.5 * (sndspdi + sndspdj);
+            double Cp_ij = 0.5 * (st->Cp[j] + Cp_i);
+            double hab = 0.5 * (hi + hj);
+            double kij = sph_epsilon_heat_conductivity(c, Cp_ij, dx, velij, hab, sndspdab);
+            double s_heat[3], dwdx_heat[3];
+            for (int k = 0; k < dim; k++) s_heat[k] = si[k] * c->heat_trans_scale_ratio;
+            for (int k = 0; k < dim; k++) {
+              double a = psph_oracle_d_weight(dim, s_heat, hij / c->heat_trans_scale_ratio, c->cutoff, k);
+              dwdx_heat[k] = 0.5 * (a + a);
+            }
+            double Fij = compute_F(dim, dwdx_heat, dx);
+            heat_tran = mj * Vj * Vi * kij * (tempi - st->T[j]) * Fij;
+          }
+          double deltae = 0.;
+          for (int k = 0; k < dim; k++)
+            deltae -= mj * (v_star[k] - x_dot_star[k]) * (p_star * (vsqdwi[k] + vsqdwj[k]) - turb_stress * dwdxi[k]);
+          rhs_e += (deltae + heat_tran);
+        }
+      }
+    }
+    double unew[3];
+    for (int k = 0; k < dim; k++) unew[k] = D3(st->v, i, k) + dt * rhs_v[k];
+    unew[dim - 1] += dt * gravity[dim - 1];
+    for (int k = 0; k < dim; k++) D3(nv, i, k) = unew[k];
+    ne[i] = st->e[i] + dt * (rhs_e + veli[dim - 1] * gravity[dim - 1]);
+  }
+  for (int64_t i = 0; i < st->n; i++)
+    if (need_neigh(st, i)) {
+      for (int k = 0; k < dim; k++) D3(st->v, i, k) = D3(nv, i, k);
+      st->e[i] = ne[i];
+      psph_oracle_eos(c, st, i);
+    }
+  free(nv); free(ne);
+  return bad;
+}
+
 int psph_oracle_mom_engr_update(const psph_config *c, psph_oracle_state *st, double dt)
 {
-  if (c->use_gsph) return -1; /* GSPH variant: oracle/psph_oracle_gsph.c (pending) */
+  if (c->use_gsph) return mom_engr_gsph(c, st, dt);
   return mom_engr_sph(c, st, dt);
 }
 
 int psph_oracle_calc_gradients(const psph_config *c, psph_oracle_state *st)
-{
-  (void) c; (void) st;
-  return -1;
+{ /* calculate_gradient.cc:22-209 (NORM_DERIVATIVE 1, DENSITY_UPDATE_SML 11: h = h_i) */
+  int dim = c->dim, neq = dim + 2;
+  for (int64_t i = 0; i < st->n; i++) {
+    if (st->guest[i]) continue;
+    double hi = st->h[i], supp = c->cutoff2 * hi;
+    double AA[3][3] = { { 0 } }, FF[3][5] = { { 0 } }, ff[3][5] = { { 0 } };
+    int nreal = 0;
+    if (st->nb_off)
+      for (int64_t q = st->nb_off[i]; q < st->nb_off[i + 1]; q++) {
+        int64_t j = st->nb_idx[q];
+        if (j == i) continue;
+        double dx[3], s[3], dwm_rho[3];
+        for (int k = 0; k < dim; k++) dx[k] = D3(st->x, i, k) - D3(st->x, j, k);
+        if (!in_support(dim, dx, supp)) continue;
+        nreal++;
+        double mj = st->mass[j], rhoj = st->rho[j];
+        for (int k = 0; k < dim; k++) s[k] = dx[k] / hi;
+        for (int k = 0; k < dim; k++) dwm_rho[k] = psph_oracle_d_weight(dim, s, hi, c->cutoff, k) * mj / rhoj;
+        for (int a = 0; a < dim; a++)
+          for (int b = 0; b < dim; b++) AA[a][b] -= dx[a] * dwm_rho[b];
+        for (int a = 0; a < dim; a++) {
+          FF[a][0] -= ((st->rho[i] - st->rho[j]) * dwm_rho[a]);
+          for (int b = 0; b < dim; b++) FF[a][b + 1] -= ((D3(st->v, i, b) - D3(st->v, j, b)) * dwm_rho[a]);
+          FF[a][neq - 1] -= ((st->p[i] - st->p[j]) * dwm_rho[a]);
+        }
+      }
+    if (nreal > 20) { /* linsolve, sph_lib.cc:158-181 */
+      double Ainv[9];
+      if (dim == 1) Ainv[0] = -1 / AA[0][0]; /* inv1 (sic), sph_lib.cc:128-134 */
+      else { /* inv3, sph_lib.cc:86-110 */
+        double A[9];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) A[3 * a + b] = AA[a][b];
+        double t4 = A[2] * A[3], t6 = A[2] * A[6], t8 = A[1] * A[3], t10 = A[1] * A[6], t12 = A[0] * A[4], t14 = A[0] * A[7];
+        double t17 = 1.0 / (t4 * A[7] - t6 * A[4] - t8 * A[8] + t10 * A[5] + t12 * A[8] - t14 * A[5]);
+        Ainv[0] = (A[4] * A[8] - A[7] * A[5]) * t17;
+        Ainv[1] = -(A[3] * A[8] - A[6] * A[5]) * t17;
+        Ainv[2] = (A[3] * A[7] - A[6] * A[4]) * t17;
+        Ainv[3] = -(-A[2] * A[7] + A[1] * A[8]) * t17;
+        Ainv[4] = (-t6 + A[0] * A[8]) * t17;
+        Ainv[5] = -(-t10 + t14) * t17;
+        Ainv[6] = (-A[2] * A[4] + A[1] * A[5]) * t17;
+        Ainv[7] = -(-t4 + A[0] * A[5]) * t17;
+        Ainv[8] = (-t8 + t12) * t17;
+      }
+      for (int a = 0; a < dim; a++)
+        for (int q = 0; q < neq; q++) {
+          ff[a][q] = 0;
+          for (int k = 0; k < dim; k++) ff[a][q] += Ainv[a * dim + k] * FF[k][q];
+        }
+    }
+    /* gradU[q*DIM + a] = ff[a][q]; rows of the 15-column layout: d_rho, d_u, d_v, d_w, d_p */
+    double *g = st->grad + 15 * i;
+    for (int a = 0; a < dim; a++) {
+      g[0 + a] = ff[a][0];
+      for (int b = 0; b < dim; b++) g[3 * (b + 1) + a] = ff[a][b + 1];
+      g[12 + a] = ff[a][neq - 1];
+    }
+  }
+  return 0;
 }
 
 /* ---------------- smooth_velocity ---------------- */

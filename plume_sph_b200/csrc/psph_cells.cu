@@ -103,7 +103,9 @@ __global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss, int
   if (ph == 2) f |= F_PH2;
   if (ph == 1 || ph == 2) f |= F_PHOK;
   if (dev_is_real(bc)) f |= F_REAL;
-  if (!guest) f |= F_GRADROW;
+  // rows that get gradients: every non-guest row that has a neighbour list (3-D GSPH build: all of them,
+  // neighs.cc:142-201; 1-D: the need_neigh rows, add_air.cc:470-479)
+  if (!guest && (K.dim == 3 || need)) f |= F_GRADROW;
   V.flags[p] = f;
   const double x[3] = { V.t.d[D_X][p], V.t.d[D_Y][p], V.t.d[D_Z][p] };
   double h = V.t.d[D_H][p];

@@ -135,6 +135,7 @@ __device__ __forceinline__ double dev_weight_in(double r2, double invh)
 //   kSkipSelf     j == i is not a pair (mom_engr_update.cc:201)
 //   kRows         RowFlags bit of the rows the stage updates (selects the row list it walks)
 //   kMinBlocks    resident CTAs per SM the register allocation must allow
+//   kCountSupport count (A::nreal) the listed rows inside in_support(), whatever their weight
 //   struct I      per-row state, identical in every lane; members h, supp (= CUTOFF2*h_i), hk
 //   struct A      per-lane accumulators
 //   void  init(V,K,ss,i,I&)             load row i
@@ -183,6 +184,10 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
           const unsigned long long ax = (unsigned long long) __double_as_longlong(dx) & 0x7fffffffffffffffull,
                                    ay = (unsigned long long) __double_as_longlong(dy) & 0x7fffffffffffffffull,
                                    az = (unsigned long long) __double_as_longlong(dz) & 0x7fffffffffffffffull;
+          if constexpr (S::kCountSupport) { // rows of the list inside in_support(), contributing or not
+            const double lim = cj < 0 ? lim_own : lim_other;
+            if (live && j != i && !(fabs(dx) > lim || fabs(dy) > lim || fabs(dz) > lim)) acc.nreal++;
+          }
           const double h = S::kSymH ? 0.5 * (st.h + gj.w) : st.hk;
           const double b = K.cutoff * h;
           const unsigned long long blo = (unsigned long long) __double_as_longlong(b * (1.0 - 0x1p-48));

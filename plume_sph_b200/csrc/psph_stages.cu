@@ -97,7 +97,7 @@ __global__ void k_pack_sml(DevView V, StepState *ss)
 template <int DIM>
 struct DensStage
 {
-  static constexpr bool kSymH = true, kSkipSelf = false;
+  static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kMinBlocks = 3;
   struct I { double h, supp, hk; };
   struct A { double rho1, rho2, wn, en; };
@@ -166,7 +166,7 @@ __global__ void k_commit_dens(DevView V, KParams K, StepState *ss)
 template <int DIM>
 struct MomStage
 {
-  static constexpr bool kSymH = true, kSkipSelf = true;
+  static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
   static constexpr int kRows = F_NEED, kMinBlocks = 2;
   struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3]; };
   struct A { double rv[3], re; };
@@ -253,7 +253,7 @@ __global__ void k_commit_mom(DevView V, KParams K, StepState *ss)
 template <int DIM>
 struct VelStage
 {
-  static constexpr bool kSymH = false, kSkipSelf = false;
+  static constexpr bool kSymH = false, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kMinBlocks = 3;
   struct I { double h, invh, supp, hk, v[3]; };
   struct A { double dv[3], wn; };
@@ -294,7 +294,7 @@ struct VelStage
 template <int DIM>
 struct SmlStage
 {
-  static constexpr bool kSymH = false, kSkipSelf = false;
+  static constexpr bool kSymH = false, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kMinBlocks = 3;
   struct I { double h, hs, hk, invhs, supp, m; };
   struct A { double rho; };
@@ -351,21 +351,6 @@ __global__ void k_update_pos(Tab V, KParams K, StepState *ss)
 // host side of the stages
 // =========================================================================================
 #define GRID(n) (unsigned) (((n) + 255) / 256), 256, 0, ctx->stream
-
-struct StageTimer
-{
-  psph_ctx *ctx; int id;
-  StageTimer(psph_ctx *c, int i) : ctx(c), id(i) { if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream); }
-  ~StageTimer()
-  {
-    if (!ctx->timing) return;
-    cudaEventRecord(ctx->ev1, ctx->stream);
-    cudaEventSynchronize(ctx->ev1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->stage_ms[id] += ms;
-  }
-};
 
 static int ensure_list(psph_ctx *ctx)
 {
@@ -439,6 +424,15 @@ extern "C" int psph_adaptive_sml(psph_ctx *ctx)
   return psph_refresh_geo(ctx);
 }
 
+// second pass of mom_engr_update: commit the scratch columns + equation of state (both variants)
+int psph_commit_mom(psph_ctx *ctx)
+{
+  k_commit_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  psph_comm_mark(ctx, DIRTY_MOM);
+  return 0;
+}
+
 extern "C" int psph_mom_engr_update(psph_ctx *ctx)
 {
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
@@ -449,10 +443,7 @@ extern "C" int psph_mom_engr_update(psph_ctx *ctx)
   k_pack_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_gather<MomStage>(ctx, KN_GATHER_MOM)) return -1;
-  k_commit_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
-  PSPH_LAUNCH_CHECK();
-  psph_comm_mark(ctx, DIRTY_MOM);
-  return 0;
+  return psph_commit_mom(ctx);
 }
 
 extern "C" int psph_smooth_density(psph_ctx *ctx)

@@ -112,6 +112,39 @@ def test_shocktube_sph_bit_exact(name):
             eq(s.a[o], z["mid"][f], ("mid", f))
 
 
+@pytest.mark.parametrize("name", ["sod_gsph", "sod0_gsph", "blast_gsph"])
+def test_shocktube_gsph_bit_exact(name):
+    """Godunov-SPH variant (calc_gradients + HLLC Riemann solver, 1-D defaults): gradients, momentum and
+    energy of the first steps and the state after 30 and 300/1000 steps, bit for bit."""
+    z = golden(name)
+    cfg = op.config_1d(gsph=True)
+    s = op.OracleState.from_dump(cfg, z["init"])
+    s.bin()
+    s.search()
+    tp = TimeProps(max_time=float(z["t_end"][0]), max_steps=10**8, timeoutput=float(z["t_out"][0]))
+    nmid, nfinal = int(z["mid_steps"][0]), int(z["final_steps"][0])
+    for step in range(1, nfinal + 1):
+        dt = tp.incrtime(s.timestep())
+        s.adaptive_sml()
+        s.calc_gradients()
+        if step <= 3:
+            assert dt == float(z["dt"][step - 1])
+            eq(s.a["grad"], z["s%d_grad_grad" % step], ("grad", step))
+        assert s.mom_engr_update(dt) == 0
+        if step <= 3:
+            eq(s.a["v"], z["s%d_mom_vel" % step], ("mom v", step))
+            eq(s.a["e"], z["s%d_mom_engr" % step], ("mom e", step))
+        s.smooth_density()
+        s.update_pos(dt, 1)
+        tp.ifoutput()
+        if step in (nmid, nfinal):
+            ref = z["mid" if step == nmid else "final"]
+            for f, o in (("coord", "x"), ("vel", "v"), ("rho", "rho"), ("engr", "e"), ("pressure", "p"), ("smlen", "h"),
+                         ("grad", "grad")):
+                eq(s.a[o], ref[f], (step, f))
+    assert tp.time == float(z["final_time"][0])
+
+
 def run_sod(nsteps, perturb=0.0):
     z = golden("sod_sph")
     cfg = op.config_1d(gsph=False)

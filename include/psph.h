@@ -202,6 +202,9 @@ int psph_comm_unique_id(void *out, size_t cap);   /* rank 0: ncclGetUniqueId; re
 int psph_comm_init(psph_ctx *ctx, const void *nccl_unique_id, size_t id_bytes);
 int psph_exchange_ghosts(psph_ctx *ctx);
 int psph_repartition(psph_ctx *ctx);
+/* position of every background cell (linear index, x-major z-minor) along the bucket Hilbert curve
+ * (preprocess.cc:196-205, hilbert.c:156-303): the order the slabs cut */
+int psph_cell_ranks(psph_ctx *ctx, int32_t *rank_of_cell, size_t cap);
 /* slab boundaries in cell-rank units (cuts[0..nranks]); returns nranks */
 int psph_slab_cuts(psph_ctx *ctx, int *cuts, size_t cap);
 int64_t psph_comm_bytes_sent(psph_ctx *ctx, int reset);

@@ -461,6 +461,13 @@ extern "C" int psph_cell_of_rows(psph_ctx *ctx, int32_t *cells, size_t cap)
   return 0;
 }
 
+extern "C" int psph_cell_ranks(psph_ctx *ctx, int32_t *rank_of_cell, size_t cap)
+{
+  if (cap < (size_t) ctx->ncells) { ctx->err = "psph_cell_ranks: buffer too small"; return -2; }
+  memcpy(rank_of_cell, ctx->h_cell2rank.data(), ctx->ncells * sizeof(int32_t));
+  return 0;
+}
+
 extern "C" int psph_column(psph_ctx *ctx, int col, double **dptr)
 {
   if (col < 0 || col >= PSPH_COL_COUNT || !dptr) return -2;

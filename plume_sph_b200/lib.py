@@ -108,6 +108,7 @@ API = {
     "psph_run": (C.c_int, [_VP, C.c_int, C.c_int]),
     "psph_comm_unique_id": (C.c_int, [_VP, C.c_size_t]),
     "psph_comm_init": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "psph_cell_ranks": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_slab_cuts": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_comm_bytes_sent": (C.c_int64, [_VP, C.c_int]),
     "psph_exchange_ghosts": (C.c_int, [_VP]),

@@ -203,6 +203,12 @@ class Solver:
         buf = (C.c_char * len(unique_id)).from_buffer_copy(unique_id)
         return self._ck(self.L.psph_comm_init(self.h, buf, len(unique_id)), "psph_comm_init")
 
+    def cell_ranks(self):
+        """rank along the bucket Hilbert curve of every background cell (linear index order)"""
+        r = np.zeros(self.cfg.ncells, np.int32)
+        self._ck(self.L.psph_cell_ranks(self.h, r.ctypes.data, r.size), "psph_cell_ranks")
+        return r
+
     def slab_cuts(self):
         cuts = (C.c_int * 64)()
         p = self._ck(self.L.psph_slab_cuts(self.h, cuts, 64), "psph_slab_cuts")

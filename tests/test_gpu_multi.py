@@ -68,13 +68,23 @@ def test_slabs_match_single_gpu(P):
         s.comm_init(uid)
         s.repartition()
         cuts = s.slab_cuts()
+        ranks = s.cell_ranks()
         got = [s.step(0.0, 0)[0] for _ in range(steps)]
         out = s.download(ORDER_DEVICE)
         sent = s.comm_bytes_sent()
         s.close()
-        return cuts, got, out, sent
+        return cuts, got, out, sent, ranks
 
     res = run_ranks(P, rank)
+    # the device cut (k_cell_weights -> ncclAllReduce -> scan -> k_find_cuts) equals the host plan (slabs.plan_cuts)
+    ranks = res[0][4]
+    mind = np.asarray([cfg.mindom[k] for k in range(3)])
+    idx = np.floor((rows["coords"] - mind) / cfg.delta).astype(np.int64)
+    cell = (idx[:, 0] * int(cfg.ncell[1]) + idx[:, 1]) * int(cfg.ncell[2]) + idx[:, 2]
+    w = np.zeros(cfg.ncells, np.int64)
+    np.add.at(w, ranks[cell], slabs.particle_weights(rows["bc_type"]))
+    assert res[0][0] == slabs.plan_cuts(w, P)
+    res = [x[:4] for x in res]
     for cuts, got, out, sent in res:
         assert cuts == res[0][0] and cuts[0] == 0 and cuts[-1] == cfg.ncells
         assert got == dts, (got, dts)                      # all-reduced dt: identical on every rank and to 1 GPU

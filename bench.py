@@ -357,9 +357,17 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=32)
     ap.add_argument("--ref-replicas", type=int, default=0)
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_b200(args)
+    except BaseException:
+        # a failed rank must not leave its peers waiting in a collective: die hard so the launcher tears the job down
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

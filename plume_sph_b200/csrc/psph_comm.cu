@@ -226,6 +226,9 @@ ColList all_columns(const psph_ctx *ctx)
   return cl;
 }
 size_t row_bytes(const ColList &cl) { return (size_t) cl.nd * sizeof(double) + (size_t) cl.ni * sizeof(int32_t); }
+// bytes a peer's segment occupies in the send/recv buffer: the payload (cnt * rb) padded so that the next
+// peer's double columns start 16-byte aligned
+size_t seg_bytes(int cnt, size_t rb) { return ((size_t) cnt * rb + 15) & ~(size_t) 15; }
 
 template <class T>
 int ensure_bytes(psph_ctx *ctx, T *&p, size_t &cap, size_t need)
@@ -309,7 +312,7 @@ int exchange_buffers(psph_ctx *ctx, const std::vector<int> &send_cnt, const std:
     if (q == C->me) continue;
     if (send_cnt[q]) PSPH_NCCL(g_nccl.Send(C->d_sendbuf + so, (size_t) send_cnt[q] * rb, ncclInt8, q, C->comm, ctx->stream));
     if (recv_cnt[q]) PSPH_NCCL(g_nccl.Recv(C->d_recvbuf + ro, (size_t) recv_cnt[q] * rb, ncclInt8, q, C->comm, ctx->stream));
-    so += (size_t) send_cnt[q] * rb; ro += (size_t) recv_cnt[q] * rb;
+    so += seg_bytes(send_cnt[q], rb); ro += seg_bytes(recv_cnt[q], rb);
     C->bytes_sent += (long long) send_cnt[q] * (long long) rb;
   }
   PSPH_NCCL(g_nccl.GroupEnd());
@@ -326,27 +329,29 @@ int ship_rows(psph_ctx *ctx, MakePred make_pred, bool as_guest, std::vector<int>
   const int P = C->P, me = C->me;
   if (share_counts(ctx)) return -1;
   std::vector<int> sc(P, 0), rc(P, 0);
-  long long stot = 0, rtot = 0;
+  long long rtot = 0;
+  size_t sbytes = 0, rbytes = 0;
+  const ColList cl = all_columns(ctx);
+  const size_t rb = row_bytes(cl);
   for (int q = 0; q < P; q++) {
     if (q == me) continue;
     sc[q] = C->h_allcounts[me * P + q]; rc[q] = C->h_allcounts[q * P + me];
-    stot += sc[q]; rtot += rc[q];
+    rtot += rc[q];
+    sbytes += seg_bytes(sc[q], rb); rbytes += seg_bytes(rc[q], rb);
   }
-  const ColList cl = all_columns(ctx);
-  const size_t rb = row_bytes(cl);
   const int n0 = ctx->n;
   if (n_before) *n_before = n0;
   if (psph_reserve(ctx, (size_t) n0 + rtot)) return -1;
   if (ensure_row_scratch(ctx)) return -1;
-  if (ensure_bytes(ctx, C->d_sendbuf, C->sendbuf_cap, (size_t) stot * rb)) return -1;
-  if (ensure_bytes(ctx, C->d_recvbuf, C->recvbuf_cap, (size_t) rtot * rb)) return -1;
+  if (ensure_bytes(ctx, C->d_sendbuf, C->sendbuf_cap, sbytes)) return -1;
+  if (ensure_bytes(ctx, C->d_recvbuf, C->recvbuf_cap, rbytes)) return -1;
   size_t so = 0;
   for (int q = 0; q < P; q++) {
     if (q == me || !sc[q]) continue;
     if (select_into(ctx, n0, make_pred(q), C->d_send_idx, &C->d_counts[q])) return -1;
     k_pack_rows<<<(sc[q] + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, C->d_send_idx, sc[q], cl, C->d_sendbuf + so);
     PSPH_LAUNCH_CHECK();
-    so += (size_t) sc[q] * rb;
+    so += seg_bytes(sc[q], rb);
   }
   if (exchange_buffers(ctx, sc, rc, rb)) return -1;
   size_t ro = 0; int base = n0;
@@ -354,7 +359,7 @@ int ship_rows(psph_ctx *ctx, MakePred make_pred, bool as_guest, std::vector<int>
     if (q == me || !rc[q]) continue;
     k_unpack_rows<<<(rc[q] + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, nullptr, base, rc[q], cl, C->d_recvbuf + ro, as_guest ? q : -1, me);
     PSPH_LAUNCH_CHECK();
-    ro += (size_t) rc[q] * rb; base += rc[q];
+    ro += seg_bytes(rc[q], rb); base += rc[q];
   }
   ctx->n = base;
   k_set_n<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, base);
@@ -445,17 +450,17 @@ int refresh_columns(psph_ctx *ctx, const ColList &cl)
   Comm *C = comm_of(ctx);
   if (ensure_lists(ctx)) return -1;
   const size_t rb = row_bytes(cl);
-  long long stot = 0, rtot = 0;
-  for (int q = 0; q < C->P; q++) { stot += C->send_cnt[q]; rtot += C->recv_cnt[q]; }
-  if (ensure_bytes(ctx, C->d_sendbuf, C->sendbuf_cap, (size_t) stot * rb)) return -1;
-  if (ensure_bytes(ctx, C->d_recvbuf, C->recvbuf_cap, (size_t) rtot * rb)) return -1;
+  size_t sbytes = 0, rbytes = 0;
+  for (int q = 0; q < C->P; q++) { sbytes += seg_bytes(C->send_cnt[q], rb); rbytes += seg_bytes(C->recv_cnt[q], rb); }
+  if (ensure_bytes(ctx, C->d_sendbuf, C->sendbuf_cap, sbytes)) return -1;
+  if (ensure_bytes(ctx, C->d_recvbuf, C->recvbuf_cap, rbytes)) return -1;
   size_t so = 0, si = 0;
   for (int q = 0; q < C->P; q++) {
     const int c = C->send_cnt[q];
     if (q == C->me || !c) continue;
     k_pack_rows<<<(c + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, C->d_send_idx + si, c, cl, C->d_sendbuf + so);
     PSPH_LAUNCH_CHECK();
-    so += (size_t) c * rb; si += c;
+    so += seg_bytes(c, rb); si += c;
   }
   if (exchange_buffers(ctx, C->send_cnt, C->recv_cnt, rb)) return -1;
   size_t ro = 0, ri = 0;
@@ -464,7 +469,7 @@ int refresh_columns(psph_ctx *ctx, const ColList &cl)
     if (q == C->me || !c) continue;
     k_unpack_rows<<<(c + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, C->d_recv_idx + ri, 0, c, cl, C->d_recvbuf + ro, -2, C->me);
     PSPH_LAUNCH_CHECK();
-    ro += (size_t) c * rb; ri += c;
+    ro += seg_bytes(c, rb); ri += c;
   }
   return 0;
 }

@@ -50,6 +50,21 @@ __device__ __forceinline__ int warp_sum_i(int v)
   return v;
 }
 
+// shared memory through 32-bit window addresses (one base register per warp instead of a generic pointer
+// that the compiler re-derives at every access)
+__device__ __forceinline__ void sts32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds32(unsigned addr)
+{
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// |x| of a double as an ordered 64-bit pattern (non-negative doubles compare like unsigned integers)
+__device__ __forceinline__ unsigned long long abs_bits(double x)
+{
+  return ((unsigned long long) (unsigned) (__double2hiint(x) & 0x7fffffff) << 32) | (unsigned) __double2loint(x);
+}
+
 // one 32-byte record with a single 256-bit load (LDG.E.256 on sm_100a), read-only path
 __device__ __forceinline__ double4 ld_rec(const double4 *__restrict__ a, int j)
 {
@@ -151,7 +166,8 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
   __shared__ WarpScratch s_scr[GW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  WarpScratch &W = s_scr[warp];
+  const unsigned s_cand = (unsigned) __cvta_generic_to_shared(&s_scr[warp].cand[0]);
+  const unsigned s_q = (unsigned) __cvta_generic_to_shared(&s_scr[warp].qj[0]);
   const int n = ss->n;
   const int cnt = S::kRows == F_NEED ? ss->n_need : ss->n_grad;
   const int32_t *__restrict__ rows = S::kRows == F_NEED ? V.need_idx : V.grad_idx;
@@ -171,6 +187,8 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
       while (again) {
         S::begin(K, st, acc, pass);
         const double lim_own = st.supp, lim_other = fmin(st.supp, rlist);
+        // the list / in_support limits can only bite when the largest possible cutoff box exceeds them
+        const bool need_lim = S::kCountSupport || K.cutoff * (S::kSymH ? 0.5 * (st.h + hmax) : st.hk) > lim_other;
         int qn = 0, qhead = 0; // queue state, identical in every lane
 
         // ---- scan phase, one candidate per lane: list gate (neighs.cc:88-92 own bucket, :130 others),
@@ -178,12 +196,9 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
         // cutoff is decided without dividing unless a component sits within 2^-48 of the face.
         auto consider = [&](bool live, int cj, const double4 &gj) {
           const int j = cj & 0x7fffffff;
-          // |dx_k| as ordered bit patterns: non-negative doubles compare like unsigned integers, which keeps
-          // the three-way test off the FP64 pipe
+          // |dx_k| compared as ordered bit patterns: keeps the three-way tests off the FP64 pipe
           const double dx = gi.x - gj.x, dy = DIM == 3 ? gi.y - gj.y : 0.0, dz = DIM == 3 ? gi.z - gj.z : 0.0;
-          const unsigned long long ax = (unsigned long long) __double_as_longlong(dx) & 0x7fffffffffffffffull,
-                                   ay = (unsigned long long) __double_as_longlong(dy) & 0x7fffffffffffffffull,
-                                   az = (unsigned long long) __double_as_longlong(dz) & 0x7fffffffffffffffull;
+          const unsigned long long ax = abs_bits(dx), ay = abs_bits(dy), az = abs_bits(dz);
           if constexpr (S::kCountSupport) { // rows of the list inside in_support(), contributing or not
             const double lim = cj < 0 ? lim_own : lim_other;
             if (live && j != i && !(fabs(dx) > lim || fabs(dy) > lim || fabs(dz) > lim)) acc.nreal++;
@@ -197,13 +212,13 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
             if (ax <= bhi && ay <= bhi && az <= bhi)
               ok = !(fabs(dx / h) > K.cutoff || fabs(dy / h) > K.cutoff || fabs(dz / h) > K.cutoff);
           }
-          if (ok) {
+          if (need_lim && ok) {
             const double lim = cj < 0 ? lim_own : lim_other;
-            if (b > lim) ok = !(fabs(dx) > lim || fabs(dy) > lim || fabs(dz) > lim);
-            if (S::kSkipSelf && j == i) ok = false;
+            ok = !(fabs(dx) > lim || fabs(dy) > lim || fabs(dz) > lim);
           }
+          if (S::kSkipSelf && j == i) ok = false;
           const unsigned m = __ballot_sync(FULL, ok);
-          if (ok) W.qj[(qhead + qn + __popc(m & lt)) & (QCAP - 1)] = j;
+          if (ok) sts32(s_q + 4u * ((qhead + qn + __popc(m & lt)) & (QCAP - 1)), j);
           qn += __popc(m);
         };
 
@@ -241,7 +256,7 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
             if (c0 < total) { // two candidates per lane, both loads in flight
               const int ca = c0 + lane, cb = ca + 32;
               const bool la = ca < total, lb = cb < total;
-              const int ja = la ? W.cand[ca] : i, jb = lb ? W.cand[cb] : i;
+              const int ja = la ? lds32(s_cand + 4u * ca) : i, jb = lb ? lds32(s_cand + 4u * cb) : i;
               const double4 ga = ld_rec(V.geo, ja & 0x7fffffff), gb = ld_rec(V.geo, jb & 0x7fffffff);
               consider(la, ja, ga);
               if (c0 + 32 < total) consider(lb, jb, gb);
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
                 const int sum = __shfl_sync(FULL, off, 31);
                 off += total - take;
                 const int tag = own ? 0x80000000 : 0;
-                for (int k = 0; k < take; k++) W.cand[off + k] = (beg + k) | tag;
+                for (int k = 0; k < take; k++) sts32(s_cand + 4u * (off + k), (beg + k) | tag);
                 beg += take; len -= take; total += sum;
                 continue;
               }
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
             __syncwarp();
             const int c = min(32, qn);
             if (lane < c) {
-              const int j = W.qj[(qhead + lane) & (QCAP - 1)];
+              const int j = lds32(s_q + 4u * ((qhead + lane) & (QCAP - 1)));
               const double4 gj = ld_rec(V.geo, j);
               S::pair(V, K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, j);
             }

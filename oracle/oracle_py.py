@@ -99,6 +99,33 @@ def config_3d(smlen=100.0, Ll=(-20800.0, -20800.0, 1666.0), Lu=(20800.0, 20800.0
     return c
 
 
+def config_jpue():
+    """BASELINE config 2, JPUE weakly-compressible jet: 3-D options with FLUID_COMPRESSIBILITY 1 (Tait EOS,
+    particle.cc:528-604) and ATMOSPHERE_TYPE 2 (g = 0), parameters.h block :404-562,
+    bin/simulation_JPUE_incomp_back.data (smoothing length 8)."""
+    c = config_3d(smlen=8.0, Ll=(-576.0, -576.0, 0.0), Lu=(576.0, 576.0, 6000.0), g=0.0)
+    c.fluid_compressibility = 1
+    c.cfl, c.eta_smooth = 0.45, 1.2
+    c.ng0, c.Cvs, c.Cvg, c.Cva, c.Rg, c.Ra = 1.0, 1617.0, 4197.0, 4197.0, 25182.0, 25182.0
+    c.rhoa0, c.pa0 = 1000.0, 1.013e5
+    return c
+
+
+CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue}
+
+
+def config_for(name, z=None):
+    """configuration of a 3-D golden fixture.  The smoothing length an erupt ghost takes when it turns real
+    (simprops->sml_of_phase2, computed by the driver in setup_erupt.cc:95-101 and handed to the hot path as
+    psph_config.smlen_real) is read off the fixture: the rows that turned real in step 1."""
+    c = CONFIGS_3D[name]()
+    if z is not None:
+        turned = (z["pre"]["bc_type"] == 0) & (z["s1_pos_bc_type"] == 100)
+        if turned.any():
+            c.smlen_real = float(z["s1_pos_smlen"][turned][0])
+    return c
+
+
 def config_1d(gsph=False):
     """Reference 1-D defaults: options.h:18-409, constant.h:14-98, parameters.h:1228-1450."""
     c = Config()

@@ -62,7 +62,37 @@ VARIANTS = {
     "1d_blast_gsph": dict(dim=1, defs=["-DSHOCK_TUBE_TESTS=4"]),
     "3d_plume": dict(dim=3, defs=[]),
     "3d_plume_gsph": dict(dim=3, defs=["-DUSE_GSPH=1"]),
+    # JPUE weakly-compressible jet (user guide "A JPUE simulation"): Tait equation of state, no gravity,
+    # and the parameters.h block at :404-562 instead of the Eyjafjallajokull one (:875-1046)
+    "3d_jpue": dict(dim=3, defs=["-DFLUID_COMPRESSIBILITY=1", "-DATMOSPHERE_TYPE=2"], params="jpue"),
 }
+
+
+def patched_parameters(odir, which):
+    """parameters.h keeps its alternative parameter sets as commented-out blocks; selecting one
+    means editing the header.  /root/reference is read-only and must stay unmodified, so a patched COPY is
+    generated into the build output (oracle/_ref/<variant>/include/parameters.h, git-ignored) and force-
+    included first; its include guard then shadows the original.  Edits: uncomment the JPUE block, put the
+    default (Eyjafjallajokull) block under #if 0."""
+    assert which == "jpue"
+    lines = open(os.path.join(SRC, "plume", "parameters.h"), encoding="latin-1").read().split("\n")
+    find = lambda text, start=0: next(i for i in range(start, len(lines)) if text in lines[i])
+    j0 = find("These parameters are for JPUE of incompressible flow")
+    j1 = find("Parameters for running RP1 with sml1=200", j0)
+    e0 = find("These parameters are for Eyjafjallaj", j1)
+    e1 = find("#else //ASH_SIMULATION", e0)
+    # block comments start one line above the text line and end two lines below it
+    for i in range(j0 + 2, j1 - 1):
+        rest = lines[i][2:].strip() if lines[i].startswith("//") else None
+        if rest is not None and (rest == "" or rest.startswith(("const", "#", "//"))):
+            lines[i] = lines[i][2:]
+    lines.insert(e1, "#endif /* default parameter block disabled: JPUE selected */")
+    lines.insert(e0 + 2, "#if 0")
+    inc = os.path.join(odir, "include")
+    os.makedirs(inc, exist_ok=True)
+    out = os.path.join(inc, "parameters.h")
+    open(out, "w", encoding="latin-1").write("\n".join(lines))
+    return out
 
 
 def run(cmd):
@@ -77,7 +107,15 @@ def build(name, jobs):
     odir = os.path.join(OUT, name)
     os.makedirs(os.path.join(odir, "obj"), exist_ok=True)
     cfg = os.path.join(HERE, "stubs", "cfg1d" if v["dim"] == 1 else "cfg3d")
-    flags = COMMON + v["defs"] + [f"-I{cfg}", f"-I{HERE}/stubs"] + INCS
+    common = list(COMMON)
+    if v.get("params"):
+        ph = patched_parameters(odir, v["params"])
+        # first of all force-includes: a -DDEBUG build (preprocess) reaches parameters.h through other headers, and
+        # whichever copy is seen first defines the include guard
+        k = common.index(f"{SRC}/plume/parameters.h")
+        del common[k - 1:k + 1]
+        common[common.index("-include"):common.index("-include")] = ["-include", "cmath", "-include", ph]
+    flags = common + v["defs"] + [f"-I{cfg}", f"-I{HERE}/stubs"] + INCS
     tus = TU_1D if v["dim"] == 1 else tu_3d()
     objs = []
     cmds = []

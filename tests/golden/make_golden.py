@@ -94,7 +94,7 @@ def golden_1d(name, variant, simdata, nfinal):
         print(name, "n =", len(init), "final time", hf["time"], "->", os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
 
 
-def golden_3d(name, variant, edits, list_stride=4):
+def golden_3d(name, variant, edits, list_stride=4, simdata="simulation.data"):
     """Small 3-D plume: the reference's default case (bin/simulation.data, Eyjafjallajokull
     parameters, Meteo sounding) with a smaller initial domain; state around every stage of step 1."""
     with tempfile.TemporaryDirectory() as top:
@@ -102,7 +102,7 @@ def golden_3d(name, variant, edits, list_stride=4):
         os.makedirs(wd)
         shutil.copytree(os.path.join(REF, "Meteo_data"), os.path.join(top, "Meteo_data"))
         shutil.copy(os.path.join(REF, "bin", "scale.data"), wd)
-        txt = open(os.path.join(REF, "bin", "simulation.data")).read()
+        txt = open(os.path.join(REF, "bin", simdata)).read()
         for a, b in edits:
             assert a in txt, a
             txt = txt.replace(a, b)
@@ -142,6 +142,9 @@ def golden_3d(name, variant, edits, list_stride=4):
 SMALL_3D = [("initial domain:-2000", "initial domain:-350"), ("initial domain:2000", "initial domain:350"),
             ("initial domain:2700", "initial domain:2400")]
 
+JPUE_3D = [("initial domain:-100", "initial domain:-60"), ("initial domain:100", "initial domain:60"),
+           ("initial domain:140", "initial domain:100")]
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["sod_sph", "sod_gsph", "sod0_gsph", "shu_sph", "shu_gsph", "blast_gsph",
                              "plume3d_small", "plume3d_small_gsph"]
@@ -155,6 +158,8 @@ if __name__ == "__main__":
         "blast_gsph": lambda: golden_1d("blast_gsph", "1d_blast_gsph", "simulation_1D_shocktube_Strong-Blast.data", 300),
         "plume3d_small": lambda: golden_3d("plume3d_small", "3d_plume", SMALL_3D),
         "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D),
+        # BASELINE config 2: JPUE weakly-compressible jet (Tait EOS, g = 0), the reference's own input file
+        "jpue3d": lambda: golden_3d("jpue3d", "3d_jpue", JPUE_3D, list_stride=16, simdata="simulation_JPUE_incomp_back.data"),
     }
     for w in which:
         table[w]()

@@ -16,10 +16,10 @@ from plume_sph_b200.solver import ORDER_REFERENCE, ORDER_DEVICE
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def case():
-    z = golden("plume3d_small")
-    ocfg = op.config_3d()
+@pytest.fixture(scope="module", params=["plume3d_small", "jpue3d"])
+def case(request):
+    z = golden(request.param)
+    ocfg = op.config_for(request.param, z)
     cfg = to_product_cfg(ocfg)
     s = psph.Solver(cfg)
     attr, _ = cell_attrs(ocfg, z)

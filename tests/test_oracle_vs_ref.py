@@ -16,9 +16,12 @@ def eq(a, b, what):
     assert np.array_equal(np.asarray(a), np.asarray(b)), what
 
 
-def test_plume3d_step1_bit_exact():
-    z = golden("plume3d_small")
-    cfg = op.config_3d()
+@pytest.mark.parametrize("name", ["plume3d_small", "jpue3d"])
+def test_plume3d_step1_bit_exact(name):
+    """every stage of time step 1 of the reference's 3-D cases: the dusty-gas plume (ideal-gas mixture EOS,
+    gravity, Meteo atmosphere) and the JPUE jet (Tait EOS, g = 0)"""
+    z = golden(name)
+    cfg = op.config_for(name, z)
     s = oracle_state_3d(cfg, z)
     assert s.timestep() == float(z["dt"][0])
     dt = float(z["dt"][0])

@@ -17,16 +17,13 @@
 //          stage's pair body — the FP64-heavy part runs with every lane busy.
 // The set of pairs that contribute is exactly the reference's; pairs that cannot contribute
 // (zero kernel weight) are never queued.  Lane partial sums are combined with warp shuffles.
-// CTAs are persistent (one resident wave) and walk chunks of 128 consecutive entries of the list
-// of rows the stage updates; rows are sorted by subcell, so the eight warps of a CTA work on one
+// CTAs are persistent, ONE per SM with 16-24 warps, and walk chunks of 256-384 consecutive entries
+// of the list of rows the stage updates; rows are sorted by subcell, so all warps of an SM work on one
 // compact block of space at a time and share its candidate rows through L1.  No CTA-wide barrier.
 #pragma once
 #include "psph_internal.cuh"
 
-constexpr int GW = 8;          // warps per CTA
-constexpr int GT = GW * 32;    // threads per CTA
-constexpr int RPW = 16;        // consecutive list entries per warp and chunk
-constexpr int CHUNK = GW * RPW;// entries per CTA chunk (spatially compact: its candidates share L1)
+constexpr int RPW = 16;        // consecutive list entries per warp and chunk; a CTA chunk is S::kWarps * RPW entries
 constexpr int QCAP = 128;      // queue slots per warp (power of two, >= 31 + 64)
 constexpr int CANDCAP = 768;   // candidate rows expanded per batch
 constexpr unsigned FULL = 0xffffffffu;
@@ -149,7 +146,8 @@ __device__ __forceinline__ double dev_weight_in(double r2, double invh)
 //   kSymH         pair smoothing length is 0.5*(h_i+h_j) (true) or S::I::hk (false)
 //   kSkipSelf     j == i is not a pair (mom_engr_update.cc:201)
 //   kRows         RowFlags bit of the rows the stage updates (selects the row list it walks)
-//   kMinBlocks    resident CTAs per SM the register allocation must allow
+//   kWarps        warps per CTA; ONE CTA per SM, so that every warp of an SM works in the same compact block
+//                 of space and the block's candidate rows stay in that SM's L1
 //   kCountSupport count (A::nreal) the listed rows inside in_support(), whatever their weight
 //   struct I      per-row state, identical in every lane; members h, supp (= CUTOFF2*h_i), hk
 //   struct A      per-lane accumulators
@@ -161,9 +159,11 @@ __device__ __forceinline__ double dev_weight_in(double r2, double invh)
 // Rows that must not contribute to a stage's sums (contr_dens / contr_vel_smooth false) carry
 // zeros in the stage record, so the scan phase needs no flag word.
 template <int DIM, class S>
-__global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridView G, KParams K, StepState *ss)
+__global__ void __launch_bounds__(S::kWarps * 32, 1) k_gather(DevView V, GridView G, KParams K, StepState *ss)
 {
-  __shared__ WarpScratch s_scr[GW];
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  WarpScratch *s_scr = reinterpret_cast<WarpScratch *>(s_raw);
+  constexpr int CHUNK = S::kWarps * RPW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const unsigned s_cand = (unsigned) __cvta_generic_to_shared(&s_scr[warp].cand[0]);
@@ -337,14 +337,18 @@ __global__ void __launch_bounds__(GT, S::kMinBlocks) k_gather(DevView V, GridVie
 template <int DIM, class S>
 int launch_gather_d(psph_ctx *ctx, int kid)
 {
+  constexpr int threads = S::kWarps * 32;
+  constexpr size_t smem = sizeof(WarpScratch) * S::kWarps;
   static int per_sm = 0; // resident CTAs per SM of this instantiation: the grid is one persistent wave
   if (per_sm == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather<DIM, S>, GT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    PSPH_CUDA(cudaFuncSetAttribute(k_gather<DIM, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather<DIM, S>, threads, smem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
   }
   KernelTimer kt(ctx, kid);
-  int nchunks = (ctx->n + CHUNK - 1) / CHUNK;
+  int nchunks = (ctx->n + S::kWarps * RPW - 1) / (S::kWarps * RPW);
   int grid = min(max(nchunks, 1), ctx->sms * per_sm);
-  k_gather<DIM, S><<<grid, GT, 0, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss);
+  k_gather<DIM, S><<<grid, threads, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   return 0;
 }

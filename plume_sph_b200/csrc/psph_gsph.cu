@@ -40,7 +40,7 @@ template <int DIM>
 struct GradStage
 {
   static constexpr bool kSymH = false, kSkipSelf = true, kCountSupport = true;
-  static constexpr int kRows = F_GRADROW, kMinBlocks = 2;
+  static constexpr int kRows = F_GRADROW, kWarps = 16;
   static constexpr int NQ = DIM + 2, NA = DIM == 3 ? 6 : 1;
   struct I { int i; double h, supp, hk, invh, rho, p, v[3]; };
   struct A { int nreal; double aa[NA]; double f[DIM][NQ]; };
@@ -168,7 +168,7 @@ template <int DIM>
 struct GsphMomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kMinBlocks = 2;
+  static constexpr int kRows = F_NEED, kWarps = 16;
   struct I { int i, pass; double h, supp, hk, rho, Vi, p, c, gamma, T, Cp, u[3], rhs[3], xdot[3]; };
   struct A { double rv[3], re; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)

@@ -98,7 +98,7 @@ template <int DIM>
 struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kMinBlocks = 3;
+  static constexpr int kRows = F_NEED, kWarps = 24;
   struct I { double h, supp, hk; };
   struct A { double rho1, rho2, wn, en; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
@@ -167,7 +167,7 @@ template <int DIM>
 struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kMinBlocks = 2;
+  static constexpr int kRows = F_NEED, kWarps = 16;
   struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3]; };
   struct A { double rv[3], re; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *ss, int i, I &s)
@@ -254,7 +254,7 @@ template <int DIM>
 struct VelStage
 {
   static constexpr bool kSymH = false, kSkipSelf = false, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kMinBlocks = 3;
+  static constexpr int kRows = F_NEED, kWarps = 24;
   struct I { double h, invh, supp, hk, v[3]; };
   struct A { double dv[3], wn; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
@@ -295,7 +295,7 @@ template <int DIM>
 struct SmlStage
 {
   static constexpr bool kSymH = false, kSkipSelf = false, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kMinBlocks = 3;
+  static constexpr int kRows = F_NEED, kWarps = 24;
   struct I { double h, hs, hk, invhs, supp, m; };
   struct A { double rho; };
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)

@@ -42,7 +42,7 @@ __global__ void k_make_keys(Tab V, GridView G, StepState *ss, int n_cap, uint32_
   if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
 }
 
-__global__ void k_reset_list_scalars(StepState *ss) { ss->hmax_bits = 0ull; ss->n_need = 0; ss->n_grad = 0; }
+__global__ void k_reset_list_scalars(StepState *ss) { ss->hmax_bits = 0ull; ss->n_need = 0; ss->n_grad = 0; ss->xmax_bits = 0u; }
 
 // after the sort: number of live rows = first row whose key is inf_key
 __global__ void k_count_live(const uint32_t *__restrict__ key, int n_cap, uint32_t inf_key, StepState *ss)
@@ -87,11 +87,9 @@ __global__ void k_ghost_cells(Tab V, const StepState *ss, uint8_t *__restrict__ 
 }
 
 // per-row flag word, geometry record, packed subcell coordinates, h at list-build time
-__global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss, int n_cap)
+__device__ __forceinline__ float row_flags(DevView &V, const GridView &G, const KParams &K, StepState *ss, int p)
 {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_cap) return;
-  if (p >= ss->n) { V.flags[p] = 0; return; }
+  if (p >= ss->n) { V.flags[p] = 0; return 0.f; }
   int bc = V.t.i[I_BC][p], guest = V.t.i[I_GUEST][p], ph = V.t.i[I_PHASE][p];
   int f = 0;
   bool need = dev_need_neigh(bc, guest);
@@ -111,6 +109,7 @@ __global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss, int
   double h = V.t.d[D_H][p];
   V.t.d[D_HLIST][p] = h;
   V.geo[p] = make_double4(x[0], x[1], x[2], h);
+  const float xm = dev_store_geo32(V.geo32, K, p, x[0], x[1], x[2], h);
   unsigned long long pk = 0;
   if (G.dim == 3) {
     // subcell of the row inside the bucket it is a member of (the same function the sort key uses),
@@ -127,6 +126,16 @@ __global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss, int
     pk |= near << 60;
   }
   V.gsub[p] = pk;
+  return xm;
+}
+__global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss, int n_cap)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  float xm = 0.f;
+  if (p < n_cap) xm = row_flags(V, G, K, ss, p);
+  // bound of the FP32 rounding error of the geo32 records (positive floats order like their bit patterns)
+  for (int o = 16; o; o >>= 1) xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+  if ((threadIdx.x & 31) == 0 && xm > 0.f) atomicMax(&ss->xmax_bits, __float_as_uint(xm));
 }
 
 struct FlagSet

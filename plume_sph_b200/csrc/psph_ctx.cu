@@ -159,6 +159,7 @@ static void fill_kparams(psph_ctx *ctx)
   k.eta_smooth = c.eta_smooth; k.c_smooth = c.c_smooth; k.thresh = c.thresh; k.num_loop = c.num_loop;
   k.ng0 = c.ng0; k.Cvs = c.Cvs; k.Cvg = c.Cvg; k.Cva = c.Cva; k.Rg = c.Rg; k.Ra = c.Ra;
   k.rhoa0 = c.rhoa0; k.pa0 = c.pa0; k.erupt_top = c.erupt_top; k.smlen_real = c.smlen_real;
+  for (int d = 0; d < 3; d++) k.org[d] = c.mindom[d] / c.len_scale;
 }
 
 extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
@@ -178,7 +179,13 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
   ctx->d_attr = nullptr; ctx->d_sortkey = ctx->d_sortkey_alt = ctx->d_perm = ctx->d_perm_alt = nullptr;
   ctx->d_cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
   ctx->list_valid = false; ctx->n_dirty = false; ctx->step = 0; ctx->launches = 0;
-  ctx->d_aos = nullptr; ctx->aos_cap = 0; ctx->comm = nullptr;
+  ctx->d_aos = nullptr; ctx->aos_cap = 0; ctx->comm = nullptr; ctx->d_gspill = nullptr;
+  {
+    const char *gm = getenv("PSPH_GATHER"); // A/B switch for profiling; both paths are CUDA
+    ctx->gather_mode = (gm && !strcmp(gm, "row")) ? 1 : 0;
+    const char *gw = getenv("PSPH_GWARPS");
+    ctx->gather_warps = gw ? atoi(gw) : 0;
+  }
   ctx->timing = 0; memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
   *out = ctx;
   ctx->sms = 0;
@@ -222,7 +229,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   free_tab(ctx->cur.t); free_tab(ctx->alt);
   for (int c = 0; c < NSCRATCH; c++) cudaFree(ctx->cur.scr[c]);
   for (int c = 0; c < NREC; c++) cudaFree(ctx->cur.rec[c]);
-  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.flags);
+  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
   cudaFree(ctx->d_cell_has_ghost);
@@ -287,6 +294,7 @@ int psph_reserve(psph_ctx *ctx, size_t rows)
   for (int c = 0; c < NSCRATCH; c++) if (grow(ctx, ctx->cur.scr[c], 0, ncap)) return -1;
   for (int c = 0; c < NREC; c++) if (grow(ctx, ctx->cur.rec[c], 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.geo, 0, ncap)) return -1;
+  if (grow(ctx, ctx->cur.geo32, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.flags, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.gsub, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.need_idx, 0, ncap)) return -1;

@@ -1,0 +1,344 @@
+// psph_gather3.cuh — the grouped pair gather of the 3-D SPH summation stages (mom_engr_update,
+// smooth_density, smooth_velocity).
+//
+// The per-particle gather of psph_gather.cuh spends 60-70 % of its instructions on finding the
+// pairs (candidate enumeration + gates), not on the pair bodies.  Here ONE WARP takes a GROUP of
+// up to GRP rows that sit in the same (x, y) subcell column of one bucket (consecutive entries of
+// the sorted row list), and
+//   enumerate : the candidate rows of the group's common box (x, y: column +- reach, z: the
+//               group's z-range +- reach) are expanded ONCE into a dense list in shared memory;
+//   scan      : every lane takes one candidate, loads its 16-byte FP32 record {x-o, y-o, z-o, h}
+//               once and tests it against each row of the group in FP32.  The FP32 test only
+//               DECIDES pairs that are clear of the cutoff face by more than its own error bound;
+//               candidates inside the band (and every candidate of a row whose list / in_support
+//               limits can bite) go through the reference's gates in FP64, bit for bit
+//               (neighs.cc:84-92,130; sph_header.h:49-60; sph_lib.cc:216-218).  Rows that pass
+//               are appended (ballot + popc) to the queue of that row of the group;
+//   pair      : then, row by row, all 32 lanes take one queued pair each and run the stage's pair
+//               body in FP64 (the same bodies as the per-particle gather), accumulators in
+//               registers, warp-shuffle reduction, one lane writes.
+// A queue that fills up before the scan ends is drained early: full rounds are run and the
+// per-lane partial sums are parked in a global spill row until the scan of the group resumes.
+// The set of contributing pairs is exactly the reference's.
+#pragma once
+#include "psph_gather.cuh"
+
+constexpr int GRP = 4;          // rows per group
+constexpr int GQCAP = 320;      // queue slots per row of the group (multiple of 32, >= 64 + 32)
+constexpr int GCAND = 512;      // candidate rows expanded per batch
+constexpr int RPWG = 32;        // consecutive list entries per warp and chunk
+constexpr int GNA = 4;          // accumulators per lane (every stage's A is four doubles)
+
+struct GrpScratch
+{
+  int cand[GCAND];              // candidate row << 1 | own-bucket flag
+  int q[GRP][GQCAP];            // rows that passed the gates, per row of the group
+  int hdr_i[GRP];               // the rows of the group
+  int hdr_n[GRP];               // queued pairs per row
+  // what the FP64 gate needs (rare path): kept here so that the call carries no kernel parameters
+  double kc[3];                 // cutoff, cutoff2, neigh_radius
+  const double4 *geo;
+  const double *hlist;
+};
+
+__device__ __forceinline__ float4 ld_rec32(const float4 *__restrict__ a, int j)
+{
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a + j));
+  return v;
+}
+
+// The reference's gates in FP64 for the candidate cj of this lane against the rows of the group flagged in
+// bandb: kernel cutoff |dx_k / h| <= cutoff (sph_lib.cc:216-218), list gate (own bucket, else
+// |dx_k| <= 4.25 h_i(list), neighs.cc:84-92,130) and in_support(dx, CUTOFF2 h_i) (sph_header.h:49-60).
+// Returns okb with the bits of the rows that fail cleared.  Rare path, kept out of line.
+__device__ __noinline__ unsigned gate_exact_grp(const GrpScratch *scr, unsigned okb, unsigned bandb, int cj, int sym)
+{
+  const double cutoff = scr->kc[0], cutoff2 = scr->kc[1], nradius = scr->kc[2];
+  const double4 gj = scr->geo[cj >> 1];
+  for (int g = 0; g < GRP; g++) {
+    if (!((bandb >> g) & 1u)) continue;
+    const int i = scr->hdr_i[g];
+    const double4 gi = scr->geo[i];
+    const double dx = gi.x - gj.x, dy = gi.y - gj.y, dz = gi.z - gj.z;
+    const double h = sym ? 0.5 * (gi.w + gj.w) : gi.w;
+    bool ok = !(fabs(dx / h) > cutoff || fabs(dy / h) > cutoff || fabs(dz / h) > cutoff);
+    if (ok) {
+      const double supp = cutoff2 * gi.w;
+      const double lim = (cj & 1) ? supp : fmin(supp, nradius * scr->hlist[i]);
+      ok = !(fabs(dx) > lim || fabs(dy) > lim || fabs(dz) > lim);
+    }
+    if (!ok) okb &= ~(1u << g);
+  }
+  return okb;
+}
+
+// Stage interface: as psph_gather.cuh, plus
+//   kWarpsGrp            warps per CTA of the grouped kernel (one CTA per SM)
+//   double reach_h(K,h,hmax)  half-width of the candidate box of a row with smoothing length h
+template <class S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict__ spill)
+{
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int CHUNK = WARPS * RPWG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  GrpScratch *scr = reinterpret_cast<GrpScratch *>(s_raw) + warp;
+  // window addresses of the warp's scratch; the volatile move keeps the compiler from re-deriving them
+  // from the thread index at every access
+  unsigned s_cand, s_q, s_hdr;
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_cand) : "r"((unsigned) __cvta_generic_to_shared(&scr->cand[0])));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_q) : "r"((unsigned) __cvta_generic_to_shared(&scr->q[0][0])));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_hdr) : "r"((unsigned) __cvta_generic_to_shared(&scr->hdr_i[0])));
+  if (lane == 0) {
+    scr->kc[0] = K.cutoff; scr->kc[1] = K.cutoff2; scr->kc[2] = K.neigh_radius;
+    scr->geo = V.geo; scr->hlist = V.t.d[D_HLIST];
+  }
+  __syncwarp();
+  const int cnt = ss->n_need;
+  const int32_t *__restrict__ rows = V.need_idx;
+  const double hmax = ss->hmax;
+  // FP32 decision band: coordinates are rounded to FP32 relative to the mesh origin (error <= 2^-24 xmax
+  // each), the limit is formed in FP32 (a few ulp) -> band of +-(2^-19 b + 2^-21 xmax) around the face
+  const float delta = __uint_as_float(ss->xmax_bits) * 0x1p-21f;
+  const float ch = (float) (S::kSymH ? 0.5 * K.cutoff : K.cutoff);
+  const float c_lo = ch * (1.0f - 0x1p-19f), c_hi = ch * (1.0f + 0x1p-19f);
+  double *__restrict__ my_spill = spill + (size_t) (blockIdx.x * WARPS + warp) * (GRP * GNA * 32) + lane;
+  const int nsubx = G.ncell[0] * SUBDIV - 1, nsuby = G.ncell[1] * SUBDIV - 1, nsubz = G.ncell[2] * SUBDIV - 1;
+
+  for (int chunk = blockIdx.x; chunk * CHUNK < cnt; chunk += gridDim.x) {
+    int e = chunk * CHUNK + warp * RPWG;
+    const int eend = min(e + RPWG, cnt);
+    while (e < eend) {
+      // ---- form the group: the leading run of list entries in the same subcell column of one bucket
+      int row = -1, cell = -1;
+      unsigned long long pk = 0;
+      if (lane < GRP && e + lane < eend) {
+        row = __ldg(&rows[e + lane]);
+        pk = V.gsub[row];
+        cell = V.t.i[I_CELL][row];
+      }
+      const unsigned long long pk0 = __shfl_sync(FULL, pk, 0);
+      const int cell0 = __shfl_sync(FULL, cell, 0);
+      const bool same = row >= 0 && cell == cell0 && ((pk ^ pk0) & 0xffffffffffull) == 0;
+      const int m = __ffs(~__ballot_sync(FULL, same)) - 1; // 1..GRP
+      const bool mine = lane < m;
+      float4 p32 = make_float4(0.f, 0.f, 0.f, 0.f);
+      int kR = 0, sz = 0;
+      bool nl = false;
+      if (mine) {
+        p32 = V.geo32[row];
+        const double hi = V.t.d[D_H][row];
+        const double supp = K.cutoff2 * hi, rlist = K.neigh_radius * V.t.d[D_HLIST][row];
+        kR = (int) ceil(S::reach_h(K, hi, hmax) * G.inv_subw - 1e-9) + (int) (pk >> 60);
+        sz = (int) ((pk >> 40) & 0xfffff);
+        // the list / in_support limits can only bite when the largest possible cutoff box exceeds them
+        nl = K.cutoff * (S::kSymH ? 0.5 * (hi + hmax) : hi) > fmin(supp, rlist);
+        sts32(s_hdr + 4u * lane, row);
+      }
+      const int kRg = __reduce_max_sync(FULL, kR);
+      const int zlo = __reduce_min_sync(FULL, mine ? sz : 0x7fffffff), zhi = __reduce_max_sync(FULL, mine ? sz : -1);
+      const unsigned nlmask = __ballot_sync(FULL, nl);
+      int ig[GRP];
+      unsigned qa[GRP];               // window address of the next free slot of every queue
+      float fx[GRP], fy[GRP], fz[GRP], blo[GRP], bhi[GRP];
+#pragma unroll
+      for (int g = 0; g < GRP; g++) {
+        ig[g] = __shfl_sync(FULL, row, g);
+        fx[g] = __shfl_sync(FULL, p32.x, g); fy[g] = __shfl_sync(FULL, p32.y, g); fz[g] = __shfl_sync(FULL, p32.z, g);
+        const float hf = __shfl_sync(FULL, p32.w, g);
+        // a row whose list / in_support limits can bite sends every candidate through the FP64 gates
+        blo[g] = ((nlmask >> g) & 1u) ? -INFINITY : hf * c_lo - delta;
+        bhi[g] = hf * c_hi + delta;
+        qa[g] = s_q + 4u * GQCAP * g;
+      }
+      // ---- candidate enumeration state (the group's common box, in global subcell coordinates)
+      const int sx = (int) (pk0 & 0xfffff), sy = (int) ((pk0 >> 20) & 0xfffff);
+      const int gx0 = max(sx - kRg, 0), gy0 = max(sy - kRg, 0), gz0 = max(zlo - kRg, 0);
+      const int gx1 = min(sx + kRg, nsubx), gy1 = min(sy + kRg, nsuby), gz1 = min(zhi + kRg, nsubz);
+      const int ncoly = gy1 - gy0 + 1, ncol = (gx1 - gx0 + 1) * ncoly;
+      const float inv_ncoly = 1.0f / (float) ncoly;
+      const int cz0 = gz0 / SUBDIV, cz1 = gz1 / SUBDIV;
+      int col_base = -32, cz = cz1, c0 = 0, total = 0, beg = 0, len = 0, cellxy = 0, subxy = 0;
+      bool have = false, own = false;
+      unsigned drained = 0;
+
+      // one candidate of the dense list (p.x = +inf in lanes without one) against every row of the group
+      auto test = [&](int cj, const float4 &p) {
+        const int j = cj >> 1;
+        const float hlo = S::kSymH ? p.w * c_lo : 0.f, hhi = S::kSymH ? p.w * c_hi : 0.f;
+        unsigned okb = 0, bandb = 0;
+#pragma unroll
+        for (int g = 0; g < GRP; g++) {
+          if (g < m) {
+            const float m3 = fmaxf(fmaxf(fabsf(fx[g] - p.x), fabsf(fy[g] - p.y)), fabsf(fz[g] - p.z));
+            bool ok = m3 <= bhi[g] + hhi;
+            if (S::kSkipSelf) ok = ok && j != ig[g];
+            if (ok) okb |= 1u << g;
+            if (ok && m3 > blo[g] + hlo) bandb |= 1u << g;
+          }
+        }
+        if (__any_sync(FULL, bandb != 0)) { // within the FP32 error band of a cutoff face: the reference's own test
+          if (bandb) okb = gate_exact_grp(scr, okb, bandb, cj, S::kSymH ? 1 : 0);
+        }
+#pragma unroll
+        for (int g = 0; g < GRP; g++) {
+          if (g < m) {
+            const bool ok = (okb >> g) & 1u;
+            const unsigned b = __ballot_sync(FULL, ok);
+            if (ok) sts32(qa[g] + 4u * __popc(b & lt), j);
+            qa[g] += 4u * __popc(b);
+          }
+        }
+      };
+
+      for (bool done = false; !done;) {
+        // ---- scan until the candidates are exhausted or a queue may overflow in the next iteration
+        int gsel = -1;
+        for (;;) {
+          if (c0 >= total) {
+            // refill: expand row ranges into the candidate list until it is full or nothing is left
+            if (total) { total = 0; c0 = 0; __syncwarp(); }
+            for (;;) {
+              if (__any_sync(FULL, len > 0)) {
+                const int quota = (GCAND - total) / 32;
+                if (quota == 0) break;
+                const int take = min(len, quota);
+                int off = take;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
+                const int sum = __shfl_sync(FULL, off, 31);
+                off += total - take;
+                const int tag = own ? 1 : 0;
+                for (int k = 0; k < take; k++) sts32(s_cand + 4u * (off + k), ((beg + k) << 1) | tag);
+                beg += take; len -= take; total += sum;
+                continue;
+              }
+              if (cz < cz1) { // the z-run of every column of this round inside the next bucket along z
+                cz++;
+                beg = 0; len = 0; own = false;
+                if (have) {
+                  const int cc = cellxy + cz;
+                  const int zl = (cz == cz0) ? (gz0 % SUBDIV) : 0, zh = (cz == cz1) ? (gz1 % SUBDIV) : SUBDIV - 1;
+                  const int t = __ldg(&G.cell2rank[cc]) * SUBS + subxy;
+                  beg = __ldg(&G.sub_start[t + zl]);
+                  len = __ldg(&G.sub_start[t + zh + 1]) - beg;
+                  own = cc == cell0;
+                }
+                continue;
+              }
+              col_base += 32; // next round of 32 (x, y) subcell columns
+              if (col_base >= ncol) break;
+              const int col = col_base + lane;
+              have = col < ncol;
+              if (have) {
+                const int ix = (int) (((float) col + 0.5f) * inv_ncoly), iy = col - ix * ncoly;
+                const int gx = gx0 + ix, gy = gy0 + iy;
+                cellxy = ((gx / SUBDIV) * G.ncell[1] + (gy / SUBDIV)) * G.ncell[2];
+                subxy = (gx % SUBDIV) * (SUBDIV * SUBDIV) + (gy % SUBDIV) * SUBDIV;
+              }
+              cz = cz0 - 1;
+            }
+            __syncwarp();
+            if (total == 0) break;
+          }
+#pragma unroll
+          for (int g = 0; g < GRP; g++)
+            if (qa[g] > s_q + 4u * (GQCAP * g + GQCAP - 64)) gsel = g;
+          if (gsel >= 0) break;
+          // two candidates per lane, both loads in flight
+          const int ca = c0 + lane, cb = ca + 32;
+          const bool la = ca < total, lb = cb < total;
+          const int ja = la ? lds32(s_cand + 4u * ca) : 0, jb = lb ? lds32(s_cand + 4u * cb) : 0;
+          float4 pa = ld_rec32(V.geo32, ja >> 1), pb = ld_rec32(V.geo32, jb >> 1);
+          if (!la) pa.x = INFINITY;
+          if (!lb) pb.x = INFINITY;
+          test(ja, pa);
+          if (c0 + 32 < total) test(jb, pb);
+          c0 += 64;
+        }
+        done = gsel < 0;
+        if (lane == 0) {
+#pragma unroll
+          for (int g = 0; g < GRP; g++) sts32(s_hdr + 16u + 4u * g, (int) (qa[g] - (s_q + 4u * GQCAP * g)) >> 2);
+        }
+        __syncwarp();
+
+        // ---- pair phase: every row of the group (scan finished) or the one whose queue is full
+        const int g0 = done ? 0 : gsel, g1 = done ? m : gsel + 1;
+        for (int g = g0; g < g1; g++) {
+          const int i = lds32(s_hdr + 4u * g), n = lds32(s_hdr + 16u + 4u * g);
+          typename S::I st;
+          S::init(V, K, ss, i, st);
+          const double4 gi = V.geo[i];
+          typename S::A acc;
+          S::begin(K, st, acc, 0);
+          double *ap = reinterpret_cast<double *>(&acc);
+          if ((drained >> g) & 1u) {
+#pragma unroll
+            for (int k = 0; k < GNA; k++) ap[k] = my_spill[(g * GNA + k) * 32];
+          }
+          const unsigned qg = s_q + 4u * GQCAP * g;
+          const int nrun = done ? n : (n & ~31);
+          for (int q0 = 0; q0 < nrun; q0 += 32) {
+            if (q0 + lane < nrun) {
+              const int j = lds32(qg + 4u * (q0 + lane));
+              const double4 gj = ld_rec(V.geo, j);
+              S::pair(V, K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, j);
+            }
+          }
+          if (done) {
+            S::end(V, K, ss, i, st, acc, 0, lane);
+          } else { // park the partial sums, keep the incomplete round at the head of the queue
+#pragma unroll
+            for (int k = 0; k < GNA; k++) my_spill[(g * GNA + k) * 32] = ap[k];
+            drained |= 1u << g;
+            const int rem = n - nrun;
+            int v = 0;
+            if (lane < rem) v = lds32(qg + 4u * (nrun + lane));
+            __syncwarp();
+            if (lane < rem) sts32(qg + 4u * lane, v);
+            __syncwarp();
+#pragma unroll
+            for (int gg = 0; gg < GRP; gg++) if (gg == g) qa[gg] = s_q + 4u * (GQCAP * gg + rem);
+          }
+        }
+      }
+      e += m;
+      __syncwarp();
+    }
+  }
+}
+
+template <class S, int WARPS>
+int launch_gather_grp_w(psph_ctx *ctx, int kid)
+{
+  static_assert(sizeof(typename S::A) == GNA * sizeof(double), "grouped gather: four accumulators per stage");
+  constexpr int threads = WARPS * 32;
+  constexpr size_t smem = sizeof(GrpScratch) * WARPS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSPH_CUDA(cudaFuncSetAttribute(k_gather_grp<S, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    attr_set = true;
+  }
+  const size_t spill_rows = (size_t) ctx->sms * 32 * GRP * GNA * 32; // up to 32 warps per CTA, one CTA per SM
+  if (!ctx->d_gspill) PSPH_CUDA(cudaMalloc(&ctx->d_gspill, spill_rows * sizeof(double)));
+  KernelTimer kt(ctx, kid);
+  const int nchunks = (ctx->n + WARPS * RPWG - 1) / (WARPS * RPWG);
+  const int grid = min(max(nchunks, 1), ctx->sms);
+  k_gather_grp<S, WARPS><<<grid, threads, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_gspill);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+// warps per CTA: the stage's default, or PSPH_GWARPS (tuning switch: 12, 16, 20, 24)
+template <class S>
+int launch_gather_grp(psph_ctx *ctx, int kid)
+{
+  switch (ctx->gather_warps ? ctx->gather_warps : S::kWarpsGrp) {
+  case 12: return launch_gather_grp_w<S, 12>(ctx, kid);
+  case 16: return launch_gather_grp_w<S, 16>(ctx, kid);
+  case 20: return launch_gather_grp_w<S, 20>(ctx, kid);
+  default: return launch_gather_grp_w<S, 24>(ctx, kid);
+  }
+}

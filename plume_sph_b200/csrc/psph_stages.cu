@@ -2,7 +2,7 @@
 // timestep, adaptive_sml, mom_engr_update, smooth_density, smooth_velocity, update_pos and the
 // fused step driver.  Every stage cites the reference code it replaces; the C ABI is
 // include/psph.h.  Pair sums run on the warp gather of psph_gather.cuh.
-#include "psph_gather.cuh"
+#include "psph_gather3.cuh"
 #include <cstring>
 
 // =========================================================================================
@@ -36,13 +36,15 @@ __global__ void k_timestep_finish(KParams K, StepState *ss, double *dt_cfl_out)
 // =========================================================================================
 // stage records (32-byte rows read by the pair loops with 128-bit loads)
 // =========================================================================================
-__global__ void k_refresh_geo(DevView V, StepState *ss)
+__global__ void k_refresh_geo(DevView V, KParams K, StepState *ss)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   double h = 0.0;
   if (p < ss->n) {
     h = V.t.d[D_H][p];
-    V.geo[p] = make_double4(V.t.d[D_X][p], V.t.d[D_Y][p], V.t.d[D_Z][p], h);
+    const double x = V.t.d[D_X][p], y = V.t.d[D_Y][p], z = V.t.d[D_Z][p];
+    V.geo[p] = make_double4(x, y, z, h);
+    dev_store_geo32(V.geo32, K, p, x, y, z, h); // positions are those of the list build: xmax_bits still bounds them
   }
   for (int o = 16; o; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
   if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
@@ -98,9 +100,11 @@ template <int DIM>
 struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kWarps = 24;
+  static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24;
   struct I { double h, supp, hk; };
   struct A { double rho1, rho2, wn, en; };
+  static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
+  { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
   {
     s.h = V.t.d[D_H][i];
@@ -167,9 +171,11 @@ template <int DIM>
 struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kWarps = 16;
+  static constexpr int kRows = F_NEED, kWarps = 16, kWarpsGrp = 16;
   struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3]; };
   struct A { double rv[3], re; };
+  static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
+  { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *ss, int i, I &s)
   {
     s.i = i;
@@ -254,9 +260,10 @@ template <int DIM>
 struct VelStage
 {
   static constexpr bool kSymH = false, kSkipSelf = false, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kWarps = 24;
+  static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24;
   struct I { double h, invh, supp, hk, v[3]; };
   struct A { double dv[3], wn; };
+  static __device__ __forceinline__ double reach_h(const KParams &K, double h, double) { return K.cutoff * h; }
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
   {
     s.h = V.t.d[D_H][i]; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
@@ -352,6 +359,14 @@ __global__ void k_update_pos(Tab V, KParams K, StepState *ss)
 // =========================================================================================
 #define GRID(n) (unsigned) (((n) + 255) / 256), 256, 0, ctx->stream
 
+// 3-D SPH stages run on the grouped gather (psph_gather3.cuh); 1-D, and PSPH_GATHER=row, on the per-row one
+template <template <int> class S>
+static int launch_stage_gather(psph_ctx *ctx, int kid)
+{
+  if (ctx->cfg.dim == 3 && ctx->gather_mode == 0) return launch_gather_grp<S<3> >(ctx, kid);
+  return launch_gather<S>(ctx, kid);
+}
+
 static int ensure_list(psph_ctx *ctx)
 {
   if (ctx->list_valid) return 0;
@@ -362,7 +377,7 @@ int psph_refresh_geo(psph_ctx *ctx)
 {
   k_hmax_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (ctx->n > 0) { k_refresh_geo<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
+  if (ctx->n > 0) { k_refresh_geo<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
   k_hmax_finish<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   return 0;
@@ -442,7 +457,7 @@ extern "C" int psph_mom_engr_update(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (launch_gather<MomStage>(ctx, KN_GATHER_MOM)) return -1;
+  if (launch_stage_gather<MomStage>(ctx, KN_GATHER_MOM)) return -1;
   return psph_commit_mom(ctx);
 }
 
@@ -454,7 +469,7 @@ extern "C" int psph_smooth_density(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (launch_gather<DensStage>(ctx, KN_GATHER_DENS)) return -1;
+  if (launch_stage_gather<DensStage>(ctx, KN_GATHER_DENS)) return -1;
   k_commit_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   psph_comm_mark(ctx, DIRTY_DENS);
@@ -470,7 +485,7 @@ extern "C" int psph_smooth_velocity(psph_ctx *ctx)
   k_pack_vel<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   psph_comm_mark(ctx, DIRTY_VEL);
-  return launch_gather<VelStage>(ctx, KN_GATHER_VEL);
+  return launch_stage_gather<VelStage>(ctx, KN_GATHER_VEL);
 }
 
 extern "C" int psph_update_pos(psph_ctx *ctx)

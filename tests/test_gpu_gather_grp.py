@@ -1,0 +1,106 @@
+"""-m gpu: the grouped pair gather (csrc/psph_gather3.cuh, the default of the 3-D SPH stages) against
+the oracle and against the per-row gather (csrc/psph_gather.cuh, PSPH_GATHER=row) on inputs that
+reach its rare paths:
+  * a dense cube (h = 1.7 lattice spacings, ~1000 pairs per particle): queues fill up before the scan of
+    a group ends -> early drains with parked partial sums;
+  * two smoothing lengths with hmax > 1.83 h_i: the neighbour-list / in_support limits bite, so every
+    candidate of the small-h rows goes through the FP64 gates;
+  * positions placed exactly ON and one ulp either side of a cutoff face: the FP32 pre-filter must hand
+    them to the FP64 gates (the pair set is bit-exact, so a wrong decision shows up as an O(1e-6) error).
+Both gathers are CUDA; the oracle (CPU) is the checker.
+"""
+import os
+import numpy as np
+import pytest
+
+import plume_sph_b200 as psph
+from plume_sph_b200 import cases
+from plume_sph_b200.solver import ORDER_REFERENCE
+from common import to_oracle_cfg, particles_to_oracle, relerr, RTOL_STAGE
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("vel", "engr", "rho", "mass_frac", "smoothed_v", "pressure")
+
+
+def run_stages(cfg, rows, mode):
+    old = os.environ.get("PSPH_GATHER")
+    if mode:
+        os.environ["PSPH_GATHER"] = mode
+    else:
+        os.environ.pop("PSPH_GATHER", None)
+    try:
+        s = psph.Solver(cfg)
+    finally:
+        if old is None:
+            os.environ.pop("PSPH_GATHER", None)
+        else:
+            os.environ["PSPH_GATHER"] = old
+    s.upload(rows)
+    dt = s.timestep()
+    s.set_dt(dt, 1, 0)
+    s.search_neighs_consth()
+    s.mom_engr_update()
+    s.smooth_density()
+    s.smooth_velocity()
+    bad = s.errors()
+    out = s.download(ORDER_REFERENCE)
+    s.close()
+    return dt, bad, out
+
+
+def oracle_stages(cfg, rows):
+    o = particles_to_oracle(to_oracle_cfg(cfg), rows)
+    o.bin()
+    dt = o.timestep()
+    o.search()
+    o.mom_engr_update(dt)
+    o.smooth_density()
+    o.smooth_velocity()
+    perm = o.table_order()
+    return dt, {"vel": o.a["v"][perm], "engr": o.a["e"][perm], "rho": o.a["rho"][perm], "mass_frac": o.a["ks"][perm],
+                "smoothed_v": o.a["sv"][perm], "pressure": o.a["p"][perm]}
+
+
+def dense_rows(n=20, hfac=1.7, two_h=False, seed=5):
+    cfg, rows = cases.cube(n, seed=seed)
+    real = rows["bc_type"] == 100
+    rows["smlen"] = hfac
+    if two_h:  # erupted material carries a smaller smoothing length (sml_of_phase2)
+        rows["smlen"][rows["phase_num"] == 2] = 0.45 * hfac
+        rows["smlen"][real & (rows["coords"][:, 0] < 6.0)] = 0.5 * hfac
+    return cfg, rows
+
+
+@pytest.mark.parametrize("two_h", [False, True])
+def test_dense_cube_grouped_vs_row_vs_oracle(two_h):
+    cfg, rows = dense_rows(two_h=two_h)
+    dt_g, bad_g, grp = run_stages(cfg, rows, None)
+    dt_r, bad_r, row = run_stages(cfg, rows, "row")
+    assert dt_g == dt_r and bad_g == 0 and bad_r == 0
+    for f in FIELDS:
+        assert relerr(grp[f], row[f]) <= RTOL_STAGE, (f, relerr(grp[f], row[f]))
+    dt_o, ora = oracle_stages(cfg, rows)
+    assert dt_o == dt_g
+    for f in FIELDS:
+        assert relerr(grp[f], ora[f]) <= 3 * RTOL_STAGE, (f, relerr(grp[f], ora[f]))  # three stages in a row
+
+
+def test_pairs_on_the_cutoff_face():
+    """neighbours exactly at |dx| = 3 h, and one ulp inside / outside, along every axis"""
+    cfg, rows = cases.cube(16, seed=3, jitter=0.0, vjit=0.02)
+    real = np.flatnonzero(rows["bc_type"] == 100)
+    rng = np.random.default_rng(11)
+    pos = rows["coords"]
+    # unjittered lattice: every real particle already has neighbours at exactly 3 h along each axis
+    # (|dx|/h == 3 passes the reference's test `fabs(dx/h) > 3`); move a sample by +-1 ulp / +-1e-7 of it
+    pick = rng.choice(real, 600, replace=False)
+    for q, p in enumerate(pick):
+        k = q % 3
+        x = pos[p, k]
+        pos[p, k] = [np.nextafter(x, np.inf), np.nextafter(x, -np.inf), x + 3e-8, x - 3e-8][(q // 3) % 4]
+    dt_g, bad_g, grp = run_stages(cfg, rows, None)
+    dt_o, ora = oracle_stages(cfg, rows)
+    assert bad_g == 0 and dt_o == dt_g
+    for f in FIELDS:
+        assert relerr(grp[f], ora[f]) <= 3 * RTOL_STAGE, (f, relerr(grp[f], ora[f]))

@@ -109,7 +109,7 @@ __device__ __forceinline__ float row_flags(DevView &V, const GridView &G, const 
   double h = V.t.d[D_H][p];
   V.t.d[D_HLIST][p] = h;
   V.geo[p] = make_double4(x[0], x[1], x[2], h);
-  const float xm = dev_store_geo32(V.geo32, K, p, x[0], x[1], x[2], h);
+  const float xm = dev_store_geo32(V.geo32, K, p, x[0], x[1], x[2], h, ss->hmax);
   unsigned long long pk = 0;
   if (G.dim == 3) {
     // subcell of the row inside the bucket it is a member of (the same function the sort key uses),
@@ -218,6 +218,7 @@ int psph_build_cell_list(psph_ctx *ctx)
     if (ctx->has_grad && select_rows(ctx, n_cap, F_GRADROW, ctx->cur.grad_idx, &ctx->d_ss->n_grad)) return -1;
   }
   ctx->list_valid = true;
+  ctx->nbr_valid = false;
   ctx->n_dirty = true;
   return 0;
 }

@@ -185,6 +185,13 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->gather_mode = (gm && !strcmp(gm, "row")) ? 1 : 0;
     const char *gw = getenv("PSPH_GWARPS");
     ctx->gather_warps = gw ? atoi(gw) : 0;
+    const char *gp = getenv("PSPH_GPF");
+    ctx->gather_pf = gp ? atoi(gp) : -1;
+    const char *lw = getenv("PSPH_LWARPS");
+    ctx->list_warps = lw ? atoi(lw) : 0;
+    const char *nb = getenv("PSPH_NBR");
+    ctx->nbr_mode = nb ? atoi(nb) : 1;
+    ctx->nbr_units = 0; ctx->nbr_valid = false;
   }
   ctx->timing = 0; memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
   *out = ctx;
@@ -229,7 +236,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   free_tab(ctx->cur.t); free_tab(ctx->alt);
   for (int c = 0; c < NSCRATCH; c++) cudaFree(ctx->cur.scr[c]);
   for (int c = 0; c < NREC; c++) cudaFree(ctx->cur.rec[c]);
-  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
+  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
   cudaFree(ctx->d_cell_has_ghost);
@@ -295,6 +302,9 @@ int psph_reserve(psph_ctx *ctx, size_t rows)
   for (int c = 0; c < NREC; c++) if (grow(ctx, ctx->cur.rec[c], 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.geo, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.geo32, 0, ncap)) return -1;
+  if (grow(ctx, ctx->cur.nbr_off, 0, ncap)) return -1;
+  if (grow(ctx, ctx->cur.nbr_cnt, 0, ncap)) return -1;
+  ctx->nbr_valid = false;
   if (grow(ctx, ctx->cur.flags, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.gsub, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.need_idx, 0, ncap)) return -1;

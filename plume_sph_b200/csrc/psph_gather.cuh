@@ -40,6 +40,22 @@ __device__ __forceinline__ double warp_sum(double v)
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// four sums at once: two exchange steps that halve the number of live values, then a three-step tree
+// (9 shuffles of doubles instead of 20); every lane returns all four totals
+__device__ __forceinline__ void warp_sum4(double &a, double &b, double &c, double &d, int lane)
+{
+  const bool hi16 = lane & 16, hi8 = lane & 8;
+  double k0 = hi16 ? b : a, t0 = hi16 ? a : b;      // lanes < 16 keep a, lanes >= 16 keep b
+  double k1 = hi16 ? d : c, t1 = hi16 ? c : d;
+  k0 += __shfl_xor_sync(FULL, t0, 16);
+  k1 += __shfl_xor_sync(FULL, t1, 16);
+  double k = hi8 ? k1 : k0, t = hi8 ? k0 : k1;      // bit 3 clear: a/b, set: c/d
+  k += __shfl_xor_sync(FULL, t, 8);
+  k += __shfl_xor_sync(FULL, k, 4);
+  k += __shfl_xor_sync(FULL, k, 2);
+  k += __shfl_xor_sync(FULL, k, 1);
+  a = __shfl_sync(FULL, k, 0); b = __shfl_sync(FULL, k, 16); c = __shfl_sync(FULL, k, 8); d = __shfl_sync(FULL, k, 24);
+}
 __device__ __forceinline__ int warp_sum_i(int v)
 {
 #pragma unroll
@@ -112,22 +128,28 @@ __device__ __forceinline__ double dev_rcp(double x)
   e = fma(-x, r, 1.0);
   return fma(r, e, r);
 }
+// polynomial coefficients as constant-bank operands (no per-use 64-bit immediate moves)
+__constant__ double c_exp[14] = { 1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01, -2.31904681384629956e-17,
+                                  1.66666666666664770e-01, 5.00000000000001221e-01, 8.33333333345504315e-03,
+                                  4.16666666665197541e-02, 1.98412695891154973e-04, 1.38888889459163798e-03,
+                                  2.75575145458824386e-06, 2.48014910390991645e-05, 2.50223225365029900e-08,
+                                  2.76309034881731077e-07 };
 // exp(x) for -700 < x <= 0 (the kernel exponent is >= -27): k = rint(x*log2 e), r = x - k ln 2,
 // degree-11 polynomial in Estrin form, scaled by 2^k through the exponent field
 __device__ __forceinline__ double dev_exp_neg(double x)
 {
-  const double kd0 = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const double kd0 = fma(x, c_exp[0], c_exp[1]);
   const int k = __double2loint(kd0);
-  const double kd = kd0 - 6755399441055744.0;
-  double r = fma(kd, -6.93147180559945286e-01, x);   // ln 2 split hi + lo
-  r = fma(kd, -2.31904681384629956e-17, r);
+  const double kd = kd0 - c_exp[1];
+  double r = fma(kd, c_exp[2], x);   // ln 2 split hi + lo
+  r = fma(kd, c_exp[3], r);
   const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
   const double p01 = r + 1.0;
-  const double p23 = fma(r, 1.66666666666664770e-01, 5.00000000000001221e-01);
-  const double p45 = fma(r, 8.33333333345504315e-03, 4.16666666665197541e-02);
-  const double p67 = fma(r, 1.98412695891154973e-04, 1.38888889459163798e-03);
-  const double p89 = fma(r, 2.75575145458824386e-06, 2.48014910390991645e-05);
-  const double pab = fma(r, 2.50223225365029900e-08, 2.76309034881731077e-07);
+  const double p23 = fma(r, c_exp[4], c_exp[5]);
+  const double p45 = fma(r, c_exp[6], c_exp[7]);
+  const double p67 = fma(r, c_exp[8], c_exp[9]);
+  const double p89 = fma(r, c_exp[10], c_exp[11]);
+  const double pab = fma(r, c_exp[12], c_exp[13]);
   const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
   const double p = fma(r8, q2, fma(r4, q1, q0));
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));

@@ -25,20 +25,26 @@
 
 constexpr int GRP = 4;          // rows per group
 constexpr int GQCAP = 320;      // queue slots per row of the group (multiple of 32, >= 64 + 32)
+constexpr int GQCAP_SCAN = 384; // ... of the scan-only kernel (LM 3), which cannot drain a queue
 constexpr int GCAND = 512;      // candidate rows expanded per batch
 constexpr int RPWG = 32;        // consecutive list entries per warp and chunk
+constexpr unsigned NBR_BLOCK = 512; // pair-list units a warp takes from the global cursor at a time
 constexpr int GNA = 4;          // accumulators per lane (every stage's A is four doubles)
 
-struct GrpScratch
+struct GrpHdr
 {
-  int cand[GCAND];              // candidate row << 1 | own-bucket flag
-  int q[GRP][GQCAP];            // rows that passed the gates, per row of the group
-  int hdr_i[GRP];               // the rows of the group
-  int hdr_n[GRP];               // queued pairs per row
   // what the FP64 gate needs (rare path): kept here so that the call carries no kernel parameters
   double kc[3];                 // cutoff, cutoff2, neigh_radius
   const double4 *geo;
   const double *hlist;
+  int hdr_i[GRP];               // the rows of the group
+  int hdr_n[GRP];               // queued pairs per row
+};
+template <int QC>
+struct GrpScratch : GrpHdr
+{
+  int cand[GCAND];              // candidate row << 1 | own-bucket flag
+  int q[GRP][QC];               // rows that passed the gates, per row of the group
 };
 
 __device__ __forceinline__ float4 ld_rec32(const float4 *__restrict__ a, int j)
@@ -52,7 +58,7 @@ __device__ __forceinline__ float4 ld_rec32(const float4 *__restrict__ a, int j)
 // bandb: kernel cutoff |dx_k / h| <= cutoff (sph_lib.cc:216-218), list gate (own bucket, else
 // |dx_k| <= 4.25 h_i(list), neighs.cc:84-92,130) and in_support(dx, CUTOFF2 h_i) (sph_header.h:49-60).
 // Returns okb with the bits of the rows that fail cleared.  Rare path, kept out of line.
-__device__ __noinline__ unsigned gate_exact_grp(const GrpScratch *scr, unsigned okb, unsigned bandb, int cj, int sym)
+__device__ __noinline__ unsigned gate_exact_grp(const GrpHdr *scr, unsigned okb, unsigned bandb, int cj, int sym)
 {
   const double cutoff = scr->kc[0], cutoff2 = scr->kc[1], nradius = scr->kc[2];
   const double4 gj = scr->geo[cj >> 1];
@@ -76,7 +82,13 @@ __device__ __noinline__ unsigned gate_exact_grp(const GrpScratch *scr, unsigned 
 // Stage interface: as psph_gather.cuh, plus
 //   kWarpsGrp            warps per CTA of the grouped kernel (one CTA per SM)
 //   double reach_h(K,h,hmax)  half-width of the candidate box of a row with smoothing length h
-template <class S, int WARPS>
+//   struct R / load / pair_r  the stage records of row j, loaded apart from the pair body
+// PF: 1 = the records of the next pair round are loaded one round ahead (registers).
+// LM (pair lists, see k_gather_list): 0 = none; 3 = scan only: when the scan of a group ends, the queue of every
+// row that qualifies (queue did not overflow, standard smoothing length in the whole candidate box, list space
+// left) is written to the global pair list, the other rows are marked and NO pairs are summed here; 1 = the same,
+// but rows that do not qualify are summed in place; 2 = rows that have a list are skipped (the fused fallback).
+template <class S, int WARPS, int PF, int LM, int QC>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict__ spill)
 {
@@ -84,7 +96,7 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
   constexpr int CHUNK = WARPS * RPWG;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  GrpScratch *scr = reinterpret_cast<GrpScratch *>(s_raw) + warp;
+  GrpScratch<QC> *scr = reinterpret_cast<GrpScratch<QC> *>(s_raw) + warp;
   // window addresses of the warp's scratch; the volatile move keeps the compiler from re-deriving them
   // from the thread index at every access
   unsigned s_cand, s_q, s_hdr;
@@ -96,14 +108,17 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
     scr->geo = V.geo; scr->hlist = V.t.d[D_HLIST];
   }
   __syncwarp();
+  if (LM == 2 && ss->n_uncached == 0) return;
   const int cnt = ss->n_need;
   const int32_t *__restrict__ rows = V.need_idx;
   const double hmax = ss->hmax;
   // FP32 decision band: coordinates are rounded to FP32 relative to the mesh origin (error <= 2^-24 xmax
   // each), the limit is formed in FP32 (a few ulp) -> band of +-(2^-19 b + 2^-21 xmax) around the face
   const float delta = __uint_as_float(ss->xmax_bits) * 0x1p-21f;
+  const float hstd_f = (float) hmax;
   const float ch = (float) (S::kSymH ? 0.5 * K.cutoff : K.cutoff);
   const float c_lo = ch * (1.0f - 0x1p-19f), c_hi = ch * (1.0f + 0x1p-19f);
+  unsigned wcur = 0, wend = 0;      // LM 1: this warp's block of pair-list space (32-entry units)
   double *__restrict__ my_spill = spill + (size_t) (blockIdx.x * WARPS + warp) * (GRP * GNA * 32) + lane;
   const int nsubx = G.ncell[0] * SUBDIV - 1, nsuby = G.ncell[1] * SUBDIV - 1, nsubz = G.ncell[2] * SUBDIV - 1;
 
@@ -119,9 +134,15 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
         pk = V.gsub[row];
         cell = V.t.i[I_CELL][row];
       }
+      bool cached = false;
+      if (LM == 2) {
+        cached = row >= 0 && V.nbr_cnt[row] >= 0;
+        const unsigned cm = __ballot_sync(FULL, cached);
+        if (cm & 1u) { e += __ffs(~cm) - 1; continue; } // leading rows with a cached list: done elsewhere
+      }
       const unsigned long long pk0 = __shfl_sync(FULL, pk, 0);
       const int cell0 = __shfl_sync(FULL, cell, 0);
-      const bool same = row >= 0 && cell == cell0 && ((pk ^ pk0) & 0xffffffffffull) == 0;
+      const bool same = row >= 0 && !cached && cell == cell0 && ((pk ^ pk0) & 0xffffffffffull) == 0;
       const int m = __ffs(~__ballot_sync(FULL, same)) - 1; // 1..GRP
       const bool mine = lane < m;
       float4 p32 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -140,6 +161,10 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
       const int kRg = __reduce_max_sync(FULL, kR);
       const int zlo = __reduce_min_sync(FULL, mine ? sz : 0x7fffffff), zhi = __reduce_max_sync(FULL, mine ? sz : -1);
       const unsigned nlmask = __ballot_sync(FULL, nl);
+      const unsigned stdmask = (LM == 1 || LM == 3) ? __ballot_sync(FULL, mine && p32.w == hstd_f) : 0u;
+      bool nonstd = false;            // LM 1: a candidate of the box has another smoothing length
+      bool guni = false;
+      unsigned ovf = 0;               // LM 3: rows whose queue overflowed
       int ig[GRP];
       unsigned qa[GRP];               // window address of the next free slot of every queue
       float fx[GRP], fy[GRP], fz[GRP], blo[GRP], bhi[GRP];
@@ -151,7 +176,7 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
         // a row whose list / in_support limits can bite sends every candidate through the FP64 gates
         blo[g] = ((nlmask >> g) & 1u) ? -INFINITY : hf * c_lo - delta;
         bhi[g] = hf * c_hi + delta;
-        qa[g] = s_q + 4u * GQCAP * g;
+        qa[g] = s_q + 4u * QC * g;
       }
       // ---- candidate enumeration state (the group's common box, in global subcell coordinates)
       const int sx = (int) (pk0 & 0xfffff), sy = (int) ((pk0 >> 20) & 0xfffff);
@@ -168,6 +193,7 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
       auto test = [&](int cj, const float4 &p) {
         const int j = cj >> 1;
         const float hlo = S::kSymH ? p.w * c_lo : 0.f, hhi = S::kSymH ? p.w * c_hi : 0.f;
+        if (LM == 1 || LM == 3) nonstd |= p.w != hstd_f;
         unsigned okb = 0, bandb = 0;
 #pragma unroll
         for (int g = 0; g < GRP; g++) {
@@ -191,6 +217,15 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
             qa[g] += 4u * __popc(b);
           }
         }
+      };
+
+      auto fetch = [&](int c, int &ja, int &jb, float4 &pa, float4 &pb) {
+        const int ca = c + lane, cb = ca + 32;
+        const bool la = ca < total, lb = cb < total;
+        ja = la ? lds32(s_cand + 4u * ca) : 0; jb = lb ? lds32(s_cand + 4u * cb) : 0;
+        pa = ld_rec32(V.geo32, ja >> 1); pb = ld_rec32(V.geo32, jb >> 1);
+        if (!la) { pa.x = INFINITY; if (LM == 1 || LM == 3) pa.w = hstd_f; }
+        if (!lb) { pb.x = INFINITY; if (LM == 1 || LM == 3) pb.w = hstd_f; }
       };
 
       for (bool done = false; !done;) {
@@ -245,23 +280,27 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
           }
 #pragma unroll
           for (int g = 0; g < GRP; g++)
-            if (qa[g] > s_q + 4u * (GQCAP * g + GQCAP - 64)) gsel = g;
+            if (qa[g] > s_q + 4u * (QC * g + QC - 64)) gsel = g;
           if (gsel >= 0) break;
           // two candidates per lane, both loads in flight
-          const int ca = c0 + lane, cb = ca + 32;
-          const bool la = ca < total, lb = cb < total;
-          const int ja = la ? lds32(s_cand + 4u * ca) : 0, jb = lb ? lds32(s_cand + 4u * cb) : 0;
-          float4 pa = ld_rec32(V.geo32, ja >> 1), pb = ld_rec32(V.geo32, jb >> 1);
-          if (!la) pa.x = INFINITY;
-          if (!lb) pb.x = INFINITY;
-          test(ja, pa);
-          if (c0 + 32 < total) test(jb, pb);
+          int ja, jb;
+          float4 pa, pb;
+          fetch(c0, ja, jb, pa, pb);
+          const bool two = c0 + 32 < total;
           c0 += 64;
+          test(ja, pa);
+          if (two) test(jb, pb);
+        }
+        if (LM == 3 && gsel >= 0) { // no pair phase here: the row's list is dropped, the fused kernel takes the row
+#pragma unroll
+          for (int g = 0; g < GRP; g++)
+            if (g == gsel) { ovf |= 1u << g; qa[g] = s_q + 4u * QC * g; bhi[g] = -INFINITY; }
+          continue;
         }
         done = gsel < 0;
         if (lane == 0) {
 #pragma unroll
-          for (int g = 0; g < GRP; g++) sts32(s_hdr + 16u + 4u * g, (int) (qa[g] - (s_q + 4u * GQCAP * g)) >> 2);
+          for (int g = 0; g < GRP; g++) sts32(s_hdr + 16u + 4u * g, (int) (qa[g] - (s_q + 4u * QC * g)) >> 2);
         }
         __syncwarp();
 
@@ -269,6 +308,38 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
         const int g0 = done ? 0 : gsel, g1 = done ? m : gsel + 1;
         for (int g = g0; g < g1; g++) {
           const int i = lds32(s_hdr + 4u * g), n = lds32(s_hdr + 16u + 4u * g);
+          if ((LM == 1 || LM == 3) && done) {
+            // publish the row's pair list and leave its pairs to k_gather_list when the row qualifies: queue
+            // complete, its own h the standard one and so that of every candidate of the group's box
+            // (geo32.w == (float) hmax  <=>  h == hmax, see dev_store_geo32), list space left
+            if (g == g0) guni = !__any_sync(FULL, nonstd);
+            int off = -1;
+            if (guni && !(((drained | ovf) >> g) & 1u) && ((stdmask >> g) & 1u)) {
+              const unsigned units = (unsigned) (n + 31) >> 5;
+              if (wcur + units > wend) { // next block of list space for this warp
+                unsigned o = 0;
+                if (lane == 0) o = atomicAdd(&ss->nbr_cursor, NBR_BLOCK);
+                o = __shfl_sync(FULL, o, 0);
+                const unsigned cap = ss->nbr_cap;
+                wcur = min(o, cap); wend = min(o + NBR_BLOCK, cap);
+                if (o + NBR_BLOCK < o) wcur = wend = cap;
+              }
+              if (wcur + units <= wend) { off = (int) wcur; wcur += units; }
+            }
+            if (lane == 0) {
+              V.nbr_off[i] = off;
+              V.nbr_cnt[i] = off >= 0 ? n : -1;
+              if (off < 0) atomicAdd(&ss->n_uncached, 1);
+            }
+            if (off >= 0) {
+              int32_t *__restrict__ dst = V.nbr + (size_t) (unsigned) off * 32u;
+              const unsigned qb = s_q + 4u * QC * g;
+              for (int k = lane; k < n; k += 32) dst[k] = lds32(qb + 4u * k);
+              continue;
+            }
+            if (LM == 3) continue;
+          }
+          if (LM == 3) continue; // (never reached: the scan-only kernel has no pair phase)
           typename S::I st;
           S::init(V, K, ss, i, st);
           const double4 gi = V.geo[i];
@@ -279,13 +350,31 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
 #pragma unroll
             for (int k = 0; k < GNA; k++) ap[k] = my_spill[(g * GNA + k) * 32];
           }
-          const unsigned qg = s_q + 4u * GQCAP * g;
-          const int nrun = done ? n : (n & ~31);
-          for (int q0 = 0; q0 < nrun; q0 += 32) {
-            if (q0 + lane < nrun) {
-              const int j = lds32(qg + 4u * (q0 + lane));
-              const double4 gj = ld_rec(V.geo, j);
-              S::pair(V, K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, j);
+          const unsigned qg = s_q + 4u * QC * g + 4u * lane;
+          const int nfull = done ? n : (n & ~31);
+          const int nrun = nfull - lane;                    // entries left for this lane's slot
+          // software pipeline: the row index of the next round is read one round ahead; PF: its records are
+          // loaded one round ahead as well (registers), so that a round never waits for its own loads
+          int jn = 0 < nrun ? lds32(qg) : -1;
+          if (PF == 1) {
+            double4 gn = ld_rec(V.geo, jn < 0 ? i : jn);
+            typename S::R rn = S::load(V, jn < 0 ? i : jn);
+            for (int q0 = 0; q0 < nfull; q0 += 32) {
+              const int j = jn;
+              const double4 gj = gn;
+              const typename S::R rj = rn;
+              jn = q0 + 32 < nrun ? lds32(qg + 4u * (q0 + 32)) : -1;
+              if (q0 + 32 < nfull) { gn = ld_rec(V.geo, jn < 0 ? i : jn); rn = S::load(V, jn < 0 ? i : jn); }
+              if (j >= 0) S::pair_r(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
+            }
+          } else {
+            for (int q0 = 0; q0 < nfull; q0 += 32) {
+              const int j = jn;
+              jn = q0 + 32 < nrun ? lds32(qg + 4u * (q0 + 32)) : -1;
+              if (j >= 0) {
+                const double4 gj = ld_rec(V.geo, j);
+                S::pair(V, K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, j);
+              }
             }
           }
           if (done) {
@@ -294,14 +383,14 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
 #pragma unroll
             for (int k = 0; k < GNA; k++) my_spill[(g * GNA + k) * 32] = ap[k];
             drained |= 1u << g;
-            const int rem = n - nrun;
+            const int rem = n - nfull;
             int v = 0;
-            if (lane < rem) v = lds32(qg + 4u * (nrun + lane));
+            if (lane < rem) v = lds32(qg + 4u * nfull);
             __syncwarp();
-            if (lane < rem) sts32(qg + 4u * lane, v);
+            if (lane < rem) sts32(qg, v);
             __syncwarp();
 #pragma unroll
-            for (int gg = 0; gg < GRP; gg++) if (gg == g) qa[gg] = s_q + 4u * (GQCAP * gg + rem);
+            for (int gg = 0; gg < GRP; gg++) if (gg == g) qa[gg] = s_q + 4u * (QC * gg + rem);
           }
         }
       }
@@ -311,15 +400,16 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
   }
 }
 
-template <class S, int WARPS>
+template <class S, int WARPS, int PF, int LM>
 int launch_gather_grp_w(psph_ctx *ctx, int kid)
 {
   static_assert(sizeof(typename S::A) == GNA * sizeof(double), "grouped gather: four accumulators per stage");
+  constexpr int QC = LM == 3 ? GQCAP_SCAN : GQCAP;
   constexpr int threads = WARPS * 32;
-  constexpr size_t smem = sizeof(GrpScratch) * WARPS;
+  constexpr size_t smem = sizeof(GrpScratch<QC>) * WARPS;
   static bool attr_set = false;
   if (!attr_set) {
-    PSPH_CUDA(cudaFuncSetAttribute(k_gather_grp<S, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    PSPH_CUDA(cudaFuncSetAttribute(k_gather_grp<S, WARPS, PF, LM, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_set = true;
   }
   const size_t spill_rows = (size_t) ctx->sms * 32 * GRP * GNA * 32; // up to 32 warps per CTA, one CTA per SM
@@ -327,18 +417,118 @@ int launch_gather_grp_w(psph_ctx *ctx, int kid)
   KernelTimer kt(ctx, kid);
   const int nchunks = (ctx->n + WARPS * RPWG - 1) / (WARPS * RPWG);
   const int grid = min(max(nchunks, 1), ctx->sms);
-  k_gather_grp<S, WARPS><<<grid, threads, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_gspill);
+  k_gather_grp<S, WARPS, PF, LM, QC><<<grid, threads, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_gspill);
   PSPH_LAUNCH_CHECK();
   return 0;
 }
-// warps per CTA: the stage's default, or PSPH_GWARPS (tuning switch: 12, 16, 20, 24)
+// lm: 0 plain, 3 find the pairs and write the lists only, 2 only rows without a list.  Warps per CTA and record prefetch:
+// the stage's defaults, or PSPH_GWARPS / PSPH_GPF (tuning switches; list modes always run the defaults)
 template <class S>
-int launch_gather_grp(psph_ctx *ctx, int kid)
+int launch_gather_grp(psph_ctx *ctx, int kid, int lm)
 {
-  switch (ctx->gather_warps ? ctx->gather_warps : S::kWarpsGrp) {
-  case 12: return launch_gather_grp_w<S, 12>(ctx, kid);
-  case 16: return launch_gather_grp_w<S, 16>(ctx, kid);
-  case 20: return launch_gather_grp_w<S, 20>(ctx, kid);
-  default: return launch_gather_grp_w<S, 24>(ctx, kid);
+  if (lm == 3) {
+    if (ctx->gather_warps == 16) return launch_gather_grp_w<S, 16, 0, 3>(ctx, kid);
+    if (ctx->gather_warps == 20) return launch_gather_grp_w<S, 20, 0, 3>(ctx, kid);
+    return launch_gather_grp_w<S, 24, 0, 3>(ctx, kid);
+  }
+  if (lm == 2) return launch_gather_grp_w<S, S::kWarpsGrp, S::kPfGrp, 2>(ctx, kid);
+  const int w = (ctx->gather_warps ? ctx->gather_warps : S::kWarpsGrp) + 100 * (ctx->gather_pf >= 0 ? ctx->gather_pf : S::kPfGrp);
+  switch (w) {
+  case 16: return launch_gather_grp_w<S, 16, 0, 0>(ctx, kid);
+  case 20: return launch_gather_grp_w<S, 20, 0, 0>(ctx, kid);
+  case 24: return launch_gather_grp_w<S, 24, 0, 0>(ctx, kid);
+  case 116: return launch_gather_grp_w<S, 16, 1, 0>(ctx, kid);
+  case 120: return launch_gather_grp_w<S, 20, 1, 0>(ctx, kid);
+  case 124: return launch_gather_grp_w<S, 24, 1, 0>(ctx, kid);
+  default: ctx->err = "PSPH_GWARPS / PSPH_GPF: no such grouped-gather variant"; return -2;
+  }
+}
+
+// =========================================================================================
+// Pair-list gather.  Between mom_engr_update, smooth_density and smooth_velocity of one time step neither
+// positions nor smoothing lengths nor the row order change, so the three stages sum over the SAME pairs
+// whenever every partner j of row i has h_j == h_i (then 0.5 (h_i + h_j) == h_i bit for bit and the
+// symmetric-h gates of mom/dens equal the h_i gates of the velocity filter; the self pair, which only
+// mom_engr_update skips, is not in the list and is added by the stages that count it).  The first stage
+// writes those rows' queues to a global list (LM 1 above); the later stages run one warp per row straight
+// off the list - no enumeration, no gates, no shared memory - and rows without a list fall back to the
+// grouped gather (LM 2).  The list lives for one time step and only when memory allows.
+// =========================================================================================
+constexpr int RPWL = 16;       // consecutive list entries per warp and chunk
+
+template <class S, int WARPS, int PF>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParams K, StepState *ss)
+{
+  constexpr int CHUNK = WARPS * RPWL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cnt = ss->n_need;
+  const int32_t *__restrict__ rows = V.need_idx;
+  for (int chunk = blockIdx.x; chunk * CHUNK < cnt; chunk += gridDim.x) {
+    const int e0 = chunk * CHUNK + warp * RPWL;
+    for (int r = 0; r < RPWL; r++) {
+      if (e0 + r >= cnt) break;
+      const int i = __ldg(&rows[e0 + r]);
+      const int n = V.nbr_cnt[i];
+      if (n < 0) continue;                       // no cached list: the grouped gather takes the row
+      const int32_t *__restrict__ lst = V.nbr + (size_t) (unsigned) V.nbr_off[i] * 32u + lane;
+      typename S::I st;
+      S::init(V, K, ss, i, st);
+      const double4 gi = V.geo[i];
+      typename S::A acc;
+      S::begin(K, st, acc, 0);
+      // entry k of the row: list[k] for k < n, then (stages that count it) the self pair, which the list omits
+      const int ntot = n + (S::kSkipSelf ? 0 : 1);
+      auto entry = [&](int k) { return k < n ? __ldg(lst + (k - lane)) : (k < ntot ? i : -1); };
+      int jn = entry(lane);
+      if (PF == 1) {
+        double4 gn = ld_rec(V.geo, jn < 0 ? i : jn);
+        typename S::R rn = S::load(V, jn < 0 ? i : jn);
+        for (int q0 = 0; q0 < ntot; q0 += 32) {
+          const int j = jn;
+          const double4 gj = gn;
+          const typename S::R rj = rn;
+          jn = entry(q0 + 32 + lane);
+          if (q0 + 32 < ntot) { gn = ld_rec(V.geo, jn < 0 ? i : jn); rn = S::load(V, jn < 0 ? i : jn); }
+          if (j >= 0) S::pair_r(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
+        }
+      } else {
+        for (int q0 = 0; q0 < ntot; q0 += 32) {
+          const int j = jn;
+          jn = entry(q0 + 32 + lane);
+          if (j >= 0) {
+            const double4 gj = ld_rec(V.geo, j);
+            S::pair(V, K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, j);
+          }
+        }
+      }
+      S::end(V, K, ss, i, st, acc, 0, lane);
+    }
+  }
+}
+
+template <class S, int WARPS, int PF>
+int launch_gather_list_w(psph_ctx *ctx, int kid)
+{
+  KernelTimer kt(ctx, kid);
+  const int nchunks = (ctx->n + WARPS * RPWL - 1) / (WARPS * RPWL);
+  const int grid = min(max(nchunks, 1), ctx->sms);
+  k_gather_list<S, WARPS, PF><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->cur, ctx->kp, ctx->d_ss);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+template <class S>
+int launch_gather_list(psph_ctx *ctx, int kid)
+{
+  const int w = (ctx->list_warps ? ctx->list_warps : S::kWarpsList) + 100 * (ctx->gather_pf >= 0 ? ctx->gather_pf : S::kPfList);
+  switch (w) {
+  case 16: return launch_gather_list_w<S, 16, 0>(ctx, kid);
+  case 20: return launch_gather_list_w<S, 20, 0>(ctx, kid);
+  case 24: return launch_gather_list_w<S, 24, 0>(ctx, kid);
+  case 32: return launch_gather_list_w<S, 32, 0>(ctx, kid);
+  case 116: return launch_gather_list_w<S, 16, 1>(ctx, kid);
+  case 120: return launch_gather_list_w<S, 20, 1>(ctx, kid);
+  case 124: return launch_gather_list_w<S, 24, 1>(ctx, kid);
+  case 132: return launch_gather_list_w<S, 32, 1>(ctx, kid);
+  default: ctx->err = "PSPH_LWARPS / PSPH_GPF: no such list-gather variant"; return -2;
   }
 }

@@ -4,6 +4,7 @@
 // include/psph.h.  Pair sums run on the warp gather of psph_gather.cuh.
 #include "psph_gather3.cuh"
 #include <cstring>
+#include <algorithm>
 
 // =========================================================================================
 // timestep  (src/plume/timestep.cc:95-135 3-D, :140-183 1-D): dt = CFL * min_i h_i / c_i over
@@ -36,18 +37,21 @@ __global__ void k_timestep_finish(KParams K, StepState *ss, double *dt_cfl_out)
 // =========================================================================================
 // stage records (32-byte rows read by the pair loops with 128-bit loads)
 // =========================================================================================
+__global__ void k_hmax_scan(Tab V, StepState *ss)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double h = p < ss->n ? V.d[D_H][p] : 0.0;
+  for (int o = 16; o; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
+  if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
+}
 __global__ void k_refresh_geo(DevView V, KParams K, StepState *ss)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  double h = 0.0;
-  if (p < ss->n) {
-    h = V.t.d[D_H][p];
-    const double x = V.t.d[D_X][p], y = V.t.d[D_Y][p], z = V.t.d[D_Z][p];
-    V.geo[p] = make_double4(x, y, z, h);
-    dev_store_geo32(V.geo32, K, p, x, y, z, h); // positions are those of the list build: xmax_bits still bounds them
-  }
-  for (int o = 16; o; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
-  if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
+  if (p >= ss->n) return;
+  const double h = V.t.d[D_H][p];
+  const double x = V.t.d[D_X][p], y = V.t.d[D_Y][p], z = V.t.d[D_Z][p];
+  V.geo[p] = make_double4(x, y, z, h);
+  dev_store_geo32(V.geo32, K, p, x, y, z, h, ss->hmax); // positions are those of the list build: xmax_bits still bounds them
 }
 __global__ void k_hmax_reset(StepState *ss) { ss->hmax_bits = 0ull; }
 __global__ void k_hmax_finish(StepState *ss) { ss->hmax = __longlong_as_double((long long) ss->hmax_bits); }
@@ -100,7 +104,7 @@ template <int DIM>
 struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24;
+  static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 24, kPfList = 0, kNRec = 1;
   struct I { double h, supp, hk; };
   struct A { double rho1, rho2, wn, en; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
@@ -113,12 +117,18 @@ struct DensStage
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double hmax)
   { return fmin(K.cutoff * 0.5 * (s.h + hmax), s.supp); }
   static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.rho1 = a.rho2 = a.wn = a.en = 0.0; }
+  struct R { double4 r0; };                                          // the stage record of row j
+  static __device__ __forceinline__ R load(const DevView &V, int j) { R r; r.r0 = ld_rec(V.rec[0], j); return r; }
+  static __device__ __forceinline__ void zero(R &r) { r.r0 = make_double4(0., 0., 0., 0.); }  // a row that adds exact zeros
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
+  { pair_r(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
+                                                const R &rec)
   {
     const double h = 0.5 * (s.h + hj);                              // :155
     const double r2 = dx * dx + dy * dy + dz * dz, invh = dev_rcp(h);
-    const double4 rj = ld_rec(V.rec[0], j);
+    const double4 rj = rec.r0;
     const double wm = dev_weight_in<DIM>(r2, invh) * rj.x;
     const bool ph2 = rj.w != 0.0;                                   // phase of j
     a.rho2 += ph2 ? wm : 0.0;
@@ -134,7 +144,8 @@ struct DensStage
   }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *ss, int i, I &, A &a, int, int lane)
   {
-    const double r1 = warp_sum(a.rho1), r2 = warp_sum(a.rho2), wn = warp_sum(a.wn), en = warp_sum(a.en);
+    double r1 = a.rho1, r2 = a.rho2, wn = a.wn, en = a.en;
+    warp_sum4(r1, r2, wn, en, lane);
     if (lane == 0) {
       const double rho = r1 + r2;                                   // :268-273
       V.scr[0][i] = rho;
@@ -171,7 +182,7 @@ template <int DIM>
 struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kWarps = 16, kWarpsGrp = 16;
+  static constexpr int kRows = F_NEED, kWarps = 16, kWarpsGrp = 16, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 16, kPfList = 0, kNRec = 3;
   struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3]; };
   struct A { double rv[3], re; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
@@ -191,12 +202,19 @@ struct MomStage
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double hmax)
   { return fmin(K.cutoff * 0.5 * (s.h + hmax), s.supp); }
   static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.rv[0] = a.rv[1] = a.rv[2] = a.re = 0.0; }
+  struct R { double4 r0, r1, r2; };                                  // the stage records of row j
+  static __device__ __forceinline__ R load(const DevView &V, int j)
+  { R r; r.r0 = ld_rec(V.rec[0], j); r.r1 = ld_rec(V.rec[1], j); r.r2 = ld_rec(V.rec[2], j); return r; }
+  static __device__ __forceinline__ void zero(R &r) { r.r0.x = 0.; }                          // m_j = 0: the pair adds exact zeros
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
+  { pair_r(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
+                                                const R &rec)
   {
     const double h = 0.5 * (s.h + hj);
     const double r2 = dx * dx + dy * dy + dz * dz, invh = dev_rcp(h);
-    const double4 r0 = ld_rec(V.rec[0], j), r1 = ld_rec(V.rec[1], j), uj = ld_rec(V.rec[2], j);
+    const double4 r0 = rec.r0, r1 = rec.r1, uj = rec.r2;
     const double w = dev_weight_in<DIM>(r2, invh);
     const double g = -2.0 * invh * invh * w;                        // dW/dx_k = g * dx_k
     const double vx = s.u[0] - uj.x, vy = s.u[1] - uj.y, vz = s.u[2] - uj.z;
@@ -225,8 +243,8 @@ struct MomStage
   }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *ss, int i, I &s, A &a, int, int lane)
   {
-    const double r0 = warp_sum(a.rv[0]), r1 = DIM == 3 ? warp_sum(a.rv[1]) : 0.0, r2 = DIM == 3 ? warp_sum(a.rv[2]) : 0.0;
-    const double re = warp_sum(a.re);
+    double r0 = a.rv[0], r1 = DIM == 3 ? a.rv[1] : 0.0, r2 = DIM == 3 ? a.rv[2] : 0.0, re = a.re;
+    warp_sum4(r0, r1, r2, re, lane);
     if (lane == 0) {
       const double dt = ss->dt, grav = -K.g;
       double un[3] = { V.t.d[D_VX][i] + dt * r0, V.t.d[D_VY][i] + dt * r1, V.t.d[D_VZ][i] + dt * r2 };
@@ -260,7 +278,7 @@ template <int DIM>
 struct VelStage
 {
   static constexpr bool kSymH = false, kSkipSelf = false, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24;
+  static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 20, kPfGrp = 1, kWarpsScan = 24, kWarpsList = 24, kPfList = 1, kNRec = 1;
   struct I { double h, invh, supp, hk, v[3]; };
   struct A { double dv[3], wn; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double) { return K.cutoff * h; }
@@ -271,10 +289,16 @@ struct VelStage
   }
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double) { return K.cutoff * s.h; }
   static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.dv[0] = a.dv[1] = a.dv[2] = a.wn = 0.0; }
+  struct R { double4 r0; };                                          // the stage record of row j
+  static __device__ __forceinline__ R load(const DevView &V, int j) { R r; r.r0 = ld_rec(V.rec[0], j); return r; }
+  static __device__ __forceinline__ void zero(R &r) { r.r0 = make_double4(0., 0., 0., 0.); }  // a row that adds exact zeros
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
-                                              double dz, double, int j)
+                                              double dz, double hj, int j)
+  { pair_r(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double,
+                                                const R &rec)
   {
-    const double4 rj = ld_rec(V.rec[0], j);
+    const double4 rj = rec.r0;
     const double mvw = dev_weight_in<DIM>(dx * dx + dy * dy + dz * dz, s.invh) * rj.x;
     a.dv[0] += mvw * (rj.y - s.v[0]);
     if (DIM == 3) { a.dv[1] += mvw * (rj.z - s.v[1]); a.dv[2] += mvw * (rj.w - s.v[2]); }
@@ -282,12 +306,13 @@ struct VelStage
   }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &, StepState *ss, int i, I &s, A &a, int, int lane)
   {
-    const double d0 = warp_sum(a.dv[0]), d1 = DIM == 3 ? warp_sum(a.dv[1]) : 0.0, d2 = DIM == 3 ? warp_sum(a.dv[2]) : 0.0;
-    const double wn = warp_sum(a.wn);
+    double d0 = a.dv[0], d1 = DIM == 3 ? a.dv[1] : 0.0, d2 = DIM == 3 ? a.dv[2] : 0.0, wn = a.wn;
+    warp_sum4(d0, d1, d2, wn, lane);
     if (lane == 0) {
       if (!(wn > 0)) atomicAdd(&ss->bad, 1);
-      V.t.d[D_SVX][i] = s.v[0] + d0 / wn;
-      if (DIM == 3) { V.t.d[D_SVY][i] = s.v[1] + d1 / wn; V.t.d[D_SVZ][i] = s.v[2] + d2 / wn; }
+      const double rw = 1.0 / wn;
+      V.t.d[D_SVX][i] = s.v[0] + d0 * rw;
+      if (DIM == 3) { V.t.d[D_SVY][i] = s.v[1] + d1 * rw; V.t.d[D_SVZ][i] = s.v[2] + d2 * rw; }
     }
     return false;
   }
@@ -360,11 +385,54 @@ __global__ void k_update_pos(Tab V, KParams K, StepState *ss)
 #define GRID(n) (unsigned) (((n) + 255) / 256), 256, 0, ctx->stream
 
 // 3-D SPH stages run on the grouped gather (psph_gather3.cuh); 1-D, and PSPH_GATHER=row, on the per-row one
+// The first summation stage of a step (mom_engr_update, `writer`) finds the pairs: the grouped gather publishes the
+// pair lists of the rows that qualify (and sums the others in place), then every stage runs the rows that have a
+// list on k_gather_list; the later stages send the rest through the grouped gather again.
 template <template <int> class S>
-static int launch_stage_gather(psph_ctx *ctx, int kid)
+static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
 {
-  if (ctx->cfg.dim == 3 && ctx->gather_mode == 0) return launch_gather_grp<S<3> >(ctx, kid);
-  return launch_gather<S>(ctx, kid);
+  if (ctx->cfg.dim != 3 || ctx->gather_mode != 0) return launch_gather<S>(ctx, kid);
+  if (writer) {
+    ctx->nbr_valid = false;
+    if (ctx->nbr_mode && psph_nbr_prepare(ctx) == 1) {
+      KernelTimer kt(ctx, kid); // the three launches are this stage's gather
+      if (launch_gather_grp<S<3> >(ctx, -1, 3)) return -1;
+      ctx->nbr_valid = true;
+      if (launch_gather_list<S<3> >(ctx, -1)) return -1;
+      return launch_gather_grp<S<3> >(ctx, -1, 2);
+    }
+    return launch_gather_grp<S<3> >(ctx, kid, 0);
+  }
+  if (ctx->nbr_valid) {
+    KernelTimer kt(ctx, kid); // both launches are this stage's gather
+    if (launch_gather_list<S<3> >(ctx, -1)) return -1;
+    return launch_gather_grp<S<3> >(ctx, -1, 2);
+  }
+  return launch_gather_grp<S<3> >(ctx, kid, 0);
+}
+
+// room for the pair lists of this step: 0 none (cache off for the step), 1 ready; < 0 error
+__global__ void k_nbr_reset(StepState *ss, unsigned cap) { ss->nbr_cursor = 0u; ss->nbr_cap = cap; ss->n_uncached = 0; }
+int psph_nbr_prepare(psph_ctx *ctx)
+{
+  // 10 units (320 pairs) per row cover the unit lattice (~230-300 pairs); rows that do not fit get no list
+  size_t want = (size_t) ctx->n * 10;
+  if (want > 0xfffffff0ull) want = 0xfffffff0ull;
+  if (ctx->nbr_units < want) {
+    size_t free_b = 0, total_b = 0;
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->cur.nbr); ctx->cur.nbr = nullptr; ctx->nbr_units = 0;
+    PSPH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t keep = (size_t) 2 << 30;                       // leave 2 GiB for everything else
+    size_t units = free_b > keep ? (free_b - keep) / 128 : 0;
+    units = std::min(units, want + want / 8);
+    if (units < (size_t) ctx->n) return 0;                       // not worth it
+    if (cudaMalloc(&ctx->cur.nbr, units * 128) != cudaSuccess) { cudaGetLastError(); ctx->cur.nbr = nullptr; return 0; }
+    ctx->nbr_units = units;
+  }
+  k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(ctx->nbr_units, 0xfffffff0ull));
+  PSPH_LAUNCH_CHECK();
+  return 1;
 }
 
 static int ensure_list(psph_ctx *ctx)
@@ -377,9 +445,11 @@ int psph_refresh_geo(psph_ctx *ctx)
 {
   k_hmax_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (ctx->n > 0) { k_refresh_geo<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
+  if (ctx->n > 0) { k_hmax_scan<<<GRID(ctx->n)>>>(ctx->cur.t, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
   k_hmax_finish<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
   PSPH_LAUNCH_CHECK();
+  if (ctx->n > 0) { k_refresh_geo<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
+  ctx->nbr_valid = false; // smoothing lengths changed: the pair lists of this step are stale
   return 0;
 }
 
@@ -457,7 +527,7 @@ extern "C" int psph_mom_engr_update(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (launch_stage_gather<MomStage>(ctx, KN_GATHER_MOM)) return -1;
+  if (launch_stage_gather<MomStage>(ctx, KN_GATHER_MOM, true)) return -1;
   return psph_commit_mom(ctx);
 }
 
@@ -469,7 +539,7 @@ extern "C" int psph_smooth_density(psph_ctx *ctx)
   if (ctx->n == 0) return 0;
   k_pack_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (launch_stage_gather<DensStage>(ctx, KN_GATHER_DENS)) return -1;
+  if (launch_stage_gather<DensStage>(ctx, KN_GATHER_DENS, false)) return -1;
   k_commit_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   psph_comm_mark(ctx, DIRTY_DENS);
@@ -485,7 +555,7 @@ extern "C" int psph_smooth_velocity(psph_ctx *ctx)
   k_pack_vel<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   psph_comm_mark(ctx, DIRTY_VEL);
-  return launch_stage_gather<VelStage>(ctx, KN_GATHER_VEL);
+  return launch_stage_gather<VelStage>(ctx, KN_GATHER_VEL, false);
 }
 
 extern "C" int psph_update_pos(psph_ctx *ctx)

@@ -3,7 +3,7 @@
 EDGE=${1:-216}
 shift
 for v in "$@"; do
-  env $(echo $v | tr ',' ' ') python bench.py --edge $EDGE --steps 2 --warmup 2 --no-e2e --no-cpu 2>/dev/null | python -c "
+  env $(echo $v | tr ',' ' ') python bench.py --edge $EDGE --steps 2 --warmup 2 --no-e2e --no-cpu 2>gpurun_out/ab_err.log | python -c "
 import json,sys
 for ln in sys.stdin:
     if ln.startswith('{'):

@@ -164,6 +164,15 @@ __device__ __forceinline__ double dev_weight_in(double r2, double invh)
   return norm * dev_exp_neg(-(r2 * invh * invh));
 }
 
+// the same with the row constants hoisted: ninvh2 = -1/h^2, norm = (pi^-1/2 / h)^DIM
+template <int DIM>
+__device__ __forceinline__ double dev_weight_norm(double invh)
+{
+  const double t = 0.564189583547756 * invh;
+  return DIM == 3 ? t * t * t : t;
+}
+__device__ __forceinline__ double dev_weight_pre(double r2, double ninvh2, double norm) { return norm * dev_exp_neg(r2 * ninvh2); }
+
 // Stage interface (static members):
 //   kSymH         pair smoothing length is 0.5*(h_i+h_j) (true) or S::I::hk (false)
 //   kSkipSelf     j == i is not a pair (mom_engr_update.cc:201)

@@ -365,7 +365,7 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
               const typename S::R rj = rn;
               jn = q0 + 32 < nrun ? lds32(qg + 4u * (q0 + 32)) : -1;
               if (q0 + 32 < nfull) { gn = ld_rec(V.geo, jn < 0 ? i : jn); rn = S::load(V, jn < 0 ? i : jn); }
-              if (j >= 0) S::pair_r(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
+              if (j >= 0) S::template pair_r<false>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
             }
           } else {
             for (int q0 = 0; q0 < nfull; q0 += 32) {
@@ -428,8 +428,8 @@ int launch_gather_grp(psph_ctx *ctx, int kid, int lm)
 {
   if (lm == 3) {
     if (ctx->gather_warps == 16) return launch_gather_grp_w<S, 16, 0, 3>(ctx, kid);
-    if (ctx->gather_warps == 20) return launch_gather_grp_w<S, 20, 0, 3>(ctx, kid);
-    return launch_gather_grp_w<S, 24, 0, 3>(ctx, kid);
+    if (ctx->gather_warps == 24) return launch_gather_grp_w<S, 24, 0, 3>(ctx, kid);
+    return launch_gather_grp_w<S, 20, 0, 3>(ctx, kid);
   }
   if (lm == 2) return launch_gather_grp_w<S, S::kWarpsGrp, S::kPfGrp, 2>(ctx, kid);
   const int w = (ctx->gather_warps ? ctx->gather_warps : S::kWarpsGrp) + 100 * (ctx->gather_pf >= 0 ? ctx->gather_pf : S::kPfGrp);
@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParam
       const int32_t *__restrict__ lst = V.nbr + (size_t) (unsigned) V.nbr_off[i] * 32u + lane;
       typename S::I st;
       S::init(V, K, ss, i, st);
+      S::init_uni(K, st);                        // every partner of a listed row has the row's own h
       const double4 gi = V.geo[i];
       typename S::A acc;
       S::begin(K, st, acc, 0);
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParam
           const typename S::R rj = rn;
           jn = entry(q0 + 32 + lane);
           if (q0 + 32 < ntot) { gn = ld_rec(V.geo, jn < 0 ? i : jn); rn = S::load(V, jn < 0 ? i : jn); }
-          if (j >= 0) S::pair_r(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
+          if (j >= 0) S::template pair_r<true>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
         }
       } else {
         for (int q0 = 0; q0 < ntot; q0 += 32) {
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParam
           jn = entry(q0 + 32 + lane);
           if (j >= 0) {
             const double4 gj = ld_rec(V.geo, j);
-            S::pair(V, K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, j);
+            S::template pair_r<true>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, S::load(V, j));
           }
         }
       }

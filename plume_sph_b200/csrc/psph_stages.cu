@@ -105,7 +105,7 @@ struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 24, kPfList = 0, kNRec = 1;
-  struct I { double h, supp, hk; };
+  struct I { double h, supp, hk, invh, ninvh2, norm, ninvh2e, norme; };  // from invh on: uniform-h rows only (init_uni)
   struct A { double rho1, rho2, wn, en; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -120,23 +120,34 @@ struct DensStage
   struct R { double4 r0; };                                          // the stage record of row j
   static __device__ __forceinline__ R load(const DevView &V, int j) { R r; r.r0 = ld_rec(V.rec[0], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0 = make_double4(0., 0., 0., 0.); }  // a row that adds exact zeros
+  // rows whose partners all carry the row's own smoothing length (pair lists): 1/h and the kernel norms once per row
+  static __device__ __forceinline__ void init_uni(const KParams &K, I &s)
+  {
+    s.invh = dev_rcp(s.h); s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);
+    const double ie = K.e_ratio * s.invh;
+    s.ninvh2e = -(ie * ie); s.norme = dev_weight_norm<DIM>(ie);
+  }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
-  { pair_r(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  template <bool UNI>
   static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
                                                 const R &rec)
   {
-    const double h = 0.5 * (s.h + hj);                              // :155
-    const double r2 = dx * dx + dy * dy + dz * dz, invh = dev_rcp(h);
+    const double h = UNI ? s.h : 0.5 * (s.h + hj);                  // :155
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double invh = UNI ? s.invh : dev_rcp(h);
     const double4 rj = rec.r0;
-    const double wm = dev_weight_in<DIM>(r2, invh) * rj.x;
+    const double wm = (UNI ? dev_weight_pre(r2, s.ninvh2, s.norm) : dev_weight_in<DIM>(r2, invh)) * rj.x;
     const bool ph2 = rj.w != 0.0;                                   // phase of j
     a.rho2 += ph2 ? wm : 0.0;
     a.rho1 += ph2 ? 0.0 : wm;
     if (K.energy_smooth == 1) {                                     // :163-168, kernel of width h/E_SMOOTH_RATIO
       const double q = K.e_ratio;
-      if (!outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) {
-        const double we = dev_weight_in<DIM>(r2, q * invh);
+      // all |q dx_k / h| <= cutoff implies r2 <= DIM (cutoff h / q)^2: most pairs are decided by this one compare
+      const double b = K.cutoff * h * (1.0 + 0x1p-40);
+      if (r2 * (q * q) <= DIM * b * b && !outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) {
+        const double we = UNI ? dev_weight_pre(r2, s.ninvh2e, s.norme) : dev_weight_in<DIM>(r2, q * invh);
         a.wn += we * rj.y;
         a.en += we * rj.z;
       }
@@ -183,7 +194,7 @@ struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 16, kWarpsGrp = 16, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 16, kPfList = 0, kNRec = 3;
-  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3]; };
+  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3], invh, ninvh2, norm; };  // from invh on: init_uni
   struct A { double rv[3], re; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -206,16 +217,20 @@ struct MomStage
   static __device__ __forceinline__ R load(const DevView &V, int j)
   { R r; r.r0 = ld_rec(V.rec[0], j); r.r1 = ld_rec(V.rec[1], j); r.r2 = ld_rec(V.rec[2], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0.x = 0.; }                          // m_j = 0: the pair adds exact zeros
+  static __device__ __forceinline__ void init_uni(const KParams &, I &s)
+  { s.invh = dev_rcp(s.h); s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh); }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
-  { pair_r(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  template <bool UNI>
   static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
                                                 const R &rec)
   {
-    const double h = 0.5 * (s.h + hj);
-    const double r2 = dx * dx + dy * dy + dz * dz, invh = dev_rcp(h);
+    const double h = UNI ? s.h : 0.5 * (s.h + hj);
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double invh = UNI ? s.invh : dev_rcp(h);
     const double4 r0 = rec.r0, r1 = rec.r1, uj = rec.r2;
-    const double w = dev_weight_in<DIM>(r2, invh);
+    const double w = UNI ? dev_weight_pre(r2, s.ninvh2, s.norm) : dev_weight_in<DIM>(r2, invh);
     const double g = -2.0 * invh * invh * w;                        // dW/dx_k = g * dx_k
     const double vx = s.u[0] - uj.x, vy = s.u[1] - uj.y, vz = s.u[2] - uj.z;
     const double vr = dx * vx + dy * vy + dz * vz, vv = vx * vx + vy * vy + vz * vz;
@@ -279,12 +294,13 @@ struct VelStage
 {
   static constexpr bool kSymH = false, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 20, kPfGrp = 1, kWarpsScan = 24, kWarpsList = 24, kPfList = 1, kNRec = 1;
-  struct I { double h, invh, supp, hk, v[3]; };
+  struct I { double h, invh, supp, hk, v[3], ninvh2, norm; };
   struct A { double dv[3], wn; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double) { return K.cutoff * h; }
   static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
   {
     s.h = V.t.d[D_H][i]; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
+    s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);
     s.v[0] = V.t.d[D_VX][i]; s.v[1] = V.t.d[D_VY][i]; s.v[2] = V.t.d[D_VZ][i];
   }
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double) { return K.cutoff * s.h; }
@@ -294,12 +310,14 @@ struct VelStage
   static __device__ __forceinline__ void zero(R &r) { r.r0 = make_double4(0., 0., 0., 0.); }  // a row that adds exact zeros
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
-  { pair_r(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  static __device__ __forceinline__ void init_uni(const KParams &, I &) {}
+  template <bool UNI>
   static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double,
                                                 const R &rec)
   {
     const double4 rj = rec.r0;
-    const double mvw = dev_weight_in<DIM>(dx * dx + dy * dy + dz * dz, s.invh) * rj.x;
+    const double mvw = dev_weight_pre(dx * dx + dy * dy + dz * dz, s.ninvh2, s.norm) * rj.x;
     a.dv[0] += mvw * (rj.y - s.v[0]);
     if (DIM == 3) { a.dv[1] += mvw * (rj.z - s.v[1]); a.dv[2] += mvw * (rj.w - s.v[2]); }
     a.wn += mvw;

@@ -370,12 +370,12 @@ int launch_gather_d(psph_ctx *ctx, int kid)
 {
   constexpr int threads = S::kWarps * 32;
   constexpr size_t smem = sizeof(WarpScratch) * S::kWarps;
+  // the attribute is per device, and a process may drive several devices (one context each): set it at every launch
+  PSPH_CUDA(cudaFuncSetAttribute(k_gather<DIM, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   static int per_sm = 0; // resident CTAs per SM of this instantiation: the grid is one persistent wave
-  if (per_sm == 0) {
-    PSPH_CUDA(cudaFuncSetAttribute(k_gather<DIM, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather<DIM, S>, threads, smem) != cudaSuccess || per_sm < 1)
-      per_sm = 1;
-  }
+  if (per_sm == 0 &&
+      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather<DIM, S>, threads, smem) != cudaSuccess || per_sm < 1))
+    per_sm = 1;
   KernelTimer kt(ctx, kid);
   int nchunks = (ctx->n + S::kWarps * RPW - 1) / (S::kWarps * RPW);
   int grid = min(max(nchunks, 1), ctx->sms * per_sm);

@@ -407,11 +407,8 @@ int launch_gather_grp_w(psph_ctx *ctx, int kid)
   constexpr int QC = LM == 3 ? GQCAP_SCAN : GQCAP;
   constexpr int threads = WARPS * 32;
   constexpr size_t smem = sizeof(GrpScratch<QC>) * WARPS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PSPH_CUDA(cudaFuncSetAttribute(k_gather_grp<S, WARPS, PF, LM, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = true;
-  }
+  // per device, and a process may drive several devices (one context each): set it at every launch
+  PSPH_CUDA(cudaFuncSetAttribute(k_gather_grp<S, WARPS, PF, LM, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const size_t spill_rows = (size_t) ctx->sms * 32 * GRP * GNA * 32; // up to 32 warps per CTA, one CTA per SM
   if (!ctx->d_gspill) PSPH_CUDA(cudaMalloc(&ctx->d_gspill, spill_rows * sizeof(double)));
   KernelTimer kt(ctx, kid);

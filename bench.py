@@ -37,6 +37,12 @@ UNIT = "particle-updates/s"
 # algorithmic bytes per real-particle-update of each pair gather
 ALG_BYTES = {"gather_mom_engr": 228, "gather_density": 148, "gather_velocity": 100}
 ALG_BYTES_STEP = 1184
+# kernel behind each timer when the pair-list path runs (3-D SPH defaults), and what ncu measured for it
+# (profiles/r01k_ncu_dram_n216.txt: DRAM bytes per launch at this workload; profiles/r01i_ncu_lists_n96.txt: FP64 pipe)
+KERNEL_OF = {"gather_mom_engr": "k_gather_list<MomStage<3>>", "gather_density": "k_gather_list<DensStage<3>>",
+             "gather_velocity": "k_gather_list<VelStage<3>>"}
+NCU = {"gather_mom_engr": {"traffic": None, "fp64_pipe_pct": 40.6}, "gather_density": {"traffic": None, "fp64_pipe_pct": 39.7},
+       "gather_velocity": {"traffic": None, "fp64_pipe_pct": 30.1}}
 
 
 def measured_peaks():
@@ -218,12 +224,15 @@ def run_b200(args):
     dom = max(ALG_BYTES, key=lambda k: kms[k][0])
     dom_ms = kms[dom][0] / max(kms[dom][1], 1)
     achieved = ALG_BYTES[dom] * n_real_local / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_gather<%s>" % dom, "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None,
+    roofline = {"bound": "hbm", "kernel": KERNEL_OF[dom], "achieved": round(achieved, 2), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 5),
+                "traffic": NCU[dom]["traffic"] if (args.n == 216 and world == 1) else None,
+                "fp64_pipe_pct_ncu": NCU[dom]["fp64_pipe_pct"],
                 "alg_bytes_per_update": ALG_BYTES[dom], "updates_per_launch": n_real_local,
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
-                "note": "FP64 pair loop: compute-bound (SURVEY.md §8d), HBM fraction is low by construction; "
-                        "see profiles/ for the FP64 pipe utilisation",
+                "note": "FP64 pair loop over cached pair lists: bound by the L1 gather rate and the FP64 pipe, not by HBM "
+                        "(SURVEY.md §8d): the HBM fraction is low by construction; fp64_pipe_pct_ncu and profiles/ "
+                        "carry the figure of merit",
                 "step_hbm": {"alg_bytes_per_update": ALG_BYTES_STEP,
                              "achieved_GBps": round(ALG_BYTES_STEP * n_real / (ms / args.steps * 1e-3) / 1e9, 2)},
                 "stage_ms_per_step": {k: round(v / ksteps, 4) for k, v in sms.items() if v > 0},

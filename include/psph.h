@@ -235,7 +235,8 @@ int psph_set_timing(psph_ctx *ctx, int on);
 double psph_stage_ms(psph_ctx *ctx, int stage, int reset);
 /* per-kernel device time (CUDA events on the context stream, only while psph_set_timing is on):
  * 0 gather mom_engr, 1 gather density, 2 gather velocity filter, 3 gather adaptive_sml,
- * 4 gather gradients, 5 gather GSPH mom_engr, 6 radix sort, 7 column reorder */
+ * 4 gather gradients, 5 gather GSPH mom_engr, 6 radix sort, 7 column reorder,
+ * 8 pair search of the 3-D SPH stages (the scan that writes the per-row pair lists) */
 double psph_kernel_ms(psph_ctx *ctx, int kernel, int reset, int64_t *calls);
 /* pinned host memory for the rows passed to psph_upload / psph_append / psph_download
  * (optional: any host pointer works, pinned ones copy at full PCIe rate) */

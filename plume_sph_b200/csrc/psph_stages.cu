@@ -413,9 +413,9 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   if (writer) {
     ctx->nbr_valid = false;
     if (ctx->nbr_mode && psph_nbr_prepare(ctx) == 1) {
-      KernelTimer kt(ctx, kid); // the three launches are this stage's gather
-      if (launch_gather_grp<S<3> >(ctx, -1, 3)) return -1;
+      if (launch_gather_grp<S<3> >(ctx, KN_PAIR_SCAN, 3)) return -1; // timed apart: the pair search
       ctx->nbr_valid = true;
+      KernelTimer kt(ctx, kid); // both launches are this stage's gather
       if (launch_gather_list<S<3> >(ctx, -1)) return -1;
       return launch_gather_grp<S<3> >(ctx, -1, 2);
     }

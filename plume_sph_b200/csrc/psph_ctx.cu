@@ -208,6 +208,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
   PSPH_CUDA(cudaMalloc(&ctx->d_rank2cell, ctx->ncells * sizeof(int32_t)));
   PSPH_CUDA(cudaMalloc(&ctx->d_sub_start, (ctx->ncells * SUBS + 1) * sizeof(int32_t)));
   PSPH_CUDA(cudaMemset(ctx->d_sub_start, 0, (ctx->ncells * SUBS + 1) * sizeof(int32_t)));
+  PSPH_CUDA(cudaMalloc(&ctx->d_blk_any, ctx->ncells * 4));
+  PSPH_CUDA(cudaMemset(ctx->d_blk_any, 0, ctx->ncells * 4));
   PSPH_CUDA(cudaMalloc(&ctx->d_cell_has_ghost, ctx->ncells));
   PSPH_CUDA(cudaMemset(ctx->d_cell_has_ghost, 0, ctx->ncells));
   PSPH_CUDA(cudaMalloc(&ctx->d_ss, sizeof(StepState)));
@@ -239,7 +241,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
-  cudaFree(ctx->d_cell_has_ghost);
+  cudaFree(ctx->d_cell_has_ghost); cudaFree(ctx->d_blk_any);
   cudaFree(ctx->d_sortkey); cudaFree(ctx->d_sortkey_alt); cudaFree(ctx->d_perm); cudaFree(ctx->d_perm_alt);
   cudaFree(ctx->d_cub_tmp); cudaFree(ctx->d_ss); cudaFreeHost(ctx->h_ss);
   cudaFree(ctx->d_aos);

@@ -2,7 +2,7 @@
 // timestep, adaptive_sml, mom_engr_update, smooth_density, smooth_velocity, update_pos and the
 // fused step driver.  Every stage cites the reference code it replaces; the C ABI is
 // include/psph.h.  Pair sums run on the warp gather of psph_gather.cuh.
-#include "psph_gather3.cuh"
+#include "psph_tile.cuh"
 #include <cstring>
 #include <algorithm>
 
@@ -120,6 +120,15 @@ struct DensStage
   struct R { double4 r0; };                                          // the stage record of row j
   static __device__ __forceinline__ R load(const DevView &V, int j) { R r; r.r0 = ld_rec(V.rec[0], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0 = make_double4(0., 0., 0., 0.); }  // a row that adds exact zeros
+  // block-tiled gather (psph_tile.cuh): columns 3.. of a tile row in shared memory, and the record read back
+  static constexpr int kNC = 7, kWarpsTile = 12, kMinbTile = 2;
+  static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
+  { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
+  static __device__ __forceinline__ R tile_rec(const double *c, int t)
+  { R r; r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]); return r; }
+  // the state of row i from its own slot of the tile; a listed row carries the table's standard smoothing length
+  static __device__ __forceinline__ void tile_init(const KParams &K, StepState *ss, const double *, int, int, I &s)
+  { s.h = ss->hmax; s.supp = K.cutoff2 * s.h; }
   // rows whose partners all carry the row's own smoothing length (pair lists): 1/h and the kernel norms once per row
   static __device__ __forceinline__ void init_uni(const KParams &K, I &s)
   {
@@ -217,6 +226,30 @@ struct MomStage
   static __device__ __forceinline__ R load(const DevView &V, int j)
   { R r; r.r0 = ld_rec(V.rec[0], j); r.r1 = ld_rec(V.rec[1], j); r.r2 = ld_rec(V.rec[2], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0.x = 0.; }                          // m_j = 0: the pair adds exact zeros
+  static constexpr int kNC = 13, kWarpsTile = 16, kMinbTile = 1;
+  static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
+  {
+    const double4 a = ld_rec(V.rec[0], row), b = ld_rec(V.rec[1], row), u = ld_rec(V.rec[2], row);
+    c[3 * TCAP + t] = a.x; c[4 * TCAP + t] = a.y; c[5 * TCAP + t] = a.z; c[6 * TCAP + t] = a.w;
+    c[7 * TCAP + t] = b.x; c[8 * TCAP + t] = b.y; c[9 * TCAP + t] = b.z;
+    c[10 * TCAP + t] = u.x; c[11 * TCAP + t] = u.y; c[12 * TCAP + t] = u.z;
+  }
+  static __device__ __forceinline__ R tile_rec(const double *c, int t)
+  {
+    R r;
+    r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]);
+    r.r1 = make_double4(c[7 * TCAP + t], c[8 * TCAP + t], c[9 * TCAP + t], 0.);
+    r.r2 = make_double4(c[10 * TCAP + t], c[11 * TCAP + t], c[12 * TCAP + t], 0.);
+    return r;
+  }
+  // the state of row i from its own slot of the tile (k_pack_mom forms V and p V^2 exactly as init() does)
+  static __device__ __forceinline__ void tile_init(const KParams &K, StepState *ss, const double *c, int t, int i, I &s)
+  {
+    s.i = i; s.h = ss->hmax; s.supp = K.cutoff2 * s.h;
+    s.pvsq = c[4 * TCAP + t]; s.Vi = c[5 * TCAP + t]; s.rho = c[6 * TCAP + t];
+    s.c = c[7 * TCAP + t]; s.Cp = c[8 * TCAP + t]; s.T = c[9 * TCAP + t];
+    s.u[0] = c[10 * TCAP + t]; s.u[1] = c[11 * TCAP + t]; s.u[2] = c[12 * TCAP + t];
+  }
   static __device__ __forceinline__ void init_uni(const KParams &, I &s)
   { s.invh = dev_rcp(s.h); s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh); }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
@@ -311,6 +344,17 @@ struct VelStage
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
   { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  static constexpr int kNC = 7, kWarpsTile = 12, kMinbTile = 2;
+  static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
+  { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
+  static __device__ __forceinline__ R tile_rec(const double *c, int t)
+  { R r; r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]); return r; }
+  static __device__ __forceinline__ void tile_init(const KParams &K, StepState *ss, const double *c, int t, int, I &s)
+  {
+    s.h = ss->hmax; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
+    s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);
+    s.v[0] = c[4 * TCAP + t]; s.v[1] = c[5 * TCAP + t]; s.v[2] = c[6 * TCAP + t];
+  }
   static __device__ __forceinline__ void init_uni(const KParams &, I &) {}
   template <bool UNI>
   static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double,
@@ -412,7 +456,14 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   if (ctx->cfg.dim != 3 || ctx->gather_mode != 0) return launch_gather<S>(ctx, kid);
   if (writer) {
     ctx->nbr_valid = false;
-    if (ctx->nbr_mode && psph_nbr_prepare(ctx) == 1) {
+    if (ctx->nbr_mode == 2 && psph_nbr_prepare(ctx) == 1) { // block-tiled: slot lists, records staged in shared memory
+      if (launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN)) return -1;
+      ctx->nbr_valid = true;
+      KernelTimer kt(ctx, kid);
+      if (launch_tile_gather<S<3>, S<3>::kWarpsTile, S<3>::kMinbTile>(ctx, -1)) return -1;
+      return launch_gather_grp<S<3> >(ctx, -1, 2);
+    }
+    if (ctx->nbr_mode == 1 && psph_nbr_prepare(ctx) == 1) {
       if (launch_gather_grp<S<3> >(ctx, KN_PAIR_SCAN, 3)) return -1; // timed apart: the pair search
       ctx->nbr_valid = true;
       KernelTimer kt(ctx, kid); // both launches are this stage's gather
@@ -423,7 +474,9 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   }
   if (ctx->nbr_valid) {
     KernelTimer kt(ctx, kid); // both launches are this stage's gather
-    if (launch_gather_list<S<3> >(ctx, -1)) return -1;
+    if (ctx->nbr_mode == 2) {
+      if (launch_tile_gather<S<3>, S<3>::kWarpsTile, S<3>::kMinbTile>(ctx, -1)) return -1;
+    } else if (launch_gather_list<S<3> >(ctx, -1)) return -1;
     return launch_gather_grp<S<3> >(ctx, -1, 2);
   }
   return launch_gather_grp<S<3> >(ctx, kid, 0);
@@ -448,7 +501,9 @@ int psph_nbr_prepare(psph_ctx *ctx)
     if (cudaMalloc(&ctx->cur.nbr, units * 128) != cudaSuccess) { cudaGetLastError(); ctx->cur.nbr = nullptr; return 0; }
     ctx->nbr_units = units;
   }
-  k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(ctx->nbr_units, 0xfffffff0ull));
+  // units of 32 entries: 128 bytes of row indices, or 64 bytes of 16-bit tile slots (block-tiled mode)
+  const size_t cap = ctx->nbr_mode == 2 ? ctx->nbr_units * 2 : ctx->nbr_units;
+  k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(cap, 0xfffffff0ull));
   PSPH_LAUNCH_CHECK();
   return 1;
 }

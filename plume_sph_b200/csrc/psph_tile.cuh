@@ -1,0 +1,425 @@
+// psph_tile.cuh — block-tiled pair search and pair sums of the 3-D SPH stages.
+//
+// The pair-list gather of psph_gather3.cuh is bound by the L1 gather rate: every record of a partner row is a
+// scattered 32-byte access (~1 sector per cycle and SM).  Here the partners' records are staged ONCE per block
+// of rows in shared memory and the pair bodies read them from there:
+//   block : the rows of one bucket (cell) with subcell x-index in {2q, 2q+1}, q = 0..3 — one contiguous row range
+//           of the sorted table (~128 rows on the unit lattice);
+//   tile  : every row that can be a partner of a row of the block when the reach is 3 subcells: the subcell
+//           columns gx = 8 cx + 2q - 3 .. + 4 (8), gy = 8 cy - 3 .. + 10 (14), and along z the bucket below
+//           (subcells 5..7), the bucket itself (0..7) and the bucket above (0..2): 8 x 14 x 3 row segments of
+//           the sorted table (~1570 rows on the unit lattice).  A row's position in that enumeration is its SLOT.
+//   k_tile_scan   : one CTA per block finds the pairs (the grouped search of psph_gather3.cuh: FP32 pre-filter, the
+//                   reference's gates in FP64 inside the error band) and writes per-row lists of 16-bit SLOTS;
+//   k_tile_gather : per stage, one CTA per block loads the tile's records into shared memory (struct of arrays
+//                   of doubles, coalesced) and sums every listed row of the block off its slot list; the row's own
+//                   state comes from its slot of the tile as well (S::tile_init).
+// Rows that do not qualify (tile larger than the shared-memory budget, reach other than 3 subcells, a row on a
+// subcell face, smoothing lengths other than the table's standard one in the candidate box, queue overflow, no
+// list space) are marked and summed by the fused grouped gather (k_gather_grp LM 2), exactly as for the row lists.
+#pragma once
+#include "psph_gather3.cuh"
+
+constexpr int TX = 8, TY = 14;                 // tile columns in x (2 + 2*3) and y (8 + 2*3)
+constexpr int TSEG = TX * TY * 3;              // (column, z-bucket) row segments of a tile
+constexpr int TCAP = 1920;                     // tile rows that fit in shared memory (13 double columns: 195 KiB)
+constexpr int TQCAP = 384;                     // queue slots per row of a group (the scan cannot drain a queue)
+constexpr int TCAND = 512;                     // candidates expanded per batch
+constexpr int TITEMS = 49 * 3;                 // (column, z-bucket) items of a group's candidate box
+
+struct TileTable
+{
+  int beg[TSEG];                               // first row of the segment
+  int base[TSEG];                              // sub_start index of subcell z = 0 of the segment's column, -1: outside
+  int off[TSEG + 1];                           // first slot of the segment; off[TSEG] = tile rows
+  int wsum[32];
+  int pad[3];                                  // sizeof % 16 == 0: the per-warp scratch / the tile follow
+};
+static_assert(sizeof(TileTable) % 16 == 0, "TileTable padding");
+
+// (beg, len, base) of segment s of the tile of block (cell (cx, cy, cz), sx-pair q)
+__device__ __forceinline__ void tile_segment(const GridView &G, int cx, int cy, int cz, int q, int s, int &beg, int &len, int &base)
+{
+  const int tx = s / (TY * 3), ty = (s / 3) % TY, k = s % 3;
+  const int gx = cx * SUBDIV + 2 * q - 3 + tx, gy = cy * SUBDIV - 3 + ty, bz = cz - 1 + k;
+  beg = 0; len = 0; base = -1;
+  if (gx < 0 || gy < 0 || bz < 0 || gx >= G.ncell[0] * SUBDIV || gy >= G.ncell[1] * SUBDIV || bz >= G.ncell[2]) return;
+  const int cell = ((gx / SUBDIV) * G.ncell[1] + gy / SUBDIV) * G.ncell[2] + bz;
+  base = __ldg(&G.cell2rank[cell]) * SUBS + (gx % SUBDIV) * (SUBDIV * SUBDIV) + (gy % SUBDIV) * SUBDIV;
+  const int zl = k == 0 ? SUBDIV - 3 : 0, zh = k == 2 ? 2 : SUBDIV - 1;
+  beg = __ldg(&G.sub_start[base + zl]);
+  len = __ldg(&G.sub_start[base + zh + 1]) - beg;
+}
+
+// every thread of the CTA calls this; fills the table (exclusive scan of the segment lengths); blockDim >= TSEG
+__device__ __forceinline__ void tile_build(const GridView &G, int cx, int cy, int cz, int q, TileTable &tab)
+{
+  const int s = threadIdx.x, lane = s & 31, w = s >> 5;
+  int beg = 0, len = 0, base = -1;
+  if (s < TSEG) tile_segment(G, cx, cy, cz, q, s, beg, len, base);
+  int inc = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) tab.wsum[w] = inc;
+  __syncthreads();
+  int pre = 0;
+  for (int k = 0; k < w; k++) pre += tab.wsum[k];
+  if (s < TSEG) { tab.beg[s] = beg; tab.base[s] = base; tab.off[s] = pre + inc - len; }
+  if (s == TSEG - 1) tab.off[TSEG] = pre + inc;
+  __syncthreads();
+}
+
+struct TileWarp                                // per-warp scratch of the scan
+{
+  GrpHdr hdr;
+  int cand[TCAND];                             // candidate row << 1 | own-bucket flag
+  unsigned short cslot[TCAND];                 // its tile slot
+  unsigned short q[GRP][TQCAP];                // slots that passed the gates, per row of the group
+};
+
+__device__ __forceinline__ void sts16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short) v) : "memory"); }
+__device__ __forceinline__ unsigned lds16(unsigned addr)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// =========================================================================================
+// pair search: writes nbr (16-bit slots, 32-entry = 64-byte units), nbr_off, nbr_cnt (-1: no list) and blk_any
+// =========================================================================================
+template <class S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__restrict__ blk_any)
+{
+  static_assert(WARPS * 32 >= TSEG, "tile_build needs one thread per segment");
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  TileTable *tabs = reinterpret_cast<TileTable *>(s_raw);                    // one per sx-pair of the cell
+  TileWarp *scr = reinterpret_cast<TileWarp *>(s_raw + 4 * sizeof(TileTable)) + (threadIdx.x >> 5);
+  __shared__ int s_any[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned s_cand, s_cslot, s_q, s_hdr;
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_cand) : "r"((unsigned) __cvta_generic_to_shared(&scr->cand[0])));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_cslot) : "r"((unsigned) __cvta_generic_to_shared(&scr->cslot[0])));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_q) : "r"((unsigned) __cvta_generic_to_shared(&scr->q[0][0])));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_hdr) : "r"((unsigned) __cvta_generic_to_shared(&scr->hdr.hdr_i[0])));
+  if (lane == 0) {
+    scr->hdr.kc[0] = K.cutoff; scr->hdr.kc[1] = K.cutoff2; scr->hdr.kc[2] = K.neigh_radius;
+    scr->hdr.geo = V.geo; scr->hdr.hlist = V.t.d[D_HLIST];
+  }
+  __syncwarp();
+  const double hmax = ss->hmax;
+  const float delta = __uint_as_float(ss->xmax_bits) * 0x1p-21f;
+  const float hstd_f = (float) hmax;
+  const float ch = (float) (S::kSymH ? 0.5 * K.cutoff : K.cutoff);
+  const float c_lo = ch * (1.0f - 0x1p-19f), c_hi = ch * (1.0f + 0x1p-19f);
+  // the tile is laid out for a reach of 3 subcells of rows with the standard smoothing length
+  const bool reach_ok = (int) ceil(S::reach_h(K, hmax, hmax) * G.inv_subw - 1e-9) == 3;
+  unsigned short *__restrict__ nbr16 = reinterpret_cast<unsigned short *>(V.nbr);
+  unsigned wcur = 0, wend = 0;                 // this warp's block of list space (64-byte units)
+  const int ncell = (int) G.ncells;
+
+  // one CTA per cell: the tables of its four blocks are built together, the rows of the cell are shared out to the
+  // warps (a group of rows lies in one subcell column, hence in one block)
+  for (int r = blockIdx.x; r < ncell; r += gridDim.x) {
+    const int rb0 = __ldg(&G.sub_start[r * SUBS]), rb1 = __ldg(&G.sub_start[r * SUBS + SUBS]);
+    if (rb0 == rb1) { if (threadIdx.x < 4) blk_any[r * 4 + threadIdx.x] = 0; continue; }
+    const int cell0 = __ldg(&G.rank2cell[r]);
+    const int cz = cell0 % G.ncell[2], cy = (cell0 / G.ncell[2]) % G.ncell[1], cx = cell0 / (G.ncell[2] * G.ncell[1]);
+    if (threadIdx.x < 4) s_any[threadIdx.x] = 0;
+    for (int qq = 0; qq < 4; qq++) tile_build(G, cx, cy, cz, qq, tabs[qq]);
+    const int per = (rb1 - rb0 + WARPS - 1) / WARPS;
+    int e = rb0 + warp * per;
+    const int eend = min(e + per, rb1);
+    while (e < eend) {
+      // ---- form the group: leading run of rows that are summed (F_NEED) and sit in the same subcell column
+      int row = -1, fl = 0;
+      unsigned long long pk = 0;
+      if (lane < GRP && e + lane < eend) { row = e + lane; fl = V.flags[row]; pk = V.gsub[row]; }
+      const bool need = row >= 0 && (fl & F_NEED);
+      const unsigned nm = __ballot_sync(FULL, need);
+      if (!(nm & 1u)) { e += nm ? __ffs(nm) - 1 : GRP; continue; } // skip rows that are not summed
+      const unsigned long long pk0 = __shfl_sync(FULL, pk, 0);
+      const bool same = need && ((pk ^ pk0) & 0xffffffffffull) == 0;
+      const int m = __ffs(~__ballot_sync(FULL, same)) - 1; // 1..GRP
+      const bool mine = lane < m;
+      const int q = ((int) (pk0 & 0xfffff) - cx * SUBDIV) >> 1;           // the block of the group
+      const TileTable &tab = tabs[q];
+      const bool tile_ok = reach_ok && tab.off[TSEG] <= TCAP;
+      float4 p32 = make_float4(0.f, 0.f, 0.f, 0.f);
+      int sz = 0;
+      if (mine) { p32 = V.geo32[row]; sz = (int) ((pk >> 40) & 0xfffff) - cz * SUBDIV; sts32(s_hdr + 4u * lane, row); }
+      // rows on a subcell face (reach widened by one) or with another smoothing length do not fit the tile layout
+      const bool fits = tile_ok && !__any_sync(FULL, mine && ((pk >> 60) != 0 || p32.w != hstd_f));
+      if (!fits) {
+        if (mine) { V.nbr_cnt[row] = -1; V.nbr_off[row] = -1; }
+        if (lane == 0) atomicAdd(&ss->n_uncached, m);
+        e += m;
+        continue;
+      }
+      const int zlo = __reduce_min_sync(FULL, mine ? sz : 0x7fffffff), zhi = __reduce_max_sync(FULL, mine ? sz : -1);
+      bool nonstd = false;
+      unsigned ovf = 0;
+      int ig[GRP];
+      unsigned qa[GRP];
+      float fx[GRP], fy[GRP], fz[GRP], blo[GRP], bhi[GRP];
+#pragma unroll
+      for (int g = 0; g < GRP; g++) {
+        ig[g] = __shfl_sync(FULL, row, g);
+        fx[g] = __shfl_sync(FULL, p32.x, g); fy[g] = __shfl_sync(FULL, p32.y, g); fz[g] = __shfl_sync(FULL, p32.z, g);
+        const float hf = __shfl_sync(FULL, p32.w, g);
+        blo[g] = hf * c_lo - delta; bhi[g] = hf * c_hi + delta;
+        qa[g] = s_q + 2u * TQCAP * g;
+      }
+      // the group's box in tile coordinates: columns (tx0 + ix, ty0 + iy), ix, iy = 0..6; local z [lz0, lz1]
+      const int tx0 = (int) (pk0 & 0xfffff) - cx * SUBDIV - 2 * q, ty0 = (int) ((pk0 >> 20) & 0xfffff) - cy * SUBDIV;
+      const int lz0 = zlo - 3, lz1 = zhi + 3;
+      int item_base = -32, c0 = 0, total = 0, beg = 0, len = 0, slot = 0;
+      bool own = false;
+
+      auto test = [&](int cj, unsigned sl, const float4 &p) {
+        const int j = cj >> 1;
+        const float hlo = S::kSymH ? p.w * c_lo : 0.f, hhi = S::kSymH ? p.w * c_hi : 0.f;
+        nonstd |= p.w != hstd_f;
+        unsigned okb = 0, bandb = 0;
+#pragma unroll
+        for (int g = 0; g < GRP; g++) {
+          if (g < m) {
+            const float m3 = fmaxf(fmaxf(fabsf(fx[g] - p.x), fabsf(fy[g] - p.y)), fabsf(fz[g] - p.z));
+            bool ok = m3 <= bhi[g] + hhi;
+            if (S::kSkipSelf) ok = ok && j != ig[g];
+            if (ok) okb |= 1u << g;
+            if (ok && m3 > blo[g] + hlo) bandb |= 1u << g;
+          }
+        }
+        if (__any_sync(FULL, bandb != 0)) { // within the FP32 error band of a cutoff face: the reference's own test
+          if (bandb) okb = gate_exact_grp(&scr->hdr, okb, bandb, cj, S::kSymH ? 1 : 0);
+        }
+#pragma unroll
+        for (int g = 0; g < GRP; g++) {
+          if (g < m) {
+            const bool ok = (okb >> g) & 1u;
+            const unsigned bal = __ballot_sync(FULL, ok);
+            if (ok) sts16(qa[g] + 2u * __popc(bal & lt), sl);
+            qa[g] += 2u * __popc(bal);
+          }
+        }
+      };
+
+      for (;;) {
+        if (c0 >= total) {
+          // refill: expand the row ranges of the (column, z-bucket) items into the candidate list
+          if (total) { total = 0; c0 = 0; __syncwarp(); }
+          for (;;) {
+            if (__any_sync(FULL, len > 0)) {
+              const int quota = (TCAND - total) / 32;
+              if (quota == 0) break;
+              const int take = min(len, quota);
+              int off = take;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
+              const int sum = __shfl_sync(FULL, off, 31);
+              off += total - take;
+              const int tag = own ? 1 : 0;
+              for (int k = 0; k < take; k++) {
+                sts32(s_cand + 4u * (off + k), ((beg + k) << 1) | tag);
+                sts16(s_cslot + 2u * (off + k), (unsigned) (slot + k));
+              }
+              beg += take; slot += take; len -= take; total += sum;
+              continue;
+            }
+            item_base += 32; // next round of 32 (column, z-bucket) items
+            if (item_base >= TITEMS) break;
+            const int it = item_base + lane;
+            len = 0;
+            if (it < TITEMS) {
+              const int col = it / 3, k = it - col * 3, ix = col / 7, iy = col - ix * 7;
+              const int s = ((tx0 + ix) * TY + ty0 + iy) * 3 + k;
+              // local z covered by z-bucket k: [-3, -1], [0, 7], [8, 10]
+              const int klo = k == 0 ? -3 : (k == 1 ? 0 : SUBDIV), khi = k == 0 ? -1 : (k == 1 ? SUBDIV - 1 : SUBDIV + 2);
+              const int a = max(lz0, klo), bb = min(lz1, khi), tb = tab.base[s];
+              if (a <= bb && tb >= 0) {
+                const int zb = (k - 1) * SUBDIV;         // local z of subcell 0 of that bucket
+                beg = __ldg(&G.sub_start[tb + a - zb]);
+                len = __ldg(&G.sub_start[tb + bb - zb + 1]) - beg;
+                slot = tab.off[s] + (beg - tab.beg[s]);
+                own = k == 1 && (tx0 + ix + 2 * q - 3) >= 0 && (tx0 + ix + 2 * q - 3) < SUBDIV && (ty0 + iy - 3) >= 0 &&
+                      (ty0 + iy - 3) < SUBDIV;
+              }
+            }
+          }
+          __syncwarp();
+          if (total == 0) break;
+        }
+#pragma unroll
+        for (int g = 0; g < GRP; g++)
+          if (qa[g] > s_q + 2u * (TQCAP * g + TQCAP - 64)) { ovf |= 1u << g; qa[g] = s_q + 2u * TQCAP * g; bhi[g] = -INFINITY; }
+        // two candidates per lane, both loads in flight
+        const int ca = c0 + lane, cb = ca + 32;
+        const bool la = ca < total, lb = cb < total;
+        const int ja = la ? lds32(s_cand + 4u * ca) : 0, jb = lb ? lds32(s_cand + 4u * cb) : 0;
+        const unsigned sa = la ? lds16(s_cslot + 2u * ca) : 0u, sb = lb ? lds16(s_cslot + 2u * cb) : 0u;
+        float4 pa = ld_rec32(V.geo32, ja >> 1), pb = ld_rec32(V.geo32, jb >> 1);
+        if (!la) { pa.x = INFINITY; pa.w = hstd_f; }
+        if (!lb) { pb.x = INFINITY; pb.w = hstd_f; }
+        const bool two = c0 + 32 < total;
+        c0 += 64;
+        test(ja, sa, pa);
+        if (two) test(jb, sb, pb);
+      }
+      // ---- publish the lists
+      const bool guni = !__any_sync(FULL, nonstd);
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < GRP; g++) {
+        if (g < m) {
+          const int n = (int) (qa[g] - (s_q + 2u * TQCAP * g)) >> 1;
+          int off = -1;
+          if (guni && !((ovf >> g) & 1u)) {
+            const unsigned units = (unsigned) (n + 31) >> 5;
+            if (wcur + units > wend) { // next block of list space for this warp
+              unsigned o = 0;
+              if (lane == 0) o = atomicAdd(&ss->nbr_cursor, NBR_BLOCK);
+              o = __shfl_sync(FULL, o, 0);
+              const unsigned cap = ss->nbr_cap;
+              wcur = min(o, cap); wend = min(o + NBR_BLOCK, cap);
+              if (o + NBR_BLOCK < o) wcur = wend = cap;
+            }
+            if (wcur + units <= wend) { off = (int) wcur; wcur += units; }
+          }
+          if (lane == 0) {
+            V.nbr_off[ig[g]] = off;
+            V.nbr_cnt[ig[g]] = off >= 0 ? n : -1;
+            if (off < 0) atomicAdd(&ss->n_uncached, 1);
+          }
+          if (off >= 0) {
+            if (lane == 0) s_any[q] = 1;
+            unsigned *__restrict__ dst = reinterpret_cast<unsigned *>(nbr16 + (size_t) (unsigned) off * 32u);
+            const unsigned qb = s_q + 2u * TQCAP * g;
+            for (int k = lane; 2 * k < n; k += 32) dst[k] = (unsigned) lds32(qb + 4u * k); // two slots per word
+          }
+        }
+      }
+      e += m;
+      __syncwarp();
+    }
+    __syncthreads();   // the tables are rebuilt for the next cell
+    if (threadIdx.x < 4) blk_any[r * 4 + threadIdx.x] = (unsigned char) s_any[threadIdx.x];
+  }
+}
+
+// =========================================================================================
+// pair sums off the slot lists; S::kNC double columns per tile row in shared memory: x, y, z + the stage's own
+// (S::tile_load writes them, S::tile_rec reads them back as the stage record)
+// =========================================================================================
+template <class S, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned char *__restrict__ blk_any)
+{
+  static_assert(WARPS * 32 >= TSEG, "tile_build needs one thread per segment");
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  TileTable &tab = *reinterpret_cast<TileTable *>(s_raw);
+  double *comp = reinterpret_cast<double *>(s_raw + sizeof(TileTable));       // [kNC][TCAP]
+  int *tile_row = reinterpret_cast<int *>(comp);                              // [TCAP] slot -> row, while the tile is staged
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned short *__restrict__ nbr16 = reinterpret_cast<const unsigned short *>(V.nbr);
+  const int nblk = (int) (G.ncells * 4);
+  for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+    if (!blk_any[b]) continue;
+    const int r = b >> 2, q = b & 3;
+    const int rb0 = __ldg(&G.sub_start[r * SUBS + q * 128]), rb1 = __ldg(&G.sub_start[r * SUBS + q * 128 + 128]);
+    const int cell0 = __ldg(&G.rank2cell[r]);
+    const int cz = cell0 % G.ncell[2], cy = (cell0 / G.ncell[2]) % G.ncell[1], cx = cell0 / (G.ncell[2] * G.ncell[1]);
+    tile_build(G, cx, cy, cz, q, tab);
+    // ---- stage the tile: slot -> row map first (one thread per segment), then one thread per tile row so that
+    // all record loads of the tile are in flight together
+    const int total = tab.off[TSEG];
+    if (threadIdx.x < TSEG) {
+      const int s = threadIdx.x, beg = tab.beg[s], o = tab.off[s], len = tab.off[s + 1] - o;
+      for (int k = 0; k < len; k++) tile_row[o + k] = beg + k;
+    }
+    __syncthreads();
+    constexpr int NPT = (TCAP + WARPS * 32 - 1) / (WARPS * 32);  // tile rows per thread
+    int myrow[NPT];
+#pragma unroll
+    for (int u = 0; u < NPT; u++) { const int t = threadIdx.x + u * WARPS * 32; myrow[u] = t < total ? tile_row[t] : -1; }
+    __syncthreads();                                              // the map shares its storage with the first column
+#pragma unroll
+    for (int u = 0; u < NPT; u++) {
+      const int t = threadIdx.x + u * WARPS * 32, row = myrow[u];
+      if (row >= 0) {
+        const double4 g = ld_rec(V.geo, row);
+        comp[0 * TCAP + t] = g.x; comp[1 * TCAP + t] = g.y; comp[2 * TCAP + t] = g.z;
+        S::tile_load(V, row, comp, t);
+      }
+    }
+    __syncthreads();
+    // ---- the rows of the block, a contiguous share per warp (at most 32: the row headers are read lane-parallel)
+    const int per = (rb1 - rb0 + WARPS - 1) / WARPS;
+    for (int eb = rb0 + warp * per, e1 = min(eb + per, rb1); eb < e1; eb += 32) {
+      int hn = -1, hoff = 0, hself = -1;
+      if (eb + lane < e1) {
+        const int i = eb + lane;
+        hn = (V.flags[i] & F_NEED) ? V.nbr_cnt[i] : -1;
+        hoff = V.nbr_off[i];
+        // the row's own slot: its state is read from the tile, and stages that count the self pair append it
+        const unsigned long long pk = V.gsub[i];
+        const int tx = (int) (pk & 0xfffff) - cx * SUBDIV - 2 * q + 3, ty = (int) ((pk >> 20) & 0xfffff) - cy * SUBDIV + 3;
+        const int s = (tx * TY + ty) * 3 + 1;
+        hself = tab.off[s] + (i - tab.beg[s]);
+      }
+      const int nrows = min(32, e1 - eb);
+      for (int rr = 0; rr < nrows; rr++) {
+        const int n = __shfl_sync(FULL, hn, rr);
+        if (n < 0) continue;
+        const int i = eb + rr, self = __shfl_sync(FULL, hself, rr);
+        const unsigned short *__restrict__ lst = nbr16 + (size_t) (unsigned) __shfl_sync(FULL, hoff, rr) * 32u + lane;
+        typename S::I st;
+        S::tile_init(K, ss, comp, self, i, st);
+        S::init_uni(K, st);
+        const double gix = comp[0 * TCAP + self], giy = comp[1 * TCAP + self], giz = comp[2 * TCAP + self];
+        typename S::A acc;
+        S::begin(K, st, acc, 0);
+        const int ntot = n + (S::kSkipSelf ? 0 : 1);
+        auto entry = [&](int k) { return k < n ? (int) __ldg(lst + (k - lane)) : (k < ntot ? self : -1); };
+        int jn = entry(lane);
+        for (int q0 = 0; q0 < ntot; q0 += 32) {
+          const int sl = jn;
+          jn = entry(q0 + 32 + lane);
+          if (sl >= 0) {
+            const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
+            S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+          }
+        }
+        S::end(V, K, ss, i, st, acc, 0, lane);
+      }
+    }
+    __syncthreads();   // the tile is overwritten for the next block
+  }
+}
+
+template <class S, int WARPS>
+int launch_tile_scan(psph_ctx *ctx, int kid)
+{
+  constexpr size_t smem = 4 * sizeof(TileTable) + sizeof(TileWarp) * WARPS;
+  PSPH_CUDA(cudaFuncSetAttribute(k_tile_scan<S, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  KernelTimer kt(ctx, kid);
+  const int grid = (int) std::min<long long>(ctx->ncells, ctx->sms);
+  k_tile_scan<S, WARPS><<<grid, WARPS * 32, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_blk_any);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+template <class S, int WARPS, int MINB>
+int launch_tile_gather(psph_ctx *ctx, int kid)
+{
+  constexpr size_t smem = sizeof(TileTable) + sizeof(double) * S::kNC * TCAP;
+  static_assert((smem + 1024) * MINB <= 227 * 1024, "tiles do not fit in shared memory");
+  PSPH_CUDA(cudaFuncSetAttribute(k_tile_gather<S, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  KernelTimer kt(ctx, kid);
+  const long long nblk = ctx->ncells * 4;
+  const int grid = (int) std::min<long long>(nblk, (long long) ctx->sms * MINB);
+  k_tile_gather<S, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_blk_any);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}

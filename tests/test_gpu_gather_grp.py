@@ -23,19 +23,23 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("vel", "engr", "rho", "mass_frac", "smoothed_v", "pressure")
 
 
-def run_stages(cfg, rows, mode):
-    old = os.environ.get("PSPH_GATHER")
-    if mode:
-        os.environ["PSPH_GATHER"] = mode
-    else:
-        os.environ.pop("PSPH_GATHER", None)
+def run_stages(cfg, rows, mode, nbr=None):
+    """mode: None (default gathers) or "row" (per-row gather); nbr: None (default pair lists), "0" (fused grouped
+    gather only), "2" (block-tiled slot lists, csrc/psph_tile.cuh).  The switches are read by psph_create."""
+    old = {k: os.environ.get(k) for k in ("PSPH_GATHER", "PSPH_NBR")}
+    for k, v in (("PSPH_GATHER", mode), ("PSPH_NBR", nbr)):
+        if v:
+            os.environ[k] = v
+        else:
+            os.environ.pop(k, None)
     try:
         s = psph.Solver(cfg)
     finally:
-        if old is None:
-            os.environ.pop("PSPH_GATHER", None)
-        else:
-            os.environ["PSPH_GATHER"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     s.upload(rows)
     dt = s.timestep()
     s.set_dt(dt, 1, 0)
@@ -84,6 +88,18 @@ def test_dense_cube_grouped_vs_row_vs_oracle(two_h):
     assert dt_o == dt_g
     for f in FIELDS:
         assert relerr(grp[f], ora[f]) <= 3 * RTOL_STAGE, (f, relerr(grp[f], ora[f]))  # three stages in a row
+
+
+@pytest.mark.parametrize("nbr", ["0", "2"])
+def test_other_pair_paths_vs_default(nbr):
+    """the fused grouped gather alone (PSPH_NBR=0) and the block-tiled slot lists (PSPH_NBR=2) against the default
+    (row pair lists) on the synthetic cube with its erupted sphere, and on the two-h dense cube"""
+    for cfg, rows in (cases.cube(24, seed=9), dense_rows(n=16, two_h=True)):
+        dt_a, bad_a, a = run_stages(cfg, rows, None)
+        dt_b, bad_b, b = run_stages(cfg, rows, None, nbr=nbr)
+        assert dt_a == dt_b and bad_a == 0 and bad_b == 0
+        for f in FIELDS:
+            assert relerr(a[f], b[f]) <= RTOL_STAGE, (nbr, f, relerr(a[f], b[f]))
 
 
 def test_pairs_on_the_cutoff_face():

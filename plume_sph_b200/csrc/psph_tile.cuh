@@ -69,14 +69,6 @@ __device__ __forceinline__ void tile_build(const GridView &G, int cx, int cy, in
   __syncthreads();
 }
 
-struct TileWarp                                // per-warp scratch of the scan
-{
-  GrpHdr hdr;
-  int cand[TCAND];                             // candidate row << 1 | own-bucket flag
-  unsigned short cslot[TCAND];                 // its tile slot
-  unsigned short q[GRP][TQCAP];                // slots that passed the gates, per row of the group
-};
-
 __device__ __forceinline__ void sts16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short) v) : "memory"); }
 __device__ __forceinline__ unsigned lds16(unsigned addr)
 {
@@ -86,24 +78,50 @@ __device__ __forceinline__ unsigned lds16(unsigned addr)
 }
 
 // =========================================================================================
-// pair search: writes nbr (16-bit slots, 32-entry = 64-byte units), nbr_off, nbr_cnt (-1: no list) and blk_any
+// pair search, one CTA per cell: writes nbr (16-bit block slots, 32-entry = 64-byte units), nbr_off, nbr_cnt
+// (-1: no list) and blk_any.  The CELL tile (columns gx = 8 cx - 3 .. + 10, gy likewise, the three z-buckets) is
+// enumerated in the same order as the block tiles (x-slab, y, z-bucket, row), so that the tile of block q is the
+// contiguous slot range of the x-slabs 2q .. 2q+7 and   block slot = cell slot - first slot of x-slab 2q.
+// Per cell: segment table, per-column slot of every z level, slot -> row map and the FP32 records of all tile
+// rows in shared memory; per group of rows the candidates of a column are then ONE slot range read off the
+// z-level table, and the records come from shared memory.
 // =========================================================================================
+constexpr int CX = 14, CY = 14;                // columns of the cell tile: 8 + 2*3 in x and in y
+constexpr int CSEG = CX * CY * 3;              // (column, z-bucket) segments
+constexpr int CCAP = 3584;                     // rows of a cell tile held in shared memory
+constexpr int CZL = 16;                        // z levels per column: local z = -3 .. 11 (15 used)
+
+struct CellTable
+{
+  float4 geo[CCAP];                            // slot -> FP32 record {x - o, y - o, z - o, h}
+  int rowmap[CCAP];                            // slot -> row << 1 | own-bucket flag
+  int beg[CSEG], base[CSEG], off[CSEG + 4];    // as TileTable; off[CSEG] = tile rows
+  unsigned short colz[CX * CY][CZL];           // column -> slot of its first row with local z >= level - 3
+  int wsum[32];
+};
+struct CellWarp                                // per-warp scratch
+{
+  GrpHdr hdr;
+  unsigned short cand[TCAND];                  // candidate slots
+  unsigned short q[GRP][TQCAP];                // block slots that passed the gates, per row of the group
+};
+
 template <class S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__restrict__ blk_any)
 {
-  static_assert(WARPS * 32 >= TSEG, "tile_build needs one thread per segment");
+  static_assert(WARPS * 32 >= CSEG, "one thread per segment");
   extern __shared__ __align__(16) unsigned char s_raw[];
-  TileTable *tabs = reinterpret_cast<TileTable *>(s_raw);                    // one per sx-pair of the cell
-  TileWarp *scr = reinterpret_cast<TileWarp *>(s_raw + 4 * sizeof(TileTable)) + (threadIdx.x >> 5);
+  CellTable &T = *reinterpret_cast<CellTable *>(s_raw);
+  CellWarp *scr = reinterpret_cast<CellWarp *>(s_raw + sizeof(CellTable)) + (threadIdx.x >> 5);
   __shared__ int s_any[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  unsigned s_cand, s_cslot, s_q, s_hdr;
+  unsigned s_cand, s_q, s_hdr, s_geo;
   asm volatile("mov.u32 %0, %1;" : "=r"(s_cand) : "r"((unsigned) __cvta_generic_to_shared(&scr->cand[0])));
-  asm volatile("mov.u32 %0, %1;" : "=r"(s_cslot) : "r"((unsigned) __cvta_generic_to_shared(&scr->cslot[0])));
   asm volatile("mov.u32 %0, %1;" : "=r"(s_q) : "r"((unsigned) __cvta_generic_to_shared(&scr->q[0][0])));
   asm volatile("mov.u32 %0, %1;" : "=r"(s_hdr) : "r"((unsigned) __cvta_generic_to_shared(&scr->hdr.hdr_i[0])));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_geo) : "r"((unsigned) __cvta_generic_to_shared(&T.geo[0])));
   if (lane == 0) {
     scr->hdr.kc[0] = K.cutoff; scr->hdr.kc[1] = K.cutoff2; scr->hdr.kc[2] = K.neigh_radius;
     scr->hdr.geo = V.geo; scr->hdr.hlist = V.t.d[D_HLIST];
@@ -114,21 +132,68 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
   const float hstd_f = (float) hmax;
   const float ch = (float) (S::kSymH ? 0.5 * K.cutoff : K.cutoff);
   const float c_lo = ch * (1.0f - 0x1p-19f), c_hi = ch * (1.0f + 0x1p-19f);
-  // the tile is laid out for a reach of 3 subcells of rows with the standard smoothing length
+  // the tiles are laid out for a reach of 3 subcells of rows with the standard smoothing length
   const bool reach_ok = (int) ceil(S::reach_h(K, hmax, hmax) * G.inv_subw - 1e-9) == 3;
   unsigned short *__restrict__ nbr16 = reinterpret_cast<unsigned short *>(V.nbr);
   unsigned wcur = 0, wend = 0;                 // this warp's block of list space (64-byte units)
   const int ncell = (int) G.ncells;
 
-  // one CTA per cell: the tables of its four blocks are built together, the rows of the cell are shared out to the
-  // warps (a group of rows lies in one subcell column, hence in one block)
   for (int r = blockIdx.x; r < ncell; r += gridDim.x) {
     const int rb0 = __ldg(&G.sub_start[r * SUBS]), rb1 = __ldg(&G.sub_start[r * SUBS + SUBS]);
     if (rb0 == rb1) { if (threadIdx.x < 4) blk_any[r * 4 + threadIdx.x] = 0; continue; }
     const int cell0 = __ldg(&G.rank2cell[r]);
     const int cz = cell0 % G.ncell[2], cy = (cell0 / G.ncell[2]) % G.ncell[1], cx = cell0 / (G.ncell[2] * G.ncell[1]);
     if (threadIdx.x < 4) s_any[threadIdx.x] = 0;
-    for (int qq = 0; qq < 4; qq++) tile_build(G, cx, cy, cz, qq, tabs[qq]);
+    // ---- the cell tile: segment table (exclusive scan of the segment lengths)
+    {
+      const int s = threadIdx.x;
+      int beg = 0, len = 0, base = -1;
+      if (s < CSEG) {
+        const int tx = s / (CY * 3), ty = (s / 3) % CY, k = s % 3;
+        const int gx = cx * SUBDIV - 3 + tx, gy = cy * SUBDIV - 3 + ty, bz = cz - 1 + k;
+        if (gx >= 0 && gy >= 0 && bz >= 0 && gx < G.ncell[0] * SUBDIV && gy < G.ncell[1] * SUBDIV && bz < G.ncell[2]) {
+          const int cc = ((gx / SUBDIV) * G.ncell[1] + gy / SUBDIV) * G.ncell[2] + bz;
+          base = __ldg(&G.cell2rank[cc]) * SUBS + (gx % SUBDIV) * (SUBDIV * SUBDIV) + (gy % SUBDIV) * SUBDIV;
+          const int zl = k == 0 ? SUBDIV - 3 : 0, zh = k == 2 ? 2 : SUBDIV - 1;
+          beg = __ldg(&G.sub_start[base + zl]);
+          len = __ldg(&G.sub_start[base + zh + 1]) - beg;
+        }
+      }
+      int inc = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+      if (lane == 31) T.wsum[warp] = inc;
+      __syncthreads();
+      int pre = 0;
+      for (int k = 0; k < warp; k++) pre += T.wsum[k];
+      if (s < CSEG) { T.beg[s] = beg; T.base[s] = base; T.off[s] = pre + inc - len; }
+      if (s == CSEG - 1) T.off[CSEG] = pre + inc;
+      __syncthreads();
+    }
+    const int ctotal = T.off[CSEG];
+    const bool cell_ok = reach_ok && ctotal <= CCAP;
+    if (cell_ok) {
+      // slot -> row map (with the own-bucket flag), per-column slot of every z level
+      if (threadIdx.x < CSEG) {
+        const int s = threadIdx.x, tx = s / (CY * 3), ty = (s / 3) % CY, k = s % 3;
+        const int own = (k == 1 && tx >= 3 && tx < 3 + SUBDIV && ty >= 3 && ty < 3 + SUBDIV) ? 1 : 0;
+        const int beg = T.beg[s], o = T.off[s], len = T.off[s + 1] - o;
+        for (int j = 0; j < len; j++) T.rowmap[o + j] = ((beg + j) << 1) | own;
+      }
+      for (int idx = threadIdx.x; idx < CX * CY * CZL; idx += WARPS * 32) {
+        const int col = idx / CZL, lvl = idx - col * CZL;            // local z = lvl - 3
+        const int k = lvl < 3 ? 0 : (lvl < 3 + SUBDIV ? 1 : 2), s = col * 3 + k;
+        const int sz = k == 0 ? SUBDIV - 3 + lvl : (k == 1 ? lvl - 3 : lvl - 3 - SUBDIV); // subcell z inside that bucket
+        int slot;
+        if (lvl >= 3 + SUBDIV + 3) slot = T.off[col * 3 + 3];        // past the last level: end of the column
+        else if (T.base[s] < 0) slot = T.off[s];
+        else slot = T.off[s] + (__ldg(&G.sub_start[T.base[s] + sz]) - T.beg[s]);
+        T.colz[col][lvl] = (unsigned short) slot;
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < ctotal; t += WARPS * 32) T.geo[t] = V.geo32[T.rowmap[t] >> 1];
+    }
+    __syncthreads();
     const int per = (rb1 - rb0 + WARPS - 1) / WARPS;
     int e = rb0 + warp * per;
     const int eend = min(e + per, rb1);
@@ -144,12 +209,17 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
       const bool same = need && ((pk ^ pk0) & 0xffffffffffull) == 0;
       const int m = __ffs(~__ballot_sync(FULL, same)) - 1; // 1..GRP
       const bool mine = lane < m;
-      const int q = ((int) (pk0 & 0xfffff) - cx * SUBDIV) >> 1;           // the block of the group
-      const TileTable &tab = tabs[q];
-      const bool tile_ok = reach_ok && tab.off[TSEG] <= TCAP;
+      const int lx = (int) (pk0 & 0xfffff) - cx * SUBDIV, ly = (int) ((pk0 >> 20) & 0xfffff) - cy * SUBDIV;
+      const int q = lx >> 1;                                         // the block of the group
+      const int qbase = T.off[2 * q * CY * 3];                       // first slot of the block's tile
+      const bool tile_ok = cell_ok && T.off[(2 * q + TX) * CY * 3] - qbase <= TCAP;
       float4 p32 = make_float4(0.f, 0.f, 0.f, 0.f);
-      int sz = 0;
-      if (mine) { p32 = V.geo32[row]; sz = (int) ((pk >> 40) & 0xfffff) - cz * SUBDIV; sts32(s_hdr + 4u * lane, row); }
+      int sz = 0, myself = -1;
+      if (mine) {
+        p32 = V.geo32[row]; sz = (int) ((pk >> 40) & 0xfffff) - cz * SUBDIV; sts32(s_hdr + 4u * lane, row);
+        const int s = ((lx + 3) * CY + ly + 3) * 3 + 1;
+        myself = T.off[s] + (row - T.beg[s]);
+      }
       // rows on a subcell face (reach widened by one) or with another smoothing length do not fit the tile layout
       const bool fits = tile_ok && !__any_sync(FULL, mine && ((pk >> 60) != 0 || p32.w != hstd_f));
       if (!fits) {
@@ -161,25 +231,23 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
       const int zlo = __reduce_min_sync(FULL, mine ? sz : 0x7fffffff), zhi = __reduce_max_sync(FULL, mine ? sz : -1);
       bool nonstd = false;
       unsigned ovf = 0;
-      int ig[GRP];
+      int ig[GRP], selfslot[GRP];
       unsigned qa[GRP];
       float fx[GRP], fy[GRP], fz[GRP], blo[GRP], bhi[GRP];
 #pragma unroll
       for (int g = 0; g < GRP; g++) {
         ig[g] = __shfl_sync(FULL, row, g);
+        selfslot[g] = __shfl_sync(FULL, myself, g);
         fx[g] = __shfl_sync(FULL, p32.x, g); fy[g] = __shfl_sync(FULL, p32.y, g); fz[g] = __shfl_sync(FULL, p32.z, g);
         const float hf = __shfl_sync(FULL, p32.w, g);
         blo[g] = hf * c_lo - delta; bhi[g] = hf * c_hi + delta;
         qa[g] = s_q + 2u * TQCAP * g;
       }
-      // the group's box in tile coordinates: columns (tx0 + ix, ty0 + iy), ix, iy = 0..6; local z [lz0, lz1]
-      const int tx0 = (int) (pk0 & 0xfffff) - cx * SUBDIV - 2 * q, ty0 = (int) ((pk0 >> 20) & 0xfffff) - cy * SUBDIV;
-      const int lz0 = zlo - 3, lz1 = zhi + 3;
-      int item_base = -32, c0 = 0, total = 0, beg = 0, len = 0, slot = 0;
-      bool own = false;
+      // the group's box: cell-tile columns (lx + ix, ly + iy), ix, iy = 0..6; z levels [zlo, zhi + 7) (local z + 3)
+      const int lv0 = zlo, lv1 = zhi + 7;
+      int col_base = -32, c0 = 0, total = 0, slot = 0, len = 0;
 
-      auto test = [&](int cj, unsigned sl, const float4 &p) {
-        const int j = cj >> 1;
+      auto test = [&](unsigned sl, const float4 &p) {
         const float hlo = S::kSymH ? p.w * c_lo : 0.f, hhi = S::kSymH ? p.w * c_hi : 0.f;
         nonstd |= p.w != hstd_f;
         unsigned okb = 0, bandb = 0;
@@ -188,20 +256,20 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
           if (g < m) {
             const float m3 = fmaxf(fmaxf(fabsf(fx[g] - p.x), fabsf(fy[g] - p.y)), fabsf(fz[g] - p.z));
             bool ok = m3 <= bhi[g] + hhi;
-            if (S::kSkipSelf) ok = ok && j != ig[g];
+            if (S::kSkipSelf) ok = ok && (int) sl != selfslot[g];
             if (ok) okb |= 1u << g;
             if (ok && m3 > blo[g] + hlo) bandb |= 1u << g;
           }
         }
         if (__any_sync(FULL, bandb != 0)) { // within the FP32 error band of a cutoff face: the reference's own test
-          if (bandb) okb = gate_exact_grp(&scr->hdr, okb, bandb, cj, S::kSymH ? 1 : 0);
+          if (bandb) okb = gate_exact_grp(&scr->hdr, okb, bandb, T.rowmap[sl], S::kSymH ? 1 : 0);
         }
 #pragma unroll
         for (int g = 0; g < GRP; g++) {
           if (g < m) {
             const bool ok = (okb >> g) & 1u;
             const unsigned bal = __ballot_sync(FULL, ok);
-            if (ok) sts16(qa[g] + 2u * __popc(bal & lt), sl);
+            if (ok) sts16(qa[g] + 2u * __popc(bal & lt), sl - (unsigned) qbase);
             qa[g] += 2u * __popc(bal);
           }
         }
@@ -209,7 +277,7 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
 
       for (;;) {
         if (c0 >= total) {
-          // refill: expand the row ranges of the (column, z-bucket) items into the candidate list
+          // refill: the slot ranges of the next 32 columns of the box, expanded into the candidate list
           if (total) { total = 0; c0 = 0; __syncwarp(); }
           for (;;) {
             if (__any_sync(FULL, len > 0)) {
@@ -221,32 +289,18 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
               for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
               const int sum = __shfl_sync(FULL, off, 31);
               off += total - take;
-              const int tag = own ? 1 : 0;
-              for (int k = 0; k < take; k++) {
-                sts32(s_cand + 4u * (off + k), ((beg + k) << 1) | tag);
-                sts16(s_cslot + 2u * (off + k), (unsigned) (slot + k));
-              }
-              beg += take; slot += take; len -= take; total += sum;
+              for (int k = 0; k < take; k++) sts16(s_cand + 2u * (off + k), (unsigned) (slot + k));
+              slot += take; len -= take; total += sum;
               continue;
             }
-            item_base += 32; // next round of 32 (column, z-bucket) items
-            if (item_base >= TITEMS) break;
-            const int it = item_base + lane;
+            col_base += 32;
+            if (col_base >= 49) break;
+            const int c = col_base + lane;
             len = 0;
-            if (it < TITEMS) {
-              const int col = it / 3, k = it - col * 3, ix = col / 7, iy = col - ix * 7;
-              const int s = ((tx0 + ix) * TY + ty0 + iy) * 3 + k;
-              // local z covered by z-bucket k: [-3, -1], [0, 7], [8, 10]
-              const int klo = k == 0 ? -3 : (k == 1 ? 0 : SUBDIV), khi = k == 0 ? -1 : (k == 1 ? SUBDIV - 1 : SUBDIV + 2);
-              const int a = max(lz0, klo), bb = min(lz1, khi), tb = tab.base[s];
-              if (a <= bb && tb >= 0) {
-                const int zb = (k - 1) * SUBDIV;         // local z of subcell 0 of that bucket
-                beg = __ldg(&G.sub_start[tb + a - zb]);
-                len = __ldg(&G.sub_start[tb + bb - zb + 1]) - beg;
-                slot = tab.off[s] + (beg - tab.beg[s]);
-                own = k == 1 && (tx0 + ix + 2 * q - 3) >= 0 && (tx0 + ix + 2 * q - 3) < SUBDIV && (ty0 + iy - 3) >= 0 &&
-                      (ty0 + iy - 3) < SUBDIV;
-              }
+            if (c < 49) {
+              const int ix = c / 7, iy = c - ix * 7, col = (lx + ix) * CY + ly + iy;
+              slot = T.colz[col][lv0];
+              len = (int) T.colz[col][lv1] - slot;
             }
           }
           __syncwarp();
@@ -255,18 +309,17 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
 #pragma unroll
         for (int g = 0; g < GRP; g++)
           if (qa[g] > s_q + 2u * (TQCAP * g + TQCAP - 64)) { ovf |= 1u << g; qa[g] = s_q + 2u * TQCAP * g; bhi[g] = -INFINITY; }
-        // two candidates per lane, both loads in flight
+        // two candidates per lane
         const int ca = c0 + lane, cb = ca + 32;
         const bool la = ca < total, lb = cb < total;
-        const int ja = la ? lds32(s_cand + 4u * ca) : 0, jb = lb ? lds32(s_cand + 4u * cb) : 0;
-        const unsigned sa = la ? lds16(s_cslot + 2u * ca) : 0u, sb = lb ? lds16(s_cslot + 2u * cb) : 0u;
-        float4 pa = ld_rec32(V.geo32, ja >> 1), pb = ld_rec32(V.geo32, jb >> 1);
+        const unsigned sa = la ? lds16(s_cand + 2u * ca) : 0u, sb = lb ? lds16(s_cand + 2u * cb) : 0u;
+        float4 pa = T.geo[sa], pb = T.geo[sb];
         if (!la) { pa.x = INFINITY; pa.w = hstd_f; }
         if (!lb) { pb.x = INFINITY; pb.w = hstd_f; }
         const bool two = c0 + 32 < total;
         c0 += 64;
-        test(ja, sa, pa);
-        if (two) test(jb, sb, pb);
+        test(sa, pa);
+        if (two) test(sb, pb);
       }
       // ---- publish the lists
       const bool guni = !__any_sync(FULL, nonstd);
@@ -402,7 +455,8 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
 template <class S, int WARPS>
 int launch_tile_scan(psph_ctx *ctx, int kid)
 {
-  constexpr size_t smem = 4 * sizeof(TileTable) + sizeof(TileWarp) * WARPS;
+  constexpr size_t smem = sizeof(CellTable) + sizeof(CellWarp) * WARPS;
+  static_assert(smem <= 227 * 1024, "cell tile does not fit in shared memory");
   PSPH_CUDA(cudaFuncSetAttribute(k_tile_scan<S, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   KernelTimer kt(ctx, kid);
   const int grid = (int) std::min<long long>(ctx->ncells, ctx->sms);

@@ -39,8 +39,8 @@ ALG_BYTES = {"gather_mom_engr": 228, "gather_density": 148, "gather_velocity": 1
 ALG_BYTES_STEP = 1184
 # kernel behind each timer when the pair-list path runs (3-D SPH defaults), and what ncu measured for it
 # (profiles/r01k_ncu_dram_n216.txt: DRAM bytes per launch at this workload; profiles/r01i_ncu_lists_n96.txt: FP64 pipe)
-KERNEL_OF = {"gather_mom_engr": "k_gather_list<MomStage<3>>", "gather_density": "k_gather_list<DensStage<3>>",
-             "gather_velocity": "k_gather_list<VelStage<3>>"}
+KERNEL_OF = {"gather_mom_engr": "k_tile_gather<MomStage<3>>", "gather_density": "k_tile_gather<DensStage<3>>",
+             "gather_velocity": "k_tile_gather<VelStage<3>>"}
 NCU = {"gather_mom_engr": {"traffic": None, "fp64_pipe_pct": 40.6}, "gather_density": {"traffic": None, "fp64_pipe_pct": 39.7},
        "gather_velocity": {"traffic": None, "fp64_pipe_pct": 30.1}}
 

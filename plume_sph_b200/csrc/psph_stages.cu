@@ -458,14 +458,14 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
     ctx->nbr_valid = false;
     if (ctx->nbr_mode == 2 && psph_nbr_prepare(ctx) == 1) { // block-tiled: slot lists, records staged in shared memory
       if (launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN)) return -1;
-      ctx->nbr_valid = true;
+      ctx->nbr_valid = true; ctx->nbr_kind = 2;
       KernelTimer kt(ctx, kid);
       if (launch_tile_gather<S<3>, S<3>::kWarpsTile, S<3>::kMinbTile>(ctx, -1)) return -1;
       return launch_gather_grp<S<3> >(ctx, -1, 2);
     }
     if (ctx->nbr_mode == 1 && psph_nbr_prepare(ctx) == 1) {
       if (launch_gather_grp<S<3> >(ctx, KN_PAIR_SCAN, 3)) return -1; // timed apart: the pair search
-      ctx->nbr_valid = true;
+      ctx->nbr_valid = true; ctx->nbr_kind = 1;
       KernelTimer kt(ctx, kid); // both launches are this stage's gather
       if (launch_gather_list<S<3> >(ctx, -1)) return -1;
       return launch_gather_grp<S<3> >(ctx, -1, 2);
@@ -474,7 +474,7 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   }
   if (ctx->nbr_valid) {
     KernelTimer kt(ctx, kid); // both launches are this stage's gather
-    if (ctx->nbr_mode == 2) {
+    if (ctx->nbr_kind == 2) {
       if (launch_tile_gather<S<3>, S<3>::kWarpsTile, S<3>::kMinbTile>(ctx, -1)) return -1;
     } else if (launch_gather_list<S<3> >(ctx, -1)) return -1;
     return launch_gather_grp<S<3> >(ctx, -1, 2);
@@ -502,7 +502,7 @@ int psph_nbr_prepare(psph_ctx *ctx)
     ctx->nbr_units = units;
   }
   // units of 32 entries: 128 bytes of row indices, or 64 bytes of 16-bit tile slots (block-tiled mode)
-  const size_t cap = ctx->nbr_mode == 2 ? ctx->nbr_units * 2 : ctx->nbr_units;
+  const size_t cap = ctx->nbr_mode == 2 ? ctx->nbr_units * 2 : ctx->nbr_units;  // (the writer that follows uses nbr_mode)
   k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(cap, 0xfffffff0ull));
   PSPH_LAUNCH_CHECK();
   return 1;
@@ -705,6 +705,10 @@ extern "C" int psph_errors(psph_ctx *ctx, int reset)
   PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
   int bad = ctx->h_ss->bad;
   ctx->n = ctx->list_valid ? ctx->h_ss->n : ctx->n;
+  // the block tiles assume a reach of 3 subcells and a bounded row count per cell: when most rows fell back to the
+  // fused gather in the last step, the row lists (no such assumptions) serve this table better
+  if (ctx->nbr_mode == 2 && ctx->nbr_valid && ctx->h_ss->n_need > 0 && 2LL * ctx->h_ss->n_uncached > ctx->h_ss->n_need)
+    ctx->nbr_mode = 1;
   if (reset && bad) {
     PSPH_CUDA(cudaMemsetAsync(&ctx->d_ss->bad, 0, sizeof(int), ctx->stream));
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));

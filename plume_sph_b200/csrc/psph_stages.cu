@@ -127,7 +127,7 @@ struct DensStage
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
   { R r; r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]); return r; }
   // the state of row i from its own slot of the tile; a listed row carries the table's standard smoothing length
-  static __device__ __forceinline__ void tile_init(const KParams &K, StepState *ss, const double *, int, int, I &s)
+  static __device__ __forceinline__ void tile_init(const DevView &, const KParams &K, StepState *ss, const double *, int, int, I &s)
   { s.h = ss->hmax; s.supp = K.cutoff2 * s.h; }
   // rows whose partners all carry the row's own smoothing length (pair lists): 1/h and the kernel norms once per row
   static __device__ __forceinline__ void init_uni(const KParams &K, I &s)
@@ -203,7 +203,7 @@ struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 16, kWarpsGrp = 16, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 16, kPfList = 0, kNRec = 3;
-  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3], invh, ninvh2, norm; };  // from invh on: init_uni
+  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3], v0[3], e0, invh, ninvh2, norm; };  // from invh on: init_uni
   struct A { double rv[3], re; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -218,7 +218,11 @@ struct MomStage
     s.c = V.t.d[D_C][i]; s.T = V.t.d[D_T][i]; s.Cp = V.t.d[D_CP][i];
     const int u = K.lans ? D_SVX : D_VX;
     s.u[0] = V.t.d[u][i]; s.u[1] = V.t.d[u + 1][i]; s.u[2] = V.t.d[u + 2][i];
+    load_old(V, i, s);
   }
+  // what end() updates, read before the pair loop so that the row does not wait for it afterwards
+  static __device__ __forceinline__ void load_old(const DevView &V, int i, I &s)
+  { s.v0[0] = V.t.d[D_VX][i]; s.v0[1] = DIM == 3 ? V.t.d[D_VY][i] : 0.0; s.v0[2] = DIM == 3 ? V.t.d[D_VZ][i] : 0.0; s.e0 = V.t.d[D_E][i]; }
   static __device__ __forceinline__ double reach(const KParams &K, const I &s, double hmax)
   { return fmin(K.cutoff * 0.5 * (s.h + hmax), s.supp); }
   static __device__ __forceinline__ void begin(const KParams &, I &, A &a, int) { a.rv[0] = a.rv[1] = a.rv[2] = a.re = 0.0; }
@@ -243,8 +247,9 @@ struct MomStage
     return r;
   }
   // the state of row i from its own slot of the tile (k_pack_mom forms V and p V^2 exactly as init() does)
-  static __device__ __forceinline__ void tile_init(const KParams &K, StepState *ss, const double *c, int t, int i, I &s)
+  static __device__ __forceinline__ void tile_init(const DevView &V, const KParams &K, StepState *ss, const double *c, int t, int i, I &s)
   {
+    load_old(V, i, s);
     s.i = i; s.h = ss->hmax; s.supp = K.cutoff2 * s.h;
     s.pvsq = c[4 * TCAP + t]; s.Vi = c[5 * TCAP + t]; s.rho = c[6 * TCAP + t];
     s.c = c[7 * TCAP + t]; s.Cp = c[8 * TCAP + t]; s.T = c[9 * TCAP + t];
@@ -295,10 +300,10 @@ struct MomStage
     warp_sum4(r0, r1, r2, re, lane);
     if (lane == 0) {
       const double dt = ss->dt, grav = -K.g;
-      double un[3] = { V.t.d[D_VX][i] + dt * r0, V.t.d[D_VY][i] + dt * r1, V.t.d[D_VZ][i] + dt * r2 };
+      double un[3] = { s.v0[0] + dt * r0, s.v0[1] + dt * r1, s.v0[2] + dt * r2 };
       un[DIM - 1] += dt * grav;                                     // :350
       V.scr[0][i] = un[0]; V.scr[1][i] = un[1]; V.scr[2][i] = un[2];
-      V.scr[3][i] = V.t.d[D_E][i] + dt * (re + s.u[DIM - 1] * grav); // :354
+      V.scr[3][i] = s.e0 + dt * (re + s.u[DIM - 1] * grav);         // :354
       if (!(s.rho > 0)) atomicAdd(&ss->bad, 1);
     }
     return false;
@@ -349,7 +354,7 @@ struct VelStage
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
   { R r; r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]); return r; }
-  static __device__ __forceinline__ void tile_init(const KParams &K, StepState *ss, const double *c, int t, int, I &s)
+  static __device__ __forceinline__ void tile_init(const DevView &, const KParams &K, StepState *ss, const double *c, int t, int, I &s)
   {
     s.h = ss->hmax; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
     s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);

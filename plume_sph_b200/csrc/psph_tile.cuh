@@ -429,7 +429,7 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
         const int i = eb + rr, self = __shfl_sync(FULL, hself, rr);
         const unsigned short *__restrict__ lst = nbr16 + (size_t) (unsigned) __shfl_sync(FULL, hoff, rr) * 32u + lane;
         typename S::I st;
-        S::tile_init(K, ss, comp, self, i, st);
+        S::tile_init(V, K, ss, comp, self, i, st);
         S::init_uni(K, st);
         const double gix = comp[0 * TCAP + self], giy = comp[1 * TCAP + self], giz = comp[2 * TCAP + self];
         typename S::A acc;

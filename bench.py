@@ -38,11 +38,12 @@ UNIT = "particle-updates/s"
 ALG_BYTES = {"gather_mom_engr": 228, "gather_density": 148, "gather_velocity": 100}
 ALG_BYTES_STEP = 1184
 # kernel behind each timer when the pair-list path runs (3-D SPH defaults), and what ncu measured for it
-# (profiles/r01k_ncu_dram_n216.txt: DRAM bytes per launch at this workload; profiles/r01i_ncu_lists_n96.txt: FP64 pipe)
+# (profiles/r01k_ncu_dram_n216.txt: DRAM bytes per launch at this workload — the slot lists, 4.6 GB, plus the tiles'
+# records; profiles/r01l_ncu_tile_n96.txt: FP64 pipe)
 KERNEL_OF = {"gather_mom_engr": "k_tile_gather<MomStage<3>>", "gather_density": "k_tile_gather<DensStage<3>>",
              "gather_velocity": "k_tile_gather<VelStage<3>>"}
-NCU = {"gather_mom_engr": {"traffic": None, "fp64_pipe_pct": 40.6}, "gather_density": {"traffic": None, "fp64_pipe_pct": 39.7},
-       "gather_velocity": {"traffic": None, "fp64_pipe_pct": 30.1}}
+NCU = {"gather_mom_engr": {"traffic": 8345665024, "fp64_pipe_pct": 51.8}, "gather_density": {"traffic": 6875210752, "fp64_pipe_pct": 40.6},
+       "gather_velocity": {"traffic": 6689056000, "fp64_pipe_pct": 32.7}}
 
 
 def measured_peaks():
@@ -230,9 +231,9 @@ def run_b200(args):
                 "fp64_pipe_pct_ncu": NCU[dom]["fp64_pipe_pct"],
                 "alg_bytes_per_update": ALG_BYTES[dom], "updates_per_launch": n_real_local,
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
-                "note": "FP64 pair loop over cached pair lists: bound by the L1 gather rate and the FP64 pipe, not by HBM "
-                        "(SURVEY.md §8d): the HBM fraction is low by construction; fp64_pipe_pct_ncu and profiles/ "
-                        "carry the figure of merit",
+                "note": "FP64 pair loop over per-step pair lists, partners' records staged in shared memory: bound by the "
+                        "FP64 pipe and the issue slots, not by HBM (SURVEY.md §8d): the HBM fraction is low by "
+                        "construction; fp64_pipe_pct_ncu and profiles/ carry the figure of merit",
                 "step_hbm": {"alg_bytes_per_update": ALG_BYTES_STEP,
                              "achieved_GBps": round(ALG_BYTES_STEP * n_real / (ms / args.steps * 1e-3) / 1e9, 2)},
                 "stage_ms_per_step": {k: round(v / ksteps, 4) for k, v in sms.items() if v > 0},

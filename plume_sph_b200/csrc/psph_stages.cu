@@ -121,11 +121,15 @@ struct DensStage
   static __device__ __forceinline__ R load(const DevView &V, int j) { R r; r.r0 = ld_rec(V.rec[0], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0 = make_double4(0., 0., 0., 0.); }  // a row that adds exact zeros
   // block-tiled gather (psph_tile.cuh): columns 3.. of a tile row in shared memory, and the record read back
-  static constexpr int kNC = 7, kWarpsTile = 12, kMinbTile = 2;
+  // tile columns 3..5: m (negative: phase 2), m/rho, m e/rho.  kDefer (the tile gather queues the pairs that can lie
+  // inside the energy-smoothing kernel and runs pair_inner on them 32 at a time) measured 6 % slower than running
+  // them in place: off
+  static constexpr int kNC = 6, kWarpsTile = 12, kMinbTile = 2;
+  static constexpr bool kDefer = false;
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
-  { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
+  { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.w != 0.0 ? -r.x : r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
-  { R r; r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]); return r; }
+  { R r; const double m = c[3 * TCAP + t]; r.r0 = make_double4(fabs(m), c[4 * TCAP + t], c[5 * TCAP + t], m < 0.0 ? 1.0 : 0.0); return r; }
   // the state of row i from its own slot of the tile; a listed row carries the table's standard smoothing length
   static __device__ __forceinline__ void tile_init(const DevView &, const KParams &K, StepState *ss, const double *, int, int, I &s)
   { s.h = ss->hmax; s.supp = K.cutoff2 * s.h; }
@@ -139,28 +143,40 @@ struct DensStage
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
   { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
+  // the density sums of one pair; returns whether the pair can lie inside the (narrower) energy-smoothing kernel:
+  // all |q dx_k / h| <= cutoff implies r2 <= DIM (cutoff h / q)^2, which decides most pairs with one compare
+  template <bool UNI>
+  static __device__ __forceinline__ bool pair_main(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
+                                                   const R &rec)
+  {
+    const double h = UNI ? s.h : 0.5 * (s.h + hj);                  // :155
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double4 rj = rec.r0;
+    const double wm = (UNI ? dev_weight_pre(r2, s.ninvh2, s.norm) : dev_weight_in<DIM>(r2, dev_rcp(h))) * rj.x;
+    const bool ph2 = rj.w != 0.0;                                   // phase of j
+    a.rho2 += ph2 ? wm : 0.0;
+    a.rho1 += ph2 ? 0.0 : wm;
+    if (K.energy_smooth != 1) return false;
+    const double b = K.cutoff * h * (1.0 + 0x1p-40);
+    return r2 * (K.e_ratio * K.e_ratio) <= DIM * b * b;
+  }
+  // the energy-smoothing sums (:163-168, kernel of width h/E_SMOOTH_RATIO) of a pair that passed pair_main's test
+  template <bool UNI>
+  static __device__ __forceinline__ void pair_inner(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
+                                                    const R &rec)
+  {
+    const double h = UNI ? s.h : 0.5 * (s.h + hj), q = K.e_ratio;
+    if (outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) return;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double we = UNI ? dev_weight_pre(r2, s.ninvh2e, s.norme) : dev_weight_in<DIM>(r2, q * dev_rcp(h));
+    a.wn += we * rec.r0.y;
+    a.en += we * rec.r0.z;
+  }
   template <bool UNI>
   static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
                                                 const R &rec)
   {
-    const double h = UNI ? s.h : 0.5 * (s.h + hj);                  // :155
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    const double invh = UNI ? s.invh : dev_rcp(h);
-    const double4 rj = rec.r0;
-    const double wm = (UNI ? dev_weight_pre(r2, s.ninvh2, s.norm) : dev_weight_in<DIM>(r2, invh)) * rj.x;
-    const bool ph2 = rj.w != 0.0;                                   // phase of j
-    a.rho2 += ph2 ? wm : 0.0;
-    a.rho1 += ph2 ? 0.0 : wm;
-    if (K.energy_smooth == 1) {                                     // :163-168, kernel of width h/E_SMOOTH_RATIO
-      const double q = K.e_ratio;
-      // all |q dx_k / h| <= cutoff implies r2 <= DIM (cutoff h / q)^2: most pairs are decided by this one compare
-      const double b = K.cutoff * h * (1.0 + 0x1p-40);
-      if (r2 * (q * q) <= DIM * b * b && !outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) {
-        const double we = UNI ? dev_weight_pre(r2, s.ninvh2e, s.norme) : dev_weight_in<DIM>(r2, q * invh);
-        a.wn += we * rj.y;
-        a.en += we * rj.z;
-      }
-    }
+    if (pair_main<UNI>(K, s, a, dx, dy, dz, hj, rec)) pair_inner<UNI>(K, s, a, dx, dy, dz, hj, rec);
   }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *ss, int i, I &, A &a, int, int lane)
   {
@@ -231,6 +247,7 @@ struct MomStage
   { R r; r.r0 = ld_rec(V.rec[0], j); r.r1 = ld_rec(V.rec[1], j); r.r2 = ld_rec(V.rec[2], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0.x = 0.; }                          // m_j = 0: the pair adds exact zeros
   static constexpr int kNC = 13, kWarpsTile = 16, kMinbTile = 1;
+  static constexpr bool kDefer = false;
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   {
     const double4 a = ld_rec(V.rec[0], row), b = ld_rec(V.rec[1], row), u = ld_rec(V.rec[2], row);
@@ -350,6 +367,7 @@ struct VelStage
                                               double dz, double hj, int j)
   { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
   static constexpr int kNC = 7, kWarpsTile = 12, kMinbTile = 2;
+  static constexpr bool kDefer = false;
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
@@ -462,7 +480,7 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   if (writer) {
     ctx->nbr_valid = false;
     if (ctx->nbr_mode == 2 && psph_nbr_prepare(ctx) == 1) { // block-tiled: slot lists, records staged in shared memory
-      if (launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN)) return -1;
+      if ((ctx->gather_warps == 24 ? launch_tile_scan<S<3>, 24>(ctx, KN_PAIR_SCAN) : launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN))) return -1;
       ctx->nbr_valid = true; ctx->nbr_kind = 2;
       KernelTimer kt(ctx, kid);
       if (launch_tile_gather<S<3>, S<3>::kWarpsTile, S<3>::kMinbTile>(ctx, -1)) return -1;

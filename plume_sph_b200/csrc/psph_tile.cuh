@@ -216,9 +216,10 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
       float4 p32 = make_float4(0.f, 0.f, 0.f, 0.f);
       int sz = 0, myself = -1;
       if (mine) {
-        p32 = V.geo32[row]; sz = (int) ((pk >> 40) & 0xfffff) - cz * SUBDIV; sts32(s_hdr + 4u * lane, row);
+        sz = (int) ((pk >> 40) & 0xfffff) - cz * SUBDIV; sts32(s_hdr + 4u * lane, row);
         const int s = ((lx + 3) * CY + ly + 3) * 3 + 1;
         myself = T.off[s] + (row - T.beg[s]);
+        p32 = cell_ok ? T.geo[myself] : V.geo32[row];
       }
       // rows on a subcell face (reach widened by one) or with another smoothing length do not fit the tile layout
       const bool fits = tile_ok && !__any_sync(FULL, mine && ((pk >> 60) != 0 || p32.w != hstd_f));
@@ -374,6 +375,8 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
   extern __shared__ __align__(16) unsigned char s_raw[];
   TileTable &tab = *reinterpret_cast<TileTable *>(s_raw);
   double *comp = reinterpret_cast<double *>(s_raw + sizeof(TileTable));       // [kNC][TCAP]
+  // per-warp queue of deferred pairs (S::kDefer), 64 slots
+  const unsigned s_dq = (unsigned) __cvta_generic_to_shared(comp + S::kNC * TCAP) + 128u * (threadIdx.x >> 5);
   int *tile_row = reinterpret_cast<int *>(comp);                              // [TCAP] slot -> row, while the tile is staged
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short *__restrict__ nbr16 = reinterpret_cast<const unsigned short *>(V.nbr);
@@ -437,12 +440,47 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
         const int ntot = n + (S::kSkipSelf ? 0 : 1);
         auto entry = [&](int k) { return k < n ? (int) __ldg(lst + (k - lane)) : (k < ntot ? self : -1); };
         int jn = entry(lane);
-        for (int q0 = 0; q0 < ntot; q0 += 32) {
-          const int sl = jn;
-          jn = entry(q0 + 32 + lane);
-          if (sl >= 0) {
-            const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
-            S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+        if constexpr (S::kDefer) {
+          // second-kernel pairs are rare (a few per row): queue their slots, run them 32 at a time
+          int dn = 0;
+          auto inner = [&](int cnt) {
+            if (lane < cnt) {
+              const int sl = (int) lds16(s_dq + 2u * lane);
+              const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
+              S::template pair_inner<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+            }
+          };
+          for (int q0 = 0; q0 < ntot; q0 += 32) {
+            const int sl = jn;
+            jn = entry(q0 + 32 + lane);
+            bool in = false;
+            if (sl >= 0) {
+              const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
+              in = S::template pair_main<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+            }
+            const unsigned bal = __ballot_sync(FULL, in);
+            if (in) sts16(s_dq + 2u * (dn + __popc(bal & ((1u << lane) - 1u))), (unsigned) sl);
+            dn += __popc(bal);
+            if (dn >= 32) {
+              __syncwarp();
+              inner(32);
+              const unsigned v = lane + 32 < dn ? lds16(s_dq + 2u * (lane + 32)) : 0u;
+              __syncwarp();
+              if (lane + 32 < dn) sts16(s_dq + 2u * lane, v);
+              dn -= 32;
+            }
+          }
+          __syncwarp();
+          inner(dn);
+          __syncwarp();
+        } else {
+          for (int q0 = 0; q0 < ntot; q0 += 32) {
+            const int sl = jn;
+            jn = entry(q0 + 32 + lane);
+            if (sl >= 0) {
+              const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
+              S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+            }
           }
         }
         S::end(V, K, ss, i, st, acc, 0, lane);
@@ -467,7 +505,7 @@ int launch_tile_scan(psph_ctx *ctx, int kid)
 template <class S, int WARPS, int MINB>
 int launch_tile_gather(psph_ctx *ctx, int kid)
 {
-  constexpr size_t smem = sizeof(TileTable) + sizeof(double) * S::kNC * TCAP;
+  constexpr size_t smem = sizeof(TileTable) + sizeof(double) * S::kNC * TCAP + (S::kDefer ? 128 * WARPS : 0);
   static_assert((smem + 1024) * MINB <= 227 * 1024, "tiles do not fit in shared memory");
   PSPH_CUDA(cudaFuncSetAttribute(k_tile_gather<S, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   KernelTimer kt(ctx, kid);

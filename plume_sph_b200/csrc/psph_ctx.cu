@@ -191,7 +191,7 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->list_warps = lw ? atoi(lw) : 0;
     const char *nb = getenv("PSPH_NBR");
     ctx->nbr_mode = nb ? atoi(nb) : 2;
-    ctx->nbr_units = 0; ctx->nbr_valid = false; ctx->nbr_kind = 0;
+    ctx->nbr_units = 0; ctx->nbr_want_tried = 0; ctx->nbr_valid = false; ctx->nbr_kind = 0;
   }
   ctx->timing = 0; memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
   *out = ctx;

@@ -509,10 +509,13 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
 __global__ void k_nbr_reset(StepState *ss, unsigned cap) { ss->nbr_cursor = 0u; ss->nbr_cap = cap; ss->n_uncached = 0; }
 int psph_nbr_prepare(psph_ctx *ctx)
 {
-  // 10 units (320 pairs) per row cover the unit lattice (~230-300 pairs); rows that do not fit get no list
-  size_t want = (size_t) ctx->n * 10;
-  if (want > 0xfffffff0ull) want = 0xfffffff0ull;
-  if (ctx->nbr_units < want) {
+  // 320 pairs per row cover the unit lattice (~230-300 pairs): 10 units of 128 bytes (row indices) or 5 (16-bit
+  // tile slots); rows that do not fit get no list.  Allocated once per table size: when memory capped the buffer
+  // below `want`, asking again every step would only cost a free + malloc of tens of GB.
+  size_t want = (size_t) ctx->n * (ctx->nbr_mode == 2 ? 5 : 10);
+  if (want > 0x7ffffff0ull) want = 0x7ffffff0ull;
+  if (ctx->nbr_units < want && want > ctx->nbr_want_tried) {
+    ctx->nbr_want_tried = want + want / 8;
     size_t free_b = 0, total_b = 0;
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->cur.nbr); ctx->cur.nbr = nullptr; ctx->nbr_units = 0;

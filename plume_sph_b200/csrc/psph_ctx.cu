@@ -189,6 +189,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->gather_pf = gp ? atoi(gp) : -1;
     const char *lw = getenv("PSPH_LWARPS");
     ctx->list_warps = lw ? atoi(lw) : 0;
+    const char *tw = getenv("PSPH_TWARPS");
+    ctx->tile_shape = tw ? atoi(tw) : 0;
     const char *nb = getenv("PSPH_NBR");
     ctx->nbr_mode = nb ? atoi(nb) : 2;
     ctx->nbr_units = 0; ctx->nbr_want_tried = 0; ctx->nbr_valid = false; ctx->nbr_kind = 0;

@@ -124,7 +124,7 @@ struct DensStage
   // tile columns 3..5: m (negative: phase 2), m/rho, m e/rho.  kDefer (the tile gather queues the pairs that can lie
   // inside the energy-smoothing kernel and runs pair_inner on them 32 at a time) measured 6 % slower than running
   // them in place: off
-  static constexpr int kNC = 6, kWarpsTile = 12, kMinbTile = 2;
+  static constexpr int kNC = 6, kWarpsTile = 16, kMinbTile = 2;
   static constexpr bool kDefer = false;
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.w != 0.0 ? -r.x : r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; }
@@ -366,7 +366,7 @@ struct VelStage
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
   { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
-  static constexpr int kNC = 7, kWarpsTile = 12, kMinbTile = 2;
+  static constexpr int kNC = 7, kWarpsTile = 16, kMinbTile = 2;
   static constexpr bool kDefer = false;
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
@@ -470,6 +470,22 @@ __global__ void k_update_pos(Tab V, KParams K, StepState *ss)
 #define GRID(n) (unsigned) (((n) + 255) / 256), 256, 0, ctx->stream
 
 // 3-D SPH stages run on the grouped gather (psph_gather3.cuh); 1-D, and PSPH_GATHER=row, on the per-row one
+// tile gather of one stage: the stage's default shape, or PSPH_TWARPS = warps * 10 + CTAs per SM (tuning switch)
+template <class S>
+static int launch_tile_gather_any(psph_ctx *ctx, int kid)
+{
+  switch (ctx->tile_shape) {
+  case 121: return launch_tile_gather<S, 12, 1>(ctx, kid);
+  case 161: return launch_tile_gather<S, 16, 1>(ctx, kid);
+  case 201: return launch_tile_gather<S, 20, 1>(ctx, kid);
+  case 241: return launch_tile_gather<S, 24, 1>(ctx, kid);
+  case 122: if constexpr (S::kNC <= 7) return launch_tile_gather<S, 12, 2>(ctx, kid); else break;
+  case 162: if constexpr (S::kNC <= 7) return launch_tile_gather<S, 16, 2>(ctx, kid); else break;
+  default: break;
+  }
+  return launch_tile_gather<S, S::kWarpsTile, S::kMinbTile>(ctx, kid);
+}
+
 // The first summation stage of a step (mom_engr_update, `writer`) finds the pairs: the grouped gather publishes the
 // pair lists of the rows that qualify (and sums the others in place), then every stage runs the rows that have a
 // list on k_gather_list; the later stages send the rest through the grouped gather again.
@@ -483,7 +499,7 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
       if ((ctx->gather_warps == 24 ? launch_tile_scan<S<3>, 24>(ctx, KN_PAIR_SCAN) : launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN))) return -1;
       ctx->nbr_valid = true; ctx->nbr_kind = 2;
       KernelTimer kt(ctx, kid);
-      if (launch_tile_gather<S<3>, S<3>::kWarpsTile, S<3>::kMinbTile>(ctx, -1)) return -1;
+      if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
       return launch_gather_grp<S<3> >(ctx, -1, 2);
     }
     if (ctx->nbr_mode == 1 && psph_nbr_prepare(ctx) == 1) {
@@ -498,7 +514,7 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   if (ctx->nbr_valid) {
     KernelTimer kt(ctx, kid); // both launches are this stage's gather
     if (ctx->nbr_kind == 2) {
-      if (launch_tile_gather<S<3>, S<3>::kWarpsTile, S<3>::kMinbTile>(ctx, -1)) return -1;
+      if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
     } else if (launch_gather_list<S<3> >(ctx, -1)) return -1;
     return launch_gather_grp<S<3> >(ctx, -1, 2);
   }

@@ -173,6 +173,8 @@ def run_b200(args):
     if world > 1 and args.weak:   # weak scaling: the global cube holds world x the per-GPU cube
         n = int(round(args.n * world ** (1.0 / 3.0)))
     cfg = cases.cube_config(n)
+    if args.sml_int > 0:               # adaptive_sml every k-th step (reference default 50): measures the regime after it
+        cfg.sml_update_int = args.sml_int
     cfg.device = local
     cfg.rank, cfg.nranks = rank, world
     from plume_sph_b200.slabs import setup_cube_ranks  # slab decomposition across ranks (no-op for 1 rank)
@@ -366,6 +368,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=32)
     ap.add_argument("--ref-replicas", type=int, default=0)
+    ap.add_argument("--sml-int", type=int, default=0, help="run adaptive_sml every k-th step (default: the reference's 50)")
     args = ap.parse_args()
     try:
         if args.impl == "reference":

@@ -749,8 +749,10 @@ extern "C" int psph_errors(psph_ctx *ctx, int reset)
   ctx->n = ctx->list_valid ? ctx->h_ss->n : ctx->n;
   // the block tiles assume a reach of 3 subcells and a bounded row count per cell: when most rows fell back to the
   // fused gather in the last step, the row lists (no such assumptions) serve this table better
-  if (ctx->nbr_mode == 2 && ctx->nbr_valid && ctx->h_ss->n_need > 0 && 2LL * ctx->h_ss->n_uncached > ctx->h_ss->n_need)
-    ctx->nbr_mode = 1;
+  // ... and when the row lists do not apply either (smoothing lengths differ from row to row, e.g. after
+  // adaptive_sml), the search that writes them is wasted work: the fused grouped gather alone serves every table
+  if (ctx->nbr_mode > 0 && ctx->nbr_valid && ctx->h_ss->n_need > 0 && 2LL * ctx->h_ss->n_uncached > ctx->h_ss->n_need)
+    ctx->nbr_mode -= 1;
   if (reset && bad) {
     PSPH_CUDA(cudaMemsetAsync(&ctx->d_ss->bad, 0, sizeof(int), ctx->stream));
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));

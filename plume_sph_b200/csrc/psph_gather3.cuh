@@ -26,6 +26,7 @@
 constexpr int GRP = 4;          // rows per group
 constexpr int GQCAP = 320;      // queue slots per row of the group (multiple of 32, >= 64 + 32)
 constexpr int GQCAP_SCAN = 384; // ... of the scan-only kernel (LM 3), which cannot drain a queue
+constexpr int GQCAP_TAG = 896;  // ... of the general scan (LM 4): rows after adaptive_sml have ~730 partners
 constexpr int GCAND = 512;      // candidate rows expanded per batch
 constexpr int RPWG = 32;        // consecutive list entries per warp and chunk
 constexpr unsigned NBR_BLOCK = 512; // pair-list units a warp takes from the global cursor at a time
@@ -87,7 +88,9 @@ __device__ __noinline__ unsigned gate_exact_grp(const GrpHdr *scr, unsigned okb,
 // LM (pair lists, see k_gather_list): 0 = none; 3 = scan only: when the scan of a group ends, the queue of every
 // row that qualifies (queue did not overflow, standard smoothing length in the whole candidate box, list space
 // left) is written to the global pair list, the other rows are marked and NO pairs are summed here; 1 = the same,
-// but rows that do not qualify are summed in place; 2 = rows that have a list are skipped (the fused fallback).
+// but rows that do not qualify are summed in place; 2 = rows that have a list are skipped (the fused fallback);
+// 4 = scan only, ANY smoothing lengths: an entry is kept when the pair passes the symmetric-h gates (mom/dens)
+// or the h_i gates (velocity filter) and carries one tag bit for each (bit 30 / bit 31 of the row index).
 template <class S, int WARPS, int PF, int LM, int QC>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict__ spill)
@@ -168,6 +171,7 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
       int ig[GRP];
       unsigned qa[GRP];               // window address of the next free slot of every queue
       float fx[GRP], fy[GRP], fz[GRP], blo[GRP], bhi[GRP];
+      float vlo[GRP], vhi[GRP];       // LM 4: the FP32 band of the h_i gate |dx_k| <= cutoff h_i
 #pragma unroll
       for (int g = 0; g < GRP; g++) {
         ig[g] = __shfl_sync(FULL, row, g);
@@ -176,6 +180,11 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
         // a row whose list / in_support limits can bite sends every candidate through the FP64 gates
         blo[g] = ((nlmask >> g) & 1u) ? -INFINITY : hf * c_lo - delta;
         bhi[g] = hf * c_hi + delta;
+        if (LM == 4) {
+          const float cv = (float) K.cutoff;
+          vlo[g] = ((nlmask >> g) & 1u) ? -INFINITY : hf * (cv * (1.0f - 0x1p-19f)) - delta;
+          vhi[g] = hf * (cv * (1.0f + 0x1p-19f)) + delta;
+        }
         qa[g] = s_q + 4u * QC * g;
       }
       // ---- candidate enumeration state (the group's common box, in global subcell coordinates)
@@ -194,7 +203,7 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
         const int j = cj >> 1;
         const float hlo = S::kSymH ? p.w * c_lo : 0.f, hhi = S::kSymH ? p.w * c_hi : 0.f;
         if (LM == 1 || LM == 3) nonstd |= p.w != hstd_f;
-        unsigned okb = 0, bandb = 0;
+        unsigned okb = 0, bandb = 0, okv = 0;
 #pragma unroll
         for (int g = 0; g < GRP; g++) {
           if (g < m) {
@@ -203,17 +212,27 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
             if (S::kSkipSelf) ok = ok && j != ig[g];
             if (ok) okb |= 1u << g;
             if (ok && m3 > blo[g] + hlo) bandb |= 1u << g;
+            if (LM == 4) { // the second gate family (velocity filter): |dx_k| <= cutoff h_i
+              const bool v = m3 <= vhi[g] && j != ig[g];
+              if (v) okv |= 1u << g;
+              if (v && m3 > vlo[g]) bandb |= 1u << g;
+            }
           }
         }
         if (__any_sync(FULL, bandb != 0)) { // within the FP32 error band of a cutoff face: the reference's own test
-          if (bandb) okb = gate_exact_grp(scr, okb, bandb, cj, S::kSymH ? 1 : 0);
+          if (bandb) {
+            if (LM == 4) { // both families exactly for the flagged rows
+              okv = (okv & ~bandb) | gate_exact_grp(scr, bandb, bandb, cj, 0);
+              okb = (okb & ~bandb) | gate_exact_grp(scr, bandb, bandb, cj, 1);
+            } else okb = gate_exact_grp(scr, okb, bandb, cj, S::kSymH ? 1 : 0);
+          }
         }
 #pragma unroll
         for (int g = 0; g < GRP; g++) {
           if (g < m) {
-            const bool ok = (okb >> g) & 1u;
+            const bool ok = ((okb | okv) >> g) & 1u;
             const unsigned b = __ballot_sync(FULL, ok);
-            if (ok) sts32(qa[g] + 4u * __popc(b & lt), j);
+            if (ok) sts32(qa[g] + 4u * __popc(b & lt), LM == 4 ? (int) ((unsigned) j | (((okb >> g) & 1u) << 30) | (((okv >> g) & 1u) << 31)) : j);
             qa[g] += 4u * __popc(b);
           }
         }
@@ -291,7 +310,7 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
           test(ja, pa);
           if (two) test(jb, pb);
         }
-        if (LM == 3 && gsel >= 0) { // no pair phase here: the row's list is dropped, the fused kernel takes the row
+        if ((LM == 3 || LM == 4) && gsel >= 0) { // no pair phase here: the row's list is dropped, the fused kernel takes the row
 #pragma unroll
           for (int g = 0; g < GRP; g++)
             if (g == gsel) { ovf |= 1u << g; qa[g] = s_q + 4u * QC * g; bhi[g] = -INFINITY; }
@@ -308,13 +327,13 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
         const int g0 = done ? 0 : gsel, g1 = done ? m : gsel + 1;
         for (int g = g0; g < g1; g++) {
           const int i = lds32(s_hdr + 4u * g), n = lds32(s_hdr + 16u + 4u * g);
-          if ((LM == 1 || LM == 3) && done) {
+          if ((LM == 1 || LM == 3 || LM == 4) && done) {
             // publish the row's pair list and leave its pairs to k_gather_list when the row qualifies: queue
             // complete, its own h the standard one and so that of every candidate of the group's box
             // (geo32.w == (float) hmax  <=>  h == hmax, see dev_store_geo32), list space left
-            if (g == g0) guni = !__any_sync(FULL, nonstd);
+            if (g == g0) guni = LM == 4 || !__any_sync(FULL, nonstd);
             int off = -1;
-            if (guni && !(((drained | ovf) >> g) & 1u) && ((stdmask >> g) & 1u)) {
+            if (guni && !(((drained | ovf) >> g) & 1u) && (LM == 4 || ((stdmask >> g) & 1u))) {
               const unsigned units = (unsigned) (n + 31) >> 5;
               if (wcur + units > wend) { // next block of list space for this warp
                 unsigned o = 0;
@@ -337,9 +356,9 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
               for (int k = lane; k < n; k += 32) dst[k] = lds32(qb + 4u * k);
               continue;
             }
-            if (LM == 3) continue;
+            if (LM == 3 || LM == 4) continue;
           }
-          if (LM == 3) continue; // (never reached: the scan-only kernel has no pair phase)
+          if (LM == 3 || LM == 4) continue; // (never reached: the scan-only kernels have no pair phase)
           typename S::I st;
           S::init(V, K, ss, i, st);
           const double4 gi = V.geo[i];
@@ -404,7 +423,7 @@ template <class S, int WARPS, int PF, int LM>
 int launch_gather_grp_w(psph_ctx *ctx, int kid)
 {
   static_assert(sizeof(typename S::A) == GNA * sizeof(double), "grouped gather: four accumulators per stage");
-  constexpr int QC = LM == 3 ? GQCAP_SCAN : GQCAP;
+  constexpr int QC = LM == 4 ? GQCAP_TAG : (LM == 3 ? GQCAP_SCAN : GQCAP);
   constexpr int threads = WARPS * 32;
   constexpr size_t smem = sizeof(GrpScratch<QC>) * WARPS;
   // per device, and a process may drive several devices (one context each): set it at every launch
@@ -423,6 +442,7 @@ int launch_gather_grp_w(psph_ctx *ctx, int kid)
 template <class S>
 int launch_gather_grp(psph_ctx *ctx, int kid, int lm)
 {
+  if (lm == 4) return launch_gather_grp_w<S, 12, 0, 4>(ctx, kid);
   if (lm == 3) {
     if (ctx->gather_warps == 16) return launch_gather_grp_w<S, 16, 0, 3>(ctx, kid);
     if (ctx->gather_warps == 24) return launch_gather_grp_w<S, 24, 0, 3>(ctx, kid);
@@ -453,7 +473,8 @@ int launch_gather_grp(psph_ctx *ctx, int kid, int lm)
 // =========================================================================================
 constexpr int RPWL = 16;       // consecutive list entries per warp and chunk
 
-template <class S, int WARPS, int PF>
+// TAG: general lists (scan LM 4): entries carry the gate-family bits, partners have their own smoothing lengths
+template <class S, int WARPS, int PF, bool TAG>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParams K, StepState *ss)
 {
   constexpr int CHUNK = WARPS * RPWL;
@@ -470,13 +491,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParam
       const int32_t *__restrict__ lst = V.nbr + (size_t) (unsigned) V.nbr_off[i] * 32u + lane;
       typename S::I st;
       S::init(V, K, ss, i, st);
-      S::init_uni(K, st);                        // every partner of a listed row has the row's own h
+      if (!TAG) S::init_uni(K, st);              // every partner of a listed row has the row's own h
       const double4 gi = V.geo[i];
       typename S::A acc;
       S::begin(K, st, acc, 0);
       // entry k of the row: list[k] for k < n, then (stages that count it) the self pair, which the list omits
       const int ntot = n + (S::kSkipSelf ? 0 : 1);
-      auto entry = [&](int k) { return k < n ? __ldg(lst + (k - lane)) : (k < ntot ? i : -1); };
+      // TAG: -1 unless the entry carries this stage's family bit (30: symmetric-h gates, 31: h_i gates)
+      auto entry = [&](int k) {
+        if (k >= n) return k < ntot ? i : -1;
+        const int raw = __ldg(lst + (k - lane));
+        if (!TAG) return raw;
+        return (((unsigned) raw >> (S::kSymH ? 30 : 31)) & 1u) ? (raw & 0x3fffffff) : -1;
+      };
       int jn = entry(lane);
       if (PF == 1) {
         double4 gn = ld_rec(V.geo, jn < 0 ? i : jn);
@@ -487,7 +514,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParam
           const typename S::R rj = rn;
           jn = entry(q0 + 32 + lane);
           if (q0 + 32 < ntot) { gn = ld_rec(V.geo, jn < 0 ? i : jn); rn = S::load(V, jn < 0 ? i : jn); }
-          if (j >= 0) S::template pair_r<true>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
+          if (j >= 0) S::template pair_r<!TAG>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, rj);
         }
       } else {
         for (int q0 = 0; q0 < ntot; q0 += 32) {
@@ -495,7 +522,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParam
           jn = entry(q0 + 32 + lane);
           if (j >= 0) {
             const double4 gj = ld_rec(V.geo, j);
-            S::template pair_r<true>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, S::load(V, j));
+            S::template pair_r<!TAG>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, S::load(V, j));
           }
         }
       }
@@ -504,19 +531,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gather_list(DevView V, KParam
   }
 }
 
-template <class S, int WARPS, int PF>
+template <class S, int WARPS, int PF, bool TAG = false>
 int launch_gather_list_w(psph_ctx *ctx, int kid)
 {
   KernelTimer kt(ctx, kid);
   const int nchunks = (ctx->n + WARPS * RPWL - 1) / (WARPS * RPWL);
   const int grid = min(max(nchunks, 1), ctx->sms);
-  k_gather_list<S, WARPS, PF><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->cur, ctx->kp, ctx->d_ss);
+  k_gather_list<S, WARPS, PF, TAG><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   return 0;
 }
 template <class S>
 int launch_gather_list(psph_ctx *ctx, int kid)
 {
+  if (ctx->nbr_kind == 3) return launch_gather_list_w<S, S::kWarpsList, 0, true>(ctx, kid);
   const int w = (ctx->list_warps ? ctx->list_warps : S::kWarpsList) + 100 * (ctx->gather_pf >= 0 ? ctx->gather_pf : S::kPfList);
   switch (w) {
   case 16: return launch_gather_list_w<S, 16, 0>(ctx, kid);

@@ -502,6 +502,13 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
       if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
       return launch_gather_grp<S<3> >(ctx, -1, 2);
     }
+    if (ctx->nbr_mode == 3 && psph_nbr_prepare(ctx) == 1) { // general row lists: any smoothing lengths, tagged entries
+      if (launch_gather_grp<S<3> >(ctx, KN_PAIR_SCAN, 4)) return -1;
+      ctx->nbr_valid = true; ctx->nbr_kind = 3;
+      KernelTimer kt(ctx, kid);
+      if (launch_gather_list<S<3> >(ctx, -1)) return -1;
+      return launch_gather_grp<S<3> >(ctx, -1, 2);
+    }
     if (ctx->nbr_mode == 1 && psph_nbr_prepare(ctx) == 1) {
       if (launch_gather_grp<S<3> >(ctx, KN_PAIR_SCAN, 3)) return -1; // timed apart: the pair search
       ctx->nbr_valid = true; ctx->nbr_kind = 1;
@@ -528,7 +535,7 @@ int psph_nbr_prepare(psph_ctx *ctx)
   // 320 pairs per row cover the unit lattice (~230-300 pairs): 10 units of 128 bytes (row indices) or 5 (16-bit
   // tile slots); rows that do not fit get no list.  Allocated once per table size: when memory capped the buffer
   // below `want`, asking again every step would only cost a free + malloc of tens of GB.
-  size_t want = (size_t) ctx->n * (ctx->nbr_mode == 2 ? 5 : 10);
+  size_t want = (size_t) ctx->n * (ctx->nbr_mode == 2 ? 5 : (ctx->nbr_mode == 3 ? 26 : 10)); // mode 3: ~730 partners
   if (want > 0x7ffffff0ull) want = 0x7ffffff0ull;
   if (ctx->nbr_units < want && want > ctx->nbr_want_tried) {
     ctx->nbr_want_tried = want + want / 8;
@@ -752,7 +759,8 @@ extern "C" int psph_errors(psph_ctx *ctx, int reset)
   // ... and when the row lists do not apply either (smoothing lengths differ from row to row, e.g. after
   // adaptive_sml), the search that writes them is wasted work: the fused grouped gather alone serves every table
   if (ctx->nbr_mode > 0 && ctx->nbr_valid && ctx->h_ss->n_need > 0 && 2LL * ctx->h_ss->n_uncached > ctx->h_ss->n_need)
-    ctx->nbr_mode -= 1;
+    ctx->nbr_mode = ctx->nbr_mode == 2 ? 1 : 0; // tiles -> uniform-h row lists -> fused (the general row lists, mode 3,
+                                                // measured no faster than the fused gather: opt-in only)
   if (reset && bad) {
     PSPH_CUDA(cudaMemsetAsync(&ctx->d_ss->bad, 0, sizeof(int), ctx->stream));
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));

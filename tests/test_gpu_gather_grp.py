@@ -25,7 +25,7 @@ FIELDS = ("vel", "engr", "rho", "mass_frac", "smoothed_v", "pressure")
 
 def run_stages(cfg, rows, mode, nbr=None):
     """mode: None (default gathers) or "row" (per-row gather); nbr: None (default pair lists), "0" (fused grouped
-    gather only), "2" (block-tiled slot lists, csrc/psph_tile.cuh).  The switches are read by psph_create."""
+    gather only), "1" / "3" (row pair lists: uniform h / any h), "2" (block-tiled slot lists, csrc/psph_tile.cuh).  The switches are read by psph_create."""
     old = {k: os.environ.get(k) for k in ("PSPH_GATHER", "PSPH_NBR")}
     for k, v in (("PSPH_GATHER", mode), ("PSPH_NBR", nbr)):
         if v:
@@ -90,10 +90,11 @@ def test_dense_cube_grouped_vs_row_vs_oracle(two_h):
         assert relerr(grp[f], ora[f]) <= 3 * RTOL_STAGE, (f, relerr(grp[f], ora[f]))  # three stages in a row
 
 
-@pytest.mark.parametrize("nbr", ["0", "2"])
+@pytest.mark.parametrize("nbr", ["0", "1", "3"])
 def test_other_pair_paths_vs_default(nbr):
-    """the fused grouped gather alone (PSPH_NBR=0) and the block-tiled slot lists (PSPH_NBR=2) against the default
-    (row pair lists) on the synthetic cube with its erupted sphere, and on the two-h dense cube"""
+    """the fused grouped gather alone (PSPH_NBR=0), the uniform-h row lists (1) and the general tagged row lists (3)
+    against the default (block tiles) on the synthetic cube with its erupted sphere, and on the two-h dense cube
+    (mixed smoothing lengths, list limits that bite, queue overflow)"""
     for cfg, rows in (cases.cube(24, seed=9), dense_rows(n=16, two_h=True)):
         dt_a, bad_a, a = run_stages(cfg, rows, None)
         dt_b, bad_b, b = run_stages(cfg, rows, None, nbr=nbr)

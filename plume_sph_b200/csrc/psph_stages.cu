@@ -105,7 +105,7 @@ struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 24, kPfList = 0, kNRec = 1;
-  struct I { double h, supp, hk, invh, ninvh2, norm, ninvh2e, norme; };  // from invh on: uniform-h rows only (init_uni)
+  struct I { double h, supp, hk, invh, ninvh2, norm, ninvh2e, norme, tin; };  // from invh on: uniform-h rows only (init_uni)
   struct A { double rho1, rho2, wn, en; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -139,6 +139,13 @@ struct DensStage
     s.invh = dev_rcp(s.h); s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);
     const double ie = K.e_ratio * s.invh;
     s.ninvh2e = -(ie * ie); s.norme = dev_weight_norm<DIM>(ie);
+    // the largest |t| with fabs(t / h) <= cutoff as the reference's division rounds it (sph_lib.cc:216-218): with one
+    // h per row the second kernel's support test is three compares per pair instead of three divisions
+    double b = K.cutoff * s.h;
+    for (int k = 0; k < 4 && b / s.h > K.cutoff; k++) b = __longlong_as_double(__double_as_longlong(b) - 1);
+    for (int k = 0; k < 4 && __longlong_as_double(__double_as_longlong(b) + 1) / s.h <= K.cutoff; k++)
+      b = __longlong_as_double(__double_as_longlong(b) + 1);
+    s.tin = b;
   }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
@@ -166,7 +173,9 @@ struct DensStage
                                                     const R &rec)
   {
     const double h = UNI ? s.h : 0.5 * (s.h + hj), q = K.e_ratio;
-    if (outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) return;
+    if (UNI) {
+      if (fabs(q * dx) > s.tin || (DIM == 3 && (fabs(q * dy) > s.tin || fabs(q * dz) > s.tin))) return;
+    } else if (outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff)) return;
     const double r2 = dx * dx + dy * dy + dz * dz;
     const double we = UNI ? dev_weight_pre(r2, s.ninvh2e, s.norme) : dev_weight_in<DIM>(r2, q * dev_rcp(h));
     a.wn += we * rec.r0.y;

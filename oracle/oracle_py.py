@@ -200,6 +200,8 @@ def lib():
         L.psph_oracle_update_pos.restype = C.c_int
         L.psph_oracle_rebin.argtypes = [cp, sp, _P(C.c_int)]
         L.psph_oracle_rebin.restype = C.c_int
+        L.psph_oracle_apply_bcond.argtypes = [cp, sp, C.c_int64, _P(C.c_int32), _P(C.c_int64), _P(C.c_double)]
+        L.psph_oracle_apply_bcond.restype = C.c_int
         L.psph_oracle_eos.argtypes = [cp, sp, C.c_int64]
         L.psph_oracle_eos.restype = None
         L.psph_oracle_table_order.argtypes = [cp, _P(C.c_uint32), C.c_int64, _P(C.c_int64)]
@@ -337,6 +339,15 @@ class OracleState:
 
     def update_pos(self, dt, erupting=1):
         return lib().psph_oracle_update_pos(C.byref(self.cfg), C.byref(self.st), dt, int(erupting))
+
+    def apply_bcond(self, img_row, img_cell, img_coord):
+        """img_row: row of every wall ghost that has an image, img_cell: linear cell of the image's bucket,
+        img_coord [n][3]: reflection points"""
+        r = np.ascontiguousarray(img_row, np.int32)
+        c = np.ascontiguousarray(img_cell, np.int64)
+        x = np.ascontiguousarray(img_coord, np.float64)
+        return lib().psph_oracle_apply_bcond(C.byref(self.cfg), C.byref(self.st), len(r), r.ctypes.data_as(_P(C.c_int32)),
+                                             c.ctypes.data_as(_P(C.c_int64)), x.ctypes.data_as(_P(C.c_double)))
 
     def rebin(self):
         lost = C.c_int(0)

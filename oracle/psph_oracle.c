@@ -673,6 +673,76 @@ int psph_oracle_smooth_velocity(const psph_config *c, psph_oracle_state *st)
   return bad;
 }
 
+/* ---------------- apply_bcond ---------------- */
+static int contr_image(const psph_oracle_state *st, int64_t j)
+{ /* particle.h:562-565: real and pressure-ghost particles contribute to a wall image */
+  return st->bc[j] == 100 || st->bc[j] == 99 || st->bc[j] == 1;
+}
+
+int psph_oracle_apply_bcond(const psph_config *c, psph_oracle_state *st, int64_t nimg, const int32_t *img_row,
+                            const int64_t *img_cell, const double *img_coord)
+{ /* bcond.cc:24-249, BC_FOR_KX == 1 (options.h:269-271, :671-673).  For every wall-ghost image: Shepard
+   * interpolation of (rho, v, e) at the reflection point over the contr_image() particles of the image's bucket
+   * (:93-126) and of its 26 neighbours in table order (:129-188; ks only there, sic), reflection of the velocity
+   * about the wall normal (:209), the ghost takes the values and its secondary variables are recomputed (:219-231) */
+  const int dim = c->dim;
+  for (int64_t q = 0; q < nimg; q++) {
+    const double *refc = img_coord + 3 * q;
+    const int64_t g = img_row[q];
+    double normal[3] = { 0, 0, 0 }, d = 0.;
+    for (int k = 0; k < dim; k++) { normal[k] = refc[k] - D3(st->x, g, k); d += normal[k] * normal[k]; } /* :66-74 */
+    for (int k = 0; k < dim; k++) normal[k] /= sqrt(d);
+    double uvec[5] = { 0, 0, 0, 0, 0 }, wnorm = 0., ks = 0.;
+    const int64_t cl = img_cell[q];
+    const int ck = (int) (cl % c->ncell[2]), cj = (int) ((cl / c->ncell[2]) % c->ncell[1]),
+              ci = (int) (cl / ((int64_t) c->ncell[2] * c->ncell[1]));
+    for (int pass = 0; pass < 28; pass++) { /* pass 0: the image's bucket; 1..27: neighbours, x-major / z-minor */
+      int64_t nl = cl;
+      if (pass) {
+        const int t = pass - 1, di = t / 9 - 1, dj = (t / 3) % 3 - 1, dk = t % 3 - 1;
+        if (!di && !dj && !dk) continue; /* neigh_proc == -2 for the bucket itself, preprocess.cc:303-304 */
+        const int ni = ci + di, nj = cj + dj, nk = ck + dk;
+        if (ni < 0 || nj < 0 || nk < 0 || ni >= c->ncell[0] || nj >= c->ncell[1] || nk >= c->ncell[2]) continue;
+        nl = cell_lin(c, ni, nj, nk);
+      }
+      for (int64_t r = st->cell_off[nl]; r < st->cell_off[nl + 1]; r++) {
+        const int64_t j = st->cell_rows[r];
+        if (!contr_image(st, j)) continue;
+        const double h = st->h[j];
+        double dx[3] = { 0, 0, 0 }, s[3] = { 0, 0, 0 };
+        for (int k = 0; k < dim; k++) dx[k] = refc[k] - D3(st->x, j, k);
+        if (!in_support(dim, dx, c->cutoff2 * h)) continue; /* :104, :156 */
+        for (int k = 0; k < dim; k++) s[k] = dx[k] / h;
+        const double w = psph_oracle_weight(dim, s, h, c->cutoff);
+        const double mj = st->mass[j], rj = st->rho[j];
+        uvec[0] += mj * w;
+        for (int k = 0; k < dim; k++) uvec[1 + k] += mj * w * D3(st->v, j, k) / rj;
+        uvec[4] += mj * w * st->e[j] / rj;
+        if (pass) ks += mj * w * st->ks[j] / rj; /* :172-174: neighbour buckets only */
+        wnorm += mj * w / rj;
+      }
+    }
+    if (wnorm > 0.) { /* :191-198 */
+      for (int k = 0; k < 5; k++) uvec[k] /= wnorm;
+      ks = ks / wnorm;
+    } else {
+      uvec[0] = 1.;
+      for (int k = 1; k < 5; k++) uvec[k] = 0.;
+      ks = 0.0;
+    }
+    double vdotn = 0., velrot[3] = { 0, 0, 0 }; /* reflect, sph_lib.cc:75-83 */
+    for (int k = 0; k < dim; k++) vdotn += uvec[1 + k] * normal[k];
+    for (int k = 0; k < dim; k++) velrot[k] = uvec[1 + k] - 2 * vdotn * normal[k];
+    st->rho[g] = uvec[0];
+    for (int k = 0; k < dim; k++) D3(st->v, g, k) = velrot[k];
+    st->e[g] = uvec[4];
+    st->ks[g] = ks;
+    if (c->fluid_compressibility == 1) st->c[g] = 1482.; /* :223-225 */
+    psph_oracle_eos(c, st, g);
+  }
+  return 0;
+}
+
 /* ---------------- update_pos ---------------- */
 int psph_oracle_update_pos(const psph_config *c, psph_oracle_state *st, double dt, int erupting)
 { /* update_pos.cc:35-168 */

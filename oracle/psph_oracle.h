@@ -71,6 +71,10 @@ int psph_oracle_update_pos(const psph_config *cfg, psph_oracle_state *st, double
 /* update_particles_in_bucket, update_pos.cc:172-462: rewrites cell_off/cell_rows, flags
  * removed rows in st->removed (rows are NOT compacted; removed rows leave every plist) */
 int psph_oracle_rebin(const psph_config *cfg, psph_oracle_state *st, int *lost);
+/* apply_bcond, bcond.cc:24-249: img_row = row of the wall ghost, img_cell = linear index of the image's bucket,
+ * img_coord [nimg][3] = reflection points */
+int psph_oracle_apply_bcond(const psph_config *cfg, psph_oracle_state *st, int64_t nimg, const int32_t *img_row,
+                            const int64_t *img_cell, const double *img_coord);
 /* Particle::update_second_var, particle.cc:528-604, for one row */
 void psph_oracle_eos(const psph_config *cfg, psph_oracle_state *st, int64_t i);
 /* THashTable iteration order (thashtab.cc:204-222 hash, :86-134 sorted chains):

@@ -332,10 +332,33 @@ void psphhook_add_new_erupt(int myid, THashTable *P, HashTable *BG, TimeProps *t
 }
 #endif
 
+/* the wall-ghost images (BndImage, bnd_image.h): bucket key, ghost key, reflection point */
+void dump_images(list<BndImage> &img)
+{
+  if (!dumping()) return;
+  char fn[512];
+  snprintf(fn, sizeof fn, "%s/s%04d_images.bin", g_dir, g_step);
+  FILE *f = fopen(fn, "wb");
+  if (!f) { perror(fn); exit(1); }
+  long long n = (long long) img.size();
+  fwrite(&n, 8, 1, f);
+  for (list<BndImage>::iterator it = img.begin(); it != img.end(); ++it) {
+    int pr[2] = { it->buckproc, it->partproc };
+    fwrite(pr, 4, 2, f);
+    fwrite(it->bucket_key, 4, KEYLENGTH, f);
+    fwrite(it->ghost_key, 4, TKEYLENGTH, f);
+    fwrite(it->coord, 8, DIMENSION, f);
+  }
+  fclose(f);
+}
+
 int psphhook_apply_bcond(int myid, THashTable *P, HashTable *BG, MatProps *mp, list<BndImage> &img)
 {
   init_once();
   if (g_step == 0) return apply_bcond(myid, P, BG, mp, img);
+  dump_table(P, "bcond", "pre");
+  dump_buckets(P, BG, "bcond");
+  dump_images(img);
   int r;
   { StageTimer st("apply_bcond"); r = apply_bcond(myid, P, BG, mp, img); }
   dump_table(P, "bcond", "post");

@@ -40,6 +40,15 @@ def read_neigh(path):
     return off, idx
 
 
+def read_images(path):
+    """-> structured array of the wall-ghost images (BndImage): procs, bucket key, ghost key, reflection point"""
+    dt = np.dtype([("buckproc", "<i4"), ("partproc", "<i4"), ("bucket_key", "<u4", 2), ("ghost_key", "<u4", 3),
+                   ("coord", "<f8", 3)])
+    with open(path, "rb") as f:
+        n, = struct.unpack("<q", f.read(8))
+        return np.fromfile(f, dtype=dt, count=n)
+
+
 def read_buckets(path):
     """-> list of dicts (key, mincrd, maxcrd, type, has_involved, active, guest, bucket_index, bnd, rows)."""
     out = []

@@ -114,9 +114,17 @@ def cell_attrs(cfg, z, tag="b0"):
     return attr, lin
 
 
-def oracle_state_3d(cfg, z, tag="b0"):
+def image_cells(cfg, z):
+    """linear cell index of the bucket of every wall-ghost image of a golden 3-D fixture"""
+    n1, n2 = int(cfg.ncell[1]), int(cfg.ncell[2])
+    mn = z["bc_img_bucket_mincrd"]
+    idx = np.rint((mn * cfg.len_scale - np.asarray([cfg.mindom[d] for d in range(3)])) / cfg.delta).astype(np.int64)
+    return (idx[:, 0] * n1 + idx[:, 1]) * n2 + idx[:, 2]
+
+
+def oracle_state_3d(cfg, z, tag="b0", rows="pre"):
     """Oracle state from a golden 3-D fixture: rows of `pre`, plists and attributes of the buckets."""
-    s = op.OracleState.from_dump(cfg, z["pre"])
+    s = op.OracleState.from_dump(cfg, z[rows])
     attr, lin = cell_attrs(cfg, z, tag)
     off, rows = z[tag + "_off"], z[tag + "_rows"]
     order = list(lin)

@@ -126,6 +126,32 @@ def golden_3d(name, variant, edits, list_stride=4, simdata="simulation.data"):
             out[tag + "_bnd"] = np.asarray([b["bnd"] for b in bk], np.float64)
             out[tag + "_off"] = np.cumsum([0] + [len(b["rows"]) for b in bk]).astype(np.int64)
             out[tag + "_rows"] = np.concatenate([b["rows"] for b in bk]).astype(np.int32)
+        # apply_bcond at the end of step 1 (main.cc:468): state before, wall-ghost images, bucket plists, and the wall
+        # ghosts' state after
+        _, bpre = refio.read_dump(os.path.join(dump, "s0001_bcond_pre.bin"))
+        _, bpost = refio.read_dump(os.path.join(dump, "s0001_bcond_post.bin"))
+        img = refio.read_images(os.path.join(dump, "s0001_images.bin"))
+        bk = refio.read_buckets(os.path.join(dump, "s0001_bcond_buckets.bin"))
+        out["bc_pre"] = bpre
+        rowof = {tuple(k): i for i, k in enumerate(bpre["key"])}
+        bmin = {tuple(b["key"]): b["mincrd"] for b in bk}
+        out["bc_img_row"] = np.asarray([rowof[tuple(k)] for k in img["ghost_key"]], np.int32)
+        out["bc_img_coord"] = np.asarray(img["coord"], np.float64)
+        out["bc_img_bucket_mincrd"] = np.asarray([bmin[tuple(k)] for k in img["bucket_key"]], np.float64)
+        out["b2_mincrd"] = np.asarray([b["mincrd"] for b in bk])
+        out["b2_attr"] = np.asarray([[b["type"], b["has_involved"], b["active"], b["guest"]] for b in bk], np.int32)
+        out["b2_bindex"] = np.asarray([b["bucket_index"] for b in bk], np.int32)
+        out["b2_bnd"] = np.asarray([b["bnd"] for b in bk], np.float64)
+        out["b2_off"] = np.cumsum([0] + [len(b["rows"]) for b in bk]).astype(np.int64)
+        out["b2_rows"] = np.concatenate([b["rows"] for b in bk]).astype(np.int32)
+        wall = np.nonzero(bpre["bc_type"] == 2)[0]
+        out["bc_wall_rows"] = wall.astype(np.int32)
+        for f in ("rho", "vel", "engr", "mass_frac", "pressure", "sound_speed", "temperature", "phase_density", "gamma",
+                  "specific_heat_p"):
+            out["bc_post_" + f] = bpost[f][wall]
+        other = np.ones(len(bpre), bool)
+        other[wall] = False
+        assert all(np.array_equal(bpre[f][other], bpost[f][other]) for f in bpre.dtype.names), "apply_bcond touched a non-wall row"
         # neighbour lists of every list_stride-th listed particle
         off, idx = refio.read_neigh(os.path.join(dump, "s0001_neigh.bin"))
         listed = np.nonzero(np.diff(off) > 0)[0]

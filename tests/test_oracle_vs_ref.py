@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_py as op
-from common import golden, oracle_state_3d, cell_attrs
+from common import golden, oracle_state_3d, cell_attrs, image_cells
 from plume_sph_b200.driver import TimeProps
 
 
@@ -48,6 +48,25 @@ def test_plume3d_step1_bit_exact(name):
     s2 = oracle_state_3d(cfg, z, "b1")
     eq(s.cell_off, s2.cell_off, "plist offsets after re-bin")
     eq(s.cell_rows[:s.cell_off[-1]], s2.cell_rows[:s2.cell_off[-1]], "plists after re-bin (order too)")
+
+
+@pytest.mark.parametrize("name", ["plume3d_small", "jpue3d"])
+def test_apply_bcond_bit_exact(name):
+    """apply_bcond at the end of time step 1 (main.cc:468): the wall ghosts' state after the call, from the state
+    before it, the reference's image table and its bucket plists"""
+    z = golden(name)
+    cfg = op.config_for(name, z)
+    s = oracle_state_3d(cfg, z, "b2", rows="bc_pre")
+    assert s.apply_bcond(z["bc_img_row"], image_cells(cfg, z), z["bc_img_coord"]) == 0
+    w = z["bc_wall_rows"]
+    for f, o in (("rho", "rho"), ("vel", "v"), ("engr", "e"), ("mass_frac", "ks"), ("pressure", "p"),
+                 ("sound_speed", "c"), ("temperature", "T"), ("phase_density", "rho_ph"), ("gamma", "gamma"),
+                 ("specific_heat_p", "Cp")):
+        eq(s.a[o][w], z["bc_post_" + f], ("bcond", f))
+    other = np.ones(s.n, bool)
+    other[w] = False
+    for f, o in (("rho", "rho"), ("vel", "v"), ("engr", "e")):
+        eq(s.a[o][other], z["bc_pre"][f][other], ("bcond leaves other rows alone", f))
 
 
 def test_table_order_matches_thashtable_iteration():

@@ -130,6 +130,15 @@ typedef struct psph_cell_attr
   double bnd[6];
 } psph_cell_attr;
 
+/* One wall-ghost image (BndImage, src/datstr/bnd_image.h:20-75): the mirror point of a wall ghost across the wall.
+ * The driver keeps the table (search_bnd_images, main.cc:188,292,458) and hands it over whenever it changes. */
+typedef struct psph_image
+{
+  uint32_t ghost_key[3];     /* TKey of the wall ghost (bc_type 2) */
+  int32_t cell;              /* linear index (x-major, z-minor) of the bucket that contains the image point */
+  double coord[3];           /* the image (reflection) point */
+} psph_image;
+
 typedef struct psph_ctx psph_ctx;
 
 enum { PSPH_ORDER_DEVICE = 0, PSPH_ORDER_REFERENCE = 1 };
@@ -183,6 +192,12 @@ int psph_smooth_density(psph_ctx *ctx);      /* smooth_density,       main.cc:37
 int psph_smooth_velocity(psph_ctx *ctx);     /* smooth_velocity,      main.cc:392 */
 int psph_update_pos(psph_ctx *ctx);          /* update_pos,           main.cc:405 */
 int psph_rebin(psph_ctx *ctx, int *lost);    /* update_particles_in_bucket, main.cc:408 */
+/* Wall boundary condition.  psph_set_images replaces the table search_bnd_images fills (main.cc:188,292,458) and is
+ * called whenever that table changes; psph_apply_bcond replaces apply_bcond (bcond.cc:24-249; main.cc:196,298,468):
+ * every wall ghost with an image takes the fluid state interpolated at its image point, velocity reflected about the
+ * wall normal, secondary variables recomputed.  Single rank (nranks == 1) in this version. */
+int psph_set_images(psph_ctx *ctx, const psph_image *images, size_t n);
+int psph_apply_bcond(psph_ctx *ctx);
 
 /* The whole per-step hot path in one call, in the reference's order (main.cc:217-408):
  * timestep -> [clip on host via cb] -> search -> [adaptive_sml] -> [gradients] -> mom/energy

@@ -93,6 +93,7 @@ def run_loop(solver, tp, on_output=None, max_steps=None):
         solver.update_pos()                          # :405 / :730
         if cfg.dim == 3:
             solver.update_particles_in_bucket()      # :408
+            solver.apply_bcond()                     # :468 (no-op until the driver hands over its Image_table)
         nsteps += 1
         if tp.ifoutput() and on_output is not None:  # :474 / :746
             on_output(solver, tp)

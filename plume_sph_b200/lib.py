@@ -76,6 +76,9 @@ assert PARTICLE_DTYPE.itemsize == 328
 CELL_ATTR_DTYPE = np.dtype([("type", "<i4"), ("has_involved", "<i4"), ("active", "<i4"),
                             ("bucket_index", "<i4", 6), ("pad", "<i4"), ("bnd", "<f8", 6)])
 assert CELL_ATTR_DTYPE.itemsize == 88
+# psph_image (include/psph.h): one wall-ghost image
+IMAGE_DTYPE = np.dtype([("ghost_key", "<u4", 3), ("cell", "<i4"), ("coord", "<f8", 3)])
+assert IMAGE_DTYPE.itemsize == 40
 
 # every symbol include/psph.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
@@ -104,6 +107,8 @@ API = {
     "psph_smooth_velocity": (C.c_int, [_VP]),
     "psph_update_pos": (C.c_int, [_VP]),
     "psph_rebin": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+    "psph_set_images": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "psph_apply_bcond": (C.c_int, [_VP]),
     "psph_step": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "psph_run": (C.c_int, [_VP, C.c_int, C.c_int]),
     "psph_comm_unique_id": (C.c_int, [_VP, C.c_size_t]),

@@ -13,7 +13,8 @@ from . import lib as _l
 ORDER_DEVICE, ORDER_REFERENCE = 0, 1
 KERNELS = ("gather_mom_engr", "gather_density", "gather_velocity", "gather_adaptive_sml", "gather_gradients",
            "gather_gsph_mom_engr", "radix_sort", "reorder", "pair_scan")
-STAGES = ("timestep", "search", "adaptive_sml", "gradients", "mom_engr", "density", "velocity", "update_pos", "rebin")
+STAGES = ("timestep", "search", "adaptive_sml", "gradients", "mom_engr", "density", "velocity", "update_pos", "rebin",
+          "apply_bcond")
 
 
 class Solver:
@@ -140,6 +141,14 @@ class Solver:
 
     def update_pos(self):
         return self._ck(self.L.psph_update_pos(self.h), "psph_update_pos")
+
+    def set_images(self, images):
+        """wall-ghost images (IMAGE_DTYPE rows: ghost key, bucket cell, image point) — the driver's Image_table"""
+        img = np.ascontiguousarray(images, dtype=_l.IMAGE_DTYPE)
+        return self._ck(self.L.psph_set_images(self.h, img.ctypes.data, len(img)), "psph_set_images")
+
+    def apply_bcond(self):
+        return self._ck(self.L.psph_apply_bcond(self.h), "psph_apply_bcond")
 
     def update_particles_in_bucket(self):
         lost = C.c_int(0)

@@ -193,6 +193,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->tile_shape = tw ? atoi(tw) : 0;
     const char *nb = getenv("PSPH_NBR");
     ctx->nbr_mode = nb ? atoi(nb) : 2;
+    const char *wc = getenv("PSPH_WCACHE");
+    ctx->wcache = wc ? atoi(wc) : 1;
     ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr; ctx->n_img = 0;
     ctx->nbr_units = 0; ctx->nbr_want_tried = 0; ctx->nbr_valid = false; ctx->nbr_kind = 0;
   }
@@ -241,7 +243,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   free_tab(ctx->cur.t); free_tab(ctx->alt);
   for (int c = 0; c < NSCRATCH; c++) cudaFree(ctx->cur.scr[c]);
   for (int c = 0; c < NREC; c++) cudaFree(ctx->cur.rec[c]);
-  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
+  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.wts); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
   cudaFree(ctx->d_cell_has_ghost); cudaFree(ctx->d_blk_any);

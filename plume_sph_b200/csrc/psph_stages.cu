@@ -105,7 +105,7 @@ struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 24, kPfList = 0, kNRec = 1;
-  struct I { double h, supp, hk, invh, ninvh2, norm, ninvh2e, norme, tin; };  // from invh on: uniform-h rows only (init_uni)
+  struct I { double h, supp, hk, invh, ninvh2, norm, ninvh2e, norme, tin, wthr; };  // from invh on: uniform-h rows only (init_uni)
   struct A { double rho1, rho2, wn, en; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -126,13 +126,19 @@ struct DensStage
   // them in place: off
   static constexpr int kNC = 6, kWarpsTile = 16, kMinbTile = 2;
   static constexpr bool kDefer = false;
+  // pair-weight cache (psph_tile.cuh): this stage reads the weights mom_engr_update stored; positions stay in the tile
+  // for the few pairs inside the energy-smoothing kernel
+  static constexpr int kWCache = 2, kNCc = kNC;
+  static constexpr bool kCachedNeedsX = true;
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.w != 0.0 ? -r.x : r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
   { R r; const double m = c[3 * TCAP + t]; r.r0 = make_double4(fabs(m), c[4 * TCAP + t], c[5 * TCAP + t], m < 0.0 ? 1.0 : 0.0); return r; }
   // the state of row i from its own slot of the tile; a listed row carries the table's standard smoothing length
-  static __device__ __forceinline__ void tile_init(const DevView &, const KParams &K, StepState *ss, const double *, int, int, I &s)
-  { s.h = ss->hmax; s.supp = K.cutoff2 * s.h; }
+  static __device__ __forceinline__ void tile_init(const DevView &, const KParams &, StepState *, const double *, int, int, I &) {}
+  // the row constants of a tile launch: every listed row carries the table's standard smoothing length
+  static __device__ __forceinline__ void tile_uni(const KParams &K, double hstd, I &s)
+  { s.h = hstd; s.supp = K.cutoff2 * s.h; init_uni(K, s); }
   // rows whose partners all carry the row's own smoothing length (pair lists): 1/h and the kernel norms once per row
   static __device__ __forceinline__ void init_uni(const KParams &K, I &s)
   {
@@ -146,6 +152,24 @@ struct DensStage
     for (int k = 0; k < 4 && __longlong_as_double(__double_as_longlong(b) + 1) / s.h <= K.cutoff; k++)
       b = __longlong_as_double(__double_as_longlong(b) + 1);
     s.tin = b;
+    // a pair can lie inside the energy-smoothing kernel only if r2 <= R2 := DIM (cutoff h (1 + 2^-40) / q)^2 (pair_main);
+    // W falls with r2, so W >= W(R2) (less a margin far above the 2 ulp of the exp) is the same pre-test on the weight
+    const double bb = K.cutoff * s.h * (1.0 + 0x1p-40);
+    s.wthr = dev_weight_pre(DIM * bb * bb / (K.e_ratio * K.e_ratio), s.ninvh2, s.norm) * (1.0 - 1e-9);
+  }
+  static __device__ __forceinline__ double self_weight(const I &s) { return dev_weight_pre(0.0, s.ninvh2, s.norm); }
+  // one listed pair with its weight from the cache: the density sums (:159-161), and the energy-smoothing sums for
+  // the pairs whose weight says they may lie inside the narrower kernel
+  static __device__ __forceinline__ void pair_c(const KParams &K, const I &s, A &a, double w, const double *c, int sl, int self)
+  {
+    const double m = c[3 * TCAP + sl], wm = w * fabs(m);
+    a.rho2 += m < 0.0 ? wm : 0.0;
+    a.rho1 += m < 0.0 ? 0.0 : wm;
+    if (K.energy_smooth == 1 && w >= s.wthr) {
+      const double dx = c[0 * TCAP + self] - c[0 * TCAP + sl], dy = c[1 * TCAP + self] - c[1 * TCAP + sl],
+                   dz = c[2 * TCAP + self] - c[2 * TCAP + sl];
+      pair_inner<true>(K, s, a, dx, dy, dz, s.h, tile_rec(c, sl));
+    }
   }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
@@ -257,6 +281,8 @@ struct MomStage
   static __device__ __forceinline__ void zero(R &r) { r.r0.x = 0.; }                          // m_j = 0: the pair adds exact zeros
   static constexpr int kNC = 13, kWarpsTile = 16, kMinbTile = 1;
   static constexpr bool kDefer = false;
+  static constexpr int kWCache = 1, kNCc = kNC;                      // first stage of a step: stores the pair weights
+  static constexpr bool kCachedNeedsX = true;
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   {
     const double4 a = ld_rec(V.rec[0], row), b = ld_rec(V.rec[1], row), u = ld_rec(V.rec[2], row);
@@ -276,19 +302,26 @@ struct MomStage
   static __device__ __forceinline__ void tile_init(const DevView &V, const KParams &K, StepState *ss, const double *c, int t, int i, I &s)
   {
     load_old(V, i, s);
-    s.i = i; s.h = ss->hmax; s.supp = K.cutoff2 * s.h;
+    s.i = i;
     s.pvsq = c[4 * TCAP + t]; s.Vi = c[5 * TCAP + t]; s.rho = c[6 * TCAP + t];
     s.c = c[7 * TCAP + t]; s.Cp = c[8 * TCAP + t]; s.T = c[9 * TCAP + t];
     s.u[0] = c[10 * TCAP + t]; s.u[1] = c[11 * TCAP + t]; s.u[2] = c[12 * TCAP + t];
   }
   static __device__ __forceinline__ void init_uni(const KParams &, I &s)
   { s.invh = dev_rcp(s.h); s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh); }
+  static __device__ __forceinline__ void tile_uni(const KParams &K, double hstd, I &s)
+  { s.h = hstd; s.supp = K.cutoff2 * s.h; init_uni(K, s); }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
   { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
   template <bool UNI>
   static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
                                                 const R &rec)
+  { (void) pair_w<UNI>(K, s, a, dx, dy, dz, hj, rec); }
+  // the pair body; returns the kernel weight W(dx / h, h) of the pair (what the weight cache keeps)
+  template <bool UNI>
+  static __device__ __forceinline__ double pair_w(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
+                                                  const R &rec)
   {
     const double h = UNI ? s.h : 0.5 * (s.h + hj);
     const double r2 = dx * dx + dy * dy + dz * dz;
@@ -319,6 +352,7 @@ struct MomStage
     a.rv[0] -= mg * dx;
     if (DIM == 3) { a.rv[1] -= mg * dy; a.rv[2] -= mg * dz; }
     a.re += 0.5 * mg * vr + heat;
+    return w;
   }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *ss, int i, I &s, A &a, int, int lane)
   {
@@ -377,16 +411,33 @@ struct VelStage
   { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
   static constexpr int kNC = 7, kWarpsTile = 16, kMinbTile = 2;
   static constexpr bool kDefer = false;
+  // pair-weight cache (psph_tile.cuh): with W read from the cache the stage needs no positions at all — the tile is
+  // the four columns m/rho, v of the stage record
+  static constexpr int kWCache = 2, kNCc = 4;
+  static constexpr bool kCachedNeedsX = false;
+  static __device__ __forceinline__ void tile_load_c(const DevView &V, int row, double *c, int t)
+  { const double4 r = ld_rec(V.rec[0], row); c[0 * TCAP + t] = r.x; c[1 * TCAP + t] = r.y; c[2 * TCAP + t] = r.z; c[3 * TCAP + t] = r.w; }
+  static __device__ __forceinline__ void tile_init_c(const DevView &, const KParams &, StepState *, const double *c, int t, int, I &s)
+  { s.v[0] = c[1 * TCAP + t]; s.v[1] = c[2 * TCAP + t]; s.v[2] = c[3 * TCAP + t]; }
+  static __device__ __forceinline__ void tile_uni(const KParams &K, double hstd, I &s)
+  {
+    s.h = hstd; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
+    s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);
+  }
+  static __device__ __forceinline__ double self_weight(const I &s) { return dev_weight_pre(0.0, s.ninvh2, s.norm); }
+  static __device__ __forceinline__ void pair_c(const KParams &, const I &s, A &a, double w, const double *c, int sl, int)
+  {
+    const double mvw = w * c[0 * TCAP + sl];
+    a.dv[0] += mvw * (c[1 * TCAP + sl] - s.v[0]);
+    if (DIM == 3) { a.dv[1] += mvw * (c[2 * TCAP + sl] - s.v[1]); a.dv[2] += mvw * (c[3 * TCAP + sl] - s.v[2]); }
+    a.wn += mvw;
+  }
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
   { R r; r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]); return r; }
-  static __device__ __forceinline__ void tile_init(const DevView &, const KParams &K, StepState *ss, const double *c, int t, int, I &s)
-  {
-    s.h = ss->hmax; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
-    s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);
-    s.v[0] = c[4 * TCAP + t]; s.v[1] = c[5 * TCAP + t]; s.v[2] = c[6 * TCAP + t];
-  }
+  static __device__ __forceinline__ void tile_init(const DevView &, const KParams &, StepState *, const double *c, int t, int, I &s)
+  { s.v[0] = c[4 * TCAP + t]; s.v[1] = c[5 * TCAP + t]; s.v[2] = c[6 * TCAP + t]; }
   static __device__ __forceinline__ void init_uni(const KParams &, I &) {}
   template <bool UNI>
   static __device__ __forceinline__ void pair_r(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double,
@@ -551,6 +602,7 @@ int psph_nbr_prepare(psph_ctx *ctx)
     size_t free_b = 0, total_b = 0;
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->cur.nbr); ctx->cur.nbr = nullptr; ctx->nbr_units = 0;
+    cudaFree(ctx->cur.wts); ctx->cur.wts = nullptr;
     PSPH_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t keep = (size_t) 2 << 30;                       // leave 2 GiB for everything else
     size_t units = free_b > keep ? (free_b - keep) / 128 : 0;
@@ -558,7 +610,14 @@ int psph_nbr_prepare(psph_ctx *ctx)
     if (units < (size_t) ctx->n) return 0;                       // not worth it
     if (cudaMalloc(&ctx->cur.nbr, units * 128) != cudaSuccess) { cudaGetLastError(); ctx->cur.nbr = nullptr; return 0; }
     ctx->nbr_units = units;
+    // pair-weight cache of the block-tiled mode: one double per 16-bit slot (4 x the list bytes), only when the full
+    // list fits and the memory is there — HBM is idle during the pair sums, the FP64 pipe is not
+    if (ctx->nbr_mode == 2 && ctx->wcache && units >= want) {
+      PSPH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      if (free_b > keep + units * 512 && cudaMalloc(&ctx->cur.wts, units * 512) != cudaSuccess) { cudaGetLastError(); ctx->cur.wts = nullptr; }
+    }
   }
+  if (ctx->nbr_mode != 2 && ctx->cur.wts) { cudaFree(ctx->cur.wts); ctx->cur.wts = nullptr; }
   // units of 32 entries: 128 bytes of row indices, or 64 bytes of 16-bit tile slots (block-tiled mode)
   const size_t cap = ctx->nbr_mode == 2 ? ctx->nbr_units * 2 : ctx->nbr_units;  // (the writer that follows uses nbr_mode)
   k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(cap, 0xfffffff0ull));

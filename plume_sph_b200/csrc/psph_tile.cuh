@@ -367,11 +367,17 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
 // pair sums off the slot lists; S::kNC double columns per tile row in shared memory: x, y, z + the stage's own
 // (S::tile_load writes them, S::tile_rec reads them back as the stage record)
 // =========================================================================================
-template <class S, int WARPS, int MINB>
+// WM — the pair-weight cache (V.wts, one double per list entry, parallel to the slot lists): between the three stages
+// of a step neither positions nor smoothing lengths change and every listed pair carries the table's standard h, so
+// the kernel weight W of a pair is the same number in all three.  0: no cache, every stage computes its weights;
+// 1: the stage computes W and stores it (mom_engr_update, the first stage of a step); 2: the stage reads W instead of
+// computing it (smooth_density, smooth_velocity) — 8 bytes of HBM per pair instead of an exp() on the FP64 pipe.
+template <class S, int WARPS, int MINB, int WM>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned char *__restrict__ blk_any)
 {
   static_assert(WARPS * 32 >= TSEG, "tile_build needs one thread per segment");
+  static_assert(!(S::kDefer && WM != 0), "the weight cache runs on the in-place loop");
   extern __shared__ __align__(16) unsigned char s_raw[];
   TileTable &tab = *reinterpret_cast<TileTable *>(s_raw);
   double *comp = reinterpret_cast<double *>(s_raw + sizeof(TileTable));       // [kNC][TCAP]
@@ -381,6 +387,12 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short *__restrict__ nbr16 = reinterpret_cast<const unsigned short *>(V.nbr);
   const int nblk = (int) (G.ncells * 4);
+  // every listed row carries the table's standard smoothing length: 1/h, the kernel norms and the cutoff bounds are
+  // constants of the launch, not of the row
+  typename S::I st;
+  S::tile_uni(K, ss->hmax, st);
+  [[maybe_unused]] double wself = 0.0;
+  if constexpr (WM == 2) wself = S::self_weight(st);
   for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
     if (!blk_any[b]) continue;
     const int r = b >> 2, q = b & 3;
@@ -405,9 +417,12 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
     for (int u = 0; u < NPT; u++) {
       const int t = threadIdx.x + u * WARPS * 32, row = myrow[u];
       if (row >= 0) {
-        const double4 g = ld_rec(V.geo, row);
-        comp[0 * TCAP + t] = g.x; comp[1 * TCAP + t] = g.y; comp[2 * TCAP + t] = g.z;
-        S::tile_load(V, row, comp, t);
+        if constexpr (WM == 2 && !S::kCachedNeedsX) S::tile_load_c(V, row, comp, t);
+        else {
+          const double4 g = ld_rec(V.geo, row);
+          comp[0 * TCAP + t] = g.x; comp[1 * TCAP + t] = g.y; comp[2 * TCAP + t] = g.z;
+          S::tile_load(V, row, comp, t);
+        }
       }
     }
     __syncthreads();
@@ -430,14 +445,44 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
         const int n = __shfl_sync(FULL, hn, rr);
         if (n < 0) continue;
         const int i = eb + rr, self = __shfl_sync(FULL, hself, rr);
-        const unsigned short *__restrict__ lst = nbr16 + (size_t) (unsigned) __shfl_sync(FULL, hoff, rr) * 32u + lane;
-        typename S::I st;
-        S::tile_init(V, K, ss, comp, self, i, st);
-        S::init_uni(K, st);
-        const double gix = comp[0 * TCAP + self], giy = comp[1 * TCAP + self], giz = comp[2 * TCAP + self];
+        const unsigned loff = (unsigned) __shfl_sync(FULL, hoff, rr);
+        const unsigned short *__restrict__ lst = nbr16 + (size_t) loff * 32u + lane;
+        if constexpr (WM == 2 && !S::kCachedNeedsX) S::tile_init_c(V, K, ss, comp, self, i, st);
+        else S::tile_init(V, K, ss, comp, self, i, st);
         typename S::A acc;
         S::begin(K, st, acc, 0);
         const int ntot = n + (S::kSkipSelf ? 0 : 1);
+        if constexpr (WM == 2) {
+          // weights from the cache: WU rounds of 32 entries per batch; the slot and weight loads of the next batch
+          // are issued before the pair bodies of the current one (the loop is bound by the rate at which the 8-byte
+          // weights stream in from HBM, not by arithmetic)
+          constexpr int WU = 3;
+          const double *__restrict__ wl = V.wts + (size_t) loff * 32u + lane;
+          int sl[WU];
+          double w[WU];
+          auto fetch = [&](int q0) {
+#pragma unroll
+            for (int u = 0; u < WU; u++) {
+              const int k = q0 + 32 * u + lane;
+              sl[u] = k < n ? (int) __ldg(lst + (k - lane)) : (k < ntot ? self : -1);
+              w[u] = k < n ? __ldcs(wl + (k - lane)) : wself;
+            }
+          };
+          fetch(0);
+          for (int q0 = 0; q0 < ntot; q0 += 32 * WU) {
+            int sc[WU];
+            double wc[WU];
+#pragma unroll
+            for (int u = 0; u < WU; u++) { sc[u] = sl[u]; wc[u] = w[u]; }
+            if (q0 + 32 * WU < ntot) fetch(q0 + 32 * WU);
+#pragma unroll
+            for (int u = 0; u < WU; u++)
+              if (sc[u] >= 0) S::pair_c(K, st, acc, wc[u], comp, sc[u], self);
+          }
+          S::end(V, K, ss, i, st, acc, 0, lane);
+          continue;
+        }
+        const double gix = comp[0 * TCAP + self], giy = comp[1 * TCAP + self], giz = comp[2 * TCAP + self];
         auto entry = [&](int k) { return k < n ? (int) __ldg(lst + (k - lane)) : (k < ntot ? self : -1); };
         int jn = entry(lane);
         if constexpr (S::kDefer) {
@@ -479,7 +524,11 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
             jn = entry(q0 + 32 + lane);
             if (sl >= 0) {
               const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
-              S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+              if constexpr (WM == 1) {
+                const double w = S::template pair_w<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+                __stcs(V.wts + (size_t) loff * 32u + (unsigned) (q0 + lane), w);   // entry q0 + lane of the row's list
+              } else
+                S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
             }
           }
         }
@@ -502,16 +551,24 @@ int launch_tile_scan(psph_ctx *ctx, int kid)
   PSPH_LAUNCH_CHECK();
   return 0;
 }
-template <class S, int WARPS, int MINB>
-int launch_tile_gather(psph_ctx *ctx, int kid)
+template <class S, int WARPS, int MINB, int WM>
+int launch_tile_gather_wm(psph_ctx *ctx, int kid)
 {
-  constexpr size_t smem = sizeof(TileTable) + sizeof(double) * S::kNC * TCAP + (S::kDefer ? 128 * WARPS : 0);
+  constexpr int nc = (WM == 2 && !S::kCachedNeedsX) ? S::kNCc : S::kNC;
+  constexpr size_t smem = sizeof(TileTable) + sizeof(double) * nc * TCAP + (S::kDefer ? 128 * WARPS : 0);
   static_assert((smem + 1024) * MINB <= 227 * 1024, "tiles do not fit in shared memory");
-  PSPH_CUDA(cudaFuncSetAttribute(k_tile_gather<S, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  PSPH_CUDA(cudaFuncSetAttribute(k_tile_gather<S, WARPS, MINB, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   KernelTimer kt(ctx, kid);
   const long long nblk = ctx->ncells * 4;
   const int grid = (int) std::min<long long>(nblk, (long long) ctx->sms * MINB);
-  k_tile_gather<S, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_blk_any);
+  k_tile_gather<S, WARPS, MINB, WM><<<grid, WARPS * 32, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_blk_any);
   PSPH_LAUNCH_CHECK();
   return 0;
+}
+// with the weight cache allocated (psph_nbr_prepare) the stage runs in its cache role S::kWCache (1 writes, 2 reads)
+template <class S, int WARPS, int MINB>
+int launch_tile_gather(psph_ctx *ctx, int kid)
+{
+  if (ctx->cur.wts) return launch_tile_gather_wm<S, WARPS, MINB, S::kWCache>(ctx, kid);
+  return launch_tile_gather_wm<S, WARPS, MINB, 0>(ctx, kid);
 }

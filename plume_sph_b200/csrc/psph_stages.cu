@@ -97,6 +97,17 @@ __global__ void k_pack_sml(DevView V, StepState *ss)
   V.scr[7][p] = (V.flags[p] & F_CDENS) ? V.t.d[D_MASS][p] : 0.0;
 }
 
+// the largest |t| with fabs(t / h) <= cutoff as the reference's division rounds it (sph_lib.cc:216-218): with one h
+// per row the support test of a kernel is three compares per pair instead of three divisions
+__device__ __forceinline__ double dev_cutoff_bound(double cutoff, double h)
+{
+  double b = cutoff * h;
+  for (int k = 0; k < 4 && b / h > cutoff; k++) b = __longlong_as_double(__double_as_longlong(b) - 1);
+  for (int k = 0; k < 4 && __longlong_as_double(__double_as_longlong(b) + 1) / h <= cutoff; k++)
+    b = __longlong_as_double(__double_as_longlong(b) + 1);
+  return b;
+}
+
 // =========================================================================================
 // smooth_density  (src/plume/density_massfrac.cc:25-359; DENSITY_UPDATE_SPH 11, DENSITY_UPDATE_SML 11)
 // =========================================================================================
@@ -105,7 +116,7 @@ struct DensStage
 {
   static constexpr bool kSymH = true, kSkipSelf = false, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 24, kWarpsGrp = 24, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 24, kPfList = 0, kNRec = 1;
-  struct I { double h, supp, hk, invh, ninvh2, norm, ninvh2e, norme, tin, wthr; };  // from invh on: uniform-h rows only (init_uni)
+  struct I { double h, supp, hk, invh, ninvh2, norm, ninvh2e, norme, tin; };  // from invh on: uniform-h rows only (init_uni)
   struct A { double rho1, rho2, wn, en; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -134,6 +145,10 @@ struct DensStage
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.w != 0.0 ? -r.x : r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
   { R r; const double m = c[3 * TCAP + t]; r.r0 = make_double4(fabs(m), c[4 * TCAP + t], c[5 * TCAP + t], m < 0.0 ? 1.0 : 0.0); return r; }
+  static __device__ __forceinline__ void tile_stage(const DevView &V, int row, double *c, int t) { tile_stage_soa<DensStage<DIM> >(V, row, c, t); }
+  static __device__ __forceinline__ void tile_xyz(const double *c, int t, double &x, double &y, double &z) { tile_xyz_soa(c, t, x, y, z); }
+  static __device__ __forceinline__ R tile_recp(const double *c, int t, double &x, double &y, double &z)
+  { tile_xyz_soa(c, t, x, y, z); return tile_rec(c, t); }
   // the state of row i from its own slot of the tile; a listed row carries the table's standard smoothing length
   static __device__ __forceinline__ void tile_init(const DevView &, const KParams &, StepState *, const double *, int, int, I &) {}
   // the row constants of a tile launch: every listed row carries the table's standard smoothing length
@@ -145,31 +160,24 @@ struct DensStage
     s.invh = dev_rcp(s.h); s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh);
     const double ie = K.e_ratio * s.invh;
     s.ninvh2e = -(ie * ie); s.norme = dev_weight_norm<DIM>(ie);
-    // the largest |t| with fabs(t / h) <= cutoff as the reference's division rounds it (sph_lib.cc:216-218): with one
-    // h per row the second kernel's support test is three compares per pair instead of three divisions
-    double b = K.cutoff * s.h;
-    for (int k = 0; k < 4 && b / s.h > K.cutoff; k++) b = __longlong_as_double(__double_as_longlong(b) - 1);
-    for (int k = 0; k < 4 && __longlong_as_double(__double_as_longlong(b) + 1) / s.h <= K.cutoff; k++)
-      b = __longlong_as_double(__double_as_longlong(b) + 1);
-    s.tin = b;
-    // a pair can lie inside the energy-smoothing kernel only if r2 <= R2 := DIM (cutoff h (1 + 2^-40) / q)^2 (pair_main);
-    // W falls with r2, so W >= W(R2) (less a margin far above the 2 ulp of the exp) is the same pre-test on the weight
-    const double bb = K.cutoff * s.h * (1.0 + 0x1p-40);
-    s.wthr = dev_weight_pre(DIM * bb * bb / (K.e_ratio * K.e_ratio), s.ninvh2, s.norm) * (1.0 - 1e-9);
+    s.tin = dev_cutoff_bound(K.cutoff, s.h);
   }
-  static __device__ __forceinline__ double self_weight(const I &s) { return dev_weight_pre(0.0, s.ninvh2, s.norm); }
-  // one listed pair with its weight from the cache: the density sums (:159-161), and the energy-smoothing sums for
-  // the pairs whose weight says they may lie inside the narrower kernel
+  static __device__ __forceinline__ double self_weight(const I &s) { return -dev_weight_pre(0.0, s.ninvh2, s.norm); }
+  // one listed pair with its weight from the cache (:159-161).  A negative sign marks the pairs inside the
+  // energy-smoothing kernel (MomStage::cache_flag; the row's own entry always is): only those run pair_inner.
+  // (Queueing them to run 32 at a time measured slower, like kDefer.)
   static __device__ __forceinline__ void pair_c(const KParams &K, const I &s, A &a, double w, const double *c, int sl, int self)
   {
-    const double m = c[3 * TCAP + sl], wm = w * fabs(m);
+    const double m = c[3 * TCAP + sl], wm = fabs(w) * fabs(m);
     a.rho2 += m < 0.0 ? wm : 0.0;
     a.rho1 += m < 0.0 ? 0.0 : wm;
-    if (K.energy_smooth == 1 && w >= s.wthr) {
-      const double dx = c[0 * TCAP + self] - c[0 * TCAP + sl], dy = c[1 * TCAP + self] - c[1 * TCAP + sl],
-                   dz = c[2 * TCAP + self] - c[2 * TCAP + sl];
-      pair_inner<true>(K, s, a, dx, dy, dz, s.h, tile_rec(c, sl));
-    }
+    if (w < 0.0) pair_ci(K, s, a, c, sl, self);
+  }
+  static __device__ __forceinline__ void pair_ci(const KParams &K, const I &s, A &a, const double *c, int sl, int self)
+  {
+    const double dx = c[0 * TCAP + self] - c[0 * TCAP + sl], dy = c[1 * TCAP + self] - c[1 * TCAP + sl],
+                 dz = c[2 * TCAP + self] - c[2 * TCAP + sl];
+    pair_inner<true>(K, s, a, dx, dy, dz, s.h, tile_rec(c, sl));
   }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
@@ -252,7 +260,7 @@ struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 16, kWarpsGrp = 16, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 16, kPfList = 0, kNRec = 3;
-  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3], v0[3], e0, invh, ninvh2, norm; };  // from invh on: init_uni
+  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3], v0[3], e0, invh, ninvh2, norm, tin_e; };  // from invh on: init_uni / tile_uni
   struct A { double rv[3], re; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -279,23 +287,34 @@ struct MomStage
   static __device__ __forceinline__ R load(const DevView &V, int j)
   { R r; r.r0 = ld_rec(V.rec[0], j); r.r1 = ld_rec(V.rec[1], j); r.r2 = ld_rec(V.rec[2], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0.x = 0.; }                          // m_j = 0: the pair adds exact zeros
-  static constexpr int kNC = 13, kWarpsTile = 16, kMinbTile = 1;
+  // The tile of this stage is seven arrays of 16-byte elements, {x, y} {z, m} {p V^2, V} {rho, c} {Cp, T} {u_x, u_y}
+  // {u_z, -}: the slots of a list come in runs of consecutive rows (the z-run of a subcell column), so the 8 lanes
+  // of a quarter warp read 8 consecutive elements — 128-bit loads at the conflict-free rate, where 64-bit loads of
+  // plain columns measured 2.3 wavefronts over the minimum (profiles/r01o_ncu_wcache_n96.txt)
+  static constexpr int kNC = 14, kWarpsTile = 16, kMinbTile = 1;
   static constexpr bool kDefer = false;
   static constexpr int kWCache = 1, kNCc = kNC;                      // first stage of a step: stores the pair weights
   static constexpr bool kCachedNeedsX = true;
-  static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
+  static __device__ __forceinline__ double2 &tp(double *c, int p, int t) { return reinterpret_cast<double2 *>(c)[p * TCAP + t]; }
+  static __device__ __forceinline__ double2 tp(const double *c, int p, int t) { return reinterpret_cast<const double2 *>(c)[p * TCAP + t]; }
+  static __device__ __forceinline__ void tile_stage(const DevView &V, int row, double *c, int t)
   {
-    const double4 a = ld_rec(V.rec[0], row), b = ld_rec(V.rec[1], row), u = ld_rec(V.rec[2], row);
-    c[3 * TCAP + t] = a.x; c[4 * TCAP + t] = a.y; c[5 * TCAP + t] = a.z; c[6 * TCAP + t] = a.w;
-    c[7 * TCAP + t] = b.x; c[8 * TCAP + t] = b.y; c[9 * TCAP + t] = b.z;
-    c[10 * TCAP + t] = u.x; c[11 * TCAP + t] = u.y; c[12 * TCAP + t] = u.z;
+    const double4 g = ld_rec(V.geo, row), a = ld_rec(V.rec[0], row), b = ld_rec(V.rec[1], row), u = ld_rec(V.rec[2], row);
+    tp(c, 0, t) = make_double2(g.x, g.y); tp(c, 1, t) = make_double2(g.z, a.x); tp(c, 2, t) = make_double2(a.y, a.z);
+    tp(c, 3, t) = make_double2(a.w, b.x); tp(c, 4, t) = make_double2(b.y, b.z); tp(c, 5, t) = make_double2(u.x, u.y);
+    tp(c, 6, t) = make_double2(u.z, 0.);
   }
-  static __device__ __forceinline__ R tile_rec(const double *c, int t)
+  static __device__ __forceinline__ void tile_xyz(const double *c, int t, double &x, double &y, double &z)
+  { const double2 p0 = tp(c, 0, t); x = p0.x; y = p0.y; z = tp(c, 1, t).x; }
+  static __device__ __forceinline__ R tile_recp(const double *c, int t, double &x, double &y, double &z)
   {
+    const double2 p0 = tp(c, 0, t), p1 = tp(c, 1, t), p2 = tp(c, 2, t), p3 = tp(c, 3, t), p4 = tp(c, 4, t), p5 = tp(c, 5, t),
+                  p6 = tp(c, 6, t);
+    x = p0.x; y = p0.y; z = p1.x;
     R r;
-    r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]);
-    r.r1 = make_double4(c[7 * TCAP + t], c[8 * TCAP + t], c[9 * TCAP + t], 0.);
-    r.r2 = make_double4(c[10 * TCAP + t], c[11 * TCAP + t], c[12 * TCAP + t], 0.);
+    r.r0 = make_double4(p1.y, p2.x, p2.y, p3.x);
+    r.r1 = make_double4(p3.y, p4.x, p4.y, 0.);
+    r.r2 = make_double4(p5.x, p5.y, p6.x, 0.);
     return r;
   }
   // the state of row i from its own slot of the tile (k_pack_mom forms V and p V^2 exactly as init() does)
@@ -303,14 +322,21 @@ struct MomStage
   {
     load_old(V, i, s);
     s.i = i;
-    s.pvsq = c[4 * TCAP + t]; s.Vi = c[5 * TCAP + t]; s.rho = c[6 * TCAP + t];
-    s.c = c[7 * TCAP + t]; s.Cp = c[8 * TCAP + t]; s.T = c[9 * TCAP + t];
-    s.u[0] = c[10 * TCAP + t]; s.u[1] = c[11 * TCAP + t]; s.u[2] = c[12 * TCAP + t];
+    const double2 p2 = tp(c, 2, t), p3 = tp(c, 3, t), p4 = tp(c, 4, t), p5 = tp(c, 5, t);
+    s.pvsq = p2.x; s.Vi = p2.y; s.rho = p3.x; s.c = p3.y; s.Cp = p4.x; s.T = p4.y;
+    s.u[0] = p5.x; s.u[1] = p5.y; s.u[2] = tp(c, 6, t).x;
   }
   static __device__ __forceinline__ void init_uni(const KParams &, I &s)
   { s.invh = dev_rcp(s.h); s.ninvh2 = -(s.invh * s.invh); s.norm = dev_weight_norm<DIM>(s.invh); }
   static __device__ __forceinline__ void tile_uni(const KParams &K, double hstd, I &s)
-  { s.h = hstd; s.supp = K.cutoff2 * s.h; init_uni(K, s); }
+  { s.h = hstd; s.supp = K.cutoff2 * s.h; init_uni(K, s); s.tin_e = dev_cutoff_bound(K.cutoff, s.h); }
+  // the bit the weight cache carries for smooth_density: the pair lies inside the support of the energy-smoothing
+  // kernel W(q dx / h, h / q) (density_massfrac.cc:163-168; the test of DensStage::pair_inner on uniform-h rows)
+  static __device__ __forceinline__ bool cache_flag(const KParams &K, const I &s, double dx, double dy, double dz)
+  {
+    const double q = K.e_ratio;
+    return K.energy_smooth == 1 && !(fabs(q * dx) > s.tin_e || fabs(q * dy) > s.tin_e || fabs(q * dz) > s.tin_e);
+  }
   static __device__ __forceinline__ void pair(const DevView &V, const KParams &K, const I &s, A &a, double dx, double dy,
                                               double dz, double hj, int j)
   { pair_r<false>(K, s, a, dx, dy, dz, hj, load(V, j)); }
@@ -415,10 +441,20 @@ struct VelStage
   // the four columns m/rho, v of the stage record
   static constexpr int kWCache = 2, kNCc = 4;
   static constexpr bool kCachedNeedsX = false;
+  // ... as two arrays of 16-byte elements {m/rho, vx}, {vy, vz}: the slots of a list come in runs of consecutive
+  // rows (the z-run of a subcell column), so the 8 lanes of a quarter warp read 8 consecutive 16-byte elements —
+  // conflict-free 128-bit loads where 64-bit loads of plain columns measured 2.5 wavefronts over the minimum
   static __device__ __forceinline__ void tile_load_c(const DevView &V, int row, double *c, int t)
-  { const double4 r = ld_rec(V.rec[0], row); c[0 * TCAP + t] = r.x; c[1 * TCAP + t] = r.y; c[2 * TCAP + t] = r.z; c[3 * TCAP + t] = r.w; }
+  {
+    const double4 r = ld_rec(V.rec[0], row);
+    reinterpret_cast<double2 *>(c)[t] = make_double2(r.x, r.y);
+    reinterpret_cast<double2 *>(c)[TCAP + t] = make_double2(r.z, r.w);
+  }
   static __device__ __forceinline__ void tile_init_c(const DevView &, const KParams &, StepState *, const double *c, int t, int, I &s)
-  { s.v[0] = c[1 * TCAP + t]; s.v[1] = c[2 * TCAP + t]; s.v[2] = c[3 * TCAP + t]; }
+  {
+    const double2 a = reinterpret_cast<const double2 *>(c)[t], b = reinterpret_cast<const double2 *>(c)[TCAP + t];
+    s.v[0] = a.y; s.v[1] = b.x; s.v[2] = b.y;
+  }
   static __device__ __forceinline__ void tile_uni(const KParams &K, double hstd, I &s)
   {
     s.h = hstd; s.hk = s.h; s.invh = 1.0 / s.h; s.supp = K.cutoff2 * s.h;
@@ -427,15 +463,20 @@ struct VelStage
   static __device__ __forceinline__ double self_weight(const I &s) { return dev_weight_pre(0.0, s.ninvh2, s.norm); }
   static __device__ __forceinline__ void pair_c(const KParams &, const I &s, A &a, double w, const double *c, int sl, int)
   {
-    const double mvw = w * c[0 * TCAP + sl];
-    a.dv[0] += mvw * (c[1 * TCAP + sl] - s.v[0]);
-    if (DIM == 3) { a.dv[1] += mvw * (c[2 * TCAP + sl] - s.v[1]); a.dv[2] += mvw * (c[3 * TCAP + sl] - s.v[2]); }
+    const double2 p = reinterpret_cast<const double2 *>(c)[sl], q = reinterpret_cast<const double2 *>(c)[TCAP + sl];
+    const double mvw = fabs(w) * p.x;                              // the sign is smooth_density's flag
+    a.dv[0] += mvw * (p.y - s.v[0]);
+    if (DIM == 3) { a.dv[1] += mvw * (q.x - s.v[1]); a.dv[2] += mvw * (q.y - s.v[2]); }
     a.wn += mvw;
   }
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; c[6 * TCAP + t] = r.w; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
   { R r; r.r0 = make_double4(c[3 * TCAP + t], c[4 * TCAP + t], c[5 * TCAP + t], c[6 * TCAP + t]); return r; }
+  static __device__ __forceinline__ void tile_stage(const DevView &V, int row, double *c, int t) { tile_stage_soa<VelStage<DIM> >(V, row, c, t); }
+  static __device__ __forceinline__ void tile_xyz(const double *c, int t, double &x, double &y, double &z) { tile_xyz_soa(c, t, x, y, z); }
+  static __device__ __forceinline__ R tile_recp(const double *c, int t, double &x, double &y, double &z)
+  { tile_xyz_soa(c, t, x, y, z); return tile_rec(c, t); }
   static __device__ __forceinline__ void tile_init(const DevView &, const KParams &, StepState *, const double *c, int t, int, I &s)
   { s.v[0] = c[4 * TCAP + t]; s.v[1] = c[5 * TCAP + t]; s.v[2] = c[6 * TCAP + t]; }
   static __device__ __forceinline__ void init_uni(const KParams &, I &) {}

@@ -363,6 +363,17 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
   }
 }
 
+// tile rows as plain double columns, x, y, z first (smooth_density, smooth_velocity): staging and position read-back
+template <class S>
+__device__ __forceinline__ void tile_stage_soa(const DevView &V, int row, double *c, int t)
+{
+  const double4 g = ld_rec(V.geo, row);
+  c[0 * TCAP + t] = g.x; c[1 * TCAP + t] = g.y; c[2 * TCAP + t] = g.z;
+  S::tile_load(V, row, c, t);
+}
+__device__ __forceinline__ void tile_xyz_soa(const double *c, int t, double &x, double &y, double &z)
+{ x = c[0 * TCAP + t]; y = c[1 * TCAP + t]; z = c[2 * TCAP + t]; }
+
 // =========================================================================================
 // pair sums off the slot lists; S::kNC double columns per tile row in shared memory: x, y, z + the stage's own
 // (S::tile_load writes them, S::tile_rec reads them back as the stage record)
@@ -372,6 +383,8 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
 // the kernel weight W of a pair is the same number in all three.  0: no cache, every stage computes its weights;
 // 1: the stage computes W and stores it (mom_engr_update, the first stage of a step); 2: the stage reads W instead of
 // computing it (smooth_density, smooth_velocity) — 8 bytes of HBM per pair instead of an exp() on the FP64 pipe.
+// W > 0, so its sign bit is free: the writer sets it on the pairs that lie inside smooth_density's second, narrower
+// kernel (energy smoothing) — a handful per row — and that stage runs the second body on exactly those.
 template <class S, int WARPS, int MINB, int WM>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned char *__restrict__ blk_any)
@@ -382,7 +395,8 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
   TileTable &tab = *reinterpret_cast<TileTable *>(s_raw);
   double *comp = reinterpret_cast<double *>(s_raw + sizeof(TileTable));       // [kNC][TCAP]
   // per-warp queue of deferred pairs (S::kDefer), 64 slots
-  const unsigned s_dq = (unsigned) __cvta_generic_to_shared(comp + S::kNC * TCAP) + 128u * (threadIdx.x >> 5);
+  constexpr int NCOL = (WM == 2 && !S::kCachedNeedsX) ? S::kNCc : S::kNC;
+  const unsigned s_dq = (unsigned) __cvta_generic_to_shared(comp + NCOL * TCAP) + 128u * (threadIdx.x >> 5);
   int *tile_row = reinterpret_cast<int *>(comp);                              // [TCAP] slot -> row, while the tile is staged
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short *__restrict__ nbr16 = reinterpret_cast<const unsigned short *>(V.nbr);
@@ -418,11 +432,7 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
       const int t = threadIdx.x + u * WARPS * 32, row = myrow[u];
       if (row >= 0) {
         if constexpr (WM == 2 && !S::kCachedNeedsX) S::tile_load_c(V, row, comp, t);
-        else {
-          const double4 g = ld_rec(V.geo, row);
-          comp[0 * TCAP + t] = g.x; comp[1 * TCAP + t] = g.y; comp[2 * TCAP + t] = g.z;
-          S::tile_load(V, row, comp, t);
-        }
+        else S::tile_stage(V, row, comp, t);
       }
     }
     __syncthreads();
@@ -482,7 +492,8 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
           S::end(V, K, ss, i, st, acc, 0, lane);
           continue;
         }
-        const double gix = comp[0 * TCAP + self], giy = comp[1 * TCAP + self], giz = comp[2 * TCAP + self];
+        double gix, giy, giz;
+        S::tile_xyz(comp, self, gix, giy, giz);
         auto entry = [&](int k) { return k < n ? (int) __ldg(lst + (k - lane)) : (k < ntot ? self : -1); };
         int jn = entry(lane);
         if constexpr (S::kDefer) {
@@ -491,8 +502,9 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
           auto inner = [&](int cnt) {
             if (lane < cnt) {
               const int sl = (int) lds16(s_dq + 2u * lane);
-              const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
-              S::template pair_inner<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+              double px, py, pz;
+              const typename S::R rec = S::tile_recp(comp, sl, px, py, pz);
+              S::template pair_inner<true>(K, st, acc, gix - px, giy - py, giz - pz, st.h, rec);
             }
           };
           for (int q0 = 0; q0 < ntot; q0 += 32) {
@@ -500,8 +512,9 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
             jn = entry(q0 + 32 + lane);
             bool in = false;
             if (sl >= 0) {
-              const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
-              in = S::template pair_main<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+              double px, py, pz;
+              const typename S::R rec = S::tile_recp(comp, sl, px, py, pz);
+              in = S::template pair_main<true>(K, st, acc, gix - px, giy - py, giz - pz, st.h, rec);
             }
             const unsigned bal = __ballot_sync(FULL, in);
             if (in) sts16(s_dq + 2u * (dn + __popc(bal & ((1u << lane) - 1u))), (unsigned) sl);
@@ -523,12 +536,15 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
             const int sl = jn;
             jn = entry(q0 + 32 + lane);
             if (sl >= 0) {
-              const double dx = gix - comp[0 * TCAP + sl], dy = giy - comp[1 * TCAP + sl], dz = giz - comp[2 * TCAP + sl];
+              double px, py, pz;
+              const typename S::R rec = S::tile_recp(comp, sl, px, py, pz);
+              const double dx = gix - px, dy = giy - py, dz = giz - pz;
               if constexpr (WM == 1) {
-                const double w = S::template pair_w<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
-                __stcs(V.wts + (size_t) loff * 32u + (unsigned) (q0 + lane), w);   // entry q0 + lane of the row's list
+                const double w = S::template pair_w<true>(K, st, acc, dx, dy, dz, st.h, rec);
+                // entry q0 + lane of the row's list; the sign carries one bit for the reading stages (S::cache_flag)
+                __stcs(V.wts + (size_t) loff * 32u + (unsigned) (q0 + lane), S::cache_flag(K, st, dx, dy, dz) ? -w : w);
               } else
-                S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, S::tile_rec(comp, sl));
+                S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, rec);
             }
           }
         }

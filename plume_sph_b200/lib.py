@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpsph.so")
+# PSPH_LIB: another build of the same library (A/B timing of compile-time variants, profiles/ab.sh)
+LIB_PATH = os.environ.get("PSPH_LIB") or os.path.join(HERE, "libpsph.so")
 
 
 class PsphError(RuntimeError):

@@ -193,6 +193,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->tile_shape = tw ? atoi(tw) : 0;
     const char *nb = getenv("PSPH_NBR");
     ctx->nbr_mode = nb ? atoi(nb) : 2;
+    const char *sc = getenv("PSPH_SCAN");
+    ctx->scan_mode = sc ? atoi(sc) : 2;
     const char *wc = getenv("PSPH_WCACHE");
     ctx->wcache = wc ? atoi(wc) : 1;
     ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr; ctx->n_img = 0;

@@ -2,7 +2,7 @@
 // timestep, adaptive_sml, mom_engr_update, smooth_density, smooth_velocity, update_pos and the
 // fused step driver.  Every stage cites the reference code it replaces; the C ABI is
 // include/psph.h.  Pair sums run on the warp gather of psph_gather.cuh.
-#include "psph_tile.cuh"
+#include "psph_scan2.cuh"
 #include <cstring>
 #include <algorithm>
 
@@ -597,7 +597,9 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   if (writer) {
     ctx->nbr_valid = false;
     if (ctx->nbr_mode == 2 && psph_nbr_prepare(ctx) == 1) { // block-tiled: slot lists, records staged in shared memory
-      if ((ctx->gather_warps == 24 ? launch_tile_scan<S<3>, 24>(ctx, KN_PAIR_SCAN) : launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN))) return -1;
+      if (ctx->scan_mode == 2) { // one lane per row (psph_scan2.cuh); PSPH_SCAN=1: one lane per candidate (psph_tile.cuh)
+        if (launch_tile_scan2<S<3>, 20, 16>(ctx, KN_PAIR_SCAN)) return -1;
+      } else if ((ctx->gather_warps == 24 ? launch_tile_scan<S<3>, 24>(ctx, KN_PAIR_SCAN) : launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN))) return -1;
       ctx->nbr_valid = true; ctx->nbr_kind = 2;
       KernelTimer kt(ctx, kid);
       if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;

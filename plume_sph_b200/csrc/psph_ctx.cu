@@ -195,6 +195,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->nbr_mode = nb ? atoi(nb) : 2;
     const char *sc = getenv("PSPH_SCAN");
     ctx->scan_mode = sc ? atoi(sc) : 2;
+    const char *dn = getenv("PSPH_DENSNEAR");
+    ctx->dens_near = dn ? atoi(dn) : 1;
     const char *wc = getenv("PSPH_WCACHE");
     ctx->wcache = wc ? atoi(wc) : 1;
     ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr; ctx->n_img = 0;
@@ -245,7 +247,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   free_tab(ctx->cur.t); free_tab(ctx->alt);
   for (int c = 0; c < NSCRATCH; c++) cudaFree(ctx->cur.scr[c]);
   for (int c = 0; c < NREC; c++) cudaFree(ctx->cur.rec[c]);
-  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.wts); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
+  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.wts); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.near); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
   cudaFree(ctx->d_cell_has_ghost); cudaFree(ctx->d_blk_any);
@@ -314,6 +316,7 @@ int psph_reserve(psph_ctx *ctx, size_t rows)
   if (grow(ctx, ctx->cur.geo32, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.nbr_off, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.nbr_cnt, 0, ncap)) return -1;
+  if (grow(ctx, ctx->cur.near, 0, ncap * 8)) return -1;
   ctx->nbr_valid = false;
   if (grow(ctx, ctx->cur.flags, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.gsub, 0, ncap)) return -1;

@@ -66,7 +66,12 @@ __global__ void k_pack_mom(DevView V, KParams K, StepState *ss)
   V.rec[0][p] = make_double4(V.t.d[D_MASS][p], V.t.d[D_P][p] * Vj * Vj, Vj, rho);
   V.rec[1][p] = make_double4(V.t.d[D_C][p], V.t.d[D_CP][p], V.t.d[D_T][p], 0.0);
   const int u = K.lans ? D_SVX : D_VX;
-  V.rec[2][p] = make_double4(V.t.d[u][p], V.t.d[u + 1][p], V.t.d[u + 2][p], 0.0);
+  // .w: the mass the row carries in smooth_density's sums (0: contr_dens() false or phase outside {1,2},
+  // density_massfrac.cc:135,141), negative for phase 2 — the tile gather forms those sums on the side (psph_tile.cuh)
+  const int f = V.flags[p];
+  double md = (f & (F_CDENS | F_PHOK)) == (F_CDENS | F_PHOK) ? V.t.d[D_MASS][p] : 0.0;
+  if (f & F_PH2) md = -md;
+  V.rec[2][p] = make_double4(V.t.d[u][p], V.t.d[u + 1][p], V.t.d[u + 2][p], md);
 }
 // smooth_density: rec0 = {m, m/rho, m*e/rho, phase_num == 2}
 __global__ void k_pack_dens(DevView V, StepState *ss)
@@ -141,6 +146,7 @@ struct DensStage
   // for the few pairs inside the energy-smoothing kernel
   static constexpr int kWCache = 2, kNCc = kNC;
   static constexpr bool kCachedNeedsX = true;
+  static constexpr bool kSkipUnlessFull = true;                      // k_dens_near serves the listed rows unless ss->dens_full
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.w != 0.0 ? -r.x : r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
@@ -235,6 +241,42 @@ struct DensStage
   }
 };
 
+// smooth_density for the rows whose sums mom_engr_update's tile gather prepared (psph_tile.cuh, WM == 1): the phase
+// densities depend on positions, masses and phases only — none of which mom_engr_update changes — so that gather
+// forms them while it has the pair weights in registers (V.scr[4], V.scr[5]: the sums over the row's list), and lists
+// the few partners inside the energy-smoothing kernel (V.near).  What is left for this stage is the row's own
+// term and the energy sums (:163-168) over those partners with the energies mom_engr_update committed: one
+// thread per row, no pass over the pair lists at all.
+__global__ void k_dens_near(DevView V, KParams K, StepState *ss)
+{
+  if (ss->dens_full) return;                                        // the tile gather sums these rows off their lists
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ss->n || !(V.flags[p] & F_NEED) || V.nbr_cnt[p] < 0) return;
+  typedef DensStage<3> S;
+  S::I st;
+  S::tile_uni(K, ss->hmax, st);
+  S::A acc;
+  S::begin(K, st, acc, 0);
+  const double4 gi = V.geo[p];
+  S::R ri = S::load(V, p);
+  double r1 = V.scr[4][p], r2 = V.scr[5][p];
+  const double wm = dev_weight_pre(0.0, st.ninvh2, st.norm) * ri.r0.x;   // the row itself (:159-161)
+  if (ri.r0.w != 0.0) r2 += wm; else r1 += wm;
+  S::pair_inner<true>(K, st, acc, 0.0, 0.0, 0.0, st.h, ri);
+  const int n = V.near[8 * p];
+  for (int k = 0; k < n; k++) {
+    const int j = V.near[8 * p + 1 + k];
+    const double4 gj = V.geo[j];
+    S::pair_inner<true>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, st.h, S::load(V, j));
+  }
+  const double rho = r1 + r2;                                       // :268-273
+  V.scr[0][p] = rho;
+  V.scr[1][p] = r2 / rho;                                           // :285
+  int bad = !(rho > 0);
+  if (K.energy_smooth == 1) { V.scr[2][p] = acc.en / acc.wn; bad += !(acc.wn > 0); } // :230
+  if (bad) atomicAdd(&ss->bad, bad);
+}
+
 // second pass of smooth_density (:337-352): commit, flag involved, equation of state
 __global__ void k_commit_dens(DevView V, KParams K, StepState *ss)
 {
@@ -288,13 +330,13 @@ struct MomStage
   { R r; r.r0 = ld_rec(V.rec[0], j); r.r1 = ld_rec(V.rec[1], j); r.r2 = ld_rec(V.rec[2], j); return r; }
   static __device__ __forceinline__ void zero(R &r) { r.r0.x = 0.; }                          // m_j = 0: the pair adds exact zeros
   // The tile of this stage is seven arrays of 16-byte elements, {x, y} {z, m} {p V^2, V} {rho, c} {Cp, T} {u_x, u_y}
-  // {u_z, -}: the slots of a list come in runs of consecutive rows (the z-run of a subcell column), so the 8 lanes
+  // {u_z, m_dens}: the slots of a list come in runs of consecutive rows (the z-run of a subcell column), so the 8 lanes
   // of a quarter warp read 8 consecutive elements — 128-bit loads at the conflict-free rate, where 64-bit loads of
   // plain columns measured 2.3 wavefronts over the minimum (profiles/r01o_ncu_wcache_n96.txt)
   static constexpr int kNC = 14, kWarpsTile = 16, kMinbTile = 1;
   static constexpr bool kDefer = false;
   static constexpr int kWCache = 1, kNCc = kNC;                      // first stage of a step: stores the pair weights
-  static constexpr bool kCachedNeedsX = true;
+  static constexpr bool kCachedNeedsX = true, kSkipUnlessFull = false;
   static __device__ __forceinline__ double2 &tp(double *c, int p, int t) { return reinterpret_cast<double2 *>(c)[p * TCAP + t]; }
   static __device__ __forceinline__ double2 tp(const double *c, int p, int t) { return reinterpret_cast<const double2 *>(c)[p * TCAP + t]; }
   static __device__ __forceinline__ void tile_stage(const DevView &V, int row, double *c, int t)
@@ -302,7 +344,7 @@ struct MomStage
     const double4 g = ld_rec(V.geo, row), a = ld_rec(V.rec[0], row), b = ld_rec(V.rec[1], row), u = ld_rec(V.rec[2], row);
     tp(c, 0, t) = make_double2(g.x, g.y); tp(c, 1, t) = make_double2(g.z, a.x); tp(c, 2, t) = make_double2(a.y, a.z);
     tp(c, 3, t) = make_double2(a.w, b.x); tp(c, 4, t) = make_double2(b.y, b.z); tp(c, 5, t) = make_double2(u.x, u.y);
-    tp(c, 6, t) = make_double2(u.z, 0.);
+    tp(c, 6, t) = make_double2(u.z, u.w);
   }
   static __device__ __forceinline__ void tile_xyz(const double *c, int t, double &x, double &y, double &z)
   { const double2 p0 = tp(c, 0, t); x = p0.x; y = p0.y; z = tp(c, 1, t).x; }
@@ -314,7 +356,7 @@ struct MomStage
     R r;
     r.r0 = make_double4(p1.y, p2.x, p2.y, p3.x);
     r.r1 = make_double4(p3.y, p4.x, p4.y, 0.);
-    r.r2 = make_double4(p5.x, p5.y, p6.x, 0.);
+    r.r2 = make_double4(p5.x, p5.y, p6.x, p6.y);
     return r;
   }
   // the state of row i from its own slot of the tile (k_pack_mom forms V and p V^2 exactly as init() does)
@@ -440,7 +482,7 @@ struct VelStage
   // pair-weight cache (psph_tile.cuh): with W read from the cache the stage needs no positions at all — the tile is
   // the four columns m/rho, v of the stage record
   static constexpr int kWCache = 2, kNCc = 4;
-  static constexpr bool kCachedNeedsX = false;
+  static constexpr bool kCachedNeedsX = false, kSkipUnlessFull = false;
   // ... as two arrays of 16-byte elements {m/rho, vx}, {vy, vz}: the slots of a list come in runs of consecutive
   // rows (the z-run of a subcell column), so the 8 lanes of a quarter warp read 8 consecutive 16-byte elements —
   // conflict-free 128-bit loads where 64-bit loads of plain columns measured 2.5 wavefronts over the minimum
@@ -624,6 +666,10 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
   if (ctx->nbr_valid) {
     KernelTimer kt(ctx, kid); // both launches are this stage's gather
     if (ctx->nbr_kind == 2) {
+      if (S<3>::kSkipUnlessFull && ctx->cur.wts && ctx->n > 0) { // smooth_density: the sums mom_engr_update prepared
+        k_dens_near<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
+        PSPH_LAUNCH_CHECK();
+      }
       if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
     } else if (launch_gather_list<S<3> >(ctx, -1)) return -1;
     return launch_gather_grp<S<3> >(ctx, -1, 2);
@@ -632,7 +678,8 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
 }
 
 // room for the pair lists of this step: 0 none (cache off for the step), 1 ready; < 0 error
-__global__ void k_nbr_reset(StepState *ss, unsigned cap) { ss->nbr_cursor = 0u; ss->nbr_cap = cap; ss->n_uncached = 0; }
+__global__ void k_nbr_reset(StepState *ss, unsigned cap, int dens_full)
+{ ss->nbr_cursor = 0u; ss->nbr_cap = cap; ss->n_uncached = 0; ss->dens_full = dens_full; }
 int psph_nbr_prepare(psph_ctx *ctx)
 {
   // 320 pairs per row cover the unit lattice (~230-300 pairs): 10 units of 128 bytes (row indices) or 5 (16-bit
@@ -663,7 +710,7 @@ int psph_nbr_prepare(psph_ctx *ctx)
   if (ctx->nbr_mode != 2 && ctx->cur.wts) { cudaFree(ctx->cur.wts); ctx->cur.wts = nullptr; }
   // units of 32 entries: 128 bytes of row indices, or 64 bytes of 16-bit tile slots (block-tiled mode)
   const size_t cap = ctx->nbr_mode == 2 ? ctx->nbr_units * 2 : ctx->nbr_units;  // (the writer that follows uses nbr_mode)
-  k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(cap, 0xfffffff0ull));
+  k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(cap, 0xfffffff0ull), ctx->dens_near ? 0 : 1);
   PSPH_LAUNCH_CHECK();
   return 1;
 }

@@ -400,6 +400,8 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
   int *tile_row = reinterpret_cast<int *>(comp);                              // [TCAP] slot -> row, while the tile is staged
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short *__restrict__ nbr16 = reinterpret_cast<const unsigned short *>(V.nbr);
+  if constexpr (WM == 2 && S::kSkipUnlessFull)
+    if (!ss->dens_full) return;                                     // k_dens_near has served every listed row
   const int nblk = (int) (G.ncells * 4);
   // every listed row carries the table's standard smoothing length: 1/h, the kernel norms and the cutoff bounds are
   // constants of the launch, not of the row
@@ -532,19 +534,49 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
           inner(dn);
           __syncwarp();
         } else {
+          // WM == 1 also prepares smooth_density (k_dens_near): the phase-density sums over the list (d1, d2) and the
+          // rows of the partners inside the energy-smoothing kernel (V.near)
+          [[maybe_unused]] double d1 = 0.0, d2 = 0.0;
+          [[maybe_unused]] int nnear = 0;
           for (int q0 = 0; q0 < ntot; q0 += 32) {
             const int sl = jn;
             jn = entry(q0 + 32 + lane);
+            [[maybe_unused]] bool fl = false;
             if (sl >= 0) {
               double px, py, pz;
               const typename S::R rec = S::tile_recp(comp, sl, px, py, pz);
               const double dx = gix - px, dy = giy - py, dz = giz - pz;
               if constexpr (WM == 1) {
                 const double w = S::template pair_w<true>(K, st, acc, dx, dy, dz, st.h, rec);
+                fl = S::cache_flag(K, st, dx, dy, dz);
                 // entry q0 + lane of the row's list; the sign carries one bit for the reading stages (S::cache_flag)
-                __stcs(V.wts + (size_t) loff * 32u + (unsigned) (q0 + lane), S::cache_flag(K, st, dx, dy, dz) ? -w : w);
+                __stcs(V.wts + (size_t) loff * 32u + (unsigned) (q0 + lane), fl ? -w : w);
+                const double md = rec.r2.w, wm = w * fabs(md);       // density_massfrac.cc:159-161
+                d2 += md < 0.0 ? wm : 0.0;
+                d1 += md < 0.0 ? 0.0 : wm;
               } else
                 S::template pair_r<true>(K, st, acc, dx, dy, dz, st.h, rec);
+            }
+            if constexpr (WM == 1) {
+              const unsigned fb = __ballot_sync(FULL, fl);
+              if (fb) {                                               // rare: a partner within 0.75 h of the row
+                const int pos = nnear + __popc(fb & ((1u << lane) - 1u));
+                if (fl && pos < NEAR_MAX) {
+                  int lo = 0, hi = TSEG;                              // the segment of the slot -> its row
+                  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tab.off[mid] <= sl) lo = mid; else hi = mid; }
+                  V.near[8 * i + 1 + pos] = tab.beg[lo] + (sl - tab.off[lo]);
+                }
+                nnear += __popc(fb);
+              }
+            }
+          }
+          if constexpr (WM == 1) {
+            double z0 = 0.0, z1 = 0.0;
+            warp_sum4(d1, d2, z0, z1, lane);
+            if (lane == 0) {
+              V.scr[4][i] = d1; V.scr[5][i] = d2;
+              V.near[8 * i] = min(nnear, NEAR_MAX);
+              if (nnear > NEAR_MAX) ss->dens_full = 1;                // smooth_density walks the lists itself this step
             }
           }
         }

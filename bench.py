@@ -37,13 +37,14 @@ UNIT = "particle-updates/s"
 # algorithmic bytes per real-particle-update of each pair gather
 ALG_BYTES = {"gather_mom_engr": 228, "gather_density": 148, "gather_velocity": 100}
 ALG_BYTES_STEP = 1184
-# kernel behind each timer when the pair-list path runs (3-D SPH defaults), and what ncu measured for it
-# (profiles/r01k_ncu_dram_n216.txt: DRAM bytes per launch at this workload — the slot lists, 4.6 GB, plus the tiles'
-# records; profiles/r01l_ncu_tile_n96.txt: FP64 pipe)
-KERNEL_OF = {"gather_mom_engr": "k_tile_gather<MomStage<3>>", "gather_density": "k_tile_gather<DensStage<3>>",
-             "gather_velocity": "k_tile_gather<VelStage<3>>"}
-NCU = {"gather_mom_engr": {"traffic": 8345665024, "fp64_pipe_pct": 51.8}, "gather_density": {"traffic": 6875210752, "fp64_pipe_pct": 40.6},
-       "gather_velocity": {"traffic": 6689056000, "fp64_pipe_pct": 32.7}}
+# kernel behind each timer when the block-tiled pair path runs (3-D SPH defaults), and what ncu measured for it
+# (profiles/r01q_ncu_dram_n216.txt: DRAM bytes read + written per launch at this workload — for mom_engr_update the slot
+# lists (4.5 GB) and the tiles' records in, the pair weights (18 GB) out; for smooth_velocity the pair weights back in;
+# profiles/r01o_ncu_wcache_n96.txt: FP64 pipe)
+KERNEL_OF = {"gather_mom_engr": "k_tile_gather<MomStage<3>, WM=1>", "gather_density": "k_dens_near",
+             "gather_velocity": "k_tile_gather<VelStage<3>, WM=2>"}
+NCU = {"gather_mom_engr": {"traffic": 28379217920, "fp64_pipe_pct": 48.5}, "gather_density": {"traffic": 1444992256, "fp64_pipe_pct": None},
+       "gather_velocity": {"traffic": 23795390208, "fp64_pipe_pct": 14.8}}
 
 
 def measured_peaks():
@@ -234,8 +235,10 @@ def run_b200(args):
                 "alg_bytes_per_update": ALG_BYTES[dom], "updates_per_launch": n_real_local,
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
                 "note": "FP64 pair loop over per-step pair lists, partners' records staged in shared memory: bound by the "
-                        "FP64 pipe and the issue slots, not by HBM (SURVEY.md §8d): the HBM fraction is low by "
-                        "construction; fp64_pipe_pct_ncu and profiles/ carry the figure of merit",
+                        "FP64 pipe and the issue slots, not by HBM (SURVEY.md §8d): the HBM fraction by ALGORITHMIC bytes "
+                        "is low by construction; `traffic` exceeds the algorithmic bytes on purpose (slot lists in, pair "
+                        "weights out: idle HBM traded for FP64 work in the two later stages); fp64_pipe_pct_ncu and "
+                        "profiles/ carry the figure of merit",
                 "step_hbm": {"alg_bytes_per_update": ALG_BYTES_STEP,
                              "achieved_GBps": round(ALG_BYTES_STEP * n_real / (ms / args.steps * 1e-3) / 1e9, 2)},
                 "stage_ms_per_step": {k: round(v / ksteps, 4) for k, v in sms.items() if v > 0},

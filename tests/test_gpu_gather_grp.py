@@ -23,11 +23,19 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("vel", "engr", "rho", "mass_frac", "smoothed_v", "pressure")
 
 
-def run_stages(cfg, rows, mode, nbr=None):
+SWITCHES = ("PSPH_GATHER", "PSPH_NBR", "PSPH_SCAN", "PSPH_WCACHE", "PSPH_DENSNEAR")
+
+
+def run_stages(cfg, rows, mode, nbr=None, env=None):
     """mode: None (default gathers) or "row" (per-row gather); nbr: None (default pair lists), "0" (fused grouped
-    gather only), "1" / "3" (row pair lists: uniform h / any h), "2" (block-tiled slot lists, csrc/psph_tile.cuh).  The switches are read by psph_create."""
-    old = {k: os.environ.get(k) for k in ("PSPH_GATHER", "PSPH_NBR")}
-    for k, v in (("PSPH_GATHER", mode), ("PSPH_NBR", nbr)):
+    gather only), "1" / "3" (row pair lists: uniform h / any h), "2" (block-tiled slot lists, csrc/psph_tile.cuh);
+    env: further switches of the block-tiled path (PSPH_SCAN, PSPH_WCACHE, PSPH_DENSNEAR).  The switches are read by
+    psph_create."""
+    old = {k: os.environ.get(k) for k in SWITCHES}
+    want = dict(env or {})
+    want.update({"PSPH_GATHER": mode, "PSPH_NBR": nbr})
+    for k in SWITCHES:
+        v = want.get(k)
         if v:
             os.environ[k] = v
         else:
@@ -101,6 +109,47 @@ def test_other_pair_paths_vs_default(nbr):
         assert dt_a == dt_b and bad_a == 0 and bad_b == 0
         for f in FIELDS:
             assert relerr(a[f], b[f]) <= RTOL_STAGE, (nbr, f, relerr(a[f], b[f]))
+
+
+def near_rows(n=24, seed=13):
+    """the synthetic cube with partners INSIDE the energy-smoothing kernel (support 0.75 h): 300 particles moved to
+    0.2-0.6 h from a lattice neighbour (one near partner each way), and two clusters of 10 particles within 0.4 h
+    of one another (more near partners than a row's near list holds: smooth_density must fall back to the list
+    walk for the step)"""
+    cfg, rows = cases.cube(n, seed=seed)
+    real = np.flatnonzero(rows["bc_type"] == 100)
+    rng = np.random.default_rng(seed)
+    pos = rows["coords"]
+    pick = rng.choice(real, 320, replace=False)
+    for p in pick[:300]:
+        q = real[np.argmin(np.abs(pos[real] - (pos[p] + [1.0, 0.0, 0.0])).sum(axis=1))]
+        pos[p] = pos[q] + rng.uniform(-1, 1, 3) * 0.35
+    return cfg, rows, pick[300:]
+
+
+@pytest.mark.parametrize("cluster", [False, True])
+def test_near_partners_and_path_switches(cluster):
+    """block-tiled path with each of its shortcuts switched off in turn (lane-per-candidate search, no pair-weight
+    cache, smooth_density walking the lists) against the default and the oracle, on inputs with partners inside
+    the energy-smoothing kernel; cluster=True overflows the near lists (the device falls back by itself)"""
+    cfg, rows, spare = near_rows()
+    if cluster:
+        pos = rows["coords"]
+        rng = np.random.default_rng(4)
+        for c in range(2):
+            centre = pos[spare[10 * c]].copy()
+            for p in spare[10 * c:10 * c + 10]:
+                pos[p] = centre + rng.uniform(-1, 1, 3) * 0.2
+    dt_o, ora = oracle_stages(cfg, rows)
+    dt_a, bad_a, a = run_stages(cfg, rows, None)
+    assert bad_a == 0 and dt_a == dt_o
+    for f in FIELDS:
+        assert relerr(a[f], ora[f]) <= 3 * RTOL_STAGE, (f, relerr(a[f], ora[f]))
+    for env in ({"PSPH_SCAN": "1"}, {"PSPH_WCACHE": "0"}, {"PSPH_DENSNEAR": "0"}):
+        dt_b, bad_b, b = run_stages(cfg, rows, None, env=env)
+        assert bad_b == 0 and dt_b == dt_a
+        for f in FIELDS:
+            assert relerr(a[f], b[f]) <= RTOL_STAGE, (env, f, relerr(a[f], b[f]))
 
 
 def test_pairs_on_the_cutoff_face():

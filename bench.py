@@ -247,18 +247,21 @@ def run_b200(args):
     # ---- end to end through the C ABI with host rows (pinned): upload + step + download per step
     e2e = None
     if not args.no_e2e:
-        host = s.host_rows(n_rows_local + 1024)
+        # rows as an SPH build of the reference exchanges them: ParticlePack carries no gradients unless USE_GSPH
+        # (pack_data.h:68-75) -> psph_particle without its gradient block, 208 B per row (PSPH_ROW_BYTES_SPH)
+        host = s.host_rows(n_rows_local + 1024, dtype=psph.PARTICLE_SPH_DTYPE)
         out = s.download(ORDER_DEVICE, out=host)
         nrow = len(out)
+        rowb = host.dtype.itemsize
         ke = max(1, min(args.steps, 3))
         import ctypes as C
         barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
-            s._ck(s.L.psph_upload(s.h, host.ctypes.data, nrow), "psph_upload")
+            s._ck(s.L.psph_upload_rows(s.h, host.ctypes.data, nrow, rowb), "psph_upload_rows")
             s.step(0.0, 0)
             got = C.c_size_t(0)
-            s._ck(s.L.psph_download(s.h, host.ctypes.data, host.size, C.byref(got), ORDER_DEVICE), "psph_download")
+            s._ck(s.L.psph_download_rows(s.h, host.ctypes.data, host.size, C.byref(got), ORDER_DEVICE, rowb), "psph_download_rows")
             nrow = got.value
         barrier()
         te = time.perf_counter() - t0
@@ -266,10 +269,11 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-        rowb = psph.PARTICLE_DTYPE.itemsize
         e2e = {"value": round(n_real * ke / te, 1), "unit": UNIT, "h2d_bytes_per_step": nrow * rowb,
                "d2h_bytes_per_step": nrow * rowb, "steps": ke,
-               "what": "psph_upload(host AoS rows, pinned) + psph_step + psph_download(host AoS rows) every step"}
+               "row_bytes": rowb,
+               "what": "psph_upload_rows(host AoS rows, pinned; SPH rows = psph_particle without the GSPH gradient block) + "
+                       "psph_step + psph_download_rows(host AoS rows) every step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -168,6 +168,14 @@ int psph_upload(psph_ctx *ctx, const psph_particle *rows, size_t n);
 int psph_append(psph_ctx *ctx, const psph_particle *rows, size_t n);
 /* before write_output (main.cc:474); order REFERENCE = THashTable iteration order */
 int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, size_t *n, int order);
+/* The same three calls for rows `row_bytes` apart: sizeof(psph_particle), or PSPH_ROW_BYTES_SPH — psph_particle cut off
+ * before its gradient block.  An SPH build of the reference (USE_GSPH == 0) does not carry gradients in what it
+ * exchanges either: ParticlePack holds d_rho..d_p only #if USE_GSPH (src/multiproc/pack_data.h:68-75); 208 instead of
+ * 328 bytes per particle over PCIe. */
+#define PSPH_ROW_BYTES_SPH offsetof(psph_particle, grad)
+int psph_upload_rows(psph_ctx *ctx, const void *rows, size_t n, size_t row_bytes);
+int psph_append_rows(psph_ctx *ctx, const void *rows, size_t n, size_t row_bytes);
+int psph_download_rows(psph_ctx *ctx, void *rows, size_t cap, size_t *n, int order, size_t row_bytes);
 size_t psph_num_particles(const psph_ctx *ctx);
 /* rows the summation stages update on this rank (need_neigh, particle.h:555-558, and the list rule of
  * neighs.cc:65-82); builds the cell list if needed and synchronises */

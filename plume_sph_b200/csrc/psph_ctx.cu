@@ -346,11 +346,13 @@ extern "C" int psph_set_cells(psph_ctx *ctx, const psph_cell_attr *attr, size_t 
 // ---------------------------------------------------------------------------------------
 // AoS (host, reference ParticlePack-like rows) <-> SoA (device columns)
 // ---------------------------------------------------------------------------------------
-__global__ void k_aos_to_soa(const psph_particle *__restrict__ rows, int n, int base, Tab V, GridView G, int has_grad, int rank)
+// rows are `stride` bytes apart: sizeof(psph_particle), or PSPH_ROW_BYTES_SPH (the struct without its gradient block)
+__global__ void k_aos_to_soa(const char *__restrict__ rows, size_t stride, int n, int base, Tab V, GridView G, int has_grad, int rank)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const psph_particle &r = rows[t];
+  const psph_particle &r = *reinterpret_cast<const psph_particle *>(rows + (size_t) t * stride);
+  has_grad = has_grad && stride >= sizeof(psph_particle);
   int p = base + t;
   V.d[D_X][p] = r.coords[0]; V.d[D_Y][p] = r.coords[1]; V.d[D_Z][p] = r.coords[2];
   V.d[D_VX][p] = r.vel[0]; V.d[D_VY][p] = r.vel[1]; V.d[D_VZ][p] = r.vel[2];
@@ -362,6 +364,8 @@ __global__ void k_aos_to_soa(const psph_particle *__restrict__ rows, int n, int 
   V.d[D_RPH0][p] = r.phase_density[0]; V.d[D_RPH1][p] = r.phase_density[1];
   if (has_grad)
     for (int k = 0; k < 15; k++) V.d[D_GRAD0 + k][p] = r.grad[k];
+  else if (V.d[D_GRAD0])
+    for (int k = 0; k < 15; k++) V.d[D_GRAD0 + k][p] = 0.0;
   V.i[I_BC][p] = r.bc_type; V.i[I_PHASE][p] = r.phase_num; V.i[I_INVOLVED][p] = r.involved;
   V.i[I_GUEST][p] = r.guest; V.i[I_MYPROC][p] = r.guest ? r.myprocess : rank;
   V.i[I_KEY0][p] = (int32_t) r.key[0]; V.i[I_KEY1][p] = (int32_t) r.key[1]; V.i[I_KEY2][p] = (int32_t) r.key[2];
@@ -373,11 +377,11 @@ __global__ void k_aos_to_soa(const psph_particle *__restrict__ rows, int n, int 
   V.i[I_CELL][p] = (idx[0] * G.ncell[1] + idx[1]) * G.ncell[2] + idx[2];
 }
 
-__global__ void k_soa_to_aos(psph_particle *__restrict__ rows, int n, Tab V, int has_grad)
+__global__ void k_soa_to_aos(char *__restrict__ rows, size_t stride, int n, Tab V, int has_grad)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  psph_particle r;
+  psph_particle &r = *reinterpret_cast<psph_particle *>(rows + (size_t) p * stride);
   r.key[0] = (uint32_t) V.i[I_KEY0][p]; r.key[1] = (uint32_t) V.i[I_KEY1][p]; r.key[2] = (uint32_t) V.i[I_KEY2][p];
   r.bc_type = V.i[I_BC][p]; r.phase_num = V.i[I_PHASE][p]; r.involved = V.i[I_INVOLVED][p];
   r.guest = V.i[I_GUEST][p]; r.myprocess = V.i[I_MYPROC][p];
@@ -389,8 +393,8 @@ __global__ void k_soa_to_aos(psph_particle *__restrict__ rows, int n, Tab V, int
   r.vel[0] = V.d[D_VX][p]; r.vel[1] = V.d[D_VY][p]; r.vel[2] = V.d[D_VZ][p];
   r.smoothed_v[0] = V.d[D_SVX][p]; r.smoothed_v[1] = V.d[D_SVY][p]; r.smoothed_v[2] = V.d[D_SVZ][p];
   r.rho = V.d[D_RHO][p]; r.engr = V.d[D_E][p]; r.smoothed_e = V.d[D_SE][p];
-  for (int k = 0; k < 15; k++) r.grad[k] = has_grad ? V.d[D_GRAD0 + k][p] : 0.0;
-  rows[p] = r;
+  if (stride >= sizeof(psph_particle))
+    for (int k = 0; k < 15; k++) r.grad[k] = has_grad ? V.d[D_GRAD0 + k][p] : 0.0;
 }
 
 static int ensure_aos(psph_ctx *ctx, size_t n)
@@ -418,15 +422,23 @@ int psph_sync_n(psph_ctx *ctx)
   return 0;
 }
 
-static int upload_at(psph_ctx *ctx, const psph_particle *rows, size_t n, size_t base)
+static bool row_bytes_ok(psph_ctx *ctx, size_t stride, const char *who)
+{
+  if (stride == sizeof(psph_particle) || stride == PSPH_ROW_BYTES_SPH) return true;
+  ctx->err = std::string(who) + ": row_bytes must be sizeof(psph_particle) or PSPH_ROW_BYTES_SPH";
+  return false;
+}
+
+static int upload_at(psph_ctx *ctx, const void *rows, size_t n, size_t base, size_t stride = sizeof(psph_particle))
 {
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   if (psph_reserve(ctx, base + n)) return -1;
   if (n) {
     if (ensure_aos(ctx, n)) return -1;
-    PSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, rows, n * sizeof(psph_particle), cudaMemcpyHostToDevice, ctx->stream));
-    k_aos_to_soa<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_aos, (int) n, (int) base, ctx->cur.t,
-                                                                         psph_grid_view(ctx), ctx->has_grad, ctx->cfg.rank);
+    PSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, rows, n * stride, cudaMemcpyHostToDevice, ctx->stream));
+    k_aos_to_soa<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const char *>(ctx->d_aos), stride, (int) n,
+                                                                         (int) base, ctx->cur.t, psph_grid_view(ctx), ctx->has_grad,
+                                                                         ctx->cfg.rank);
     PSPH_LAUNCH_CHECK();
   }
   psph_comm_mark(ctx, DIRTY_LAYOUT);
@@ -445,8 +457,27 @@ extern "C" int psph_append(psph_ctx *ctx, const psph_particle *rows, size_t n)
   return upload_at(ctx, rows, n, ctx->n);
 }
 
-extern "C" int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, size_t *n_out, int order)
+extern "C" int psph_upload_rows(psph_ctx *ctx, const void *rows, size_t n, size_t row_bytes)
 {
+  if (!row_bytes_ok(ctx, row_bytes, "psph_upload_rows")) return -2;
+  ctx->n = 0;
+  return upload_at(ctx, rows, n, 0, row_bytes);
+}
+extern "C" int psph_append_rows(psph_ctx *ctx, const void *rows, size_t n, size_t row_bytes)
+{
+  if (!row_bytes_ok(ctx, row_bytes, "psph_append_rows")) return -2;
+  if (psph_sync_n(ctx)) return -1;
+  return upload_at(ctx, rows, n, ctx->n, row_bytes);
+}
+
+extern "C" int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, size_t *n_out, int order)
+{ return psph_download_rows(ctx, rows, cap, n_out, order, sizeof(psph_particle)); }
+
+extern "C" int psph_download_rows(psph_ctx *ctx, void *rows_v, size_t cap, size_t *n_out, int order, size_t stride)
+{
+  if (!row_bytes_ok(ctx, stride, "psph_download_rows")) return -2;
+  char *rows = static_cast<char *>(rows_v);
+  auto key_of = [&](size_t i) { return reinterpret_cast<const psph_particle *>(rows + i * stride)->key; };
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   if (psph_sync_n(ctx)) return -1;
   size_t n = ctx->n;
@@ -455,9 +486,10 @@ extern "C" int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, siz
   if (cap < n) { ctx->err = "psph_download: buffer too small"; return -2; }
   if (n == 0) return 0;
   if (ensure_aos(ctx, n)) return -1;
-  k_soa_to_aos<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_aos, (int) n, ctx->cur.t, ctx->has_grad);
+  k_soa_to_aos<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<char *>(ctx->d_aos), stride, (int) n, ctx->cur.t,
+                                                                       ctx->has_grad);
   PSPH_LAUNCH_CHECK();
-  PSPH_CUDA(cudaMemcpyAsync(rows, ctx->d_aos, n * sizeof(psph_particle), cudaMemcpyDeviceToHost, ctx->stream));
+  PSPH_CUDA(cudaMemcpyAsync(rows, ctx->d_aos, n * stride, cudaMemcpyDeviceToHost, ctx->stream));
   PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
   if (order == PSPH_ORDER_REFERENCE) {
     // THashTable iteration order: ascending hash slot, chains sorted by key
@@ -466,18 +498,19 @@ extern "C" int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, siz
     const double umax = 4294967295.0;
     int S02 = ctx->cfg.ptable_size / 10, S01 = ctx->cfg.ptable_size - S02;
     for (size_t i = 0; i < n; i++) {
-      long long s = ctx->cfg.dim == 1 ? (long long) rows[i].key[0]
-        : (long long) (int) ((double) rows[i].key[0] / umax * S01) + (int) ((double) rows[i].key[1] / umax * S02);
+      const uint32_t *ki = key_of(i);
+      long long s = ctx->cfg.dim == 1 ? (long long) ki[0]
+        : (long long) (int) ((double) ki[0] / umax * S01) + (int) ((double) ki[1] / umax * S02);
       slot[i] = std::make_pair(s, i);
     }
     std::sort(slot.begin(), slot.end(), [&](const std::pair<long long, size_t> &a, const std::pair<long long, size_t> &b) {
       if (a.first != b.first) return a.first < b.first;
-      const uint32_t *ka = rows[a.second].key, *kb = rows[b.second].key;
+      const uint32_t *ka = key_of(a.second), *kb = key_of(b.second);
       for (int k = 0; k < 3; k++) if (ka[k] != kb[k]) return ka[k] < kb[k];
       return a.second < b.second;
     });
-    std::vector<psph_particle> tmp(rows, rows + n);
-    for (size_t i = 0; i < n; i++) rows[i] = tmp[slot[i].second];
+    std::vector<char> tmp(rows, rows + n * stride);
+    for (size_t i = 0; i < n; i++) memcpy(rows + i * stride, tmp.data() + slot[i].second * stride, stride);
   }
   return 0;
 }

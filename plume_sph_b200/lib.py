@@ -73,6 +73,10 @@ PARTICLE_DTYPE = np.dtype([
     ("grad", "<f8", 15),
 ])
 assert PARTICLE_DTYPE.itemsize == 328
+# PSPH_ROW_BYTES_SPH rows: psph_particle without its gradient block (what an SPH build exchanges, pack_data.h:68-75)
+PARTICLE_SPH_DTYPE = np.dtype([(n, PARTICLE_DTYPE.fields[n][0]) for n in PARTICLE_DTYPE.names if n != "grad"])
+assert PARTICLE_SPH_DTYPE.itemsize == 208 and all(
+    PARTICLE_SPH_DTYPE.fields[n][1] == PARTICLE_DTYPE.fields[n][1] for n in PARTICLE_SPH_DTYPE.names)
 
 CELL_ATTR_DTYPE = np.dtype([("type", "<i4"), ("has_involved", "<i4"), ("active", "<i4"),
                             ("bucket_index", "<i4", 6), ("pad", "<i4"), ("bnd", "<f8", 6)])
@@ -110,6 +114,9 @@ API = {
     "psph_rebin": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "psph_set_images": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_apply_bcond": (C.c_int, [_VP]),
+    "psph_upload_rows": (C.c_int, [_VP, _VP, C.c_size_t, C.c_size_t]),
+    "psph_append_rows": (C.c_int, [_VP, _VP, C.c_size_t, C.c_size_t]),
+    "psph_download_rows": (C.c_int, [_VP, _VP, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_size_t]),
     "psph_step": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "psph_run": (C.c_int, [_VP, C.c_int, C.c_int]),
     "psph_comm_unique_id": (C.c_int, [_VP, C.c_size_t]),

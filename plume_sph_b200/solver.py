@@ -55,30 +55,40 @@ class Solver:
         attr = np.ascontiguousarray(attr, dtype=_l.CELL_ATTR_DTYPE)
         return self._ck(self.L.psph_set_cells(self.h, attr.ctypes.data, attr.size), "psph_set_cells")
 
-    def host_rows(self, n):
-        """n psph_particle rows in pinned host memory (psph_host_alloc); freed with the solver"""
-        nbytes = max(int(n), 1) * _l.PARTICLE_DTYPE.itemsize
+    def host_rows(self, n, dtype=None):
+        """n rows (psph_particle, or lib.PARTICLE_SPH_DTYPE) in pinned host memory (psph_host_alloc); freed with the solver"""
+        dtype = dtype or _l.PARTICLE_DTYPE
+        nbytes = max(int(n), 1) * dtype.itemsize
         p = self.L.psph_host_alloc(nbytes)
         if not p:
             raise _l.PsphError("psph_host_alloc failed")
         self._pinned = getattr(self, "_pinned", []) + [p]
         buf = (C.c_char * nbytes).from_address(p)
-        return np.frombuffer(buf, dtype=_l.PARTICLE_DTYPE, count=int(n))
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    @staticmethod
+    def _rows(rows):
+        """contiguous rows in one of the two row layouts (PARTICLE_SPH_DTYPE arrays stay as they are)"""
+        if getattr(rows, "dtype", None) == _l.PARTICLE_SPH_DTYPE:
+            return np.ascontiguousarray(rows)
+        return np.ascontiguousarray(rows, dtype=_l.PARTICLE_DTYPE)
 
     def upload(self, rows):
-        rows = np.ascontiguousarray(rows, dtype=_l.PARTICLE_DTYPE)
-        return self._ck(self.L.psph_upload(self.h, rows.ctypes.data, rows.size), "psph_upload")
+        rows = self._rows(rows)
+        return self._ck(self.L.psph_upload_rows(self.h, rows.ctypes.data, rows.size, rows.dtype.itemsize), "psph_upload_rows")
 
     def append(self, rows):
-        rows = np.ascontiguousarray(rows, dtype=_l.PARTICLE_DTYPE)
-        return self._ck(self.L.psph_append(self.h, rows.ctypes.data, rows.size), "psph_append")
+        rows = self._rows(rows)
+        return self._ck(self.L.psph_append_rows(self.h, rows.ctypes.data, rows.size, rows.dtype.itemsize), "psph_append_rows")
 
-    def download(self, order=ORDER_REFERENCE, out=None):
+    def download(self, order=ORDER_REFERENCE, out=None, dtype=None):
+        """rows as psph_particle (default) or, with dtype=lib.PARTICLE_SPH_DTYPE / such an `out`, without gradients"""
         n = C.c_size_t(0)
         self._ck(self.L.psph_download(self.h, None, 0, C.byref(n), order), "psph_download")
         if out is None:
-            out = np.zeros(n.value, _l.PARTICLE_DTYPE)
-        self._ck(self.L.psph_download(self.h, out.ctypes.data, out.size, C.byref(n), order), "psph_download")
+            out = np.zeros(n.value, dtype or _l.PARTICLE_DTYPE)
+        self._ck(self.L.psph_download_rows(self.h, out.ctypes.data, out.size, C.byref(n), order, out.dtype.itemsize),
+                 "psph_download_rows")
         return out[:n.value]
 
     def upload_device_soa(self, cols, bc=None, phase=None, n=0):

@@ -112,3 +112,37 @@ def test_fused_step_equals_staged(case):
     for f in ("coords", "vel", "smoothed_v", "rho", "engr", "mass_frac", "pressure", "smlen", "bc_type"):
         assert np.array_equal(fused[f], staged[f]), f
     s2.close()
+
+
+def test_sph_rows_round_trip():
+    """psph_upload_rows / psph_download_rows with PSPH_ROW_BYTES_SPH rows (psph_particle without the GSPH gradient block,
+    what an SPH build of the reference exchanges, pack_data.h:68-75): the same table as the full rows, in both orders"""
+    z = golden("plume3d_small")
+    ocfg = op.config_for("plume3d_small", z)
+    full = dump_to_particles(z["pre"])
+    sph = np.zeros(len(full), psph.PARTICLE_SPH_DTYPE)
+    for f in psph.PARTICLE_SPH_DTYPE.names:
+        sph[f] = full[f]
+    a, b = psph.Solver(to_product_cfg(ocfg)), psph.Solver(to_product_cfg(ocfg))
+    try:
+        attr, _ = cell_attrs(ocfg, z)
+        for s, rows in ((a, full), (b, sph)):
+            s.set_cells(attr)
+            s.upload(rows)
+        b.append(sph[:0])
+        for order in (ORDER_REFERENCE, ORDER_DEVICE):
+            fa, fb = a.download(order), b.download(order)
+            ca, cb = a.download(order, dtype=psph.PARTICLE_SPH_DTYPE), b.download(order, dtype=psph.PARTICLE_SPH_DTYPE)
+            assert len(fa) == len(fb) == len(ca) == len(cb) == len(full)
+            for f in psph.PARTICLE_SPH_DTYPE.names:
+                assert np.array_equal(fa[f], fb[f]) and np.array_equal(fa[f], ca[f]) and np.array_equal(fa[f], cb[f]), f
+            assert not fb["grad"].any()
+        # one step from either upload: identical tables
+        ra, rb = a.step(0.0, 1), b.step(0.0, 1)
+        assert ra == rb
+        fa, cb = a.download(ORDER_REFERENCE), b.download(ORDER_REFERENCE, dtype=psph.PARTICLE_SPH_DTYPE)
+        for f in psph.PARTICLE_SPH_DTYPE.names:
+            assert np.array_equal(fa[f], cb[f]), f
+    finally:
+        a.close()
+        b.close()

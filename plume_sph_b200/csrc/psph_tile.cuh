@@ -20,6 +20,10 @@
 #pragma once
 #include "psph_gather3.cuh"
 
+#ifndef PSPH_WU
+#define PSPH_WU 4              // rounds of 32 list entries per batch of the weight-cache readers (3: 3 % slower at 216^3)
+#endif
+
 constexpr int TX = 8, TY = 14;                 // tile columns in x (2 + 2*3) and y (8 + 2*3)
 constexpr int TSEG = TX * TY * 3;              // (column, z-bucket) row segments of a tile
 constexpr int TCAP = 1920;                     // tile rows that fit in shared memory (13 double columns: 195 KiB)
@@ -468,7 +472,7 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
           // weights from the cache: WU rounds of 32 entries per batch; the slot and weight loads of the next batch
           // are issued before the pair bodies of the current one (the loop is bound by the rate at which the 8-byte
           // weights stream in from HBM, not by arithmetic)
-          constexpr int WU = 3;
+          constexpr int WU = PSPH_WU;
           const double *__restrict__ wl = V.wts + (size_t) loff * 32u + lane;
           int sl[WU];
           double w[WU];

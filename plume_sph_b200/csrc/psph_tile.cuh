@@ -20,9 +20,6 @@
 #pragma once
 #include "psph_gather3.cuh"
 
-#ifndef PSPH_PF2
-#define PSPH_PF2 0             // computing stages: slot-list entries fetched two rounds ahead instead of one
-#endif
 #ifndef PSPH_WU
 #define PSPH_WU 4              // rounds of 32 list entries per batch of the weight-cache readers (3: 3 % slower at 216^3)
 #endif
@@ -545,17 +542,9 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
           // rows of the partners inside the energy-smoothing kernel (V.near)
           [[maybe_unused]] double d1 = 0.0, d2 = 0.0;
           [[maybe_unused]] int nnear = 0;
-#if PSPH_PF2
-          int jn2 = entry(32 + lane);                                 // list entries two rounds ahead
-#endif
           for (int q0 = 0; q0 < ntot; q0 += 32) {
             const int sl = jn;
-#if PSPH_PF2
-            jn = jn2;
-            jn2 = entry(q0 + 64 + lane);
-#else
-            jn = entry(q0 + 32 + lane);
-#endif
+            jn = entry(q0 + 32 + lane);                              // (two rounds ahead measured 2 % slower)
             [[maybe_unused]] bool fl = false;
             if (sl >= 0) {
               double px, py, pz;

@@ -36,10 +36,11 @@ struct TileTable
   int beg[TSEG];                               // first row of the segment
   int base[TSEG];                              // sub_start index of subcell z = 0 of the segment's column, -1: outside
   int off[TSEG + 1];                           // first slot of the segment; off[TSEG] = tile rows
+  int pad[3];                                  // wsum 16-byte aligned (its vector loads must not cover off[TSEG], which
+                                               // another thread writes meanwhile: racecheck) and sizeof % 16 == 0
   int wsum[32];
-  int pad[3];                                  // sizeof % 16 == 0: the per-warp scratch / the tile follow
 };
-static_assert(sizeof(TileTable) % 16 == 0, "TileTable padding");
+static_assert(sizeof(TileTable) % 16 == 0 && offsetof(TileTable, wsum) % 16 == 0, "TileTable padding");
 
 // (beg, len, base) of segment s of the tile of block (cell (cx, cy, cz), sx-pair q)
 __device__ __forceinline__ void tile_segment(const GridView &G, int cx, int cy, int cz, int q, int s, int &beg, int &len, int &base)

@@ -139,6 +139,23 @@ typedef struct psph_image
   double coord[3];           /* the image (reflection) point */
 } psph_image;
 
+/* What add_new_erupt (src/plume/setup_erupt.cc:390-670) reads besides the particle table: the vent
+ * constants of parameters.h, the SimProps members it uses and the key range of the particle table. */
+typedef struct psph_erupt
+{
+  double pos_v[2];           /* Pos_v_P[0], Pos_v_P[1]: centre of the duct's particle lattice */
+  double rv;                 /* rv_P: duct radius (columns with x^2 + y^2 <= rv^2 inject) */
+  double Vv0;                /* Vv0_P: average velocity */
+  int32_t vel_prof;          /* ERUPT_VELOCITY_PROF: 0 uniform, 1 parabolic (sph_lib.cc:1223-1243) */
+  int32_t pad;
+  double bot;                /* SimProps::get_bot(): z where a column's particles are born */
+  double sml;                /* SimProps::sml_of_phase2: lattice spacing and smoothing length (x ratio_sml_dx) */
+  double mass;               /* SimProps::mass_of_phase2 */
+  double ratio_sml_dx;       /* RATIO_SML_DX (constant.h:90) */
+  double ev0, rhov, pv0, gamma_v, sndspd;   /* state of the erupted material (Particle ctor, particle.cc:210-316) */
+  double kmin[3], kmax[3];   /* THashTable::get_minDom() / get_maxDom(): the box the birth keys are normalised to */
+} psph_erupt;
+
 typedef struct psph_ctx psph_ctx;
 
 enum { PSPH_ORDER_DEVICE = 0, PSPH_ORDER_REFERENCE = 1 };
@@ -204,6 +221,13 @@ int psph_rebin(psph_ctx *ctx, int *lost);    /* update_particles_in_bucket, main
  * called whenever that table changes; psph_apply_bcond replaces apply_bcond (bcond.cc:24-249; main.cc:196,298,468):
  * every wall ghost with an image takes the fluid state interpolated at its image point, velocity reflected about the
  * wall normal, secondary variables recomputed.  Single rank (nranks == 1) in this version. */
+/* Eruption boundary: psph_set_erupt hands over the vent record and the boxes [mincrd[3], maxcrd[3]] of the buckets
+ * flagged is_erupt(); psph_add_new_erupt replaces add_new_erupt (setup_erupt.cc:390-670; main.cc:414-417): every duct
+ * column injects floor((fmod(t - dt, t_each) + dt) / t_each) erupt ghosts (bc_type 0, phase 2) at the bottom, born with a
+ * Hilbert key of their position and add_step as third key word.  time = TimeProps::time after incrtime.  *added gets
+ * the number of new particles (may be NULL; reading it synchronises).  Single rank in this version. */
+int psph_set_erupt(psph_ctx *ctx, const psph_erupt *erupt, const double *cell_boxes, size_t ncells);
+int psph_add_new_erupt(psph_ctx *ctx, double time, double dt, uint32_t add_step, int *added);
 int psph_set_images(psph_ctx *ctx, const psph_image *images, size_t n);
 int psph_apply_bcond(psph_ctx *ctx);
 

@@ -53,6 +53,23 @@ class CellAttr(C.Structure):
                 ("bucket_index", C.c_int32 * 6), ("pad", C.c_int32), ("bnd", C.c_double * 6)]
 
 
+
+class Erupt(C.Structure):
+    """Mirror of ``psph_erupt`` (include/psph.h): what add_new_erupt reads (setup_erupt.cc:390-670)."""
+    _fields_ = [("pos_v", C.c_double * 2), ("rv", C.c_double), ("Vv0", C.c_double), ("vel_prof", C.c_int32),
+                ("pad", C.c_int32), ("bot", C.c_double), ("sml", C.c_double), ("mass", C.c_double),
+                ("ratio_sml_dx", C.c_double), ("ev0", C.c_double), ("rhov", C.c_double), ("pv0", C.c_double),
+                ("gamma_v", C.c_double), ("sndspd", C.c_double), ("kmin", C.c_double * 3), ("kmax", C.c_double * 3)]
+
+
+# host rows of the boundary (psph_particle, include/psph.h): what psph_oracle_add_new_erupt writes
+PARTICLE_DTYPE = np.dtype([("key", "<u4", 3), ("bc_type", "<i4"), ("phase_num", "<i4"), ("involved", "<i4"), ("guest", "<i4"),
+                           ("myprocess", "<i4"), ("mass", "<f8"), ("smlen", "<f8"), ("mass_frac", "<f8"), ("pressure", "<f8"),
+                           ("gamma", "<f8"), ("sound_speed", "<f8"), ("temperature", "<f8"), ("specific_heat_p", "<f8"),
+                           ("phase_density", "<f8", 2), ("coords", "<f8", 3), ("vel", "<f8", 3), ("smoothed_v", "<f8", 3),
+                           ("rho", "<f8"), ("engr", "<f8"), ("smoothed_e", "<f8"), ("grad", "<f8", 15)])
+assert PARTICLE_DTYPE.itemsize == 328
+
 CELL_ATTR_DTYPE = np.dtype([("type", "<i4"), ("has_involved", "<i4"), ("active", "<i4"),
                             ("bucket_index", "<i4", 6), ("pad", "<i4"), ("bnd", "<f8", 6)])
 assert CELL_ATTR_DTYPE.itemsize == C.sizeof(CellAttr)
@@ -210,6 +227,9 @@ def lib():
         L.psph_oracle_weight.restype = C.c_double
         L.psph_oracle_d_weight.argtypes = [C.c_int, _P(C.c_double), C.c_double, C.c_double, C.c_int]
         L.psph_oracle_d_weight.restype = C.c_double
+        L.psph_oracle_add_new_erupt.argtypes = [cp, C.POINTER(Erupt), _P(C.c_double), C.c_int, C.c_double, C.c_double,
+                                                C.c_uint32, C.c_void_p, C.c_int]
+        L.psph_oracle_add_new_erupt.restype = C.c_int
         L.psph_oracle_hsfc3d.argtypes = [_P(C.c_double), _P(C.c_uint32)]
         L.psph_oracle_hsfc3d.restype = None
     return _lib
@@ -361,3 +381,27 @@ class OracleState:
 
     def free(self):
         lib().psph_oracle_free_lists(C.byref(self.st))
+
+
+def add_new_erupt(cfg, erupt, boxes, time, dt, add_step, cap=65536):
+    """psph_oracle_add_new_erupt: the rows (psph_particle layout) add_new_erupt adds at this time step"""
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 6)
+    out = np.zeros(cap, PARTICLE_DTYPE)
+    n = lib().psph_oracle_add_new_erupt(C.byref(cfg), C.byref(erupt), boxes.ctypes.data_as(_P(C.c_double)), len(boxes),
+                                        float(time), float(dt), int(add_step), out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("psph_oracle_add_new_erupt: more than %d particles" % cap)
+    return out[:n]
+
+
+def erupt_from_params(names, v):
+    """Erupt record from the parameter dump of a golden eruption fixture (tests/golden/make_golden.py ERUPT_PARAMS)"""
+    d = dict(zip([str(n) for n in names], [float(x) for x in v]))
+    e = Erupt()
+    e.pos_v[0], e.pos_v[1] = d["pos_v0"], d["pos_v1"]
+    e.rv, e.Vv0, e.vel_prof = d["rv"], d["Vv0"], int(d["vel_prof"])
+    e.bot, e.sml, e.mass, e.ratio_sml_dx = d["bot"], d["sml_of_phase2"], d["mass_of_phase2"], d["ratio_sml_dx"]
+    e.ev0, e.rhov, e.pv0, e.gamma_v, e.sndspd = d["ev0"], d["rhov"], d["pv0"], d["gamma_v"], d["sndspd"]
+    for k in range(3):
+        e.kmin[k], e.kmax[k] = d["kmin%d" % k], d["kmax%d" % k]
+    return e, d

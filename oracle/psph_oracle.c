@@ -877,6 +877,83 @@ void psph_oracle_table_order(const psph_config *c, const uint32_t *key, int64_t 
   free(o);
 }
 
+/* ---------------- add_new_erupt ---------------- */
+static double erupt_vel(const psph_erupt *er, double rsq)
+{ /* vel_prof, sph_lib.cc:1223-1243 */
+  if (er->vel_prof == 0) return er->Vv0;
+  double umax = er->Vv0 * 2;
+  return umax * (1 - (rsq / (er->rv * er->rv)));
+}
+
+static int erupt_column(const psph_config *c, const psph_erupt *er, const double *boxes, int nbox, double t_prev, double dt,
+                        uint32_t add_step, double x, double y, psph_particle *out, int cap, int n_out)
+{ /* the body of the four y-loops, setup_erupt.cc:458-490 (and its three copies) + the bucket filter :609-650 */
+  double dist = x * x + y * y;
+  if (!(dist <= er->rv * er->rv)) return n_out;
+  double vel = erupt_vel(er, dist);
+  double t_each = er->sml / vel;
+  double t_add = fmod(t_prev, t_each) + dt;
+  int n = (int) floor(t_add / t_each);
+  t_add = t_add - n * t_each;
+  for (int i = 0; i < n; i++) {
+    double crd[3] = { x, y, er->bot + (t_add + i * t_each) * vel };
+    int inside = 0; /* in_bucket (sph_lib.cc:1057-1065, both faces inclusive) of an erupt bucket */
+    for (int b = 0; b < nbox && !inside; b++) {
+      const double *mn = boxes + 6 * b, *mx = mn + 3;
+      inside = crd[0] <= mx[0] && crd[0] >= mn[0] && crd[1] <= mx[1] && crd[1] >= mn[1] && crd[2] <= mx[2] && crd[2] >= mn[2];
+    }
+    if (!inside) continue;
+    if (n_out >= cap) return -1;
+    psph_particle *p = out + n_out++;
+    memset(p, 0, sizeof *p);
+    double normc[3];
+    for (int k = 0; k < 3; k++) normc[k] = (crd[k] - er->kmin[k]) / (er->kmax[k] - er->kmin[k]);
+    psph_oracle_hsfc3d(normc, p->key); /* THSFC3d, hilbert.c:329-359 */
+    p->key[2] = add_step;
+    /* Particle ctor for erupted material, particle.cc:210-316 */
+    p->bc_type = 0; p->phase_num = 2; p->involved = 0; p->guest = 0; p->myprocess = c->rank;
+    p->mass = er->mass;
+    p->smlen = er->ratio_sml_dx * er->sml;
+    for (int k = 0; k < 3; k++) p->coords[k] = crd[k];
+    p->vel[2] = vel;
+    p->smoothed_e = er->ev0;
+    p->engr = er->ev0;
+    p->mass_frac = 1.;
+    p->rho = er->rhov;
+    { /* update_second_var, particle.cc:528-604, with ks = 1; pressure, sound speed and gamma are then overwritten */
+      double ks = 1., na = 1 - ks, ng = c->ng0 * ks, ns = ks - ng;
+      double Cvm = ns * c->Cvs + ng * c->Cvg + na * c->Cva;
+      p->phase_density[0] = p->rho * na;
+      p->phase_density[1] = p->rho * ks;
+      p->temperature = p->engr / Cvm;
+      p->specific_heat_p = c->have_turbulence_lans != 0 ? Cvm : 0.;
+    }
+    p->pressure = er->pv0;
+    p->sound_speed = er->sndspd;
+    p->gamma = er->gamma_v;
+  }
+  return n_out;
+}
+
+int psph_oracle_add_new_erupt(const psph_config *c, const psph_erupt *er, const double *boxes, int nbox, double time,
+                              double dt, uint32_t add_step, psph_particle *out, int cap)
+{ /* setup_erupt.cc:390-670.  The duct's rough range is [-rv, rv] about the ORIGIN (:446-449) and the distance to the
+   * axis is that of the origin too (:463-465), whatever Pos_v_P is; coordinates are built by repeated addition */
+  const double sml = er->sml, sml2 = 0.5 * sml, t_prev = time - dt; /* :454 */
+  int n = 0;
+  for (int half = 0; half < 2 && n >= 0; half++) {
+    double x = half == 0 ? er->pos_v[0] + sml2 : er->pos_v[0] - sml2;
+    while (n >= 0 && (half == 0 ? x <= er->rv : x >= -er->rv)) {
+      double y = er->pos_v[1] + sml2;
+      while (n >= 0 && y <= er->rv) { n = erupt_column(c, er, boxes, nbox, t_prev, dt, add_step, x, y, out, cap, n); y += sml; }
+      y = er->pos_v[1] - sml2;
+      while (n >= 0 && y >= -er->rv) { n = erupt_column(c, er, boxes, nbox, t_prev, dt, add_step, x, y, out, cap, n); y -= sml; }
+      if (half == 0) x += sml; else x -= sml;
+    }
+  }
+  return n;
+}
+
 /* ---------------- Hilbert key ---------------- */
 void psph_oracle_hsfc3d(const double coord[3], uint32_t key[2])
 { /* HSFC3d + hsfc3d, hilbert.c:156-271,289-303 (Zoltan's 3-D Hilbert curve), restated as a

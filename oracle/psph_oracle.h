@@ -83,6 +83,11 @@ void psph_oracle_table_order(const psph_config *cfg, const uint32_t *key, int64_
 /* kernel functions, exposed for unit tests: weight sph_lib.cc:210-230, d_weight :240-253 */
 double psph_oracle_weight(int dim, const double *s, double h, double cutoff);
 double psph_oracle_d_weight(int dim, const double *s, double h, double cutoff, int dir);
+/* add_new_erupt, setup_erupt.cc:390-670: writes the particles the call adds to out[] (generation order: x+ / x- halves,
+ * y+ / y- runs of every x column, bottom first) and returns their number (-1: more than cap).  boxes: [nbox][6] mincrd,
+ * maxcrd of the erupt buckets.  time = TimeProps::time after incrtime. */
+int psph_oracle_add_new_erupt(const psph_config *cfg, const psph_erupt *er, const double *boxes, int nbox, double time,
+                              double dt, uint32_t add_step, psph_particle *out, int cap);
 /* Hilbert key of a normalised position, hilbert.c:289-303 (HSFC3d) */
 void psph_oracle_hsfc3d(const double coord[3], uint32_t key[2]);
 

@@ -324,8 +324,53 @@ void psphhook_update_particles_in_bucket(int myid, THashTable *P, HashTable *BG,
 }
 
 #ifndef SIMULATE_ASH
+/* what add_new_erupt (setup_erupt.cc:390-670) reads besides the particle table: its arguments, the compile-time vent
+ * constants of parameters.h, the key range of the particle table and the buckets flagged is_erupt().
+ * "<dir>/s<step>_erupt_params.bin": f64 v[24] (see below), i64 nb, then per erupt bucket f64 mincrd[3], f64 maxcrd[3],
+ * i32 guest, i32 pad. */
+void dump_erupt_params(THashTable *P, HashTable *BG, TimeProps *tp, MatProps *mp, SimProps *sp, double dt)
+{
+  if (!dumping()) return;
+  char fn[512];
+  snprintf(fn, sizeof fn, "%s/s%04d_erupt_params.bin", g_dir, g_step);
+  FILE *f = fopen(fn, "wb");
+  if (!f) { perror(fn); exit(1); }
+#if FLUID_COMPRESSIBILITY == 0
+  const double sndspd = 340.;
+#else
+  const double sndspd = 1482.;
+#endif
+  double v[24] = { tp->time, dt, (double) tp->step, sp->get_bot(), sp->sml_of_phase2, sp->mass_of_phase2,
+                   rv_P, Pos_v_P[0], Pos_v_P[1], Vv0_P, ev0_P, rhov_P, pv0_P, gamma_v_P, sndspd,
+                   (double) ERUPT_VELOCITY_PROF, (double) RATIO_SML_DX,
+                   *(P->get_minDom()), *(P->get_minDom() + 1), *(P->get_minDom() + 2),
+                   *(P->get_maxDom()), *(P->get_maxDom() + 1), *(P->get_maxDom() + 2), (double) tp->iferupt() };
+  fwrite(v, 8, 24, f);
+  long long nb = 0;
+  long pos = ftell(f);
+  fwrite(&nb, 8, 1, f);
+  HTIterator it(BG);
+  void *t;
+  while ((t = it.next())) {
+    BriefBucket *bb = (BriefBucket *) t;
+    if (bb->check_brief()) continue;
+    Bucket *b = (Bucket *) t;
+    if (!b->is_erupt()) continue;
+    fwrite(b->get_mincrd(), 8, 3, f);
+    fwrite(b->get_maxcrd(), 8, 3, f);
+    int g[2] = { (int) b->is_guest(), 0 };
+    fwrite(g, 4, 2, f);
+    nb++;
+  }
+  fseek(f, pos, SEEK_SET);
+  fwrite(&nb, 8, 1, f);
+  fclose(f);
+  (void) mp;
+}
+
 void psphhook_add_new_erupt(int myid, THashTable *P, HashTable *BG, TimeProps *tp, MatProps *mp, SimProps *sp, double dt)
 {
+  dump_erupt_params(P, BG, tp, mp, sp, dt);
   { StageTimer st("add_new_erupt"); add_new_erupt(myid, P, BG, tp, mp, sp, dt); }
   dump_table(P, "erupt", "post");
   dump_buckets(P, BG, "erupt");

@@ -85,6 +85,14 @@ assert CELL_ATTR_DTYPE.itemsize == 88
 IMAGE_DTYPE = np.dtype([("ghost_key", "<u4", 3), ("cell", "<i4"), ("coord", "<f8", 3)])
 assert IMAGE_DTYPE.itemsize == 40
 
+class PsphErupt(C.Structure):
+    """Mirror of ``psph_erupt`` (include/psph.h): what add_new_erupt reads (setup_erupt.cc:390-670)."""
+    _fields_ = [("pos_v", C.c_double * 2), ("rv", C.c_double), ("Vv0", C.c_double), ("vel_prof", C.c_int32),
+                ("pad", C.c_int32), ("bot", C.c_double), ("sml", C.c_double), ("mass", C.c_double),
+                ("ratio_sml_dx", C.c_double), ("ev0", C.c_double), ("rhov", C.c_double), ("pv0", C.c_double),
+                ("gamma_v", C.c_double), ("sndspd", C.c_double), ("kmin", C.c_double * 3), ("kmax", C.c_double * 3)]
+
+
 # every symbol include/psph.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
 _CFG = C.POINTER(PsphConfig)
@@ -112,6 +120,8 @@ API = {
     "psph_smooth_velocity": (C.c_int, [_VP]),
     "psph_update_pos": (C.c_int, [_VP]),
     "psph_rebin": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+    "psph_set_erupt": (C.c_int, [_VP, _VP, _VP, C.c_size_t]),
+    "psph_add_new_erupt": (C.c_int, [_VP, C.c_double, C.c_double, C.c_uint32, C.POINTER(C.c_int)]),
     "psph_set_images": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_apply_bcond": (C.c_int, [_VP]),
     "psph_upload_rows": (C.c_int, [_VP, _VP, C.c_size_t, C.c_size_t]),

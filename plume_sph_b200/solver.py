@@ -152,6 +152,19 @@ class Solver:
     def update_pos(self):
         return self._ck(self.L.psph_update_pos(self.h), "psph_update_pos")
 
+    def set_erupt(self, erupt, boxes):
+        """vent record (lib.PsphErupt) + [n][6] mincrd, maxcrd of the buckets flagged is_erupt()"""
+        b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 6)
+        e = _l.PsphErupt()
+        C.memmove(C.byref(e), C.byref(erupt), C.sizeof(e))
+        return self._ck(self.L.psph_set_erupt(self.h, C.byref(e), b.ctypes.data, len(b)), "psph_set_erupt")
+
+    def add_new_erupt(self, time, dt, add_step):
+        """add_new_erupt (setup_erupt.cc:390-670) on the device; returns the number of particles added"""
+        added = C.c_int(0)
+        self._ck(self.L.psph_add_new_erupt(self.h, float(time), float(dt), int(add_step), C.byref(added)), "psph_add_new_erupt")
+        return added.value
+
     def set_images(self, images):
         """wall-ghost images (IMAGE_DTYPE rows: ghost key, bucket cell, image point) — the driver's Image_table"""
         img = np.ascontiguousarray(images, dtype=_l.IMAGE_DTYPE)

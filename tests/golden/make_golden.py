@@ -165,6 +165,60 @@ def golden_3d(name, variant, edits, list_stride=4, simdata="simulation.data"):
         print(name, "n =", len(pre), "listed", len(listed), "->", os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
 
 
+ERUPT_PARAMS = ("time", "dt", "step", "bot", "sml_of_phase2", "mass_of_phase2", "rv", "pos_v0", "pos_v1", "Vv0", "ev0", "rhov",
+                "pv0", "gamma_v", "sndspd", "vel_prof", "ratio_sml_dx", "kmin0", "kmin1", "kmin2", "kmax0", "kmax1", "kmax2",
+                "iferupt")
+
+
+def read_erupt_params(fn):
+    raw = open(fn, "rb").read()
+    v = np.frombuffer(raw, np.float64, 24)
+    nb = int(np.frombuffer(raw, np.int64, 1, 192)[0])
+    rec = np.frombuffer(raw, np.dtype([("mincrd", "<f8", 3), ("maxcrd", "<f8", 3), ("guest", "<i4"), ("pad", "<i4")]), nb, 200)
+    return v.copy(), rec.copy()
+
+
+def golden_erupt(name="erupt3d", variant="3d_plume", edits=None, steps=(2, 3)):
+    """add_new_erupt (setup_erupt.cc:390-670) of the small 3-D plume at time steps 2 and 3 (step 1 adds nothing: dt is
+    still shorter than the injection period of every duct column): what the function reads (arguments, vent constants,
+    key range of the particle table, erupt buckets) and the particles it added, in THashTable order."""
+    edits = SMALL_3D if edits is None else edits
+    with tempfile.TemporaryDirectory() as top:
+        wd = os.path.join(top, "run")
+        os.makedirs(wd)
+        shutil.copytree(os.path.join(REF, "Meteo_data"), os.path.join(top, "Meteo_data"))
+        shutil.copy(os.path.join(REF, "bin", "scale.data"), wd)
+        txt = open(os.path.join(REF, "bin", "simulation.data")).read()
+        for a, b in edits:
+            assert a in txt, a
+            txt = txt.replace(a, b)
+        open(os.path.join(wd, "simulation.data"), "w").write(txt)
+        smlen = [l for l in txt.splitlines() if l.startswith("smoothing length")][0].split(":")[1]
+        subprocess.run([os.path.join(REFBIN, variant, "preprocess"), "1", smlen, "0"], cwd=wd, check=True,
+                       stdout=subprocess.DEVNULL)
+        dump = os.path.join(wd, "dump")
+        os.makedirs(dump)
+        run_ref(variant, wd, dict(PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="%d-%d" % (min(steps), max(steps)),
+                                  PSPH_MAX_STEPS=max(steps)))
+        out = dict(param_names=np.asarray(ERUPT_PARAMS))
+        for st in steps:
+            _, a = refio.read_dump(os.path.join(dump, "s%04d_rebin_post.bin" % st))
+            _, b = refio.read_dump(os.path.join(dump, "s%04d_erupt_post.bin" % st))
+            v, cells = read_erupt_params(os.path.join(dump, "s%04d_erupt_params.bin" % st))
+            ka = {tuple(k): i for i, k in enumerate(a["key"])}
+            new = np.asarray([i for i, k in enumerate(b["key"]) if tuple(k) not in ka], np.int64)
+            old = np.asarray([i for i, k in enumerate(b["key"]) if tuple(k) in ka], np.int64)
+            assert len(old) == len(a) and all(np.array_equal(a[f], b[f][old]) for f in a.dtype.names), "add_new_erupt touched an old row"
+            out["s%d_params" % st] = v
+            out["s%d_cell_min" % st] = cells["mincrd"]
+            out["s%d_cell_max" % st] = cells["maxcrd"]
+            out["s%d_cell_guest" % st] = cells["guest"]
+            out["s%d_new" % st] = b[new]
+            out["s%d_nold" % st] = np.asarray([len(a)])
+            print(name, "step", st, "added", len(new), "of", len(b), "erupt buckets", len(cells))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 SMALL_3D = [("initial domain:-2000", "initial domain:-350"), ("initial domain:2000", "initial domain:350"),
             ("initial domain:2700", "initial domain:2400")]
 
@@ -182,6 +236,7 @@ if __name__ == "__main__":
         "shu_gsph": lambda: golden_1d("shu_gsph", "1d_shu_gsph", "simulation_1D_shocktube_shu-Osher.data", 200),
         # (the reference's own plain-SPH build aborts on the strong blast at step 4: assert c>0, timestep.cc:167)
         "blast_gsph": lambda: golden_1d("blast_gsph", "1d_blast_gsph", "simulation_1D_shocktube_Strong-Blast.data", 300),
+        "erupt3d": lambda: golden_erupt(),
         "plume3d_small": lambda: golden_3d("plume3d_small", "3d_plume", SMALL_3D),
         "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D),
         # BASELINE config 2: JPUE weakly-compressible jet (Tait EOS, g = 0), the reference's own input file

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_py as op
-from common import golden, oracle_state_3d, cell_attrs, image_cells
+from common import golden, oracle_state_3d, cell_attrs, image_cells, D2P
 from plume_sph_b200.driver import TimeProps
 
 
@@ -212,3 +212,25 @@ def test_reference_algorithm_is_sensitive():
     from common import RTOL_LONG            # ... and inside the stated long-run tolerances
     for f, k in (("x", "coord"), ("v", "vel"), ("rho", "rho"), ("e", "engr"), ("h", "smlen")):
         assert d400[f] < RTOL_LONG[k] and d100[f] < RTOL_LONG[k], (f, d100[f], d400[f])
+
+
+def test_add_new_erupt_bit_exact():
+    """add_new_erupt (setup_erupt.cc:390-670) at time steps 2 and 3 of the small plume: the particles the unmodified
+    reference added (tests/golden/erupt3d.npz: its arguments, vent constants, erupt buckets and new rows) against the
+    restatement — keys, coordinates, velocities and every other field, bit for bit"""
+    z = golden("erupt3d")
+    cfg = op.config_for("plume3d_small", golden("plume3d_small"))
+    for st in (2, 3):
+        er, d = op.erupt_from_params(z["param_names"], z["s%d_params" % st])
+        boxes = np.concatenate([z["s%d_cell_min" % st], z["s%d_cell_max" % st]], axis=1)
+        got = op.add_new_erupt(cfg, er, boxes, d["time"], d["dt"], int(d["step"]))
+        want = z["s%d_new" % st]
+        assert len(got) == len(want) > 0
+        gi = {tuple(int(x) for x in k): i for i, k in enumerate(got["key"])}
+        perm = np.asarray([gi[tuple(int(x) for x in k)] for k in want["key"]])   # every reference key is there
+        got = got[perm]
+        for f, pf in D2P.items():
+            if f in want.dtype.names:
+                eq(got[pf], want[f], ("erupt", st, f))
+        eq(got["bc_type"], want["bc_type"], "bc")
+        assert not got["guest"].any() and not want["guest"].any()

@@ -199,6 +199,7 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->dens_near = dn ? atoi(dn) : 1;
     const char *wc = getenv("PSPH_WCACHE");
     ctx->wcache = wc ? atoi(wc) : 1;
+    ctx->has_erupt = false; ctx->d_erupt_boxes = nullptr; ctx->n_erupt_boxes = 0;
     ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr; ctx->n_img = 0;
     ctx->nbr_units = 0; ctx->nbr_want_tried = 0; ctx->nbr_valid = false; ctx->nbr_kind = 0;
   }
@@ -251,6 +252,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
   cudaFree(ctx->d_cell_has_ghost); cudaFree(ctx->d_blk_any);
+  cudaFree(ctx->d_erupt_boxes);
   cudaFree(ctx->d_img_keys); cudaFree(ctx->d_img_coord); cudaFree(ctx->d_img_cell);
   cudaFree(ctx->d_sortkey); cudaFree(ctx->d_sortkey_alt); cudaFree(ctx->d_perm); cudaFree(ctx->d_perm_alt);
   cudaFree(ctx->d_cub_tmp); cudaFree(ctx->d_ss); cudaFreeHost(ctx->h_ss);

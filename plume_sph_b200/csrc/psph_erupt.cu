@@ -1,0 +1,179 @@
+// psph_erupt.cu — eruption boundary on the device.
+//
+// Replaces add_new_erupt (src/plume/setup_erupt.cc:390-670): the duct is a lattice of columns, spacing sml_of_phase2,
+// inside the circle x^2 + y^2 <= rv^2; per time step a column injects n = floor((fmod(t - dt, t_each) + dt) / t_each)
+// erupt ghosts (bc_type 0, phase 2) at z = bot + (t_add + i t_each) vel, t_each = sml / vel(r) — a closed form, so the
+// reference's four nested while-loops become ONE thread per column.  The thread rebuilds its column's coordinates by
+// the reference's own repeated additions and evaluates every expression with explicit IEEE operations (__dmul_rn,
+// __dadd_rn, ... : no FMA contraction), so positions, velocities and the birth keys (Hilbert index of the position +
+// add_step, THSFC3d, hilbert.c:329-359) are bit-identical to the reference's.  New rows are appended to the table
+// (slots from one atomic counter; the row order of the table is rebuilt by the next list build anyway), each with the
+// state the erupted-material constructor gives it (Particle ctor, particle.cc:210-316).
+#include "psph_internal.cuh"
+
+struct EruptPar
+{
+  psph_erupt e;
+  int nxp, nxm, nyp, nym;        // columns of the x+ / x- halves and of the y+ / y- runs (setup_erupt.cc:456-600)
+  double t_prev, dt;
+  uint32_t add_step;
+  int base, cap, rank, has_grad, nbox;
+};
+
+// Hilbert key of a normalised position: HSFC3d + hsfc3d (hilbert.c:156-271,289-303), the 63-bit index walk of
+// psph_ctx.cu on the device
+__device__ void dev_hsfc3d(const double nc[3], uint32_t key[2])
+{
+  const unsigned char gray_inv[8] = { 0, 1, 3, 2, 7, 6, 4, 5 };
+  const unsigned char from[8][3] = { {2,1,0}, {0,2,1}, {0,1,2}, {2,0,1}, {2,0,1}, {0,1,2}, {0,2,1}, {2,1,0} };
+  const unsigned char refl[8][3] = { {0,0,0}, {0,0,0}, {0,0,0}, {1,1,0}, {0,1,1}, {0,0,0}, {0,1,1}, {1,0,1} };
+  uint32_t q[3];
+  for (int d = 0; d < 3; d++) {
+    const double v = nc[d] <= 0 ? 0.0 : __dmul_rn(4294967295.0, nc[d]);
+    q[d] = (uint32_t) (v > 4294967295.0 ? 4294967295.0 : v);
+  }
+  unsigned char ax[3] = { 0, 2, 4 };
+  unsigned long long H = 0;
+  for (int lvl = 1; lvl <= 21; lvl++) {
+    const unsigned s = 32 - lvl;
+    unsigned g = 0;
+    for (int a = 0; a < 3; a++) g |= (((q[ax[a] >> 1] >> s) ^ ax[a]) & 1u) << a;
+    const unsigned oct = gray_inv[g];
+    H = (H << 3) | oct;
+    const unsigned char o[3] = { ax[0], ax[1], ax[2] };
+    for (int a = 0; a < 3; a++) ax[a] = o[from[oct][a]] ^ refl[oct][a];
+  }
+  const unsigned long long K = H >> 1;        // the 2-word key drops the last bit
+  key[0] = (uint32_t) (K >> 32);
+  key[1] = (uint32_t) (K & 0xffffffffu);
+}
+
+__global__ void k_add_erupt(Tab V, GridView G, KParams K, StepState *ss, EruptPar P, const double *__restrict__ boxes)
+{
+  const int ny = P.nyp + P.nym, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (P.nxp + P.nxm) * ny) return;
+  const int ix = t / ny, iy = t - ix * ny;
+  const psph_erupt &e = P.e;
+  const double sml = e.sml, sml2 = __dmul_rn(0.5, sml);
+  // the column's coordinates, built as the loops build them: start + repeated addition (:456,:526,:530,:598)
+  double x, y;
+  if (ix < P.nxp) { x = __dadd_rn(e.pos_v[0], sml2); for (int k = 0; k < ix; k++) x = __dadd_rn(x, sml); }
+  else { x = __dsub_rn(e.pos_v[0], sml2); for (int k = 0; k < ix - P.nxp; k++) x = __dsub_rn(x, sml); }
+  if (iy < P.nyp) { y = __dadd_rn(e.pos_v[1], sml2); for (int k = 0; k < iy; k++) y = __dadd_rn(y, sml); }
+  else { y = __dsub_rn(e.pos_v[1], sml2); for (int k = 0; k < iy - P.nyp; k++) y = __dsub_rn(y, sml); }
+  const double dist = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));                   // :461-464
+  if (!(dist <= __dmul_rn(e.rv, e.rv))) return;
+  double vel = e.Vv0;                                                                // vel_prof, sph_lib.cc:1223-1243
+  if (e.vel_prof != 0) vel = __dmul_rn(__dmul_rn(e.Vv0, 2.0), __dsub_rn(1.0, __ddiv_rn(dist, __dmul_rn(e.rv, e.rv))));
+  const double t_each = __ddiv_rn(sml, vel);
+  double t_add = __dadd_rn(fmod(P.t_prev, t_each), P.dt);                            // :469
+  const int n = (int) floor(__ddiv_rn(t_add, t_each));
+  t_add = __dsub_rn(t_add, __dmul_rn((double) n, t_each));
+  // state of the erupted material (Particle ctor, particle.cc:210-316; update_second_var with ks = 1, then pressure,
+  // sound speed and gamma overwritten)
+  const double ks = 1.0, na = __dsub_rn(1.0, ks), ng = __dmul_rn(K.ng0, ks), ns = __dsub_rn(ks, ng);
+  const double Cvm = __dadd_rn(__dadd_rn(__dmul_rn(ns, K.Cvs), __dmul_rn(ng, K.Cvg)), __dmul_rn(na, K.Cva));
+  for (int i = 0; i < n; i++) {
+    const double crd[3] = { x, y, __dadd_rn(e.bot, __dmul_rn(__dadd_rn(t_add, __dmul_rn((double) i, t_each)), vel)) };
+    bool inside = false;                      // in_bucket of a bucket flagged is_erupt() (:609-650; both faces inclusive)
+    for (int b = 0; b < P.nbox && !inside; b++) {
+      const double *mn = boxes + 6 * b, *mx = mn + 3;
+      inside = crd[0] <= mx[0] && crd[0] >= mn[0] && crd[1] <= mx[1] && crd[1] >= mn[1] && crd[2] <= mx[2] && crd[2] >= mn[2];
+    }
+    if (!inside) continue;
+    const int slot = atomicAdd(&ss->work, 1);
+    const int p = P.base + slot;
+    if (p >= P.cap) continue;                 // (the host reserves an upper bound: cannot happen)
+    double nc[3];
+    for (int k = 0; k < 3; k++) nc[k] = __ddiv_rn(__dsub_rn(crd[k], e.kmin[k]), __dsub_rn(e.kmax[k], e.kmin[k]));
+    uint32_t key[2];
+    dev_hsfc3d(nc, key);
+    V.d[D_X][p] = crd[0]; V.d[D_Y][p] = crd[1]; V.d[D_Z][p] = crd[2];
+    V.d[D_VX][p] = 0.0; V.d[D_VY][p] = 0.0; V.d[D_VZ][p] = vel;
+    V.d[D_SVX][p] = 0.0; V.d[D_SVY][p] = 0.0; V.d[D_SVZ][p] = 0.0;
+    V.d[D_RHO][p] = e.rhov; V.d[D_E][p] = e.ev0; V.d[D_SE][p] = e.ev0;
+    V.d[D_MASS][p] = e.mass;
+    const double h = __dmul_rn(e.ratio_sml_dx, sml);
+    V.d[D_H][p] = h; V.d[D_HLIST][p] = h; V.d[D_KS][p] = ks;
+    V.d[D_P][p] = e.pv0; V.d[D_GAMMA][p] = e.gamma_v; V.d[D_C][p] = e.sndspd;
+    V.d[D_T][p] = __ddiv_rn(e.ev0, Cvm); V.d[D_CP][p] = K.lans ? Cvm : 0.0;
+    V.d[D_RPH0][p] = __dmul_rn(e.rhov, na); V.d[D_RPH1][p] = __dmul_rn(e.rhov, ks);
+    if (P.has_grad)
+      for (int k = 0; k < 15; k++) V.d[D_GRAD0 + k][p] = 0.0;
+    V.i[I_BC][p] = 0; V.i[I_PHASE][p] = 2; V.i[I_INVOLVED][p] = 0; V.i[I_GUEST][p] = 0; V.i[I_MYPROC][p] = P.rank;
+    V.i[I_KEY0][p] = (int32_t) key[0]; V.i[I_KEY1][p] = (int32_t) key[1]; V.i[I_KEY2][p] = (int32_t) P.add_step;
+    int idx[3];
+    for (int d = 0; d < 3; d++) idx[d] = dev_cell_index(G, d, crd[d]);
+    V.i[I_CELL][p] = (idx[0] * G.ncell[1] + idx[1]) * G.ncell[2] + idx[2];
+  }
+}
+
+__global__ void k_erupt_finish(StepState *ss, int base, int cap) { ss->n = min(base + ss->work, cap); }
+
+extern "C" int psph_set_erupt(psph_ctx *ctx, const psph_erupt *er, const double *boxes, size_t nbox)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->d_erupt_boxes); ctx->d_erupt_boxes = nullptr; ctx->n_erupt_boxes = 0; ctx->has_erupt = false;
+  if (!er) return 0;
+  if (!(er->sml > 0) || !(er->rv >= 0) || !(er->Vv0 > 0)) { ctx->err = "psph_set_erupt: sml, rv, Vv0 must be positive"; return -2; }
+  ctx->erupt = *er;
+  if (nbox) {
+    PSPH_CUDA(cudaMalloc(&ctx->d_erupt_boxes, nbox * 6 * sizeof(double)));
+    PSPH_CUDA(cudaMemcpy(ctx->d_erupt_boxes, boxes, nbox * 6 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  ctx->n_erupt_boxes = (int) nbox;
+  ctx->has_erupt = true;
+  return 0;
+}
+
+extern "C" int psph_add_new_erupt(psph_ctx *ctx, double time, double dt, uint32_t add_step, int *added)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (added) *added = 0;
+  if (ctx->cfg.dim != 3) return 0;                                   // the 1-D loop has no eruption (main.cc:676-751)
+  if (!ctx->has_erupt) { ctx->err = "psph_add_new_erupt: psph_set_erupt has not been called"; return -2; }
+  if (ctx->cfg.nranks > 1) { ctx->err = "psph_add_new_erupt: single-rank only in this version"; return -2; }
+  const psph_erupt &e = ctx->erupt;
+  EruptPar P;
+  P.e = e;
+  // the extent of the reference's while-loops (setup_erupt.cc:446-449,456-600): columns per half / per run
+  const double sml2 = 0.5 * e.sml;
+  P.nxp = P.nxm = P.nyp = P.nym = 0;
+  for (double x = e.pos_v[0] + sml2; x <= e.rv; x += e.sml) P.nxp++;
+  for (double x = e.pos_v[0] - sml2; x >= -e.rv; x -= e.sml) P.nxm++;
+  for (double y = e.pos_v[1] + sml2; y <= e.rv; y += e.sml) P.nyp++;
+  for (double y = e.pos_v[1] - sml2; y >= -e.rv; y -= e.sml) P.nym++;
+  const long long ncol = (long long) (P.nxp + P.nxm) * (P.nyp + P.nym);
+  if (ncol == 0 || ctx->n_erupt_boxes == 0) return 0;
+  // upper bound of the particles one call adds: every column at the fastest injection rate
+  const double vmax = e.vel_prof ? 2.0 * e.Vv0 : e.Vv0;
+  const long long per_col = (long long) (dt * vmax / e.sml) + 2;
+  if (ncol * per_col > 0x3fffffffLL) { ctx->err = "psph_add_new_erupt: time step too long for the duct lattice"; return -2; }
+  if (psph_sync_n(ctx)) return -1;
+  const int base = ctx->n;
+  if (psph_reserve(ctx, (size_t) base + (size_t) (ncol * per_col))) return -1;
+  StageTimer tm(ctx, ST_ERUPT);
+  P.t_prev = time - dt;                                              // :454
+  P.dt = dt; P.add_step = add_step;
+  P.base = base; P.cap = (int) std::min<size_t>(ctx->cap, 0x7fffffff); P.rank = ctx->cfg.rank; P.has_grad = ctx->has_grad;
+  P.nbox = ctx->n_erupt_boxes;
+  PSPH_CUDA(cudaMemsetAsync(&ctx->d_ss->work, 0, sizeof(int), ctx->stream));
+  k_add_erupt<<<(unsigned) ((ncol + 127) / 128), 128, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), ctx->kp, ctx->d_ss, P,
+                                                                        ctx->d_erupt_boxes);
+  PSPH_LAUNCH_CHECK();
+  k_erupt_finish<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, base, P.cap);
+  PSPH_LAUNCH_CHECK();
+  psph_comm_mark(ctx, DIRTY_LAYOUT);
+  ctx->n = base + (int) (ncol * per_col);                            // upper bound until the count is read back
+  ctx->n_dirty = true;
+  ctx->list_valid = false;
+  if (added) {
+    PSPH_CUDA(cudaMemcpyAsync(ctx->h_ss, ctx->d_ss, sizeof(StepState), cudaMemcpyDeviceToHost, ctx->stream));
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    *added = ctx->h_ss->n - base;
+    ctx->n = ctx->h_ss->n;
+    ctx->n_dirty = false;
+  }
+  return 0;
+}

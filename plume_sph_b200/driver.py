@@ -71,7 +71,7 @@ def timeprops_from(d, time_scale=1.0):
     return TimeProps(d["max_time"], d["max_steps"], d["timeoutput"], d["stat_erupt"], d["end_erupt"], time_scale)
 
 
-def run_loop(solver, tp, on_output=None, max_steps=None):
+def run_loop(solver, tp, on_output=None, max_steps=None, erupt=False):
     """The reference time loop with the stage calls on the GPU.  One host round trip per step
     (the CFL dt comes back, is clipped by TimeProps.incrtime and goes down again) exactly as
     main.cc:220-231 does; ``Solver.run`` is the variant without it."""
@@ -93,6 +93,8 @@ def run_loop(solver, tp, on_output=None, max_steps=None):
         solver.update_pos()                          # :405 / :730
         if cfg.dim == 3:
             solver.update_particles_in_bucket()      # :408
+            if erupt and tp.iferupt():
+                solver.add_new_erupt(tp.time, dt, tp.step)   # :414-417 (after Solver.set_erupt)
             solver.apply_bcond()                     # :468 (no-op until the driver hands over its Image_table)
         nsteps += 1
         if tp.ifoutput() and on_output is not None:  # :474 / :746

@@ -178,7 +178,7 @@ def read_erupt_params(fn):
     return v.copy(), rec.copy()
 
 
-def golden_erupt(name="erupt3d", variant="3d_plume", edits=None, steps=(2, 3)):
+def golden_erupt(name="erupt3d", variant="3d_plume", edits=None, steps=(2, 3), simdata="simulation.data"):
     """add_new_erupt (setup_erupt.cc:390-670) of the small 3-D plume at time steps 2 and 3 (step 1 adds nothing: dt is
     still shorter than the injection period of every duct column): what the function reads (arguments, vent constants,
     key range of the particle table, erupt buckets) and the particles it added, in THashTable order."""
@@ -188,7 +188,7 @@ def golden_erupt(name="erupt3d", variant="3d_plume", edits=None, steps=(2, 3)):
         os.makedirs(wd)
         shutil.copytree(os.path.join(REF, "Meteo_data"), os.path.join(top, "Meteo_data"))
         shutil.copy(os.path.join(REF, "bin", "scale.data"), wd)
-        txt = open(os.path.join(REF, "bin", "simulation.data")).read()
+        txt = open(os.path.join(REF, "bin", simdata)).read()
         for a, b in edits:
             assert a in txt, a
             txt = txt.replace(a, b)
@@ -237,6 +237,8 @@ if __name__ == "__main__":
         # (the reference's own plain-SPH build aborts on the strong blast at step 4: assert c>0, timestep.cc:167)
         "blast_gsph": lambda: golden_1d("blast_gsph", "1d_blast_gsph", "simulation_1D_shocktube_Strong-Blast.data", 300),
         "erupt3d": lambda: golden_erupt(),
+        "erupt3d_jpue": lambda: golden_erupt("erupt3d_jpue", "3d_jpue", JPUE_3D, steps=(2, 3, 4),
+                                             simdata="simulation_JPUE_incomp_back.data"),
         "plume3d_small": lambda: golden_3d("plume3d_small", "3d_plume", SMALL_3D),
         "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D),
         # BASELINE config 2: JPUE weakly-compressible jet (Tait EOS, g = 0), the reference's own input file

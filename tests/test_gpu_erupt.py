@@ -1,5 +1,6 @@
 """-m gpu: psph_add_new_erupt (CUDA, through the C ABI) against the particles the unmodified reference's add_new_erupt
-added at time steps 2 and 3 of the small plume (tests/golden/erupt3d.npz; setup_erupt.cc:390-670) and against the
+added at the first injecting time steps of the small plume and of the JPUE jet (tests/golden/erupt3d*.npz;
+setup_erupt.cc:390-670) and against the
 oracle restatement.  Bar: bit-exact — birth keys (Hilbert index + add_step), coordinates, velocities and every other
 field of the new rows; the rows that were there before are untouched; the table stays consistent (a time step runs)."""
 import numpy as np
@@ -13,10 +14,11 @@ from plume_sph_b200.solver import ORDER_DEVICE
 pytestmark = pytest.mark.gpu
 
 
-def test_add_new_erupt_matches_reference():
-    z = golden("erupt3d")
-    zp = golden("plume3d_small")
-    ocfg = op.config_for("plume3d_small", zp)
+@pytest.mark.parametrize("name,base,steps", [("erupt3d", "plume3d_small", (2, 3)), ("erupt3d_jpue", "jpue3d", (2, 3, 4))])
+def test_add_new_erupt_matches_reference(name, base, steps):
+    z = golden(name)
+    zp = golden(base)
+    ocfg = op.config_for(base, zp)
     s = psph.Solver(to_product_cfg(ocfg))
     try:
         attr, _ = cell_attrs(ocfg, zp)
@@ -25,7 +27,7 @@ def test_add_new_erupt_matches_reference():
         s.upload(pre)
         nrows = len(pre)
         seen = {tuple(int(x) for x in k) for k in pre["key"]}
-        for st in (2, 3):
+        for st in steps:
             er, d = op.erupt_from_params(z["param_names"], z["s%d_params" % st])
             boxes = np.concatenate([z["s%d_cell_min" % st], z["s%d_cell_max" % st]], axis=1)
             s.set_erupt(er, boxes)

@@ -214,13 +214,17 @@ def test_reference_algorithm_is_sensitive():
         assert d400[f] < RTOL_LONG[k] and d100[f] < RTOL_LONG[k], (f, d100[f], d400[f])
 
 
-def test_add_new_erupt_bit_exact():
-    """add_new_erupt (setup_erupt.cc:390-670) at time steps 2 and 3 of the small plume: the particles the unmodified
-    reference added (tests/golden/erupt3d.npz: its arguments, vent constants, erupt buckets and new rows) against the
-    restatement — keys, coordinates, velocities and every other field, bit for bit"""
-    z = golden("erupt3d")
-    cfg = op.config_for("plume3d_small", golden("plume3d_small"))
-    for st in (2, 3):
+ERUPT_CASES = [("erupt3d", "plume3d_small", (2, 3)), ("erupt3d_jpue", "jpue3d", (2, 3, 4))]
+
+
+@pytest.mark.parametrize("name,base,steps", ERUPT_CASES)
+def test_add_new_erupt_bit_exact(name, base, steps):
+    """add_new_erupt (setup_erupt.cc:390-670) at the first time steps of the small plume and of the JPUE jet that add
+    particles: what the unmodified reference added (tests/golden/erupt3d*.npz: its arguments, vent constants, erupt
+    buckets and new rows) against the restatement — keys, coordinates, velocities and every other field, bit for bit"""
+    z = golden(name)
+    cfg = op.config_for(base, golden(base))
+    for st in steps:
         er, d = op.erupt_from_params(z["param_names"], z["s%d_params" % st])
         boxes = np.concatenate([z["s%d_cell_min" % st], z["s%d_cell_max" % st]], axis=1)
         got = op.add_new_erupt(cfg, er, boxes, d["time"], d["dt"], int(d["step"]))

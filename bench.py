@@ -231,7 +231,14 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": KERNEL_OF[dom], "achieved": round(achieved, 2), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 5),
                 "traffic": NCU[dom]["traffic"] if (args.n == 216 and world == 1) else None,
+                # measured DRAM rate of that kernel: ncu bytes per launch / the live launch duration
+                "traffic_GBps": round(NCU[dom]["traffic"] / (dom_ms * 1e-3) / 1e9, 1) if (args.n == 216 and world == 1) else None,
                 "fp64_pipe_pct_ncu": NCU[dom]["fp64_pipe_pct"],
+                # the stage that streams the cached pair weights back is the HBM-bound one: its measured DRAM rate
+                "hbm_bound_kernel": ({"kernel": KERNEL_OF["gather_velocity"], "ms_per_launch": round(kms["gather_velocity"][0] / max(kms["gather_velocity"][1], 1), 4),
+                                      "traffic": NCU["gather_velocity"]["traffic"],
+                                      "frac_of_peak": round(NCU["gather_velocity"]["traffic"] / (kms["gather_velocity"][0] / max(kms["gather_velocity"][1], 1) * 1e-3) / 1e9 / peak, 4)}
+                                     if (args.n == 216 and world == 1 and kms["gather_velocity"][1] > 0) else None),
                 "alg_bytes_per_update": ALG_BYTES[dom], "updates_per_launch": n_real_local,
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
                 "note": "FP64 pair loop over per-step pair lists, partners' records staged in shared memory: bound by the "

@@ -6,9 +6,9 @@
 // reference's four nested while-loops become ONE thread per column.  The thread rebuilds its column's coordinates by
 // the reference's own repeated additions and evaluates every expression with explicit IEEE operations (__dmul_rn,
 // __dadd_rn, ... : no FMA contraction), so positions, velocities and the birth keys (Hilbert index of the position +
-// add_step, THSFC3d, hilbert.c:329-359) are bit-identical to the reference's.  New rows are appended to the table
-// (slots from one atomic counter; the row order of the table is rebuilt by the next list build anyway), each with the
-// state the erupted-material constructor gives it (Particle ctor, particle.cc:210-316).
+// add_step, THSFC3d, hilbert.c:329-359) are bit-identical to the reference's.  New rows are appended to the table in
+// column order (slots from a block-wide scan of the per-column counts: deterministic), each with the state the
+// erupted-material constructor gives it (Particle ctor, particle.cc:210-316).
 #include "psph_internal.cuh"
 
 struct EruptPar
@@ -48,67 +48,100 @@ __device__ void dev_hsfc3d(const double nc[3], uint32_t key[2])
   key[1] = (uint32_t) (K & 0xffffffffu);
 }
 
-__global__ void k_add_erupt(Tab V, GridView G, KParams K, StepState *ss, EruptPar P, const double *__restrict__ boxes)
+// One block: the columns are few (tens to thousands) and the slots must not depend on scheduling — a row's place in
+// the table decides its place among the rows of its subcell after the (stable) sort, hence summation orders.  Columns
+// are taken 256 at a time; a block-wide exclusive scan of the per-column counts gives every column its slots.
+constexpr int ERUPT_THREADS = 256;
+constexpr int ERUPT_MAX_PER_COL = 64;         // particles one column can inject per call that are tracked in the mask
+__global__ void __launch_bounds__(ERUPT_THREADS) k_add_erupt(Tab V, GridView G, KParams K, StepState *ss, EruptPar P,
+                                                             const double *__restrict__ boxes)
 {
-  const int ny = P.nyp + P.nym, t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (P.nxp + P.nxm) * ny) return;
-  const int ix = t / ny, iy = t - ix * ny;
+  __shared__ int s_warp[ERUPT_THREADS / 32], s_base;
+  const int ny = P.nyp + P.nym, ncol = (P.nxp + P.nxm) * ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const psph_erupt &e = P.e;
   const double sml = e.sml, sml2 = __dmul_rn(0.5, sml);
-  // the column's coordinates, built as the loops build them: start + repeated addition (:456,:526,:530,:598)
-  double x, y;
-  if (ix < P.nxp) { x = __dadd_rn(e.pos_v[0], sml2); for (int k = 0; k < ix; k++) x = __dadd_rn(x, sml); }
-  else { x = __dsub_rn(e.pos_v[0], sml2); for (int k = 0; k < ix - P.nxp; k++) x = __dsub_rn(x, sml); }
-  if (iy < P.nyp) { y = __dadd_rn(e.pos_v[1], sml2); for (int k = 0; k < iy; k++) y = __dadd_rn(y, sml); }
-  else { y = __dsub_rn(e.pos_v[1], sml2); for (int k = 0; k < iy - P.nyp; k++) y = __dsub_rn(y, sml); }
-  const double dist = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));                   // :461-464
-  if (!(dist <= __dmul_rn(e.rv, e.rv))) return;
-  double vel = e.Vv0;                                                                // vel_prof, sph_lib.cc:1223-1243
-  if (e.vel_prof != 0) vel = __dmul_rn(__dmul_rn(e.Vv0, 2.0), __dsub_rn(1.0, __ddiv_rn(dist, __dmul_rn(e.rv, e.rv))));
-  const double t_each = __ddiv_rn(sml, vel);
-  double t_add = __dadd_rn(fmod(P.t_prev, t_each), P.dt);                            // :469
-  const int n = (int) floor(__ddiv_rn(t_add, t_each));
-  t_add = __dsub_rn(t_add, __dmul_rn((double) n, t_each));
   // state of the erupted material (Particle ctor, particle.cc:210-316; update_second_var with ks = 1, then pressure,
   // sound speed and gamma overwritten)
   const double ks = 1.0, na = __dsub_rn(1.0, ks), ng = __dmul_rn(K.ng0, ks), ns = __dsub_rn(ks, ng);
   const double Cvm = __dadd_rn(__dadd_rn(__dmul_rn(ns, K.Cvs), __dmul_rn(ng, K.Cvg)), __dmul_rn(na, K.Cva));
-  for (int i = 0; i < n; i++) {
-    const double crd[3] = { x, y, __dadd_rn(e.bot, __dmul_rn(__dadd_rn(t_add, __dmul_rn((double) i, t_each)), vel)) };
-    bool inside = false;                      // in_bucket of a bucket flagged is_erupt() (:609-650; both faces inclusive)
-    for (int b = 0; b < P.nbox && !inside; b++) {
-      const double *mn = boxes + 6 * b, *mx = mn + 3;
-      inside = crd[0] <= mx[0] && crd[0] >= mn[0] && crd[1] <= mx[1] && crd[1] >= mn[1] && crd[2] <= mx[2] && crd[2] >= mn[2];
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < ncol; c0 += ERUPT_THREADS) {
+    const int t = c0 + threadIdx.x;
+    int n = 0;
+    double x = 0., y = 0., vel = 0., t_each = 0., t_add = 0.;
+    if (t < ncol) {
+      const int ix = t / ny, iy = t - ix * ny;
+      // the column's coordinates, built as the loops build them: start + repeated addition (:456,:526,:530,:598)
+      if (ix < P.nxp) { x = __dadd_rn(e.pos_v[0], sml2); for (int k = 0; k < ix; k++) x = __dadd_rn(x, sml); }
+      else { x = __dsub_rn(e.pos_v[0], sml2); for (int k = 0; k < ix - P.nxp; k++) x = __dsub_rn(x, sml); }
+      if (iy < P.nyp) { y = __dadd_rn(e.pos_v[1], sml2); for (int k = 0; k < iy; k++) y = __dadd_rn(y, sml); }
+      else { y = __dsub_rn(e.pos_v[1], sml2); for (int k = 0; k < iy - P.nyp; k++) y = __dsub_rn(y, sml); }
+      const double dist = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));               // :461-464
+      if (dist <= __dmul_rn(e.rv, e.rv)) {
+        vel = e.Vv0;                                                                 // vel_prof, sph_lib.cc:1223-1243
+        if (e.vel_prof != 0) vel = __dmul_rn(__dmul_rn(e.Vv0, 2.0), __dsub_rn(1.0, __ddiv_rn(dist, __dmul_rn(e.rv, e.rv))));
+        t_each = __ddiv_rn(sml, vel);
+        t_add = __dadd_rn(fmod(P.t_prev, t_each), P.dt);                             // :469
+        n = (int) floor(__ddiv_rn(t_add, t_each));
+        t_add = __dsub_rn(t_add, __dmul_rn((double) n, t_each));
+        n = max(0, min(n, ERUPT_MAX_PER_COL));
+      }
     }
-    if (!inside) continue;
-    const int slot = atomicAdd(&ss->work, 1);
-    const int p = P.base + slot;
-    if (p >= P.cap) continue;                 // (the host reserves an upper bound: cannot happen)
-    double nc[3];
-    for (int k = 0; k < 3; k++) nc[k] = __ddiv_rn(__dsub_rn(crd[k], e.kmin[k]), __dsub_rn(e.kmax[k], e.kmin[k]));
-    uint32_t key[2];
-    dev_hsfc3d(nc, key);
-    V.d[D_X][p] = crd[0]; V.d[D_Y][p] = crd[1]; V.d[D_Z][p] = crd[2];
-    V.d[D_VX][p] = 0.0; V.d[D_VY][p] = 0.0; V.d[D_VZ][p] = vel;
-    V.d[D_SVX][p] = 0.0; V.d[D_SVY][p] = 0.0; V.d[D_SVZ][p] = 0.0;
-    V.d[D_RHO][p] = e.rhov; V.d[D_E][p] = e.ev0; V.d[D_SE][p] = e.ev0;
-    V.d[D_MASS][p] = e.mass;
-    const double h = __dmul_rn(e.ratio_sml_dx, sml);
-    V.d[D_H][p] = h; V.d[D_HLIST][p] = h; V.d[D_KS][p] = ks;
-    V.d[D_P][p] = e.pv0; V.d[D_GAMMA][p] = e.gamma_v; V.d[D_C][p] = e.sndspd;
-    V.d[D_T][p] = __ddiv_rn(e.ev0, Cvm); V.d[D_CP][p] = K.lans ? Cvm : 0.0;
-    V.d[D_RPH0][p] = __dmul_rn(e.rhov, na); V.d[D_RPH1][p] = __dmul_rn(e.rhov, ks);
-    if (P.has_grad)
-      for (int k = 0; k < 15; k++) V.d[D_GRAD0 + k][p] = 0.0;
-    V.i[I_BC][p] = 0; V.i[I_PHASE][p] = 2; V.i[I_INVOLVED][p] = 0; V.i[I_GUEST][p] = 0; V.i[I_MYPROC][p] = P.rank;
-    V.i[I_KEY0][p] = (int32_t) key[0]; V.i[I_KEY1][p] = (int32_t) key[1]; V.i[I_KEY2][p] = (int32_t) P.add_step;
-    int idx[3];
-    for (int d = 0; d < 3; d++) idx[d] = dev_cell_index(G, d, crd[d]);
-    V.i[I_CELL][p] = (idx[0] * G.ncell[1] + idx[1]) * G.ncell[2] + idx[2];
+    // which of the column's n particles lie in a bucket flagged is_erupt() (in_bucket, :609-650; both faces inclusive)
+    unsigned long long keep = 0ull;
+    for (int i = 0; i < n; i++) {
+      const double z = __dadd_rn(e.bot, __dmul_rn(__dadd_rn(t_add, __dmul_rn((double) i, t_each)), vel));
+      bool inside = false;
+      for (int b = 0; b < P.nbox && !inside; b++) {
+        const double *mn = boxes + 6 * b, *mx = mn + 3;
+        inside = x <= mx[0] && x >= mn[0] && y <= mx[1] && y >= mn[1] && z <= mx[2] && z >= mn[2];
+      }
+      if (inside) keep |= 1ull << i;
+    }
+    const int cnt = __popcll(keep);
+    int inc = cnt;                               // block-wide exclusive scan of cnt
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int pre = s_base;
+    for (int k = 0; k < warp; k++) pre += s_warp[k];
+    int slot = pre + inc - cnt;
+    for (int i = 0; i < n; i++) {
+      if (!((keep >> i) & 1ull)) continue;
+      const int p = P.base + slot++;
+      if (p >= P.cap) continue;               // (the host reserves an upper bound: cannot happen)
+      const double crd[3] = { x, y, __dadd_rn(e.bot, __dmul_rn(__dadd_rn(t_add, __dmul_rn((double) i, t_each)), vel)) };
+      double nc[3];
+      for (int k = 0; k < 3; k++) nc[k] = __ddiv_rn(__dsub_rn(crd[k], e.kmin[k]), __dsub_rn(e.kmax[k], e.kmin[k]));
+      uint32_t key[2];
+      dev_hsfc3d(nc, key);
+      V.d[D_X][p] = crd[0]; V.d[D_Y][p] = crd[1]; V.d[D_Z][p] = crd[2];
+      V.d[D_VX][p] = 0.0; V.d[D_VY][p] = 0.0; V.d[D_VZ][p] = vel;
+      V.d[D_SVX][p] = 0.0; V.d[D_SVY][p] = 0.0; V.d[D_SVZ][p] = 0.0;
+      V.d[D_RHO][p] = e.rhov; V.d[D_E][p] = e.ev0; V.d[D_SE][p] = e.ev0;
+      V.d[D_MASS][p] = e.mass;
+      const double h = __dmul_rn(e.ratio_sml_dx, sml);
+      V.d[D_H][p] = h; V.d[D_HLIST][p] = h; V.d[D_KS][p] = ks;
+      V.d[D_P][p] = e.pv0; V.d[D_GAMMA][p] = e.gamma_v; V.d[D_C][p] = e.sndspd;
+      V.d[D_T][p] = __ddiv_rn(e.ev0, Cvm); V.d[D_CP][p] = K.lans ? Cvm : 0.0;
+      V.d[D_RPH0][p] = __dmul_rn(e.rhov, na); V.d[D_RPH1][p] = __dmul_rn(e.rhov, ks);
+      if (P.has_grad)
+        for (int k = 0; k < 15; k++) V.d[D_GRAD0 + k][p] = 0.0;
+      V.i[I_BC][p] = 0; V.i[I_PHASE][p] = 2; V.i[I_INVOLVED][p] = 0; V.i[I_GUEST][p] = 0; V.i[I_MYPROC][p] = P.rank;
+      V.i[I_KEY0][p] = (int32_t) key[0]; V.i[I_KEY1][p] = (int32_t) key[1]; V.i[I_KEY2][p] = (int32_t) P.add_step;
+      int idx[3];
+      for (int d = 0; d < 3; d++) idx[d] = dev_cell_index(G, d, crd[d]);
+      V.i[I_CELL][p] = (idx[0] * G.ncell[1] + idx[1]) * G.ncell[2] + idx[2];
+    }
+    __syncthreads();                            // every warp has read s_base and s_warp
+    if (threadIdx.x == ERUPT_THREADS - 1) s_base = pre + inc;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) ss->n = min(P.base + s_base, P.cap);
 }
-
-__global__ void k_erupt_finish(StepState *ss, int base, int cap) { ss->n = min(base + ss->work, cap); }
 
 extern "C" int psph_set_erupt(psph_ctx *ctx, const psph_erupt *er, const double *boxes, size_t nbox)
 {
@@ -149,6 +182,7 @@ extern "C" int psph_add_new_erupt(psph_ctx *ctx, double time, double dt, uint32_
   // upper bound of the particles one call adds: every column at the fastest injection rate
   const double vmax = e.vel_prof ? 2.0 * e.Vv0 : e.Vv0;
   const long long per_col = (long long) (dt * vmax / e.sml) + 2;
+  if (per_col > ERUPT_MAX_PER_COL) { ctx->err = "psph_add_new_erupt: more than 64 particles per column and call"; return -2; }
   if (ncol * per_col > 0x3fffffffLL) { ctx->err = "psph_add_new_erupt: time step too long for the duct lattice"; return -2; }
   if (psph_sync_n(ctx)) return -1;
   const int base = ctx->n;
@@ -158,11 +192,7 @@ extern "C" int psph_add_new_erupt(psph_ctx *ctx, double time, double dt, uint32_
   P.dt = dt; P.add_step = add_step;
   P.base = base; P.cap = (int) std::min<size_t>(ctx->cap, 0x7fffffff); P.rank = ctx->cfg.rank; P.has_grad = ctx->has_grad;
   P.nbox = ctx->n_erupt_boxes;
-  PSPH_CUDA(cudaMemsetAsync(&ctx->d_ss->work, 0, sizeof(int), ctx->stream));
-  k_add_erupt<<<(unsigned) ((ncol + 127) / 128), 128, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), ctx->kp, ctx->d_ss, P,
-                                                                        ctx->d_erupt_boxes);
-  PSPH_LAUNCH_CHECK();
-  k_erupt_finish<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, base, P.cap);
+  k_add_erupt<<<1, ERUPT_THREADS, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), ctx->kp, ctx->d_ss, P, ctx->d_erupt_boxes);
   PSPH_LAUNCH_CHECK();
   psph_comm_mark(ctx, DIRTY_LAYOUT);
   ctx->n = base + (int) (ncol * per_col);                            // upper bound until the count is read back

@@ -49,3 +49,35 @@ def test_cube_case_shape_and_eos():
     lo = np.array([cfg.mindom[k] for k in range(3)])
     hi = lo + np.array([cfg.ncell[k] for k in range(3)]) * cfg.delta
     assert (rows["coords"] > lo + cfg.delta - 1e-9).all() and (rows["coords"] < hi - cfg.delta + 1e-9).all()
+
+
+def test_run_loop_calls_the_stages_in_the_reference_order():
+    """driver.run_loop forwards the stage calls in the order of main.cc:217-486 (3-D): eruption injection after the
+    re-bin (:414-417), the wall boundary condition at the end of the step (:468)"""
+    from plume_sph_b200 import driver
+
+    class Cfg:
+        adaptive_sml, dim, sml_update_int, use_gsph, have_turbulence_lans = 1, 3, 2, 0, 1
+
+    class Rec:
+        cfg = Cfg()
+
+        def __init__(self):
+            self.calls = []
+
+        def __getattr__(self, name):
+            def f(*a):
+                self.calls.append(name)
+                return 0.25 if name == "timestep" else 0
+            return f
+
+    tp = driver.TimeProps(max_time=10.0, max_steps=100, timeoutput=100.0)
+    s = Rec()
+    assert driver.run_loop(s, tp, max_steps=2, erupt=True) == 2
+    step1 = ["timestep", "set_dt", "search_neighs_consth", "mom_engr_update", "smooth_density", "smooth_velocity",
+             "update_pos", "update_particles_in_bucket", "add_new_erupt", "apply_bcond"]
+    step2 = step1[:3] + ["adaptive_sml"] + step1[3:]          # SML_UPDATE_INT = 2: every second step
+    assert s.calls == step1 + step2
+    s2 = Rec()
+    driver.run_loop(s2, driver.TimeProps(max_time=10.0, max_steps=100, timeoutput=100.0, stat_erupt=5.0), max_steps=1, erupt=True)
+    assert "add_new_erupt" not in s2.calls                     # outside the eruption window (properties.h iferupt)

@@ -2,6 +2,7 @@
 simulation.data parsing (dataread.cc:109-235), synthetic case generator."""
 import os
 import numpy as np
+import pytest
 
 from plume_sph_b200.driver import TimeProps, stof
 from plume_sph_b200 import cases
@@ -81,3 +82,24 @@ def test_run_loop_calls_the_stages_in_the_reference_order():
     s2 = Rec()
     driver.run_loop(s2, driver.TimeProps(max_time=10.0, max_steps=100, timeoutput=100.0, stat_erupt=5.0), max_steps=1, erupt=True)
     assert "add_new_erupt" not in s2.calls                     # outside the eruption window (properties.h iferupt)
+
+
+@pytest.mark.parametrize("name,Ll,Lu,smlen,imin,imax", [
+    ("plume3d_small", (-20800., -20800., 1666.), (20800., 20800., 24000.), 100.0, (-350., -350., 1666.), (350., 350., 2400.)),
+    ("jpue3d", (-576., -576., 0.), (576., 576., 6000.), 8.0, (-60., -60., 0.), (60., 60., 100.))])
+def test_background_mesh_matches_the_reference_buckets(name, Ll, Lu, smlen, imin, imax):
+    """mesh.background_mesh (the lattice of preprocess.cc + Read_Grid, computed instead of read from funky*.h5) against
+    the buckets of the unmodified reference at the start of step 1 (tests/golden/*.npz, `b0_*`): the same lattice, the
+    same set of non-brief buckets, and bit-identical type, has_involved, bucket_index and bnd for every one of them"""
+    import oracle_py as op
+    from common import golden, cell_attrs
+    from plume_sph_b200 import mesh
+    z = golden(name)
+    cfg = op.config_for(name, z)
+    attr, lin = cell_attrs(cfg, z, "b0")
+    mindom, n, d, mine = mesh.background_mesh(Ll, Lu, smlen, imin, imax)
+    assert [float(x) for x in mindom] == [cfg.mindom[k] for k in range(3)]
+    assert [int(x) for x in n] == [cfg.ncell[k] for k in range(3)] and d == cfg.delta
+    assert set(np.flatnonzero(mine["type"] != 0).tolist()) == set(int(x) for x in lin)
+    for f in ("type", "has_involved", "bucket_index", "bnd"):
+        assert np.array_equal(mine[f][lin], attr[f][lin]), f

@@ -73,3 +73,38 @@ def background_mesh(Ll, Lu, smlen, idom_min, idom_max, particle_density=8, ext=1
     bnd = np.where((typ == MIXED)[:, None] & (bt != 0), flat[None, :], 0.1)
     attr["bnd"] = np.where(exists[:, None], bnd, 0.0)
     return mindom, n, d, attr
+
+
+def wall_ghost_images(rows, mindom, ncell, d, attr, len_scale=1.0):
+    """search_bnd_images (src/datstr/bnd_image.cc:27-270) for a FLAT ground, in closed form: every wall ghost (bc_type 2,
+    not a guest) of an on-ground MIXED bucket (bucket_index[4] == -1, [5] == 0) gets the mirror point across the ground
+    plane z = bnd[4] (Bucket::calc_intersection_ground, bucket.cc:320-354; refc = 2 intsct - coord, bnd_image.cc),
+    and the bucket that contains it, found from the ghost's own bucket by the reference's walk (a point ON a face
+    of the current bucket stays there).  -> IMAGE_DTYPE array (ghost_key, cell, coord) in row order, and the rows.
+    Ghosts in UNDERGROUND buckets get no image, as in the reference."""
+    n = np.asarray(ncell, np.int64)
+    x = np.asarray(rows["coords"], np.float64)
+    lo0 = np.asarray(mindom, np.float64)
+    ci = np.floor((x * len_scale - lo0) / d).astype(np.int64)
+    ci = np.clip(ci, 0, n - 1)
+    for k in range(3):                                       # membership [mincrd, maxcrd) against the stored bounds
+        ci[:, k] -= x[:, k] < (lo0[k] + ci[:, k] * d) / len_scale
+        ci[:, k] += x[:, k] >= (lo0[k] + (ci[:, k] + 1) * d) / len_scale
+    lin = (ci[:, 0] * n[1] + ci[:, 1]) * n[2] + ci[:, 2]
+    a = attr[lin]
+    sel = np.flatnonzero((rows["bc_type"] == 2) & (rows["guest"] == 0) & (a["type"] == MIXED) &
+                         (a["bucket_index"][:, 4] == -1) & (a["bucket_index"][:, 5] == 0))
+    xs, cs = x[sel], ci[sel].copy()
+    ref = np.stack([2 * xs[:, 0] - xs[:, 0], 2 * xs[:, 1] - xs[:, 1], 2 * a["bnd"][sel, 4] - xs[:, 2]], axis=1)
+    for _ in range(int(n.max()) + 1):                        # the walk: left if below mincrd, right if above maxcrd
+        lo = (lo0 + cs * d) / len_scale
+        hi = (lo0 + (cs + 1) * d) / len_scale
+        step = (ref > hi).astype(np.int64) - (ref < lo).astype(np.int64)
+        if not step.any():
+            break
+        cs += step
+    img = np.zeros(len(sel), _l.IMAGE_DTYPE)
+    img["ghost_key"] = rows["key"][sel]
+    img["cell"] = (cs[:, 0] * n[1] + cs[:, 1]) * n[2] + cs[:, 2]
+    img["coord"] = ref
+    return img, sel

@@ -103,3 +103,23 @@ def test_background_mesh_matches_the_reference_buckets(name, Ll, Lu, smlen, imin
     assert set(np.flatnonzero(mine["type"] != 0).tolist()) == set(int(x) for x in lin)
     for f in ("type", "has_involved", "bucket_index", "bnd"):
         assert np.array_equal(mine[f][lin], attr[f][lin]), f
+
+
+@pytest.mark.parametrize("name", ["plume3d_small", "jpue3d"])
+def test_wall_ghost_images_match_the_reference_table(name):
+    """mesh.wall_ghost_images (search_bnd_images for a flat ground in closed form, bnd_image.cc:27-270) against the
+    Image_table the unmodified reference held at the end of step 1: the same wall ghosts get an image, with bit-identical
+    mirror points, inside the same buckets"""
+    import oracle_py as op
+    from common import golden, cell_attrs, image_cells, dump_to_particles
+    from plume_sph_b200 import mesh
+    z = golden(name)
+    cfg = op.config_for(name, z)
+    attr, _ = cell_attrs(cfg, z, "b2")
+    rows = dump_to_particles(z["bc_pre"])
+    img, sel = mesh.wall_ghost_images(rows, [cfg.mindom[k] for k in range(3)], [cfg.ncell[k] for k in range(3)], cfg.delta, attr)
+    o = np.argsort(z["bc_img_row"])
+    assert np.array_equal(sel, z["bc_img_row"][o])
+    assert np.array_equal(img["coord"], z["bc_img_coord"][o])
+    assert np.array_equal(img["cell"], image_cells(cfg, z)[o])
+    assert np.array_equal(img["ghost_key"], z["bc_pre"]["key"][sel])

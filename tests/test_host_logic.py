@@ -123,3 +123,12 @@ def test_wall_ghost_images_match_the_reference_table(name):
     assert np.array_equal(img["coord"], z["bc_img_coord"][o])
     assert np.array_equal(img["cell"], image_cells(cfg, z)[o])
     assert np.array_equal(img["ghost_key"], z["bc_pre"]["key"][sel])
+
+
+def test_default_lattice_has_the_bucket_count_of_the_reference_run():
+    """the default 3-D case (bin/simulation.data: smoothing length 100, parameters.h box) has 93 775 buckets
+    (counted in the reference run); 55 x 55 x 31 from preprocess.cc:99-133"""
+    from plume_sph_b200 import mesh
+    mindom, n, d = mesh.lattice((-20800., -20800., 1666.), (20800., 20800., 24000.), 100.0)
+    assert [int(x) for x in n] == [55, 55, 31] and int(np.prod(n)) == 93775 and d == 800.0
+    assert [float(x) for x in mindom] == [-22000.0, -22000.0, 466.0]

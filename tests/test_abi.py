@@ -65,3 +65,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_header_compiles_as_c_and_cxx_with_the_mirrored_layouts(tmp_path):
+    """include/psph.h is a plain C ABI: it compiles as C99 and as C++ on its own, and the compilers agree with the
+    Python mirrors (ctypes / numpy) on the size of every record that crosses the boundary"""
+    import subprocess
+    import oracle_py as op
+    sizes = {"psph_config": C.sizeof(psph.PsphConfig), "psph_particle": psph.PARTICLE_DTYPE.itemsize,
+             "psph_cell_attr": psph.CELL_ATTR_DTYPE.itemsize, "psph_image": psph.IMAGE_DTYPE.itemsize,
+             "psph_erupt": C.sizeof(psph.PsphErupt)}
+    assert C.sizeof(op.Erupt) == sizes["psph_erupt"]
+    body = '#include "psph.h"\n' + "".join(
+        "typedef char check_%s[sizeof(%s) == %d ? 1 : -1];\n" % (n, n, s) for n, s in sizes.items())
+    body += "typedef char check_sph_row[PSPH_ROW_BYTES_SPH == %d ? 1 : -1];\n" % psph.PARTICLE_SPH_DTYPE.itemsize
+    body += "int main(void) { return 0; }\n"
+    for comp, ext, std in (("gcc", "c", "-std=c99"), ("g++", "cc", "-std=c++11")):
+        src = tmp_path / ("abi_check." + ext)
+        src.write_text(body)
+        r = subprocess.run([comp, std, "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

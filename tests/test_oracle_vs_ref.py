@@ -238,3 +238,23 @@ def test_add_new_erupt_bit_exact(name, base, steps):
                 eq(got[pf], want[f], ("erupt", st, f))
         eq(got["bc_type"], want["bc_type"], "bc")
         assert not got["guest"].any() and not want["guest"].any()
+
+
+def test_reference_side_binding_compiles():
+    """INTEGRATION.md's reference-side glue (oracle/ref_build/binding/psph_binding.cc: Particle / Bucket / BndImage /
+    SimProps -> the records of include/psph.h, one forwarded time step) compiles against the reference's own headers
+    with the 3-D option set.  Build container only: the reference tree is not on the GPU box."""
+    import os
+    import subprocess
+    ref = os.environ.get("PSPH_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src", "plume")):
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rb = os.path.join(root, "oracle", "ref_build")
+    src = os.path.join(ref, "src")
+    cmd = ["g++", "-std=c++11", "-fsyntax-only", "-DHAVE_CONFIG_H", "-w", "-fpermissive", "-include", "cmath",
+           "-I" + os.path.join(rb, "stubs", "cfg3d"), "-I" + os.path.join(rb, "stubs"),
+           "-I" + os.path.join(src, "datstr"), "-I" + os.path.join(src, "plume"), "-I" + os.path.join(src, "multiproc"),
+           "-I" + os.path.join(root, "include"), os.path.join(rb, "binding", "psph_binding.cc")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

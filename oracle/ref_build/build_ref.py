@@ -139,6 +139,16 @@ def build(name, jobs):
         list(ex.map(run, cmds))
     run(["g++", "-o", os.path.join(odir, "particler")] + objs + [o_main, "-lm"])
     run(["g++", "-o", os.path.join(odir, "particler_hooked")] + objs + [o_hook, "-lm"])
+    # third driver (3-D SPH builds, when the product library is built): main.cc with its stage calls forwarded to
+    # libpsph.so (ref_b200.cc) — the drop-in as a program; needs a GPU to run
+    libdir = os.path.join(os.path.dirname(os.path.dirname(HERE)), "plume_sph_b200")
+    if v["dim"] == 3 and "-DUSE_GSPH=1" not in v["defs"] and not v.get("gsph") and os.path.exists(os.path.join(libdir, "libpsph.so")):
+        o_b200 = os.path.join(odir, "obj", "main_b200.o")
+        inc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "include")
+        run(["g++"] + flags + [f"-I{inc}", f'-DPSPH_REF_MAIN_CC="{SRC}/plume/main.cc"',
+                               "-c", os.path.join(HERE, "ref_b200.cc"), "-o", o_b200])
+        run(["g++", "-o", os.path.join(odir, "particler_b200")] + objs + [o_b200, "-lm", f"-L{libdir}", "-lpsph",
+             "-Wl,-rpath,$ORIGIN/../../../plume_sph_b200", "-Wl,--allow-shlib-undefined"])
     if v["dim"] == 3:
         # preprocess only compiles with -DDEBUG
         pre = []

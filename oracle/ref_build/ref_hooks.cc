@@ -456,6 +456,7 @@ void psphhook_update_pos(THashTable *P, TimeProps *tp, MatProps *mp)
 }
 
 /* ---- the unmodified reference driver, with its stage calls renamed ---- */
+#ifndef PSPH_HOOKS_NO_MAIN   /* ref_b200.cc includes this file for the dump helpers and brings its own wrappers */
 #define timestep psphhook_timestep
 #define search_neighs_consth psphhook_search_neighs_consth
 #define adaptive_sml psphhook_adaptive_sml
@@ -468,3 +469,4 @@ void psphhook_update_pos(THashTable *P, TimeProps *tp, MatProps *mp)
 #define add_new_erupt psphhook_add_new_erupt
 #define apply_bcond psphhook_apply_bcond
 #include PSPH_REF_MAIN_CC
+#endif

@@ -128,7 +128,7 @@ def config_jpue():
     return c
 
 
-CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue}
+CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue, "plume3d_sml": config_3d}
 
 
 def config_for(name, z=None):
@@ -136,10 +136,17 @@ def config_for(name, z=None):
     (simprops->sml_of_phase2, computed by the driver in setup_erupt.cc:95-101 and handed to the hot path as
     psph_config.smlen_real) is read off the fixture: the rows that turned real in step 1."""
     c = CONFIGS_3D[name]()
-    if z is not None:
+    if z is not None and "pre" in z:
         turned = (z["pre"]["bc_type"] == 0) & (z["s1_pos_bc_type"] == 100)
         if turned.any():
             c.smlen_real = float(z["s1_pos_smlen"][turned][0])
+    elif z is not None:   # sparse stage outputs (plume3d_sml): the rows update_pos turned real
+        for st in (1, 2):
+            rows, bc = z["s%d_pos_bc_type__rows" % st], z["s%d_pos_bc_type" % st]
+            hr = dict(zip(z["s%d_pos_smlen__rows" % st].tolist(), z["s%d_pos_smlen" % st].tolist()))
+            for r, b in zip(rows.tolist(), bc.tolist()):
+                if b == 100 and r in hr:
+                    c.smlen_real = float(hr[r])
     return c
 
 

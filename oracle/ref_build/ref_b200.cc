@@ -90,7 +90,7 @@ void make_config(THashTable *P, HashTable *BG)
   psph_config &c = g_cfg;
   c.use_gsph = USE_GSPH; c.have_turbulence_lans = HAVE_TURBULENCE_LANS; c.have_energy_smooth = HAVE_ENERGY_SMOOTH;
   c.pghost_contribute_des = PGHOST_CONTRIBUTE_DES; c.fluid_compressibility = FLUID_COMPRESSIBILITY;
-  c.adaptive_sml = ADAPTIVE_SML >= 1; c.sml_update_int = SML_UPDATE_INT;
+  c.adaptive_sml = ADAPTIVE_SML >= 1; c.sml_update_int = psphhook_sml_update_int();
   c.cutoff = CUTOFF; c.cutoff2 = CUTOFF2; c.msfrc_thresh = MSFRC_THRESH; c.epsilon_half = EPSILON_HALF;
   c.prandtl_num = PRANDTL_NUM; c.heat_trans_scale_ratio = HEAT_TRANS_SCALE_RATIO; c.e_smooth_ratio = E_SMOOTH_RATIO;
   c.tiny = TINY;

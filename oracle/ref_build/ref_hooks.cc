@@ -16,6 +16,7 @@
  *   PSPH_DUMP_NEIGH   1 -> also dump neighbour lists after search_neighs_consth
  *   PSPH_MAX_STEPS    stop the run (exit 0) once this many steps completed
  *   PSPH_STAGE_TIMES  1 -> print accumulated wall time per stage at exit
+ *   PSPH_SML_INT      adaptive_sml every k-th step instead of every SML_UPDATE_INT-th (constant.h:189)
  *
  * Dump file "<dir>/s<step>_<stage>_<pre|post>.bin":
  *   i32 magic 0x50535048, i32 dim, i32 gsph, i64 n, f64 time, f64 dt, then n rows
@@ -313,6 +314,7 @@ int psphhook_search_neighs_consth(int myid, THashTable *P, HashTable *BG)
   int r;
   { StageTimer st("search_neighs_consth"); r = search_neighs_consth(myid, P, BG); }
   dump_table(P, "search", "post", g_neigh);
+  dump_buckets(P, BG, "search");   /* the adapt block (main.cc:256-304) may have changed the table since timestep() */
   return r;
 }
 
@@ -454,6 +456,18 @@ void psphhook_update_pos(THashTable *P, TimeProps *tp, MatProps *mp)
   { StageTimer st("update_pos"); update_pos(P, tp, mp); }
   dump_table(P, "pos", "post");
 }
+
+/* SML_UPDATE_INT (constant.h:189, a const int, not a macro) decides at main.cc:319-322 which steps call adaptive_sml.
+ * PSPH_SML_INT overrides it for the text of main.cc that follows, so that a short run crosses adaptive_sml (goldens of
+ * the regime after it: every particle with its own smoothing length); unset = the reference's value. */
+static const int psph_ref_sml_update_int = SML_UPDATE_INT;
+int psphhook_sml_update_int()
+{
+  static int v = 0;
+  if (!v) { const char *s = getenv("PSPH_SML_INT"); v = (s && atoi(s) > 0) ? atoi(s) : psph_ref_sml_update_int; }
+  return v;
+}
+#define SML_UPDATE_INT (psphhook_sml_update_int())
 
 /* ---- the unmodified reference driver, with its stage calls renamed ---- */
 #ifndef PSPH_HOOKS_NO_MAIN   /* ref_b200.cc includes this file for the dump helpers and brings its own wrappers */

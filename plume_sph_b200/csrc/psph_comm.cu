@@ -20,6 +20,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <algorithm>
 #include <cstring>
 
 namespace {
@@ -63,7 +64,8 @@ struct Comm
   int32_t *d_owner = nullptr;            // [ncells] owner rank of every cell
   uint32_t *d_cellmask = nullptr;        // [ncells] ranks (bit q) that own a cell touching this (owned) cell
   int32_t *d_dest = nullptr;             // [cap] per-row scratch (destination rank / select key)
-  int32_t *d_send_idx = nullptr, *d_recv_idx = nullptr; size_t idx_cap = 0;
+  int32_t *d_send_idx = nullptr, *d_recv_idx = nullptr; size_t idx_cap = 0;   // idx_cap: rows d_dest holds
+  size_t send_idx_cap = 0, recv_idx_cap = 0;  // entries; a boundary row is listed once per peer that mirrors it
   std::vector<int> send_cnt, recv_cnt;   // per peer, of the current ghost layout
   bool lists_stale = true;               // idx lists do not match the current row order
   char *d_sendbuf = nullptr, *d_recvbuf = nullptr; size_t sendbuf_cap = 0, recvbuf_cap = 0;
@@ -250,11 +252,30 @@ int ensure_row_scratch(psph_ctx *ctx)
   int32_t *nd = nullptr; // the per-row destinations survive a growth (migrate() computes them before it knows the arrivals)
   PSPH_CUDA(cudaMalloc(&nd, ctx->cap * sizeof(int32_t)));
   if (C->d_dest && C->idx_cap) PSPH_CUDA(cudaMemcpy(nd, C->d_dest, C->idx_cap * sizeof(int32_t), cudaMemcpyDeviceToDevice));
-  cudaFree(C->d_dest); cudaFree(C->d_send_idx); cudaFree(C->d_recv_idx);
+  cudaFree(C->d_dest);
   C->d_dest = nd;
-  PSPH_CUDA(cudaMalloc(&C->d_send_idx, ctx->cap * sizeof(int32_t)));
-  PSPH_CUDA(cudaMalloc(&C->d_recv_idx, ctx->cap * sizeof(int32_t)));
   C->idx_cap = ctx->cap;
+  return 0;
+}
+
+// room for `ns` send-list and `nr` receive-list entries.  One peer's selection never exceeds the row count, but the
+// lists of ALL peers are kept back to back (ensure_lists) and a boundary row appears once for every peer whose slab
+// touches its cell: the sum over peers can exceed the table size.
+int ensure_idx_lists(psph_ctx *ctx, size_t ns, size_t nr)
+{
+  Comm *C = comm_of(ctx);
+  if (ns <= C->send_idx_cap && nr <= C->recv_idx_cap) return 0;
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ns > C->send_idx_cap) {
+    cudaFree(C->d_send_idx); C->d_send_idx = nullptr;
+    C->send_idx_cap = ns + ns / 4 + 1024;
+    PSPH_CUDA(cudaMalloc(&C->d_send_idx, C->send_idx_cap * sizeof(int32_t)));
+  }
+  if (nr > C->recv_idx_cap) {
+    cudaFree(C->d_recv_idx); C->d_recv_idx = nullptr;
+    C->recv_idx_cap = nr + nr / 4 + 1024;
+    PSPH_CUDA(cudaMalloc(&C->d_recv_idx, C->recv_idx_cap * sizeof(int32_t)));
+  }
   C->lists_stale = true;
   return 0;
 }
@@ -343,6 +364,11 @@ int ship_rows(psph_ctx *ctx, MakePred make_pred, bool as_guest, std::vector<int>
   if (n_before) *n_before = n0;
   if (psph_reserve(ctx, (size_t) n0 + rtot)) return -1;
   if (ensure_row_scratch(ctx)) return -1;
+  {
+    int smax = 0;
+    for (int q = 0; q < P; q++) smax = std::max(smax, sc[q]);
+    if (ensure_idx_lists(ctx, (size_t) smax, 0)) return -1;      // one peer's selection at a time
+  }
   if (ensure_bytes(ctx, C->d_sendbuf, C->sendbuf_cap, sbytes)) return -1;
   if (ensure_bytes(ctx, C->d_recvbuf, C->recvbuf_cap, rbytes)) return -1;
   size_t so = 0;
@@ -425,6 +451,11 @@ int ensure_lists(psph_ctx *ctx)
   if (!C->lists_stale) return 0;
   if (psph_sync_n(ctx)) return -1; // builds the cell list if needed; exact row count on the host
   if (ensure_row_scratch(ctx)) return -1;
+  {
+    size_t ns = 0, nr = 0;
+    for (int q = 0; q < C->P; q++) { if (q == C->me) continue; ns += (size_t) C->send_cnt[q]; nr += (size_t) C->recv_cnt[q]; }
+    if (ensure_idx_lists(ctx, ns, nr)) return -1;
+  }
   const int32_t *cell = ctx->cur.t.i[I_CELL], *guest = ctx->cur.t.i[I_GUEST], *myproc = ctx->cur.t.i[I_MYPROC];
   size_t so = 0, ro = 0;
   for (int q = 0; q < C->P; q++) {

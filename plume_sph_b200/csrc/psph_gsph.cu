@@ -249,7 +249,7 @@ int psph_gsph_gradients(psph_ctx *ctx)
 {
   if (!ctx->has_grad) { ctx->err = "psph_calc_gradients: context was not created with use_gsph"; return -2; }
   if (!ctx->list_valid && psph_build_cell_list(ctx)) return -1;
-  if (ctx->n == 0) return 0;
+  if (ctx->n == 0) { psph_comm_mark(ctx, DIRTY_GRAD); return 0; }   // an empty slab still enters the exchange that follows
   k_pack_grad<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_gather<GradStage>(ctx, KN_GATHER_GRAD)) return -1;
@@ -268,7 +268,7 @@ int psph_gsph_mom_engr(psph_ctx *ctx)
 {
   StageTimer tm(ctx, ST_MOM);
   if (!ctx->list_valid && psph_build_cell_list(ctx)) return -1;
-  if (ctx->n == 0) return 0;
+  if (ctx->n == 0) { psph_comm_mark(ctx, DIRTY_MOM); return 0; }
   k_pack_gsph<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_gather<GsphMomStage>(ctx, KN_GATHER_GSPH)) return -1;

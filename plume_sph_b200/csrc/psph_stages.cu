@@ -781,7 +781,7 @@ extern "C" int psph_adaptive_sml(psph_ctx *ctx)
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   StageTimer tm(ctx, ST_SML);
   if (ensure_list(ctx)) return -1;
-  if (ctx->n == 0) return 0;
+  if (ctx->n == 0) { psph_comm_mark(ctx, DIRTY_H); return 0; }
   k_pack_sml<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_gather<SmlStage>(ctx, KN_GATHER_SML)) return -1;
@@ -804,7 +804,9 @@ extern "C" int psph_mom_engr_update(psph_ctx *ctx)
   if (ctx->cfg.use_gsph) return psph_gsph_mom_engr(ctx);
   StageTimer tm(ctx, ST_MOM);
   if (ensure_list(ctx)) return -1;
-  if (ctx->n == 0) return 0;
+  // a rank that holds no rows right now still takes part in the exchange that follows (the dirty mask decides which
+  // collective every rank enters: it must not depend on the local row count)
+  if (ctx->n == 0) { psph_comm_mark(ctx, DIRTY_MOM); return 0; }
   k_pack_mom<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_stage_gather<MomStage>(ctx, KN_GATHER_MOM, true)) return -1;
@@ -816,7 +818,7 @@ extern "C" int psph_smooth_density(psph_ctx *ctx)
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   StageTimer tm(ctx, ST_DENS);
   if (ensure_list(ctx)) return -1;
-  if (ctx->n == 0) return 0;
+  if (ctx->n == 0) { psph_comm_mark(ctx, DIRTY_DENS); return 0; }
   k_pack_dens<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_stage_gather<DensStage>(ctx, KN_GATHER_DENS, false)) return -1;
@@ -831,10 +833,10 @@ extern "C" int psph_smooth_velocity(psph_ctx *ctx)
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   StageTimer tm(ctx, ST_VEL);
   if (ensure_list(ctx)) return -1;
+  psph_comm_mark(ctx, DIRTY_VEL);
   if (ctx->n == 0) return 0;
   k_pack_vel<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  psph_comm_mark(ctx, DIRTY_VEL);
   return launch_stage_gather<VelStage>(ctx, KN_GATHER_VEL, false);
 }
 
@@ -842,10 +844,10 @@ extern "C" int psph_update_pos(psph_ctx *ctx)
 {
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   StageTimer tm(ctx, ST_POS);
+  psph_comm_mark(ctx, DIRTY_LAYOUT);
   if (ctx->n == 0) return 0;
   k_update_pos<<<GRID(ctx->n)>>>(ctx->cur.t, ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  psph_comm_mark(ctx, DIRTY_LAYOUT);
   return 0;
 }
 

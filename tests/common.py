@@ -142,6 +142,14 @@ def oracle_state_3d(cfg, z, tag="b0", rows="pre"):
     return s
 
 
+def sparse_field(z, key, base):
+    """a stage output stored sparse (tests/golden/make_golden.py::golden_3d_sml): `base` with the rows z[key + "__rows"]
+    replaced by z[key]"""
+    out = np.array(base, copy=True)
+    out[z[key + "__rows"]] = z[key]
+    return out
+
+
 def relerr(a, b):
     """max |a-b| relative to max |b| (per field, as the tolerance is stated)"""
     a = np.asarray(a, np.float64)

@@ -165,6 +165,73 @@ def golden_3d(name, variant, edits, list_stride=4, simdata="simulation.data"):
         print(name, "n =", len(pre), "listed", len(listed), "->", os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
 
 
+def pack_buckets(out, tag, fn):
+    bk = refio.read_buckets(fn)
+    out[tag + "_mincrd"] = np.asarray([b["mincrd"] for b in bk])
+    out[tag + "_key"] = np.asarray([b["key"] for b in bk], np.uint32)
+    out[tag + "_attr"] = np.asarray([[b["type"], b["has_involved"], b["active"], b["guest"]] for b in bk], np.int32)
+    out[tag + "_bindex"] = np.asarray([b["bucket_index"] for b in bk], np.int32)
+    out[tag + "_bnd"] = np.asarray([b["bnd"] for b in bk], np.float64)
+    out[tag + "_off"] = np.cumsum([0] + [len(b["rows"]) for b in bk]).astype(np.int64)
+    out[tag + "_rows"] = np.concatenate([b["rows"] for b in bk]).astype(np.int32)
+    return bk
+
+
+def golden_3d_sml(name="plume3d_sml", variant="3d_plume", edits=None, simdata="simulation.data"):
+    """The regime AFTER adaptive_sml (neighs.cc:479-693; main.cc:319-322 calls it every SML_UPDATE_INT = 50 steps): the
+    small plume with PSPH_SML_INT=1 (the hook TU's override of that constant, nothing else changes), time steps 1 and 2.
+    Step 1 runs adaptive_sml from the uniform initial smoothing lengths; step 2 starts with every real particle carrying
+    its own h (and, the domain having grown in its adapt block, with freshly converted real particles that still carry
+    the initial one), runs adaptive_sml again from there and every summation stage with mixed smoothing lengths.
+    Per step: the state search_neighs_consth sees (after the adapt block) with the bucket plists, dt, and what every
+    stage changed — stored sparse: <key>__rows = the rows whose value differs from the state before the stage,
+    <key> = their new values (tests/common.py::sparse_field puts them back)."""
+    edits = SMALL_3D if edits is None else edits
+    with tempfile.TemporaryDirectory() as top:
+        wd = os.path.join(top, "run")
+        os.makedirs(wd)
+        shutil.copytree(os.path.join(REF, "Meteo_data"), os.path.join(top, "Meteo_data"))
+        shutil.copy(os.path.join(REF, "bin", "scale.data"), wd)
+        txt = open(os.path.join(REF, "bin", simdata)).read()
+        for a, b in edits:
+            assert a in txt, a
+            txt = txt.replace(a, b)
+        open(os.path.join(wd, "simulation.data"), "w").write(txt)
+        smlen = [l for l in txt.splitlines() if l.startswith("smoothing length")][0].split(":")[1]
+        subprocess.run([os.path.join(REFBIN, variant, "preprocess"), "1", smlen, "0"], cwd=wd, check=True,
+                       stdout=subprocess.DEVNULL)
+        dump = os.path.join(wd, "dump")
+        os.makedirs(dump)
+        run_ref(variant, wd, dict(PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="1-2", PSPH_MAX_STEPS=2, PSPH_SML_INT=1))
+        out = {}
+        dts = []
+        for st in (1, 2):
+            h, pre = refio.read_dump(os.path.join(dump, "s%04d_search_post.bin" % st))
+            dts.append(h["dt"])
+            out["pre%d" % st] = pre
+            pack_buckets(out, "b%d" % st, os.path.join(dump, "s%04d_search_buckets.bin" % st))
+            cur = {f: pre[f].copy() for f in pre.dtype.names}
+            for stage in ("sml", "mom", "dens", "svel", "pos"):
+                fn = os.path.join(dump, "s%04d_%s_post.bin" % (st, stage))
+                assert os.path.exists(fn), fn
+                _, rows = refio.read_dump(fn)
+                assert np.array_equal(rows["key"], pre["key"])
+                for f in rows.dtype.names:
+                    a, b = cur[f], rows[f]
+                    ch = (a != b) if a.ndim == 1 else (a != b).any(axis=1)
+                    if f in STAGE_FIELDS[stage]:
+                        idx = np.nonzero(ch)[0].astype(np.int32)
+                        out["s%d_%s_%s__rows" % (st, stage, f)] = idx
+                        out["s%d_%s_%s" % (st, stage, f)] = b[idx]
+                    cur[f] = b.copy()
+        out["dt"] = np.asarray(dts)
+        real = out["pre2"]["bc_type"] == 100
+        print(name, "n =", len(out["pre1"]), len(out["pre2"]), "real", int(real.sum()), "distinct h of real rows at the start of step 2:",
+              len(np.unique(out["pre2"]["smlen"][real])))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "->", os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
+
+
 ERUPT_PARAMS = ("time", "dt", "step", "bot", "sml_of_phase2", "mass_of_phase2", "rv", "pos_v0", "pos_v1", "Vv0", "ev0", "rhov",
                 "pv0", "gamma_v", "sndspd", "vel_prof", "ratio_sml_dx", "kmin0", "kmin1", "kmin2", "kmax0", "kmax1", "kmax2",
                 "iferupt")
@@ -241,6 +308,7 @@ if __name__ == "__main__":
                                              simdata="simulation_JPUE_incomp_back.data"),
         "plume3d_small": lambda: golden_3d("plume3d_small", "3d_plume", SMALL_3D),
         "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D),
+        "plume3d_sml": lambda: golden_3d_sml(),
         # BASELINE config 2: JPUE weakly-compressible jet (Tait EOS, g = 0), the reference's own input file
         "jpue3d": lambda: golden_3d("jpue3d", "3d_jpue", JPUE_3D, list_stride=16, simdata="simulation_JPUE_incomp_back.data"),
     }

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_py as op
-from common import golden, oracle_state_3d, cell_attrs, image_cells, D2P
+from common import golden, oracle_state_3d, cell_attrs, image_cells, D2P, sparse_field
 from plume_sph_b200.driver import TimeProps
 
 
@@ -48,6 +48,44 @@ def test_plume3d_step1_bit_exact(name):
     s2 = oracle_state_3d(cfg, z, "b1")
     eq(s.cell_off, s2.cell_off, "plist offsets after re-bin")
     eq(s.cell_rows[:s.cell_off[-1]], s2.cell_rows[:s2.cell_off[-1]], "plists after re-bin (order too)")
+
+
+@pytest.mark.parametrize("step", [1, 2])
+def test_plume3d_adaptive_sml_and_mixed_h_bit_exact(step):
+    """adaptive_sml in 3-D (neighs.cc:479-693) and every summation stage with per-particle smoothing lengths: time steps
+    1 and 2 of the small plume with adaptive_sml called every step (PSPH_SML_INT=1 on the reference's hook build).
+    Step 2 starts from mixed h (675 distinct values among the real particles)."""
+    z = golden("plume3d_sml")
+    cfg = op.config_for("plume3d_sml", z)
+    pre = z["pre%d" % step]
+    s = oracle_state_3d(cfg, z, "b%d" % step, rows="pre%d" % step)
+    dt = float(z["dt"][step - 1])
+    if step == 1:
+        assert s.timestep() == dt
+    else:
+        assert len(np.unique(pre["smlen"][pre["bc_type"] == 100])) > 100
+    s.search()
+    cur = {f: pre[f] for f in pre.dtype.names}
+
+    def check(stage, pairs):
+        for f, o in pairs:
+            want = sparse_field(z, "s%d_%s_%s" % (step, stage, f), cur[f])
+            eq(s.a[o], want, (step, stage, f))
+            cur[f] = want
+
+    s.adaptive_sml()
+    check("sml", [("smlen", "h")])
+    assert len(z["s%d_sml_smlen__rows" % step]) > 500
+    assert s.mom_engr_update(dt) == 0
+    check("mom", [("vel", "v"), ("engr", "e"), ("pressure", "p"), ("sound_speed", "c"), ("temperature", "T"),
+                  ("specific_heat_p", "Cp"), ("gamma", "gamma"), ("phase_density", "rho_ph")])
+    assert s.smooth_density() == 0
+    check("dens", [("rho", "rho"), ("mass_frac", "ks"), ("engr", "e"), ("pressure", "p"), ("sound_speed", "c"),
+                   ("temperature", "T"), ("involved", "involved")])
+    assert s.smooth_velocity() == 0
+    check("svel", [("smoothed_v", "sv")])
+    s.update_pos(dt, 1)
+    check("pos", [("coord", "x"), ("bc_type", "bc"), ("smlen", "h"), ("involved", "involved")])
 
 
 @pytest.mark.parametrize("name", ["plume3d_small", "jpue3d"])
@@ -134,7 +172,7 @@ def test_shocktube_sph_bit_exact(name):
             eq(s.a[o], z["mid"][f], ("mid", f))
 
 
-@pytest.mark.parametrize("name", ["sod_gsph", "sod0_gsph", "blast_gsph"])
+@pytest.mark.parametrize("name", ["sod_gsph", "sod0_gsph", "blast_gsph", "shu_gsph"])
 def test_shocktube_gsph_bit_exact(name):
     """Godunov-SPH variant (calc_gradients + HLLC Riemann solver, 1-D defaults): gradients, momentum and
     energy of the first steps and the state after 30 and 300/1000 steps, bit for bit."""

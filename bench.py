@@ -32,19 +32,19 @@ for p in (ROOT,):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-METRIC = "particle-updates/sec (3D plume)"
+METRIC = "particle-updates/sec (3D SPH hot path, synthetic particle cube)"
 UNIT = "particle-updates/s"
 # algorithmic bytes per real-particle-update of each pair gather
 ALG_BYTES = {"gather_mom_engr": 228, "gather_density": 148, "gather_velocity": 100}
 ALG_BYTES_STEP = 1184
-# kernel behind each timer when the block-tiled pair path runs (3-D SPH defaults), and what ncu measured for it
-# (profiles/r01q_ncu_dram_n216.txt: DRAM bytes read + written per launch at this workload — for mom_engr_update the slot
-# lists (4.5 GB) and the tiles' records in, the pair weights (18 GB) out; for smooth_velocity the pair weights back in;
-# profiles/r01o_ncu_wcache_n96.txt: FP64 pipe)
-KERNEL_OF = {"gather_mom_engr": "k_tile_gather<MomStage<3>, WM=1>", "gather_density": "k_dens_near",
-             "gather_velocity": "k_tile_gather<VelStage<3>, WM=2>"}
-NCU = {"gather_mom_engr": {"traffic": 28379217920, "fp64_pipe_pct": 48.5}, "gather_density": {"traffic": 1444992256, "fp64_pipe_pct": None},
-       "gather_velocity": {"traffic": 23795390208, "fp64_pipe_pct": 14.8}}
+# kernel behind each timer, per regime (3-D SPH defaults)
+KERNEL_OF = {"uniform_h": {"gather_mom_engr": "k_tile_gather<MomStage<3>, WM=1>", "gather_density": "k_dens_near",
+                           "gather_velocity": "k_tile_gather<VelStage<3>, WM=2>"},
+             "mixed_h": {"gather_mom_engr": "k_mix_gather<MomStage<3>>", "gather_density": "k_mix_dens_near",
+                         "gather_velocity": "k_mix_gather<VelStage<3>>"}}
+# Figures that come from ncu captures, NOT from this run: reported under roofline.from_profile with their source file
+# and problem size, never mixed into the live numbers.
+PROFILE_FIGURES = os.path.join(ROOT, "profiles", "ncu_figures.json")
 
 
 def measured_peaks():
@@ -182,7 +182,7 @@ def run_b200(args):
     s, n_real_local, n_rows_local = setup_cube_ranks(torch, dist, psph, cfg, n, dev, rank, world, cube_columns)
 
     stream = torch.cuda.ExternalStream(s.stream(), device=dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    peak, peak_src = measured_peaks()
 
     def barrier():
         s.sync()
@@ -190,66 +190,86 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
-    for _ in range(args.warmup):
-        s.run(1, erupting=0)
-    barrier()
-    s.launch_count(reset=True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        s.run(1, erupting=0)
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = s.launch_count(reset=True)
-    clk = clocks.stop() if rank == 0 else None
-    bad = s.errors()
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    cnt = torch.tensor([float(n_real_local), float(launches)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms = float(t.item())
-    n_real = int(cnt[0].item())
-    value = n_real * args.steps / (ms * 1e-3)
-
-    # ---- per-kernel device times (separate pass, events around every kernel; not the timed region)
-    s.set_timing(True)
-    ksteps = max(1, min(2, args.steps))
-    for _ in range(ksteps):
-        s.run(1, erupting=0)
-    s.sync()
-    kms = s.kernel_ms()
-    sms = s.stage_ms()
-    s.set_timing(False)
-    peak, peak_src = measured_peaks()
-    dom = max(ALG_BYTES, key=lambda k: kms[k][0])
-    dom_ms = kms[dom][0] / max(kms[dom][1], 1)
-    achieved = ALG_BYTES[dom] * n_real_local / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": KERNEL_OF[dom], "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5),
-                "traffic": NCU[dom]["traffic"] if (args.n == 216 and world == 1) else None,
-                # measured DRAM rate of that kernel: ncu bytes per launch / the live launch duration
-                "traffic_GBps": round(NCU[dom]["traffic"] / (dom_ms * 1e-3) / 1e9, 1) if (args.n == 216 and world == 1) else None,
-                "fp64_pipe_pct_ncu": NCU[dom]["fp64_pipe_pct"],
-                # the stage that streams the cached pair weights back is the HBM-bound one: its measured DRAM rate
-                "hbm_bound_kernel": ({"kernel": KERNEL_OF["gather_velocity"], "ms_per_launch": round(kms["gather_velocity"][0] / max(kms["gather_velocity"][1], 1), 4),
-                                      "traffic": NCU["gather_velocity"]["traffic"],
-                                      "frac_of_peak": round(NCU["gather_velocity"]["traffic"] / (kms["gather_velocity"][0] / max(kms["gather_velocity"][1], 1) * 1e-3) / 1e9 / peak, 4)}
-                                     if (args.n == 216 and world == 1 and kms["gather_velocity"][1] > 0) else None),
+    def measure(regime, warmup, steps, sample_clocks):
+        """W untimed + K timed steps of psph_run (CUDA events on the context stream, barrier + synchronize on both sides,
+        max over ranks), then a separate pass with events around every kernel for the per-kernel / per-stage times."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(warmup):
+            s.run(1, erupting=0)
+        barrier()
+        s.launch_count(reset=True)
+        clocks = ClockSampler(local)
+        if rank == 0 and sample_clocks:
+            clocks.start()
+        ev0.record(stream)
+        for _ in range(steps):
+            s.run(1, erupting=0)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = s.launch_count(reset=True)
+        clk = clocks.stop() if (rank == 0 and sample_clocks) else None
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        cnt = torch.tensor([float(n_real_local), float(launches)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ms = float(t.item())
+        n_real = int(cnt[0].item())
+        # per-kernel device times: separate pass, not the timed region
+        s.set_timing(True)
+        ksteps = max(1, min(2, steps))
+        for _ in range(ksteps):
+            s.run(1, erupting=0)
+        s.sync()
+        kms, sms = s.kernel_ms(), s.stage_ms()
+        s.set_timing(False)
+        dom = max(ALG_BYTES, key=lambda k: kms[k][0])
+        dom_ms = kms[dom][0] / max(kms[dom][1], 1)
+        achieved = ALG_BYTES[dom] * n_real_local / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": KERNEL_OF[regime][dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5),
+                "traffic": None,   # DRAM bytes per launch come from ncu captures only: see from_profile
                 "alg_bytes_per_update": ALG_BYTES[dom], "updates_per_launch": n_real_local,
                 "ms_per_launch": round(dom_ms, 4), "peak_source": peak_src,
-                "note": "FP64 pair loop over per-step pair lists, partners' records staged in shared memory: bound by the "
-                        "FP64 pipe and the issue slots, not by HBM (SURVEY.md §8d): the HBM fraction by ALGORITHMIC bytes "
-                        "is low by construction; `traffic` exceeds the algorithmic bytes on purpose (slot lists in, pair "
-                        "weights out: idle HBM traded for FP64 work in the two later stages); fp64_pipe_pct_ncu and "
-                        "profiles/ carry the figure of merit",
                 "step_hbm": {"alg_bytes_per_update": ALG_BYTES_STEP,
-                             "achieved_GBps": round(ALG_BYTES_STEP * n_real / (ms / args.steps * 1e-3) / 1e9, 2)},
+                             "achieved_GBps": round(ALG_BYTES_STEP * n_real / (ms / steps * 1e-3) / 1e9, 2)},
                 "stage_ms_per_step": {k: round(v / ksteps, 4) for k, v in sms.items() if v > 0},
                 "kernel_ms_per_launch": {k: round(v[0] / max(v[1], 1), 4) for k, v in kms.items() if v[1] > 0}}
+        return {"value": round(n_real * steps / (ms * 1e-3), 1), "ms_per_step": round(ms / steps, 4), "steps": steps,
+                "warmup": warmup, "n_real": n_real, "gpu_launches": int(cnt[1].item()), "clocks": clk, "roofline": roof}
+
+    regimes = {}
+    # ---- regime 1: uniform h (time steps 1-49 of a default run: before the first adaptive_sml call, main.cc:319-322)
+    if args.regime in ("both", "uniform"):
+        regimes["uniform_h"] = measure("uniform_h", args.warmup, args.steps, args.headline == "uniform")
+    # ---- regime 2: per-particle h (every step after the first adaptive_sml call: the production regime).  The bench
+    # makes the call the reference makes at step 50 (search_neighs_consth + adaptive_sml) and keeps stepping.
+    sml_ms = None
+    if args.regime in ("both", "mixed"):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.search_neighs_consth()
+        barrier()
+        ev0.record(stream)
+        s.adaptive_sml()
+        ev1.record(stream)
+        barrier()
+        sml_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            s.exchange_ghosts()                                    # main.cc:326
+        regimes["mixed_h"] = measure("mixed_h", args.warmup, args.steps, args.headline == "mixed")
+        regimes["mixed_h"]["adaptive_sml_ms_per_call"] = round(sml_ms, 3)
+    head = regimes["mixed_h" if args.headline == "mixed" else "uniform_h"]
+    value, ms_step, n_real, clk = head["value"], head["ms_per_step"], head["n_real"], head["clocks"]
+    roofline = dict(head["roofline"])
+    roofline["note"] = ("FP64 pair loop over per-step pair lists, partners' records staged in shared memory: bound by the FP64 "
+                        "pipe and the issue slots, not by HBM (SURVEY.md §8d): the HBM fraction by ALGORITHMIC bytes is low by "
+                        "construction; from_profile carries the ncu figures (FP64 pipe, DRAM bytes per launch) with their source")
+    try:
+        roofline["from_profile"] = json.load(open(PROFILE_FIGURES))
+    except Exception:
+        roofline["from_profile"] = None
+    bad = s.errors()
 
     # ---- end to end through the C ABI with host rows (pinned): upload + step + download per step
     e2e = None
@@ -276,7 +296,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-        e2e = {"value": round(n_real * ke / te, 1), "unit": UNIT, "h2d_bytes_per_step": nrow * rowb,
+        e2e = {"value": round(n_real * ke / te, 1), "unit": UNIT, "regime": "mixed_h" if args.headline == "mixed" else "uniform_h", "h2d_bytes_per_step": nrow * rowb,
                "d2h_bytes_per_step": nrow * rowb, "steps": ke,
                "row_bytes": rowb,
                "what": "psph_upload_rows(host AoS rows, pinned; SPH rows = psph_particle without the GSPH gradient block) + "
@@ -287,17 +307,21 @@ def run_b200(args):
         cpu = cpu_baseline_port(args.cpu_n)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        other = {k: {kk: vv for kk, vv in v.items() if kk != "clocks"} for k, v in regimes.items()}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "synthetic 3-D particle cube, %d^3 real (%d^3 per GPU) + 8h pressure-ghost shell, "
                                        "3-D SPH defaults (art. viscosity + LANS + energy smoothing), g=0" % (n, args.n),
+                           "regime": ("per-particle smoothing lengths: the state after adaptive_sml (every step of a default run "
+                                      "from step 50 on)" if args.headline == "mixed" else
+                                      "uniform smoothing length: steps 1-49 of a default run, before the first adaptive_sml call"),
                            "real_particles": n_real, "rows_rank0": n_rows_local, "edge": n,
                            "l2": "inputs (%.1f GB of SoA columns) far larger than the 126 MB L2" %
                                  (n_rows_local * 700 / 1e9),
                            "parallelism": "key-range slabs x%d" % world if world > 1 else "1 GPU"},
-                "roofline": roofline, "gpu_launches": int(cnt[1].item()), "clocks": clk, "e2e": e2e,
-                "invariant_violations": bad}
+                "roofline": roofline, "gpu_launches": head["gpu_launches"], "clocks": clk, "e2e": e2e,
+                "regimes": other, "invariant_violations": bad}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -342,31 +366,33 @@ def run_reference(args):
     ncpu = os.cpu_count() or 1
     if ref_run.have_inputs():
         reps = max(1, min(ncpu, args.ref_replicas if args.ref_replicas > 0 else ncpu))
-        steps, warm = max(1, args.steps), 0  # CPU code: no warm-up effect; every step is timed
-        steps = min(steps, 2)
-        r = ref_run.time_plume3d(steps, warm, replicas=reps, edits=ref_run.MEDIUM)
+        # CPU code: no warm-up effect, every step is timed; bounded sample: at most 2 steps (a step is ~7 s on one core)
+        steps_run = min(max(1, args.steps), 2)
+        r = ref_run.time_plume3d(steps_run, 0, replicas=reps, edits=ref_run.MEDIUM)
         path = ("timestep", "search_neighs_consth", "adaptive_sml", "mom_engr_update", "smooth_density",
                 "smooth_velocity", "update_pos", "update_particles_in_bucket")
         t_loop = max(r["seconds"])
-        # like for like: only the stages the B200 path replaces (apply_bcond / add_new_erupt stay with
-        # the reference driver); stage times are those of the last replica
+        # raw value of the reference's whole loop; the share of it that the B200 path replaces is reported beside it
         t_path = sum(r["stages"].get(k, 0.0) for k in path)
         frac = t_path / max(sum(r["stages"].values()), 1e-30)
-        value = r["updates"] * reps / (t_loop * frac)
+        value = r["updates"] * reps / t_loop
         sample = ("unmodified reference, its own 3-D plume case (bin/simulation.data, initial domain shrunk to "
-                  "+-1000 m: %d real / %d total particles), %d step(s), %d single-rank replicas side by side "
-                  "(no MPI in the image); hot-path stages only = %.0f%% of its loop (apply_bcond excluded); "
-                  "loop wall %.1f s" % (r["real"], r["total"], steps, reps, 100 * frac, t_loop))
-        kind, cores, ms = "reference", reps, t_loop * frac * 1e3 / steps
+                  "+-1000 m: %d real / %d total particles), %d step(s) timed (steps_requested %d), %d single-rank replicas side "
+                  "by side (no MPI in the image); value = whole loop; the stages the B200 path replaces are %.0f%% of it; "
+                  "loop wall %.1f s" % (r["real"], r["total"], steps_run, args.steps, reps, 100 * frac, t_loop))
+        kind, cores, ms = "reference", reps, t_loop * 1e3 / steps_run
+        extra = {"steps_run": steps_run, "hot_path_share_of_loop": round(frac, 4)}
     else:
         cpu = cpu_baseline_port(args.cpu_n)
         value, sample, kind, cores, ms = cpu["value"], cpu["sample"], "port", 1, None
+        steps_run, extra = 1, {"steps_run": 1}
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "steps": steps_run, "warmup": 0, "steps_requested": args.steps, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3-D dusty-gas plume hot path on host cores (bounded sample)"},
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line.update(extra)
     print(json.dumps(line), flush=True)
 
 
@@ -383,7 +409,13 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=32)
     ap.add_argument("--ref-replicas", type=int, default=0)
     ap.add_argument("--sml-int", type=int, default=0, help="run adaptive_sml every k-th step (default: the reference's 50)")
+    ap.add_argument("--regime", default="both", choices=["both", "uniform", "mixed"],
+                    help="which regimes to time: uniform h (steps 1-49 of a default run), per-particle h (after adaptive_sml), both")
+    ap.add_argument("--headline", default="mixed", choices=["uniform", "mixed"],
+                    help="regime whose numbers are the line's value / roofline / e2e (the other one is under `regimes`)")
     args = ap.parse_args()
+    if args.regime != "both":
+        args.headline = args.regime
     try:
         if args.impl == "reference":
             return run_reference(args)

@@ -65,7 +65,8 @@ void from_row(const psph_particle *r, Particle *p, bool all)
   if (!all) return;
   double v[3] = { r->vel[0], r->vel[1], r->vel[2] }, sv[3] = { r->smoothed_v[0], r->smoothed_v[1], r->smoothed_v[2] };
   double ph[2] = { r->phase_density[0], r->phase_density[1] };
-  p->put_velocity(v); p->put_smoothed_velocity(sv);
+  p->put_vel(v);                                    /* (put_velocity() writes new_state_vars, particle.h:773-778) */
+  p->put_smoothed_velocity(sv);
   p->put_density(r->rho); p->put_energy(r->engr); p->put_smoothed_energy(r->smoothed_e);
   p->put_mass_frac(r->mass_frac); p->put_pressure(r->pressure); p->put_gamma(r->gamma);
   p->put_sound_speed(r->sound_speed); p->put_temperature(r->temperature); p->put_specific_heat_p(r->specific_heat_p);
@@ -97,7 +98,7 @@ void make_config(THashTable *P, HashTable *BG)
   c.alf = alf_P; c.beta = beta_P; c.ata = ata_P; c.g = ::g_P;  /* (ref_hooks.cc has a g_P of its own in the unnamed namespace) */ c.cfl = CFL_P; c.eta_smooth = eta_smooth_P;
   c.c_smooth = C_smooth_P; c.thresh = thresh_P; c.num_loop = num_loop_P;
   c.ng0 = ng0_P; c.Cvs = Cvs_P; c.Cvg = Cvg_P; c.Cva = Cva_P; c.Rg = Rg_P; c.Ra = Ra_P; c.rhoa0 = rhoa0_P; c.pa0 = pa0_P;
-  c.erupt_top = Ll_P[2]; c.smlen_real = g_mp->smoothing_length;
+  c.erupt_top = Ll_P[2]; c.smlen_real = g_sp->sml_of_phase2;                  /* update_pos.cc:137-142 */
   c.len_scale = g_mp->LENGTH_SCALE;
   c.del = PARTICLE_DENSITY * g_mp->smoothing_length * g_mp->LENGTH_SCALE;      /* preprocess.cc:99 */
   for (int d = 0; d < 3; d++) {

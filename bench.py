@@ -40,7 +40,7 @@ ALG_BYTES_STEP = 1184
 # kernel behind each timer, per regime (3-D SPH defaults)
 KERNEL_OF = {"uniform_h": {"gather_mom_engr": "k_tile_gather<MomStage<3>, WM=1>", "gather_density": "k_dens_near",
                            "gather_velocity": "k_tile_gather<VelStage<3>, WM=2>"},
-             "mixed_h": {"gather_mom_engr": "k_mix_gather<MomStage<3>>", "gather_density": "k_mix_dens_near",
+             "mixed_h": {"gather_mom_engr": "k_mix_gather<MomStage<3>>", "gather_density": "k_dens_near<false>",
                          "gather_velocity": "k_mix_gather<VelStage<3>>"}}
 # Figures that come from ncu captures, NOT from this run: reported under roofline.from_profile with their source file
 # and problem size, never mixed into the live numbers.

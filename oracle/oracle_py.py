@@ -128,7 +128,7 @@ def config_jpue():
     return c
 
 
-CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue, "plume3d_sml": config_3d}
+CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue, "plume3d_sml": config_3d, "plume3d_grow": config_3d}
 
 
 def config_for(name, z=None):

@@ -10,6 +10,11 @@
  *   apply_bcond (end of step)         -> psph_apply_bcond, then the whole state comes back to the host particles
  * so that everything the driver keeps for itself (time bookkeeping, domain growth, ghost generation, image search,
  * output) sees current data, and whatever it changes is uploaded again before the next device call.
+ * PSPH_LOCKSTEP=1: the host runs the reference's own stages as well (its table stays the pure reference trajectory), the
+ * device is loaded with that table at the start of EVERY step and runs the same step beside it; at the end of each step
+ * (after apply_bcond) the two tables are compared field by field and one "LOCKSTEP step field err" line per field goes to
+ * stderr — one whole step from identical states, at every step, with domain growth, injection and wall ghosts in play
+ * (end states of free-running programs part company for a reason that is not an error: see tests/test_gpu_dropin.py).
  * Input, set-up and output are the reference's.  PSPH_MAX_STEPS / PSPH_DUMP_DIR work as in ref_hooks.cc: the final
  * dump of this program against the final dump of particler_hooked is the end-to-end parity check of the boundary.
  *
@@ -23,6 +28,7 @@ namespace {
 psph_ctx *G = NULL;
 psph_config g_cfg;
 bool g_dirty = true;            /* host table changed since the last upload */
+bool g_lock = false;            /* PSPH_LOCKSTEP: reference stages on the host beside the device's, compared every step */
 bool g_in_loop = false;
 TimeProps *g_tp = NULL;
 MatProps *g_mp = NULL;
@@ -85,6 +91,43 @@ void download_to_host(THashTable *P, bool all)
   }
 }
 
+/* lock-step: device table against the host's (pure reference) table at the end of a step */
+void lockstep_compare(THashTable *P)
+{
+  size_t n = 0, nhost = 0;
+  CK(psph_download(G, NULL, 0, &n, PSPH_ORDER_DEVICE));
+  g_rows.resize(n);
+  CK(psph_download(G, g_rows.data(), g_rows.size(), &n, PSPH_ORDER_DEVICE));
+  { THTIterator it(P); while (it.next()) nhost++; }
+  const char *names[] = { "coord", "vel", "smoothed_v", "rho", "engr", "mass_frac", "pressure", "smlen", "sound_speed", "temperature",
+                          "phase_density", "gamma", "specific_heat_p", "smoothed_e" };
+  const int NF = sizeof names / sizeof names[0];
+  double dmax[NF], smax[NF];
+  for (int f = 0; f < NF; f++) { dmax[f] = 0.; smax[f] = 0.; }
+  long long missing = 0, flags = 0;
+  for (size_t i = 0; i < n; i++) {
+    const psph_particle &r = g_rows[i];
+    Particle *p = (Particle *) P->lookup(r.key);
+    if (!p) { missing++; continue; }
+    if (r.bc_type != p->get_bc_type() || r.involved != p->get_involved() || r.phase_num != p->which_phase()) flags++;
+    psph_particle h;
+    to_row(p, &h);
+    const double *a[NF] = { r.coords, r.vel, r.smoothed_v, &r.rho, &r.engr, &r.mass_frac, &r.pressure, &r.smlen, &r.sound_speed,
+                            &r.temperature, r.phase_density, &r.gamma, &r.specific_heat_p, &r.smoothed_e };
+    const double *b[NF] = { h.coords, h.vel, h.smoothed_v, &h.rho, &h.engr, &h.mass_frac, &h.pressure, &h.smlen, &h.sound_speed,
+                            &h.temperature, h.phase_density, &h.gamma, &h.specific_heat_p, &h.smoothed_e };
+    const int len[NF] = { 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1 };
+    for (int f = 0; f < NF; f++)
+      for (int k = 0; k < len[f]; k++) {
+        dmax[f] = std::max(dmax[f], fabs(a[f][k] - b[f][k]));
+        smax[f] = std::max(smax[f], fabs(b[f][k]));
+      }
+  }
+  fprintf(stderr, "LOCKSTEP %d rows device=%zu host=%zu missing=%lld flags=%lld\n", g_step, n, nhost, missing, flags);
+  for (int f = 0; f < NF; f++)
+    fprintf(stderr, "LOCKSTEP %d %s %.3e\n", g_step, names[f], smax[f] > 0. ? dmax[f] / smax[f] : dmax[f]);
+}
+
 void make_config(THashTable *P, HashTable *BG)
 {
   psph_config_default_3d(&g_cfg);
@@ -98,7 +141,7 @@ void make_config(THashTable *P, HashTable *BG)
   c.alf = alf_P; c.beta = beta_P; c.ata = ata_P; c.g = ::g_P;  /* (ref_hooks.cc has a g_P of its own in the unnamed namespace) */ c.cfl = CFL_P; c.eta_smooth = eta_smooth_P;
   c.c_smooth = C_smooth_P; c.thresh = thresh_P; c.num_loop = num_loop_P;
   c.ng0 = ng0_P; c.Cvs = Cvs_P; c.Cvg = Cvg_P; c.Cva = Cva_P; c.Rg = Rg_P; c.Ra = Ra_P; c.rhoa0 = rhoa0_P; c.pa0 = pa0_P;
-  c.erupt_top = Ll_P[2]; c.smlen_real = g_sp->sml_of_phase2;                  /* update_pos.cc:137-142 */
+  c.erupt_top = Ll_P[2]; c.smlen_real = g_mp->smoothing_length;              /* update_pos.cc:40,141 (sic: not simprops->sml_of_phase2) */
   c.len_scale = g_mp->LENGTH_SCALE;
   c.del = PARTICLE_DENSITY * g_mp->smoothing_length * g_mp->LENGTH_SCALE;      /* preprocess.cc:99 */
   for (int d = 0; d < 3; d++) {
@@ -217,9 +260,15 @@ double psphb200_timestep(HashTable *BG, THashTable *P, TimeProps *tp)
   init_once();
   begin_step(P, 0);
   g_tp = tp; g_in_loop = true;
+  if (getenv("PSPH_LOCKSTEP")) { g_lock = true; g_dirty = true; }    /* the device restarts every step from the host's table */
   sync_up(P, BG);
   double dt = 0.;
   CK(psph_timestep(G, &dt));
+  if (g_lock) {
+    const double dth = timestep(BG, P, tp);
+    if (dth != dt) fprintf(stderr, "LOCKSTEP %d dt device %.17g host %.17g\n", g_step + 1, dt, dth);
+    dt = dth;
+  }
   g_step++;
   return dt;
 }
@@ -230,18 +279,48 @@ int psphb200_search_neighs_consth(int myid, THashTable *P, HashTable *BG)
   sync_up(P, BG);                                                     /* the adapt block may have changed the table */
   CK(psph_set_dt(G, g_tp->dtime, g_tp->step, g_tp->iferupt()));       /* incrtime has run (main.cc:231) */
   CK(psph_search_neighs(G));
+  if (g_lock) return search_neighs_consth(myid, P, BG);
   return 0;
 }
-void psphb200_adaptive_sml(int myid, THashTable *P) { (void) myid; (void) P; CK(psph_adaptive_sml(G)); }
+/* with PSPH_DUMP_DIR set and the step inside PSPH_DUMP_STEPS, the device state comes back after every stage and is dumped
+ * under the same names particler_hooked uses (profiles/dropin_diff.py finds the first stage where the two programs part) */
+void stage_dump(THashTable *P, const char *stage)
+{
+  if (!dumping() || g_lock) return;
+  download_to_host(P, true);
+  dump_table(P, stage, "post");
+}
+void psphb200_adaptive_sml(int myid, THashTable *P)
+{
+  CK(psph_adaptive_sml(G));
+  if (g_lock) adaptive_sml(myid, P);
+  stage_dump(P, "sml");
+}
 int psphb200_mom_engr_update(int myid, THashTable *P, TimeProps *tp, SimProps *sp)
-{ (void) myid; (void) P; (void) tp; (void) sp; int r = psph_mom_engr_update(G); if (r < 0) die("psph_mom_engr_update"); return r; }
-void psphb200_smooth_density(THashTable *P) { (void) P; CK(psph_smooth_density(G)); }
-void psphb200_smooth_velocity(THashTable *P) { (void) P; CK(psph_smooth_velocity(G)); }
-void psphb200_update_pos(THashTable *P, TimeProps *tp, MatProps *mp) { (void) P; (void) tp; (void) mp; CK(psph_update_pos(G)); }
+{
+  if (dumping() && !g_lock) { download_to_host(P, true); dump_table(P, "mom", "pre"); }
+  int r = psph_mom_engr_update(G);
+  if (r < 0) die("psph_mom_engr_update");
+  if (g_lock) {
+    const int rh = mom_engr_update(myid, P, tp, sp);
+    if (rh != r) fprintf(stderr, "LOCKSTEP %d mom_engr_update device %d host %d\n", g_step, r, rh);
+    return rh;
+  }
+  stage_dump(P, "mom");
+  return r;
+}
+void psphb200_smooth_density(THashTable *P) { CK(psph_smooth_density(G)); if (g_lock) smooth_density(P); stage_dump(P, "dens"); }
+void psphb200_smooth_velocity(THashTable *P) { CK(psph_smooth_velocity(G)); if (g_lock) smooth_velocity(P); stage_dump(P, "svel"); }
+void psphb200_update_pos(THashTable *P, TimeProps *tp, MatProps *mp)
+{
+  CK(psph_update_pos(G));
+  if (g_lock) update_pos(P, tp, mp);
+  stage_dump(P, "pos");
+}
 
 void psphb200_update_particles_in_bucket(int myid, THashTable *P, HashTable *BG, int *lost)
 {
-  download_to_host(P, false);                      /* positions, bc_type, smlen, involved of this step */
+  if (!g_lock) download_to_host(P, false);         /* positions, bc_type, smlen, involved of this step */
   update_particles_in_bucket(myid, P, BG, lost);   /* the reference's own bucket lists follow */
   int dlost = 0;
   CK(psph_rebin(G, &dlost));
@@ -268,7 +347,13 @@ int psphb200_apply_bcond(int myid, THashTable *P, HashTable *BG, MatProps *mp, l
   upload_images(BG, img);
   int r = psph_apply_bcond(G);
   if (r < 0) die("psph_apply_bcond");
+  if (g_lock) {
+    const int rh = apply_bcond(myid, P, BG, mp, img);
+    lockstep_compare(P);
+    return rh;
+  }
   download_to_host(P, true);                       /* end of the step: the host particles are current again */
+  dump_table(P, "bcond", "post");
   return r;
 }
 

@@ -13,30 +13,35 @@
 
 struct ImgKey { uint32_t k[3]; int32_t idx; };
 
-// rows that carry an image: binary search of the row's birth key among the sorted image keys
-__global__ void k_bc_match(Tab V, const StepState *ss, const ImgKey *__restrict__ keys, int nimg, int32_t *__restrict__ img_of_row,
-                           int32_t *__restrict__ list, int *__restrict__ count)
+// rows that carry an image: binary search of the row's birth key among the sorted image keys.  img_row[q] = the local
+// row (owned or guest) of image q's wall ghost; `list` collects the images this rank computes: all of them on a single
+// rank, with slabs those whose image point lies in a bucket this rank owns — the rank that holds every bucket around it
+// (the reference computes an image on the owner of its bucket too: buckproc, bcond.cc:53).
+__global__ void k_bc_match(Tab V, const StepState *ss, const ImgKey *__restrict__ keys, int nimg, int32_t *__restrict__ img_row,
+                           int32_t *__restrict__ list, int *__restrict__ count, const int32_t *__restrict__ img_cell,
+                           const int32_t *__restrict__ owner, int me)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ss->n) return;
-  int found = -1;
-  if (V.i[I_BC][p] == 2 && !V.i[I_GUEST][p]) {
-    const uint32_t k0 = (uint32_t) V.i[I_KEY0][p], k1 = (uint32_t) V.i[I_KEY1][p], k2 = (uint32_t) V.i[I_KEY2][p];
-    int lo = 0, hi = nimg;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const ImgKey &q = keys[mid];
-      const bool less = q.k[0] < k0 || (q.k[0] == k0 && (q.k[1] < k1 || (q.k[1] == k1 && q.k[2] < k2)));
-      if (less) lo = mid + 1; else hi = mid;
-    }
-    if (lo < nimg && keys[lo].k[0] == k0 && keys[lo].k[1] == k1 && keys[lo].k[2] == k2) found = keys[lo].idx;
+  if (V.i[I_BC][p] != 2 || V.i[I_CELL][p] < 0) return;
+  if (!owner && V.i[I_GUEST][p]) return;
+  const uint32_t k0 = (uint32_t) V.i[I_KEY0][p], k1 = (uint32_t) V.i[I_KEY1][p], k2 = (uint32_t) V.i[I_KEY2][p];
+  int lo = 0, hi = nimg;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const ImgKey &q = keys[mid];
+    const bool less = q.k[0] < k0 || (q.k[0] == k0 && (q.k[1] < k1 || (q.k[1] == k1 && q.k[2] < k2)));
+    if (less) lo = mid + 1; else hi = mid;
   }
-  img_of_row[p] = found;
-  if (found >= 0) list[atomicAdd(count, 1)] = p;
+  if (lo < nimg && keys[lo].k[0] == k0 && keys[lo].k[1] == k1 && keys[lo].k[2] == k2) {
+    const int q = keys[lo].idx;
+    img_row[q] = p;
+    if (!owner || owner[img_cell[q]] == me) list[atomicAdd(count, 1)] = q;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_apply_bcond(DevView V, GridView G, KParams K, const StepState *ss, const int32_t *__restrict__ list,
-                                                     const int *__restrict__ count, const int32_t *__restrict__ img_of_row,
+                                                     const int *__restrict__ count, const int32_t *__restrict__ img_row,
                                                      const double *__restrict__ img_coord, const int32_t *__restrict__ img_cell)
 {
   const int lane = threadIdx.x & 31;
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(256) k_apply_bcond(DevView V, GridView G, KPar
   const int n = *count;
   const double hmax = ss->hmax;
   for (int e = wglobal; e < n; e += nw) {
-    const int g = list[e], q = img_of_row[g];
+    const int q = list[e], g = img_row[q];
     const double rx = img_coord[3 * q], ry = img_coord[3 * q + 1], rz = img_coord[3 * q + 2];
     const int cl = img_cell[q];
     const int ck = cl % G.ncell[2], cj = (cl / G.ncell[2]) % G.ncell[1], ci = cl / (G.ncell[2] * G.ncell[1]);
@@ -119,8 +124,8 @@ extern "C" int psph_set_images(psph_ctx *ctx, const psph_image *img, size_t n)
 {
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(ctx->d_img_keys); cudaFree(ctx->d_img_coord); cudaFree(ctx->d_img_cell);
-  ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr;
+  cudaFree(ctx->d_img_keys); cudaFree(ctx->d_img_coord); cudaFree(ctx->d_img_cell); cudaFree(ctx->d_img_row);
+  ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr; ctx->d_img_row = nullptr;
   ctx->n_img = 0;
   if (!img || n == 0) return 0;
   std::vector<ImgKey> keys(n);
@@ -138,6 +143,7 @@ extern "C" int psph_set_images(psph_ctx *ctx, const psph_image *img, size_t n)
   PSPH_CUDA(cudaMalloc(&ctx->d_img_keys, n * sizeof(ImgKey)));
   PSPH_CUDA(cudaMalloc(&ctx->d_img_coord, 3 * n * sizeof(double)));
   PSPH_CUDA(cudaMalloc(&ctx->d_img_cell, n * sizeof(int32_t)));
+  PSPH_CUDA(cudaMalloc(&ctx->d_img_row, n * sizeof(int32_t)));
   PSPH_CUDA(cudaMemcpy(ctx->d_img_keys, keys.data(), n * sizeof(ImgKey), cudaMemcpyHostToDevice));
   PSPH_CUDA(cudaMemcpy(ctx->d_img_coord, coord.data(), 3 * n * sizeof(double), cudaMemcpyHostToDevice));
   PSPH_CUDA(cudaMemcpy(ctx->d_img_cell, cell.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -149,21 +155,31 @@ extern "C" int psph_apply_bcond(psph_ctx *ctx)
 {
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   if (ctx->cfg.dim != 3) return 0;                     // the 1-D loop has no wall ghosts (main.cc:676-751)
-  if (ctx->cfg.nranks > 1) { ctx->err = "psph_apply_bcond: single-rank only (images across slabs need a two-cell ghost layer)"; return -2; }
-  if (ctx->n_img == 0 || ctx->n == 0) return 0;
+  const bool slabs = ctx->cfg.nranks > 1;
+  const int32_t *owner = nullptr;
+  if (slabs && !(owner = psph_comm_owner_table(ctx))) { ctx->err = "psph_apply_bcond: psph_comm_init was not called"; return -2; }
+  if (ctx->n_img == 0) return 0;                       // (every rank holds the same image table: all return here together)
   StageTimer tm(ctx, ST_BCOND);
   if (!ctx->list_valid && psph_build_cell_list(ctx)) return -1;   // positions moved since the last list build
-  // scratch: image of every row, list of the rows that have one, their count (reuses the sort scratch, free here)
-  int32_t *img_of_row = reinterpret_cast<int32_t *>(ctx->d_sortkey), *list = reinterpret_cast<int32_t *>(ctx->d_perm);
+  // scratch: local row of every image's ghost, the images this rank computes, their count
+  int32_t *list = reinterpret_cast<int32_t *>(ctx->d_perm);
+  if ((size_t) ctx->n_img > ctx->cap && psph_reserve(ctx, ctx->n_img)) return -1;       // (the list lives in the sort scratch)
+  list = reinterpret_cast<int32_t *>(ctx->d_perm);
   int *count = &ctx->d_ss->work;
   PSPH_CUDA(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream));
-  k_bc_match<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, ctx->d_ss, (const ImgKey *) ctx->d_img_keys, ctx->n_img,
-                                                          img_of_row, list, count);
-  PSPH_LAUNCH_CHECK();
-  const int grid = std::min((ctx->n_img + 7) / 8, ctx->sms * 8);
-  k_apply_bcond<<<grid, 256, 0, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, list, count, img_of_row, ctx->d_img_coord,
-                                               ctx->d_img_cell);
-  PSPH_LAUNCH_CHECK();
+  PSPH_CUDA(cudaMemsetAsync(ctx->d_img_row, 0xff, (size_t) ctx->n_img * sizeof(int32_t), ctx->stream));
+  if (ctx->n > 0) {
+    k_bc_match<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, ctx->d_ss, (const ImgKey *) ctx->d_img_keys, ctx->n_img,
+                                                            ctx->d_img_row, list, count, ctx->d_img_cell, owner, ctx->cfg.rank);
+    PSPH_LAUNCH_CHECK();
+    const int grid = std::min((ctx->n_img + 7) / 8, ctx->sms * 8);
+    k_apply_bcond<<<grid, 256, 0, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, list, count, ctx->d_img_row,
+                                                 ctx->d_img_coord, ctx->d_img_cell);
+    PSPH_LAUNCH_CHECK();
+  }
+  // slabs: a ghost whose image this rank computed may be another rank's row (here a guest copy): the state goes back to
+  // its owner (move_bnd_images, move_bnd_img.cc:32-210), whose next ghost refresh hands it to everybody
+  if (slabs && psph_comm_return_images(ctx, ctx->d_img_row, ctx->d_img_cell, ctx->n_img)) return -1;
   psph_comm_mark(ctx, DIRTY_MOM | DIRTY_DENS);
   return 0;
 }

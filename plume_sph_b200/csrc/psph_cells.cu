@@ -42,7 +42,7 @@ __global__ void k_make_keys(Tab V, GridView G, StepState *ss, int n_cap, uint32_
   if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
 }
 
-__global__ void k_reset_list_scalars(StepState *ss) { ss->hmax_bits = 0ull; ss->n_need = 0; ss->n_grad = 0; ss->xmax_bits = 0u; }
+__global__ void k_reset_list_scalars(StepState *ss) { ss->hmax_bits = 0ull; ss->n_need = 0; ss->n_grad = 0; ss->xmax_bits = 0u; ss->n_std = 0; }
 
 // after the sort: number of live rows = first row whose key is inf_key
 __global__ void k_count_live(const uint32_t *__restrict__ key, int n_cap, uint32_t inf_key, StepState *ss)
@@ -77,13 +77,17 @@ __global__ void k_sub_table(const uint32_t *__restrict__ key, const StepState *s
   sub_start[e] = lo;
 }
 
-// bucket "has a ghost particle" flags (neighs.cc:69)
-__global__ void k_ghost_cells(Tab V, const StepState *ss, uint8_t *__restrict__ has_ghost)
+// bucket "has a ghost particle" flags (neighs.cc:69) and the largest smoothing length of every bucket (the mixed-h pair
+// search bounds a row's reach by the largest h a partner can have: a partner sits in one of the 27 buckets around it)
+__global__ void k_ghost_cells(Tab V, const StepState *ss, uint8_t *__restrict__ has_ghost, unsigned long long *__restrict__ cell_hmax)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ss->n) return;
   int b = V.i[I_BC][p];
-  if (b == 0 || b == 1 || b == 2) has_ghost[V.i[I_CELL][p]] = 1;
+  const int cell = V.i[I_CELL][p];
+  if (b == 0 || b == 1 || b == 2) has_ghost[cell] = 1;
+  const unsigned long long hb = (unsigned long long) __double_as_longlong(V.d[D_H][p]);
+  if (hb > cell_hmax[cell]) atomicMax(&cell_hmax[cell], hb);
 }
 
 // per-row flag word, geometry record, packed subcell coordinates, h at list-build time
@@ -133,6 +137,10 @@ __global__ void k_row_flags(DevView V, GridView G, KParams K, StepState *ss, int
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   float xm = 0.f;
   if (p < n_cap) xm = row_flags(V, G, K, ss, p);
+  // summed rows that carry the table's standard (largest) smoothing length: what k_pair_mode decides on
+  const bool std_h = p < ss->n && (V.flags[p] & F_NEED) && V.t.d[D_H][p] == ss->hmax;
+  const unsigned sb = __ballot_sync(0xffffffffu, std_h);
+  if ((threadIdx.x & 31) == 0 && sb) atomicAdd(&ss->n_std, __popc(sb));
   // bound of the FP32 rounding error of the geo32 records (positive floats order like their bit patterns)
   for (int o = 16; o; o >>= 1) xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, o));
   if ((threadIdx.x & 31) == 0 && xm > 0.f) atomicMax(&ss->xmax_bits, __float_as_uint(xm));
@@ -209,14 +217,16 @@ int psph_build_cell_list(psph_ctx *ctx)
   k_sub_table<<<(unsigned) ((nent + 1 + 255) / 256), 256, 0, s>>>(ctx->d_sortkey_alt, ctx->d_ss, nent, ctx->d_sub_start);
   PSPH_LAUNCH_CHECK();
   PSPH_CUDA(cudaMemsetAsync(ctx->d_cell_has_ghost, 0, ctx->ncells, s));
+  PSPH_CUDA(cudaMemsetAsync(ctx->d_cell_hmax, 0, ctx->ncells * sizeof(unsigned long long), s));
   if (n_cap > 0) {
-    k_ghost_cells<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur.t, ctx->d_ss, ctx->d_cell_has_ghost);
+    k_ghost_cells<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur.t, ctx->d_ss, ctx->d_cell_has_ghost, ctx->d_cell_hmax);
     PSPH_LAUNCH_CHECK();
     k_row_flags<<<(n_cap + 255) / 256, 256, 0, s>>>(ctx->cur, G, ctx->kp, ctx->d_ss, n_cap);
     PSPH_LAUNCH_CHECK();
     if (select_rows(ctx, n_cap, F_NEED, ctx->cur.need_idx, &ctx->d_ss->n_need)) return -1;
     if (ctx->has_grad && select_rows(ctx, n_cap, F_GRADROW, ctx->cur.grad_idx, &ctx->d_ss->n_grad)) return -1;
   }
+  if (psph_pair_mode(ctx)) return -1;
   ctx->list_valid = true;
   ctx->nbr_valid = false;
   ctx->n_dirty = true;

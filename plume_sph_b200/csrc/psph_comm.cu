@@ -505,7 +505,104 @@ int refresh_columns(psph_ctx *ctx, const ColList &cl)
   return 0;
 }
 
+// ---- apply_bcond across slabs -------------------------------------------------------------------------------------
+// image q is computed by the owner of its bucket (psph_bcond.cu); when the wall ghost it belongs to is another rank's row,
+// the computing rank holds a guest copy and the state travels back to the owner.  Both sides enumerate the images in
+// ascending q, so the payload needs no keys.
+struct ImgToPeer     // computed here, ghost owned by rank r
+{
+  const int32_t *img_row, *img_cell, *guest, *myproc, *owner; int me, r;
+  __device__ __forceinline__ bool operator()(int q) const
+  {
+    const int row = img_row[q];
+    return row >= 0 && owner[img_cell[q]] == me && guest[row] && myproc[row] == r;
+  }
+};
+struct ImgFromPeer   // ghost owned here, computed by rank r
+{
+  const int32_t *img_row, *img_cell, *guest, *owner; int r;
+  __device__ __forceinline__ bool operator()(int q) const
+  {
+    const int row = img_row[q];
+    return row >= 0 && !guest[row] && owner[img_cell[q]] == r;
+  }
+};
+__global__ void k_img_counts(const int32_t *__restrict__ img_row, const int32_t *__restrict__ img_cell, const int32_t *__restrict__ guest,
+                             const int32_t *__restrict__ myproc, const int32_t *__restrict__ owner, int me, int n_img, int *__restrict__ counts)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_img) return;
+  const int row = img_row[q];
+  if (row >= 0 && owner[img_cell[q]] == me && guest[row] && myproc[row] != me) atomicAdd(&counts[myproc[row]], 1);
+}
+__global__ void k_img_to_rows(int32_t *__restrict__ idx, int cnt, const int32_t *__restrict__ img_row)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < cnt) idx[t] = img_row[idx[t]];
+}
+
 } // namespace
+
+int psph_comm_return_images(psph_ctx *ctx, const int32_t *img_row, const int32_t *img_cell, int n_img)
+{
+  Comm *C = comm_of(ctx);
+  if (!C) return 0;
+  const int P = C->P, me = C->me;
+  const int32_t *guest = ctx->cur.t.i[I_GUEST], *myproc = ctx->cur.t.i[I_MYPROC];
+  PSPH_CUDA(cudaMemsetAsync(C->d_counts, 0, P * sizeof(int), ctx->stream));
+  k_img_counts<<<(n_img + 255) / 256, 256, 0, ctx->stream>>>(img_row, img_cell, guest, myproc, C->d_owner, me, n_img, C->d_counts);
+  PSPH_LAUNCH_CHECK();
+  if (share_counts(ctx)) return -1;
+  std::vector<int> sc(P, 0), rc(P, 0);
+  size_t ns = 0, nr = 0;
+  for (int q = 0; q < P; q++) {
+    if (q == me) continue;
+    sc[q] = C->h_allcounts[me * P + q]; rc[q] = C->h_allcounts[q * P + me];
+    ns += sc[q]; nr += rc[q];
+  }
+  bool any = false;
+  for (int k = 0; k < P * P; k++) any = any || C->h_allcounts[k] != 0;
+  if (!any) return 0;                                    // every rank sees the same table: all leave together
+  ColList cl; cl.ni = 0; cl.nd = 0;
+  const int cols[] = { D_RHO, D_VX, D_VY, D_VZ, D_E, D_KS, D_P, D_GAMMA, D_C, D_T, D_CP, D_RPH0, D_RPH1 };
+  for (int c : cols) cl.d[cl.nd++] = c;
+  const size_t rb = row_bytes(cl);
+  if (ensure_idx_lists(ctx, ns, nr)) return -1;
+  C->lists_stale = true;                                 // the ghost-refresh row lists shared these buffers
+  size_t sbytes = 0, rbytes = 0;
+  for (int q = 0; q < P; q++) { sbytes += seg_bytes(sc[q], rb); rbytes += seg_bytes(rc[q], rb); }
+  if (ensure_bytes(ctx, C->d_sendbuf, C->sendbuf_cap, sbytes)) return -1;
+  if (ensure_bytes(ctx, C->d_recvbuf, C->recvbuf_cap, rbytes)) return -1;
+  size_t so = 0, si = 0, ri = 0;
+  for (int q = 0; q < P; q++) {
+    if (q == me) continue;
+    if (sc[q]) {
+      ImgToPeer p = { img_row, img_cell, guest, myproc, C->d_owner, me, q };
+      if (select_into(ctx, n_img, p, C->d_send_idx + si, &C->d_counts[q])) return -1;
+      k_img_to_rows<<<(sc[q] + 255) / 256, 256, 0, ctx->stream>>>(C->d_send_idx + si, sc[q], img_row);
+      PSPH_LAUNCH_CHECK();
+      k_pack_rows<<<(sc[q] + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, C->d_send_idx + si, sc[q], cl, C->d_sendbuf + so);
+      PSPH_LAUNCH_CHECK();
+      so += seg_bytes(sc[q], rb); si += sc[q];
+    }
+    if (rc[q]) {
+      ImgFromPeer p = { img_row, img_cell, guest, C->d_owner, q };
+      if (select_into(ctx, n_img, p, C->d_recv_idx + ri, &C->d_counts[q])) return -1;
+      k_img_to_rows<<<(rc[q] + 255) / 256, 256, 0, ctx->stream>>>(C->d_recv_idx + ri, rc[q], img_row);
+      PSPH_LAUNCH_CHECK();
+      ri += rc[q];
+    }
+  }
+  if (exchange_buffers(ctx, sc, rc, rb)) return -1;
+  size_t ro = 0; ri = 0;
+  for (int q = 0; q < P; q++) {
+    if (q == me || !rc[q]) continue;
+    k_unpack_rows<<<(rc[q] + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, C->d_recv_idx + ri, 0, rc[q], cl, C->d_recvbuf + ro, -2, me);
+    PSPH_LAUNCH_CHECK();
+    ro += seg_bytes(rc[q], rb); ri += rc[q];
+  }
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------
 void psph_comm_destroy(psph_ctx *ctx)
@@ -558,6 +655,8 @@ extern "C" int psph_comm_init(psph_ctx *ctx, const void *nccl_unique_id, size_t 
   C->dirty = DIRTY_LAYOUT;
   return update_owner_tables(ctx);
 }
+
+const int32_t *psph_comm_owner_table(psph_ctx *ctx) { return comm_of(ctx) ? comm_of(ctx)->d_owner : nullptr; }
 
 // the stages tell the exchange what they changed
 void psph_comm_mark(psph_ctx *ctx, unsigned what) { if (comm_of(ctx)) comm_of(ctx)->dirty |= what; }

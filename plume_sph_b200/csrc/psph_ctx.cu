@@ -141,6 +141,7 @@ GridView psph_grid_view(const psph_ctx *ctx)
   G.inv_subw = 1.0 / (ctx->cfg.del / (ctx->cfg.len_scale * SUBDIV));
   G.cell2rank = ctx->d_cell2rank; G.rank2cell = ctx->d_rank2cell; G.sub_start = ctx->d_sub_start;
   G.cell_has_ghost = ctx->d_cell_has_ghost;
+  G.cell_hmax = ctx->d_cell_hmax;
   G.attr = ctx->d_attr;
   return G;
 }
@@ -192,7 +193,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     const char *tw = getenv("PSPH_TWARPS");
     ctx->tile_shape = tw ? atoi(tw) : 0;
     const char *nb = getenv("PSPH_NBR");
-    ctx->nbr_mode = nb ? atoi(nb) : 2;
+    ctx->nbr_mode = nb ? atoi(nb) : 5;
+    ctx->mix_rows = 0; ctx->mix_wanted = ctx->nbr_mode == 4; ctx->h_unknown = true;
     const char *sc = getenv("PSPH_SCAN");
     ctx->scan_mode = sc ? atoi(sc) : 2;
     const char *dn = getenv("PSPH_DENSNEAR");
@@ -200,7 +202,7 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     const char *wc = getenv("PSPH_WCACHE");
     ctx->wcache = wc ? atoi(wc) : 1;
     ctx->has_erupt = false; ctx->d_erupt_boxes = nullptr; ctx->n_erupt_boxes = 0;
-    ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr; ctx->n_img = 0;
+    ctx->d_img_keys = nullptr; ctx->d_img_coord = nullptr; ctx->d_img_cell = nullptr; ctx->d_img_row = nullptr; ctx->n_img = 0;
     ctx->nbr_units = 0; ctx->nbr_want_tried = 0; ctx->nbr_valid = false; ctx->nbr_kind = 0;
   }
   ctx->timing = 0; memset(ctx->stage_ms, 0, sizeof ctx->stage_ms);
@@ -222,6 +224,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
   PSPH_CUDA(cudaMemset(ctx->d_blk_any, 0, ctx->ncells * 4));
   PSPH_CUDA(cudaMalloc(&ctx->d_cell_has_ghost, ctx->ncells));
   PSPH_CUDA(cudaMemset(ctx->d_cell_has_ghost, 0, ctx->ncells));
+  PSPH_CUDA(cudaMalloc(&ctx->d_cell_hmax, ctx->ncells * sizeof(unsigned long long)));
+  PSPH_CUDA(cudaMemset(ctx->d_cell_hmax, 0, ctx->ncells * sizeof(unsigned long long)));
   PSPH_CUDA(cudaMalloc(&ctx->d_ss, sizeof(StepState)));
   PSPH_CUDA(cudaMemset(ctx->d_ss, 0, sizeof(StepState)));
   PSPH_CUDA(cudaMallocHost(&ctx->h_ss, sizeof(StepState)));
@@ -248,12 +252,12 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   free_tab(ctx->cur.t); free_tab(ctx->alt);
   for (int c = 0; c < NSCRATCH; c++) cudaFree(ctx->cur.scr[c]);
   for (int c = 0; c < NREC; c++) cudaFree(ctx->cur.rec[c]);
-  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.wts); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.near); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
+  cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.wts); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.near); cudaFree(ctx->cur.mlist); cudaFree(ctx->cur.mseg); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
-  cudaFree(ctx->d_cell_has_ghost); cudaFree(ctx->d_blk_any);
+  cudaFree(ctx->d_cell_has_ghost); cudaFree(ctx->d_cell_hmax); cudaFree(ctx->d_blk_any);
   cudaFree(ctx->d_erupt_boxes);
-  cudaFree(ctx->d_img_keys); cudaFree(ctx->d_img_coord); cudaFree(ctx->d_img_cell);
+  cudaFree(ctx->d_img_keys); cudaFree(ctx->d_img_coord); cudaFree(ctx->d_img_cell); cudaFree(ctx->d_img_row);
   cudaFree(ctx->d_sortkey); cudaFree(ctx->d_sortkey_alt); cudaFree(ctx->d_perm); cudaFree(ctx->d_perm_alt);
   cudaFree(ctx->d_cub_tmp); cudaFree(ctx->d_ss); cudaFreeHost(ctx->h_ss);
   cudaFree(ctx->d_aos);
@@ -318,7 +322,7 @@ int psph_reserve(psph_ctx *ctx, size_t rows)
   if (grow(ctx, ctx->cur.geo32, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.nbr_off, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.nbr_cnt, 0, ncap)) return -1;
-  if (grow(ctx, ctx->cur.near, 0, ncap * 8)) return -1;
+  if (grow(ctx, ctx->cur.near, 0, ncap * NEARW)) return -1;
   ctx->nbr_valid = false;
   if (grow(ctx, ctx->cur.flags, 0, ncap)) return -1;
   if (grow(ctx, ctx->cur.gsub, 0, ncap)) return -1;
@@ -420,6 +424,7 @@ int psph_sync_n(psph_ctx *ctx)
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->n = ctx->h_ss->n;
     ctx->n_dirty = false;
+    if (ctx->h_ss->pair_mode == 4) ctx->mix_wanted = true;   // per-row smoothing lengths arrived with the rows
   }
   return 0;
 }
@@ -444,6 +449,7 @@ static int upload_at(psph_ctx *ctx, const void *rows, size_t n, size_t base, siz
     PSPH_LAUNCH_CHECK();
   }
   psph_comm_mark(ctx, DIRTY_LAYOUT);
+  ctx->h_unknown = true;
   ctx->n = (int) (base + n);
   ctx->h_ss->n = ctx->n;
   PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->n, &ctx->h_ss->n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -571,6 +577,7 @@ extern "C" int psph_upload_device_soa(psph_ctx *ctx, const double *const *cols, 
     PSPH_LAUNCH_CHECK();
   }
   psph_comm_mark(ctx, DIRTY_LAYOUT);
+  ctx->h_unknown = true;
   ctx->n = (int) n; ctx->h_ss->n = ctx->n;
   PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->n, &ctx->h_ss->n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   PSPH_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -54,7 +54,7 @@ __device__ void dev_hsfc3d(const double nc[3], uint32_t key[2])
 constexpr int ERUPT_THREADS = 256;
 constexpr int ERUPT_MAX_PER_COL = 64;         // particles one column can inject per call that are tracked in the mask
 __global__ void __launch_bounds__(ERUPT_THREADS) k_add_erupt(Tab V, GridView G, KParams K, StepState *ss, EruptPar P,
-                                                             const double *__restrict__ boxes)
+                                                             const double *__restrict__ boxes, const int32_t *__restrict__ owner)
 {
   __shared__ int s_warp[ERUPT_THREADS / 32], s_base;
   const int ny = P.nyp + P.nym, ncol = (P.nxp + P.nxm) * ny;
@@ -97,6 +97,14 @@ __global__ void __launch_bounds__(ERUPT_THREADS) k_add_erupt(Tab V, GridView G, 
       for (int b = 0; b < P.nbox && !inside; b++) {
         const double *mn = boxes + 6 * b, *mx = mn + 3;
         inside = x <= mx[0] && x >= mn[0] && y <= mx[1] && y >= mn[1] && z <= mx[2] && z >= mn[2];
+      }
+      // key-range slabs: every rank runs every column (as every MPI rank of the reference does, :456-600) and keeps the
+      // particles born in a bucket it owns; the others' copies arrive with the next ghost refresh
+      if (inside && owner) {
+        const double crd[3] = { x, y, z };
+        int idx[3];
+        for (int d = 0; d < 3; d++) idx[d] = dev_cell_index(G, d, crd[d]);
+        inside = owner[(idx[0] * G.ncell[1] + idx[1]) * G.ncell[2] + idx[2]] == P.rank;
       }
       if (inside) keep |= 1ull << i;
     }
@@ -166,7 +174,8 @@ extern "C" int psph_add_new_erupt(psph_ctx *ctx, double time, double dt, uint32_
   if (added) *added = 0;
   if (ctx->cfg.dim != 3) return 0;                                   // the 1-D loop has no eruption (main.cc:676-751)
   if (!ctx->has_erupt) { ctx->err = "psph_add_new_erupt: psph_set_erupt has not been called"; return -2; }
-  if (ctx->cfg.nranks > 1) { ctx->err = "psph_add_new_erupt: single-rank only in this version"; return -2; }
+  const int32_t *owner = nullptr;                                    // slabs: owner rank of every cell
+  if (ctx->cfg.nranks > 1 && !(owner = psph_comm_owner_table(ctx))) { ctx->err = "psph_add_new_erupt: psph_comm_init was not called"; return -2; }
   const psph_erupt &e = ctx->erupt;
   EruptPar P;
   P.e = e;
@@ -192,7 +201,7 @@ extern "C" int psph_add_new_erupt(psph_ctx *ctx, double time, double dt, uint32_
   P.dt = dt; P.add_step = add_step;
   P.base = base; P.cap = (int) std::min<size_t>(ctx->cap, 0x7fffffff); P.rank = ctx->cfg.rank; P.has_grad = ctx->has_grad;
   P.nbox = ctx->n_erupt_boxes;
-  k_add_erupt<<<1, ERUPT_THREADS, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), ctx->kp, ctx->d_ss, P, ctx->d_erupt_boxes);
+  k_add_erupt<<<1, ERUPT_THREADS, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), ctx->kp, ctx->d_ss, P, ctx->d_erupt_boxes, owner);
   PSPH_LAUNCH_CHECK();
   psph_comm_mark(ctx, DIRTY_LAYOUT);
   ctx->n = base + (int) (ncol * per_col);                            // upper bound until the count is read back

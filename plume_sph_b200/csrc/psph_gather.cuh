@@ -189,9 +189,11 @@ __device__ __forceinline__ double dev_weight_pre(double r2, double ninvh2, doubl
 //   bool  end(V,K,ss,i,I&,A&,pass,lane) warp-reduce + write; true = run another pass
 // Rows that must not contribute to a stage's sums (contr_dens / contr_vel_smooth false) carry
 // zeros in the stage record, so the scan phase needs no flag word.
-template <int DIM, class S>
+// OVF: only the rows whose near list overflowed in this step's mom_engr_update (smooth_density: the rows k_dens_near left)
+template <int DIM, class S, bool OVF = false>
 __global__ void __launch_bounds__(S::kWarps * 32, 1) k_gather(DevView V, GridView G, KParams K, StepState *ss)
 {
+  if (OVF && ss->n_near_ovf == 0) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   WarpScratch *s_scr = reinterpret_cast<WarpScratch *>(s_raw);
   constexpr int CHUNK = S::kWarps * RPW;
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(S::kWarps * 32, 1) k_gather(DevView V, GridVie
     for (int r = 0; r < RPW; r++) {
       if (e0 + r >= cnt) break;
       const int i = __ldg(&rows[e0 + r]);
+      if (OVF && (V.nbr_cnt[i] < 0 || V.near[NEARW * i] != NEAR_OVF)) continue;
       typename S::I st;
       S::init(V, K, ss, i, st);
       const double4 gi = V.geo[i];
@@ -365,21 +368,21 @@ __global__ void __launch_bounds__(S::kWarps * 32, 1) k_gather(DevView V, GridVie
   }
 }
 
-template <int DIM, class S>
+template <int DIM, class S, bool OVF = false>
 int launch_gather_d(psph_ctx *ctx, int kid)
 {
   constexpr int threads = S::kWarps * 32;
   constexpr size_t smem = sizeof(WarpScratch) * S::kWarps;
   // the attribute is per device, and a process may drive several devices (one context each): set it at every launch
-  PSPH_CUDA(cudaFuncSetAttribute(k_gather<DIM, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  PSPH_CUDA(cudaFuncSetAttribute(k_gather<DIM, S, OVF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   static int per_sm = 0; // resident CTAs per SM of this instantiation: the grid is one persistent wave
   if (per_sm == 0 &&
-      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather<DIM, S>, threads, smem) != cudaSuccess || per_sm < 1))
+      (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather<DIM, S, OVF>, threads, smem) != cudaSuccess || per_sm < 1))
     per_sm = 1;
   KernelTimer kt(ctx, kid);
   int nchunks = (ctx->n + S::kWarps * RPW - 1) / (S::kWarps * RPW);
   int grid = min(max(nchunks, 1), ctx->sms * per_sm);
-  k_gather<DIM, S><<<grid, threads, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss);
+  k_gather<DIM, S, OVF><<<grid, threads, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   return 0;
 }

@@ -64,6 +64,7 @@ k_tile_scan2(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__r
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Scan2Warp &W = reinterpret_cast<Scan2Warp *>(s_raw + sizeof(CellTable))[warp < WORK ? warp : 0];
   __shared__ int s_any[4];
+  if (ss->pair_mode != 2) return;              // the step runs on another pair path (k_pair_mode)
   unsigned s_geo, s_cslot;                     // 32-bit shared-window addresses (one base register each)
   asm volatile("mov.u32 %0, %1;" : "=r"(s_geo) : "r"((unsigned) __cvta_generic_to_shared(&T.geo[0])));
   asm volatile("mov.u32 %0, %1;" : "=r"(s_cslot) : "r"((unsigned) __cvta_generic_to_shared(&W.cslot[0])));

@@ -2,7 +2,7 @@
 // timestep, adaptive_sml, mom_engr_update, smooth_density, smooth_velocity, update_pos and the
 // fused step driver.  Every stage cites the reference code it replaces; the C ABI is
 // include/psph.h.  Pair sums run on the warp gather of psph_gather.cuh.
-#include "psph_scan2.cuh"
+#include "psph_mix.cuh"
 #include <cstring>
 #include <algorithm>
 
@@ -44,16 +44,42 @@ __global__ void k_hmax_scan(Tab V, StepState *ss)
   for (int o = 16; o; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
   if ((threadIdx.x & 31) == 0 && h > 0.0) atomicMax(&ss->hmax_bits, (unsigned long long) __double_as_longlong(h));
 }
-__global__ void k_refresh_geo(DevView V, KParams K, StepState *ss)
+__global__ void k_refresh_geo(DevView V, KParams K, StepState *ss, unsigned long long *__restrict__ cell_hmax)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= ss->n) return;
-  const double h = V.t.d[D_H][p];
-  const double x = V.t.d[D_X][p], y = V.t.d[D_Y][p], z = V.t.d[D_Z][p];
-  V.geo[p] = make_double4(x, y, z, h);
-  dev_store_geo32(V.geo32, K, p, x, y, z, h, ss->hmax); // positions are those of the list build: xmax_bits still bounds them
+  bool std_h = false;
+  if (p < ss->n) {
+    const double h = V.t.d[D_H][p];
+    const int cell = V.t.i[I_CELL][p];
+    const unsigned long long hb = (unsigned long long) __double_as_longlong(h);
+    if (cell >= 0 && hb > cell_hmax[cell]) atomicMax(&cell_hmax[cell], hb);
+    const double x = V.t.d[D_X][p], y = V.t.d[D_Y][p], z = V.t.d[D_Z][p];
+    V.geo[p] = make_double4(x, y, z, h);
+    dev_store_geo32(V.geo32, K, p, x, y, z, h, ss->hmax); // positions are those of the list build: xmax_bits still bounds them
+    std_h = (V.flags[p] & F_NEED) && h == ss->hmax;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, std_h);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ss->n_std, __popc(b));
 }
-__global__ void k_hmax_reset(StepState *ss) { ss->hmax_bits = 0ull; }
+__global__ void k_hmax_reset(StepState *ss) { ss->hmax_bits = 0ull; ss->n_std = 0; }
+// The pair path of the step (StepState::pair_mode), decided where the data is: block tiles need one standard smoothing
+// length in a row's whole neighbourhood, so they serve the table while most summed rows carry it (every step before the
+// first adaptive_sml call); after that every row has its own h and the sub-tiled mixed-h gather takes over.
+// forced: 2 / 4 = that path whatever the table looks like, 0 = decide, -1 = neither (legacy list modes, host-driven)
+__global__ void k_pair_mode(StepState *ss, int forced, int dens_near)
+{
+  int mode = forced > 0 ? forced : (forced == 0 ? (2LL * ss->n_std >= ss->n_need ? 2 : 4) : 0);
+  if (mode == 4 && !dens_near) mode = 0;       // (the mixed-h gather has no density pass of its own: PSPH_DENSNEAR=0 -> fused gather)
+  ss->pair_mode = mode;
+}
+// a step on neither tile path: no row has a list, the fused grouped gather sums them all
+__global__ void k_no_lists(DevView V, StepState *ss)
+{
+  if (ss->pair_mode == 2 || ss->pair_mode == 4) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) ss->n_uncached = ss->n_need;
+  if (p < ss->n) V.nbr_cnt[p] = -1;
+}
 __global__ void k_hmax_finish(StepState *ss) { ss->hmax = __longlong_as_double((long long) ss->hmax_bits); }
 
 // mom_engr_update: rec0 = {m, p*V*V, V, rho}  rec1 = {c, Cp, T, -}  rec2 = {u_x, u_y, u_z, -}
@@ -147,6 +173,7 @@ struct DensStage
   static constexpr int kWCache = 2, kNCc = kNC;
   static constexpr bool kCachedNeedsX = true;
   static constexpr bool kSkipUnlessFull = true;                      // k_dens_near serves the listed rows unless ss->dens_full
+  static constexpr int kNAm = 0;                                     // no pass of its own in the mixed-h gather (psph_mix.cuh)
   static __device__ __forceinline__ void tile_load(const DevView &V, int row, double *c, int t)
   { const double4 r = ld_rec(V.rec[0], row); c[3 * TCAP + t] = r.w != 0.0 ? -r.x : r.x; c[4 * TCAP + t] = r.y; c[5 * TCAP + t] = r.z; }
   static __device__ __forceinline__ R tile_rec(const double *c, int t)
@@ -247,27 +274,35 @@ struct DensStage
 // the few partners inside the energy-smoothing kernel (V.near).  What is left for this stage is the row's own
 // term and the energy sums (:163-168) over those partners with the energies mom_engr_update committed: one
 // thread per row, no pass over the pair lists at all.
+// UNI: every listed row carries the table's standard smoothing length (block tiles, pair_mode 2); otherwise the rows
+// have their own (sub-tiled mixed-h gather, pair_mode 4) and a pair's h is (h_i + h_j) / 2.  A row whose near list
+// overflowed (count NEAR_OVF) is left to k_gather<DensStage, OVF>.
+template <bool UNI>
 __global__ void k_dens_near(DevView V, KParams K, StepState *ss)
 {
+  if (ss->pair_mode != (UNI ? 2 : 4)) return;
   if (ss->dens_full) return;                                        // the tile gather sums these rows off their lists
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ss->n || !(V.flags[p] & F_NEED) || V.nbr_cnt[p] < 0) return;
+  const int n = V.near[NEARW * p];
+  if (n == NEAR_OVF) return;
   typedef DensStage<3> S;
   S::I st;
-  S::tile_uni(K, ss->hmax, st);
+  if (UNI) S::tile_uni(K, ss->hmax, st);
+  else S::init(V, K, ss, p, st);
   S::A acc;
   S::begin(K, st, acc, 0);
   const double4 gi = V.geo[p];
   S::R ri = S::load(V, p);
   double r1 = V.scr[4][p], r2 = V.scr[5][p];
-  const double wm = dev_weight_pre(0.0, st.ninvh2, st.norm) * ri.r0.x;   // the row itself (:159-161)
+  // the row itself (:159-161)
+  const double wm = (UNI ? dev_weight_pre(0.0, st.ninvh2, st.norm) : dev_weight_in<3>(0.0, dev_rcp(st.h))) * ri.r0.x;
   if (ri.r0.w != 0.0) r2 += wm; else r1 += wm;
-  S::pair_inner<true>(K, st, acc, 0.0, 0.0, 0.0, st.h, ri);
-  const int n = V.near[8 * p];
+  S::pair_inner<UNI>(K, st, acc, 0.0, 0.0, 0.0, st.h, ri);
   for (int k = 0; k < n; k++) {
-    const int j = V.near[8 * p + 1 + k];
+    const int j = V.near[NEARW * p + 1 + k];
     const double4 gj = V.geo[j];
-    S::pair_inner<true>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, st.h, S::load(V, j));
+    S::pair_inner<UNI>(K, st, acc, gi.x - gj.x, gi.y - gj.y, gi.z - gj.z, gj.w, S::load(V, j));
   }
   const double rho = r1 + r2;                                       // :268-273
   V.scr[0][p] = rho;
@@ -422,19 +457,65 @@ struct MomStage
     a.re += 0.5 * mg * vr + heat;
     return w;
   }
+  // explicit Euler update of the row from its summed right-hand sides (:340-354)
+  static __device__ __forceinline__ void finish(const DevView &V, const KParams &K, StepState *ss, int i, const I &s, double r0,
+                                                double r1, double r2, double re)
+  {
+    const double dt = ss->dt, grav = -K.g;
+    double un[3] = { s.v0[0] + dt * r0, s.v0[1] + dt * r1, s.v0[2] + dt * r2 };
+    un[DIM - 1] += dt * grav;                                       // :350
+    V.scr[0][i] = un[0]; V.scr[1][i] = un[1]; V.scr[2][i] = un[2];
+    V.scr[3][i] = s.e0 + dt * (re + s.u[DIM - 1] * grav);           // :354
+    if (!(s.rho > 0)) atomicAdd(&ss->bad, 1);
+  }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &K, StepState *ss, int i, I &s, A &a, int, int lane)
   {
     double r0 = a.rv[0], r1 = DIM == 3 ? a.rv[1] : 0.0, r2 = DIM == 3 ? a.rv[2] : 0.0, re = a.re;
     warp_sum4(r0, r1, r2, re, lane);
-    if (lane == 0) {
-      const double dt = ss->dt, grav = -K.g;
-      double un[3] = { s.v0[0] + dt * r0, s.v0[1] + dt * r1, s.v0[2] + dt * r2 };
-      un[DIM - 1] += dt * grav;                                     // :350
-      V.scr[0][i] = un[0]; V.scr[1][i] = un[1]; V.scr[2][i] = un[2];
-      V.scr[3][i] = s.e0 + dt * (re + s.u[DIM - 1] * grav);         // :354
-      if (!(s.rho > 0)) atomicAdd(&ss->bad, 1);
-    }
+    if (lane == 0) finish(V, K, ss, i, s, r0, r1, r2, re);
     return false;
+  }
+  // ---- sub-tiled mixed-h gather (psph_mix.cuh): seven arrays of 16-byte elements as above, then the partner's own h
+  static constexpr int kNCm = 15, kNAm = 6;
+  static constexpr unsigned kTagMix = MTAG_SYM;
+  static __device__ __forceinline__ double2 &tm(double *c, int p, int t) { return reinterpret_cast<double2 *>(c)[p * MCAP + t]; }
+  static __device__ __forceinline__ double2 tm(const double *c, int p, int t) { return reinterpret_cast<const double2 *>(c)[p * MCAP + t]; }
+  static __device__ __forceinline__ void mix_stage(const DevView &V, int row, double *c, int t)
+  {
+    const double4 g = ld_rec(V.geo, row), a = ld_rec(V.rec[0], row), b = ld_rec(V.rec[1], row), u = ld_rec(V.rec[2], row);
+    tm(c, 0, t) = make_double2(g.x, g.y); tm(c, 1, t) = make_double2(g.z, a.x); tm(c, 2, t) = make_double2(a.y, a.z);
+    tm(c, 3, t) = make_double2(a.w, b.x); tm(c, 4, t) = make_double2(b.y, b.z); tm(c, 5, t) = make_double2(u.x, u.y);
+    tm(c, 6, t) = make_double2(u.z, u.w);
+    c[14 * MCAP + t] = g.w;
+  }
+  // one listed pair: right-hand sides into a[0..3], the phase-density sums of smooth_density into a[4], a[5]
+  // (density_massfrac.cc:159-161; same pairs, same symmetric-h weight); near: the pair lies inside the support of the
+  // energy-smoothing kernel W(q dx / h, h / q) (:163-168), decided exactly as DensStage::pair_inner<false> does
+  static __device__ __forceinline__ void mix_pair(const KParams &K, const I &s, double *a, const double *c, int sl, double gx, double gy,
+                                                  double gz, bool &near)
+  {
+    const double2 p0 = tm(c, 0, sl), p1 = tm(c, 1, sl), p2 = tm(c, 2, sl), p3 = tm(c, 3, sl), p4 = tm(c, 4, sl), p5 = tm(c, 5, sl),
+                  p6 = tm(c, 6, sl);
+    const double hj = c[14 * MCAP + sl];
+    const double dx = gx - p0.x, dy = gy - p0.y, dz = gz - p1.x;
+    R r;
+    r.r0 = make_double4(p1.y, p2.x, p2.y, p3.x);
+    r.r1 = make_double4(p3.y, p4.x, p4.y, 0.);
+    r.r2 = make_double4(p5.x, p5.y, p6.x, p6.y);
+    const double w = pair_w<false>(K, s, *reinterpret_cast<A *>(a), dx, dy, dz, hj, r);
+    const double md = p6.y, wm = w * fabs(md);
+    a[5] += md < 0.0 ? wm : 0.0;
+    a[4] += md < 0.0 ? 0.0 : wm;
+    if (K.energy_smooth == 1) {
+      const double h = 0.5 * (s.h + hj), q = K.e_ratio, b = K.cutoff * h * (1.0 + 0x1p-40);
+      // all |q dx_k / h| <= cutoff implies q^2 r2 <= DIM (cutoff h)^2: one compare clears most pairs
+      if ((dx * dx + dy * dy + dz * dz) * (q * q) <= DIM * b * b) near = !outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff);
+    }
+  }
+  static __device__ __forceinline__ void mix_finish(const DevView &V, const KParams &K, StepState *ss, int i, const I &s, const double *t)
+  {
+    finish(V, K, ss, i, s, t[0], t[1], t[2], t[3]);
+    V.scr[4][i] = t[4]; V.scr[5][i] = t[5];                         // k_dens_near<false> adds the row's own term
   }
 };
 
@@ -532,17 +613,45 @@ struct VelStage
     if (DIM == 3) { a.dv[1] += mvw * (rj.z - s.v[1]); a.dv[2] += mvw * (rj.w - s.v[2]); }
     a.wn += mvw;
   }
+  static __device__ __forceinline__ void finish(const DevView &V, StepState *ss, int i, const I &s, double d0, double d1, double d2, double wn)
+  {
+    if (!(wn > 0)) atomicAdd(&ss->bad, 1);
+    const double rw = 1.0 / wn;
+    V.t.d[D_SVX][i] = s.v[0] + d0 * rw;
+    if (DIM == 3) { V.t.d[D_SVY][i] = s.v[1] + d1 * rw; V.t.d[D_SVZ][i] = s.v[2] + d2 * rw; }
+  }
   static __device__ __forceinline__ bool end(const DevView &V, const KParams &, StepState *ss, int i, I &s, A &a, int, int lane)
   {
     double d0 = a.dv[0], d1 = DIM == 3 ? a.dv[1] : 0.0, d2 = DIM == 3 ? a.dv[2] : 0.0, wn = a.wn;
     warp_sum4(d0, d1, d2, wn, lane);
-    if (lane == 0) {
-      if (!(wn > 0)) atomicAdd(&ss->bad, 1);
-      const double rw = 1.0 / wn;
-      V.t.d[D_SVX][i] = s.v[0] + d0 * rw;
-      if (DIM == 3) { V.t.d[D_SVY][i] = s.v[1] + d1 * rw; V.t.d[D_SVZ][i] = s.v[2] + d2 * rw; }
-    }
+    if (lane == 0) finish(V, ss, i, s, d0, d1, d2, wn);
     return false;
+  }
+  // ---- sub-tiled mixed-h gather (psph_mix.cuh): {x, y} {z, m/rho} {vx, vy} as 16-byte elements, then vz; the weight
+  // uses the ROW's smoothing length (smooth_velocity.cc:104-118), entries carry the h_i gate tag
+  static constexpr int kNCm = 7, kNAm = 4;
+  static constexpr unsigned kTagMix = MTAG_HI;
+  static __device__ __forceinline__ void mix_stage(const DevView &V, int row, double *c, int t)
+  {
+    const double4 g = ld_rec(V.geo, row), r = ld_rec(V.rec[0], row);
+    double2 *c2 = reinterpret_cast<double2 *>(c);
+    c2[t] = make_double2(g.x, g.y); c2[MCAP + t] = make_double2(g.z, r.x); c2[2 * MCAP + t] = make_double2(r.y, r.z);
+    c[6 * MCAP + t] = r.w;
+  }
+  static __device__ __forceinline__ void mix_pair(const KParams &K, const I &s, double *a, const double *c, int sl, double gx, double gy,
+                                                  double gz, bool &)
+  {
+    const double2 *c2 = reinterpret_cast<const double2 *>(c);
+    const double2 p0 = c2[sl], p1 = c2[MCAP + sl], p2 = c2[2 * MCAP + sl];
+    R r;
+    r.r0 = make_double4(p1.y, p2.x, p2.y, c[6 * MCAP + sl]);
+    pair_r<false>(K, s, *reinterpret_cast<A *>(a), gx - p0.x, gy - p0.y, gz - p1.x, 0.0, r);
+  }
+  static __device__ __forceinline__ void mix_finish(const DevView &V, const KParams &, StepState *ss, int i, const I &s, const double *t)
+  {
+    // the row itself (the lists leave it out): weight W(0, h_i), zero velocity difference
+    const double mvw = dev_weight_pre(0.0, s.ninvh2, s.norm) * ld_rec(V.rec[0], i).x;
+    finish(V, ss, i, s, t[0], t[1], t[2], t[3] + mvw);
   }
 };
 
@@ -632,19 +741,30 @@ static int launch_tile_gather_any(psph_ctx *ctx, int kid)
 // The first summation stage of a step (mom_engr_update, `writer`) finds the pairs: the grouped gather publishes the
 // pair lists of the rows that qualify (and sums the others in place), then every stage runs the rows that have a
 // list on k_gather_list; the later stages send the rest through the grouped gather again.
+static bool tile_modes(const psph_ctx *ctx) { return ctx->nbr_mode == 5 || ctx->nbr_mode == 2 || ctx->nbr_mode == 4; }
+
 template <template <int> class S>
 static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
 {
   if (ctx->cfg.dim != 3 || ctx->gather_mode != 0) return launch_gather<S>(ctx, kid);
   if (writer) {
     ctx->nbr_valid = false;
-    if (ctx->nbr_mode == 2 && psph_nbr_prepare(ctx) == 1) { // block-tiled: slot lists, records staged in shared memory
-      if (ctx->scan_mode == 2) { // one lane per row (psph_scan2.cuh); PSPH_SCAN=1: one lane per candidate (psph_tile.cuh)
-        if (launch_tile_scan2<S<3>, 20, 16>(ctx, KN_PAIR_SCAN)) return -1;
-      } else if ((ctx->gather_warps == 24 ? launch_tile_scan<S<3>, 24>(ctx, KN_PAIR_SCAN) : launch_tile_scan<S<3>, 20>(ctx, KN_PAIR_SCAN))) return -1;
+    if (tile_modes(ctx) && psph_nbr_prepare(ctx) == 1) {
+      // Slot lists + records staged in shared memory.  Which of the two layouts runs is the device's choice
+      // (StepState::pair_mode, k_pair_mode): the kernels of the other one return at once, so no host round trip
+      {
+        KernelTimer kt(ctx, KN_PAIR_SCAN);
+        if (ctx->scan_mode == 2) { // one lane per row (psph_scan2.cuh); PSPH_SCAN=1: one lane per candidate (psph_tile.cuh)
+          if (launch_tile_scan2<S<3>, 20, 16>(ctx, -1)) return -1;
+        } else if ((ctx->gather_warps == 24 ? launch_tile_scan<S<3>, 24>(ctx, -1) : launch_tile_scan<S<3>, 20>(ctx, -1))) return -1;
+        if (launch_mix_scan<16>(ctx, -1)) return -1;
+        k_no_lists<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
+        PSPH_LAUNCH_CHECK();
+      }
       ctx->nbr_valid = true; ctx->nbr_kind = 2;
       KernelTimer kt(ctx, kid);
       if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
+      if constexpr (S<3>::kNAm == 6) { if (launch_mix_gather<S<3>, 16, 1>(ctx, -1)) return -1; }   // (the writer is mom_engr_update)
       return launch_gather_grp<S<3> >(ctx, -1, 2);
     }
     if (ctx->nbr_mode == 3 && psph_nbr_prepare(ctx) == 1) { // general row lists: any smoothing lengths, tagged entries
@@ -664,13 +784,20 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
     return launch_gather_grp<S<3> >(ctx, kid, 0);
   }
   if (ctx->nbr_valid) {
-    KernelTimer kt(ctx, kid); // both launches are this stage's gather
+    KernelTimer kt(ctx, kid); // every launch is this stage's gather
     if (ctx->nbr_kind == 2) {
-      if (S<3>::kSkipUnlessFull && ctx->cur.wts && ctx->n > 0) { // smooth_density: the sums mom_engr_update prepared
-        k_dens_near<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
-        PSPH_LAUNCH_CHECK();
+      if constexpr (S<3>::kSkipUnlessFull) { // smooth_density: the sums mom_engr_update's pass prepared + the near lists
+        if (ctx->n > 0) {
+          if (ctx->cur.wts) { k_dens_near<true><<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
+          k_dens_near<false><<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss);
+          PSPH_LAUNCH_CHECK();
+          if (launch_gather_d<3, S<3>, true>(ctx, -1)) return -1;     // rows whose near list overflowed
+        }
+        if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
+      } else {
+        if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
+        if constexpr (S<3>::kNAm == 4) { if (launch_mix_gather<S<3>, 16, 2>(ctx, -1)) return -1; }
       }
-      if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
     } else if (launch_gather_list<S<3> >(ctx, -1)) return -1;
     return launch_gather_grp<S<3> >(ctx, -1, 2);
   }
@@ -678,14 +805,15 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
 }
 
 // room for the pair lists of this step: 0 none (cache off for the step), 1 ready; < 0 error
-__global__ void k_nbr_reset(StepState *ss, unsigned cap, int dens_full)
-{ ss->nbr_cursor = 0u; ss->nbr_cap = cap; ss->n_uncached = 0; ss->dens_full = dens_full; }
+__global__ void k_nbr_reset(StepState *ss, unsigned cap, int dens_full, int mix_rows)
+{ ss->nbr_cursor = 0u; ss->nbr_cap = cap; ss->n_uncached = 0; ss->dens_full = dens_full; ss->n_near_ovf = 0; ss->mix_rows = mix_rows; }
 int psph_nbr_prepare(psph_ctx *ctx)
 {
   // 320 pairs per row cover the unit lattice (~230-300 pairs): 10 units of 128 bytes (row indices) or 5 (16-bit
   // tile slots); rows that do not fit get no list.  Allocated once per table size: when memory capped the buffer
   // below `want`, asking again every step would only cost a free + malloc of tens of GB.
-  size_t want = (size_t) ctx->n * (ctx->nbr_mode == 2 ? 5 : (ctx->nbr_mode == 3 ? 26 : 10)); // mode 3: ~730 partners
+  const bool tiles = tile_modes(ctx);
+  size_t want = (size_t) ctx->n * (tiles ? 5 : (ctx->nbr_mode == 3 ? 26 : 10)); // mode 3: ~730 partners
   if (want > 0x7ffffff0ull) want = 0x7ffffff0ull;
   if (ctx->nbr_units < want && want > ctx->nbr_want_tried) {
     ctx->nbr_want_tried = want + want / 8;
@@ -702,15 +830,38 @@ int psph_nbr_prepare(psph_ctx *ctx)
     ctx->nbr_units = units;
     // pair-weight cache of the block-tiled mode: one double per 16-bit slot (4 x the list bytes), only when the full
     // list fits and the memory is there — HBM is idle during the pair sums, the FP64 pipe is not
-    if (ctx->nbr_mode == 2 && ctx->wcache && units >= want) {
+    if (tiles && ctx->wcache && units >= want) {
       PSPH_CUDA(cudaMemGetInfo(&free_b, &total_b));
       if (free_b > keep + units * 512 && cudaMalloc(&ctx->cur.wts, units * 512) != cudaSuccess) { cudaGetLastError(); ctx->cur.wts = nullptr; }
     }
   }
-  if (ctx->nbr_mode != 2 && ctx->cur.wts) { cudaFree(ctx->cur.wts); ctx->cur.wts = nullptr; }
+  if (!tiles && ctx->cur.wts) { cudaFree(ctx->cur.wts); ctx->cur.wts = nullptr; }
+  // mixed-h lists (psph_mix.cuh): MSTRIDE 16-bit entries per row at a fixed stride + one int per row; allocated once the
+  // table is known to carry per-row smoothing lengths (adaptive_sml ran, or a host read-back of the step state said so)
+  if (tiles && !ctx->mix_wanted && ctx->h_unknown) {
+    // rows that came in from outside may carry per-row smoothing lengths already: one look at the path the device
+    // picked for this list (only after an upload; a running loop learns it from adaptive_sml)
+    PSPH_CUDA(cudaMemcpyAsync(&ctx->h_ss->pair_mode, &ctx->d_ss->pair_mode, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ss->pair_mode == 4) ctx->mix_wanted = true;
+  }
+  ctx->h_unknown = false;
+  if (tiles && ctx->mix_wanted && ctx->mix_rows < (size_t) ctx->n) {
+    PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->cur.mlist); cudaFree(ctx->cur.mseg); ctx->cur.mlist = nullptr; ctx->cur.mseg = nullptr; ctx->mix_rows = 0;
+    size_t free_b = 0, total_b = 0;
+    PSPH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t keep = (size_t) 2 << 30, per_row = (size_t) MSTRIDE * 2 + 4;
+    size_t rows = std::max(ctx->cap, (size_t) ctx->n);
+    if (free_b < keep + rows * per_row) rows = free_b > keep ? (free_b - keep) / per_row : 0;  // the rows beyond get no list
+    if (rows > 0 && cudaMalloc(&ctx->cur.mlist, rows * MSTRIDE * 2) == cudaSuccess && cudaMalloc(&ctx->cur.mseg, rows * 4) == cudaSuccess)
+      ctx->mix_rows = rows;
+    else { cudaGetLastError(); cudaFree(ctx->cur.mlist); ctx->cur.mlist = nullptr; }
+  }
   // units of 32 entries: 128 bytes of row indices, or 64 bytes of 16-bit tile slots (block-tiled mode)
-  const size_t cap = ctx->nbr_mode == 2 ? ctx->nbr_units * 2 : ctx->nbr_units;  // (the writer that follows uses nbr_mode)
-  k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(cap, 0xfffffff0ull), ctx->dens_near ? 0 : 1);
+  const size_t cap = tiles ? ctx->nbr_units * 2 : ctx->nbr_units;  // (the writer that follows uses nbr_mode)
+  k_nbr_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, (unsigned) std::min<size_t>(cap, 0xfffffff0ull), ctx->dens_near ? 0 : 1,
+                                        (int) std::min<size_t>(ctx->mix_rows, 0x7fffffff));
   PSPH_LAUNCH_CHECK();
   return 1;
 }
@@ -721,6 +872,14 @@ static int ensure_list(psph_ctx *ctx)
   return psph_build_cell_list(ctx);
 }
 
+int psph_pair_mode(psph_ctx *ctx)
+{
+  const int forced = ctx->nbr_mode == 5 ? 0 : (ctx->nbr_mode == 2 || ctx->nbr_mode == 4 ? ctx->nbr_mode : -1);
+  k_pair_mode<<<1, 1, 0, ctx->stream>>>(ctx->d_ss, forced, ctx->dens_near);
+  PSPH_LAUNCH_CHECK();
+  return 0;
+}
+
 int psph_refresh_geo(psph_ctx *ctx)
 {
   k_hmax_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
@@ -728,7 +887,9 @@ int psph_refresh_geo(psph_ctx *ctx)
   if (ctx->n > 0) { k_hmax_scan<<<GRID(ctx->n)>>>(ctx->cur.t, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
   k_hmax_finish<<<1, 1, 0, ctx->stream>>>(ctx->d_ss);
   PSPH_LAUNCH_CHECK();
-  if (ctx->n > 0) { k_refresh_geo<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
+  PSPH_CUDA(cudaMemsetAsync(ctx->d_cell_hmax, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
+  if (ctx->n > 0) { k_refresh_geo<<<GRID(ctx->n)>>>(ctx->cur, ctx->kp, ctx->d_ss, ctx->d_cell_hmax); PSPH_LAUNCH_CHECK(); }
+  if (psph_pair_mode(ctx)) return -1;
   ctx->nbr_valid = false; // smoothing lengths changed: the pair lists of this step are stale
   return 0;
 }
@@ -785,6 +946,7 @@ extern "C" int psph_adaptive_sml(psph_ctx *ctx)
   k_pack_sml<<<GRID(ctx->n)>>>(ctx->cur, ctx->d_ss);
   PSPH_LAUNCH_CHECK();
   if (launch_gather<SmlStage>(ctx, KN_GATHER_SML)) return -1;
+  ctx->mix_wanted = true;                                   // every row has its own smoothing length from here on
   psph_comm_mark(ctx, DIRTY_H);
   return psph_refresh_geo(ctx);
 }
@@ -918,9 +1080,11 @@ extern "C" int psph_errors(psph_ctx *ctx, int reset)
   // fused gather in the last step, the row lists (no such assumptions) serve this table better
   // ... and when the row lists do not apply either (smoothing lengths differ from row to row, e.g. after
   // adaptive_sml), the search that writes them is wasted work: the fused grouped gather alone serves every table
-  if (ctx->nbr_mode > 0 && ctx->nbr_valid && ctx->h_ss->n_need > 0 && 2LL * ctx->h_ss->n_uncached > ctx->h_ss->n_need)
+  // (the default, nbr_mode 5, needs none of this: the device picks block tiles or the sub-tiled mixed-h gather per step)
+  if (ctx->nbr_mode > 0 && ctx->nbr_mode < 4 && ctx->nbr_valid && ctx->h_ss->n_need > 0 && 2LL * ctx->h_ss->n_uncached > ctx->h_ss->n_need)
     ctx->nbr_mode = ctx->nbr_mode == 2 ? 1 : 0; // tiles -> uniform-h row lists -> fused (the general row lists, mode 3,
                                                 // measured no faster than the fused gather: opt-in only)
+  if (ctx->h_ss->pair_mode == 4) ctx->mix_wanted = true;
   if (reset && bad) {
     PSPH_CUDA(cudaMemsetAsync(&ctx->d_ss->bad, 0, sizeof(int), ctx->stream));
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -120,6 +120,7 @@ k_tile_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__re
   CellTable &T = *reinterpret_cast<CellTable *>(s_raw);
   CellWarp *scr = reinterpret_cast<CellWarp *>(s_raw + sizeof(CellTable)) + (threadIdx.x >> 5);
   __shared__ int s_any[4];
+  if (ss->pair_mode != 2) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   unsigned s_cand, s_q, s_hdr, s_geo;
@@ -405,6 +406,7 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
   int *tile_row = reinterpret_cast<int *>(comp);                              // [TCAP] slot -> row, while the tile is staged
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short *__restrict__ nbr16 = reinterpret_cast<const unsigned short *>(V.nbr);
+  if (ss->pair_mode != 2) return;                                   // the step runs on another pair path (k_pair_mode)
   if constexpr (WM == 2 && S::kSkipUnlessFull)
     if (!ss->dens_full) return;                                     // k_dens_near has served every listed row
   const int nblk = (int) (G.ncells * 4);
@@ -569,7 +571,7 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
                 if (fl && pos < NEAR_MAX) {
                   int lo = 0, hi = TSEG;                              // the segment of the slot -> its row
                   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tab.off[mid] <= sl) lo = mid; else hi = mid; }
-                  V.near[8 * i + 1 + pos] = tab.beg[lo] + (sl - tab.off[lo]);
+                  V.near[NEARW * i + 1 + pos] = tab.beg[lo] + (sl - tab.off[lo]);
                 }
                 nnear += __popc(fb);
               }
@@ -580,8 +582,9 @@ k_tile_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned ch
             warp_sum4(d1, d2, z0, z1, lane);
             if (lane == 0) {
               V.scr[4][i] = d1; V.scr[5][i] = d2;
-              V.near[8 * i] = min(nnear, NEAR_MAX);
-              if (nnear > NEAR_MAX) ss->dens_full = 1;                // smooth_density walks the lists itself this step
+              // a near list that overflowed flags ITS row: smooth_density sums that row by itself (k_gather<DensStage, OVF>)
+              V.near[NEARW * i] = nnear <= NEAR_MAX ? nnear : NEAR_OVF;
+              if (nnear > NEAR_MAX) atomicAdd(&ss->n_near_ovf, 1);
             }
           }
         }

@@ -177,7 +177,7 @@ def pack_buckets(out, tag, fn):
     return bk
 
 
-def golden_3d_sml(name="plume3d_sml", variant="3d_plume", edits=None, simdata="simulation.data"):
+def golden_3d_sml(name="plume3d_sml", variant="3d_plume", edits=None, simdata="simulation.data", sml_int=1):
     """The regime AFTER adaptive_sml (neighs.cc:479-693; main.cc:319-322 calls it every SML_UPDATE_INT = 50 steps): the
     small plume with PSPH_SML_INT=1 (the hook TU's override of that constant, nothing else changes), time steps 1 and 2.
     Step 1 runs adaptive_sml from the uniform initial smoothing lengths; step 2 starts with every real particle carrying
@@ -202,7 +202,10 @@ def golden_3d_sml(name="plume3d_sml", variant="3d_plume", edits=None, simdata="s
                        stdout=subprocess.DEVNULL)
         dump = os.path.join(wd, "dump")
         os.makedirs(dump)
-        run_ref(variant, wd, dict(PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="1-2", PSPH_MAX_STEPS=2, PSPH_SML_INT=1))
+        env = dict(PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="1-2", PSPH_MAX_STEPS=2)
+        if sml_int:
+            env["PSPH_SML_INT"] = sml_int       # (sml_int = 0: the reference's own SML_UPDATE_INT, no adaptive_sml in steps 1-2)
+        run_ref(variant, wd, env)
         out = {}
         dts = []
         for st in (1, 2):
@@ -213,6 +216,8 @@ def golden_3d_sml(name="plume3d_sml", variant="3d_plume", edits=None, simdata="s
             cur = {f: pre[f].copy() for f in pre.dtype.names}
             for stage in ("sml", "mom", "dens", "svel", "pos"):
                 fn = os.path.join(dump, "s%04d_%s_post.bin" % (st, stage))
+                if stage == "sml" and not sml_int:
+                    continue
                 assert os.path.exists(fn), fn
                 _, rows = refio.read_dump(fn)
                 assert np.array_equal(rows["key"], pre["key"])
@@ -309,6 +314,8 @@ if __name__ == "__main__":
         "plume3d_small": lambda: golden_3d("plume3d_small", "3d_plume", SMALL_3D),
         "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D),
         "plume3d_sml": lambda: golden_3d_sml(),
+        # the same two steps with the reference's own SML_UPDATE_INT: uniform h, and a step (2) that follows a domain growth
+        "plume3d_grow": lambda: golden_3d_sml("plume3d_grow", sml_int=0),
         # BASELINE config 2: JPUE weakly-compressible jet (Tait EOS, g = 0), the reference's own input file
         "jpue3d": lambda: golden_3d("jpue3d", "3d_jpue", JPUE_3D, list_stride=16, simdata="simulation_JPUE_incomp_back.data"),
     }

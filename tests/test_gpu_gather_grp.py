@@ -170,3 +170,62 @@ def test_pairs_on_the_cutoff_face():
     assert bad_g == 0 and dt_o == dt_g
     for f in FIELDS:
         assert relerr(grp[f], ora[f]) <= 3 * RTOL_STAGE, (f, relerr(grp[f], ora[f]))
+
+
+# ---- per-row smoothing lengths: the sub-tiled mixed-h gather (csrc/psph_mix.cuh) ----------------------------------------
+def mixed_h_rows(n=24, seed=21, spread=0.03, hfac=1.5, cluster=0):
+    """the synthetic cube as adaptive_sml leaves it: every real particle with its own h = hfac (1 +- spread) lattice
+    spacings (the ghost shell keeps h = 1); cluster > 0: that many extra-close particles around one site, so that their
+    near lists (partners inside the energy-smoothing kernel, 0.75 h) overflow"""
+    cfg, rows = cases.cube(n, seed=seed)
+    real = np.flatnonzero(rows["bc_type"] == 100)
+    rng = np.random.default_rng(seed)
+    rows["smlen"][real] = hfac * (1.0 + spread * rng.uniform(-1, 1, len(real)))
+    if cluster:
+        pos = rows["coords"]
+        pick = rng.choice(real, cluster, replace=False)
+        centre = pos[pick[0]].copy()
+        for p in pick:
+            pos[p] = centre + rng.uniform(-1, 1, 3) * 0.3
+    return cfg, rows
+
+
+@pytest.mark.parametrize("cluster", [0, 60])
+def test_mixed_h_subtiled_gather_vs_oracle(cluster):
+    """default path on a table with per-row h (the device picks the mixed-h gather: StepState::pair_mode 4), the same
+    forced (PSPH_NBR=4), and the fused grouped gather alone (PSPH_NBR=0), against the oracle; cluster: 60 particles
+    within 0.3 spacings of one site — more near partners than a near list holds, those rows are summed by themselves"""
+    cfg, rows = mixed_h_rows(cluster=cluster)
+    dt_o, ora = oracle_stages(cfg, rows)
+    runs = {}
+    for nbr in (None, "4", "0"):
+        dt, bad, out = run_stages(cfg, rows, None, nbr=nbr)
+        assert bad == 0 and dt == dt_o
+        for f in FIELDS:
+            assert relerr(out[f], ora[f]) <= 3 * RTOL_STAGE, (nbr, f, relerr(out[f], ora[f]))
+        runs[nbr] = out
+    for f in FIELDS:   # default == forced mixed-h path, bit for bit (same kernels)
+        assert np.array_equal(runs[None][f], runs["4"][f]), f
+
+
+def test_mixed_h_pairs_on_the_cutoff_face():
+    """unjittered lattice with h = 4/3 spacings for every real particle: partners sit exactly on the cutoff faces
+    3 (h_i + h_j) / 2 = 4 spacings and 3 h_i = 4 spacings; a sample is moved one ulp / 3e-8 either side.  The FP32
+    pre-filter of the mixed-h search must hand these to the FP64 gates (a wrong decision is an O(1e-6) error)."""
+    cfg, rows = cases.cube(16, seed=3, jitter=0.0, vjit=0.02)
+    real = np.flatnonzero(rows["bc_type"] == 100)
+    rows["smlen"][real] = 4.0 / 3.0
+    rng = np.random.default_rng(12)
+    rows["smlen"][real[::7]] = 4.0 / 3.0 * (1 + 1e-9)      # a second length, so that pairs differ between the two gate families
+    pos = rows["coords"]
+    pick = rng.choice(real, 600, replace=False)
+    for q, p in enumerate(pick):
+        k = q % 3
+        x = pos[p, k]
+        pos[p, k] = [np.nextafter(x, np.inf), np.nextafter(x, -np.inf), x + 3e-8, x - 3e-8][(q // 3) % 4]
+    dt_o, ora = oracle_stages(cfg, rows)
+    for nbr in ("4", "0"):
+        dt, bad, out = run_stages(cfg, rows, None, nbr=nbr)
+        assert bad == 0 and dt == dt_o
+        for f in FIELDS:
+            assert relerr(out[f], ora[f]) <= 3 * RTOL_STAGE, (nbr, f, relerr(out[f], ora[f]))

@@ -26,10 +26,10 @@ STAGES = (("sml", ["smlen"], ()),
           ("pos", ["coord", "bc_type", "smlen", "involved"], ("bc_type", "involved")))
 
 
-def run_step(z, step, env_solver=None):
-    ocfg = op.config_for("plume3d_sml", z)
+def run_step(z, step, name="plume3d_sml", sml_int=1):
+    ocfg = op.config_for(name, z)
     cfg = to_product_cfg(ocfg)
-    cfg.sml_update_int = 1
+    cfg.sml_update_int = sml_int
     pre = z["pre%d" % step]
     s = psph.Solver(cfg)
     try:
@@ -45,6 +45,8 @@ def run_step(z, step, env_solver=None):
         calls = dict(sml=s.adaptive_sml, mom=s.mom_engr_update, dens=s.smooth_density, svel=s.smooth_velocity, pos=s.update_pos)
         worst = {}
         for stage, fields, exact in STAGES:
+            if stage == "sml" and sml_int != 1:
+                continue
             calls[stage]()
             out = s.download(ORDER_REFERENCE)
             assert np.array_equal(out["key"], pre["key"])
@@ -70,6 +72,16 @@ def test_adaptive_sml_and_mixed_h_stages(step):
         pre = z["pre2"]
         assert len(np.unique(pre["smlen"][pre["bc_type"] == 100])) > 100     # the regime under test
     worst = run_step(z, step)
+    print("step", step, "worst relative errors:", {k: "%.1e" % v for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("step", [1, 2])
+def test_uniform_h_stages_after_domain_growth(step):
+    """tests/golden/plume3d_grow.npz: the same two steps with the reference's own SML_UPDATE_INT (uniform h, block-tiled
+    path).  Step 2 follows the adapt block of main.cc:257-303 (pressure ghosts turned real, new ghost layers and buckets)
+    and keeps hundreds of partners exactly ON the cutoff faces of the unmoved lattice."""
+    z = golden("plume3d_grow")
+    worst = run_step(z, step, name="plume3d_grow", sml_int=50)
     print("step", step, "worst relative errors:", {k: "%.1e" % v for k, v in worst.items()})
 
 

@@ -51,6 +51,39 @@ def test_plume3d_step1_bit_exact(name):
 
 
 @pytest.mark.parametrize("step", [1, 2])
+def test_plume3d_uniform_h_after_domain_growth_bit_exact(step):
+    """time steps 1 and 2 of the small plume with the reference's own SML_UPDATE_INT (no adaptive_sml yet): step 2 follows
+    the adapt block (main.cc:257-303) — pressure ghosts turned real, new ghost layers, new buckets — and keeps the lattice's
+    partners exactly ON the cutoff faces"""
+    z = golden("plume3d_grow")
+    cfg = op.config_for("plume3d_grow", z)
+    pre = z["pre%d" % step]
+    s = oracle_state_3d(cfg, z, "b%d" % step, rows="pre%d" % step)
+    dt = float(z["dt"][step - 1])
+    if step == 1:
+        assert s.timestep() == dt
+    s.search()
+    cur = {f: pre[f] for f in pre.dtype.names}
+
+    def check(stage, pairs):
+        for f, o in pairs:
+            want = sparse_field(z, "s%d_%s_%s" % (step, stage, f), cur[f])
+            eq(s.a[o], want, (step, stage, f))
+            cur[f] = want
+
+    assert s.mom_engr_update(dt) == 0
+    check("mom", [("vel", "v"), ("engr", "e"), ("pressure", "p"), ("sound_speed", "c"), ("temperature", "T"),
+                  ("specific_heat_p", "Cp"), ("gamma", "gamma"), ("phase_density", "rho_ph")])
+    assert s.smooth_density() == 0
+    check("dens", [("rho", "rho"), ("mass_frac", "ks"), ("engr", "e"), ("pressure", "p"), ("sound_speed", "c"),
+                   ("temperature", "T"), ("involved", "involved")])
+    assert s.smooth_velocity() == 0
+    check("svel", [("smoothed_v", "sv")])
+    s.update_pos(dt, 1)
+    check("pos", [("coord", "x"), ("bc_type", "bc"), ("smlen", "h"), ("involved", "involved")])
+
+
+@pytest.mark.parametrize("step", [1, 2])
 def test_plume3d_adaptive_sml_and_mixed_h_bit_exact(step):
     """adaptive_sml in 3-D (neighs.cc:479-693) and every summation stage with per-particle smoothing lengths: time steps
     1 and 2 of the small plume with adaptive_sml called every step (PSPH_SML_INT=1 on the reference's hook build).

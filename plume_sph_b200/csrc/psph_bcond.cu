@@ -160,6 +160,8 @@ extern "C" int psph_apply_bcond(psph_ctx *ctx)
   if (slabs && !(owner = psph_comm_owner_table(ctx))) { ctx->err = "psph_apply_bcond: psph_comm_init was not called"; return -2; }
   if (ctx->n_img == 0) return 0;                       // (every rank holds the same image table: all return here together)
   StageTimer tm(ctx, ST_BCOND);
+  // slabs: rows injected since the last exchange (add_new_erupt) reach their neighbours' ghost layers first (main.cc:430)
+  if (slabs && psph_exchange_ghosts(ctx)) return -1;
   if (!ctx->list_valid && psph_build_cell_list(ctx)) return -1;   // positions moved since the last list build
   // scratch: local row of every image's ghost, the images this rank computes, their count
   int32_t *list = reinterpret_cast<int32_t *>(ctx->d_perm);

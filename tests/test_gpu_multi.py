@@ -11,7 +11,8 @@ import pytest
 import plume_sph_b200 as psph
 from plume_sph_b200 import cases, slabs
 from plume_sph_b200.solver import ORDER_REFERENCE, ORDER_DEVICE
-from common import relerr
+import oracle_py as op
+from common import relerr, golden, to_product_cfg, dump_to_particles, cell_attrs, image_cells
 
 pytestmark = pytest.mark.gpu
 
@@ -114,3 +115,88 @@ def test_slabs_match_single_gpu(P):
     # load balance: the weighted cut (reference weights) is within one cell of even
     w = [int(slabs.particle_weights(o[o["guest"] == 0]["bc_type"]).sum()) for _, _, o, _ in res]
     assert max(w) - min(w) <= 2 * 512 * 200, w
+
+
+
+def key64(rows):
+    k = rows["key"].astype(np.uint64)
+    return (k[:, 0] << np.uint64(32)) | k[:, 1]
+
+
+@pytest.mark.skipif(ndev() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("P", [2, 4])
+def test_plume_with_wall_ghosts_and_vent_across_slabs(P):
+    """the reference's small plume (tests/golden/plume3d_small.npz: air, pressure ghosts, wall ghosts with their image
+    table, the duct's erupt ghosts) advanced 4 steps — psph_step, psph_add_new_erupt, psph_apply_bcond — on P key-range
+    slabs against one GPU: images are computed by the owner of their bucket and travel back to the ghost's owner
+    (move_bnd_img.cc:32-210, send_reflections.cc:34-165), every rank injects the particles born in its own buckets
+    (setup_erupt.cc:609-650).  Same particles on exactly one rank each, fields within 1e-12."""
+    if ndev() < P:
+        pytest.skip("needs %d GPUs" % P)
+    z, ze = golden("plume3d_small"), golden("erupt3d")
+    ocfg = op.config_for("plume3d_small", z)
+    cfg = to_product_cfg(ocfg)
+    attr, _ = cell_attrs(ocfg, z)
+    rows = dump_to_particles(z["pre"])
+    img = np.zeros(len(z["bc_img_row"]), psph.IMAGE_DTYPE)
+    img["ghost_key"] = z["bc_pre"]["key"][z["bc_img_row"]]
+    img["cell"] = image_cells(ocfg, z)
+    img["coord"] = z["bc_img_coord"]
+    er, _ = op.erupt_from_params(ze["param_names"], ze["s2_params"])
+    boxes = np.concatenate([ze["s2_cell_min"], ze["s2_cell_max"]], axis=1)
+    steps = 4
+
+    def advance(s, multi):
+        t, dts, added = 0.0, [], []
+        for k in range(1, steps + 1):
+            dt, lost, ierr = s.step(0.0, 1)
+            assert ierr == 0
+            t += dt
+            dts.append(dt)
+            added.append(s.add_new_erupt(t, dt, k))
+            assert s.apply_bcond() == 0
+        if multi:
+            s.exchange_ghosts()          # the wall ghosts' new state reaches the guest copies (main.cc:471)
+        return dts, added
+
+    s1 = psph.Solver(cfg)
+    s1.set_cells(attr); s1.upload(rows); s1.set_images(img); s1.set_erupt(er, boxes)
+    dts, added1 = advance(s1, False)
+    ref = s1.download(ORDER_REFERENCE)
+    s1.close()
+    assert sum(added1) > 0                                   # the vent did inject
+    uid = psph.Solver.comm_unique_id()
+    parts = np.array_split(np.argsort(rows["coords"][:, 0], kind="stable"), P)
+
+    def rank(r):
+        c = cfg.copy()
+        c.device, c.rank, c.nranks = r, r, P
+        s = psph.Solver(c)
+        s.set_cells(attr); s.upload(rows[parts[r]]); s.set_images(img); s.set_erupt(er, boxes)
+        s.comm_init(uid)
+        s.repartition()
+        got, added = advance(s, True)
+        out = s.download(ORDER_DEVICE)
+        s.close()
+        return got, added, out
+
+    res = run_ranks(P, rank)
+    for got, added, out in res:
+        assert got == dts, (got, dts)
+    assert [sum(a[k] for _, a, _ in res) for k in range(steps)] == added1     # every new particle on exactly one rank
+    owned = np.concatenate([o[o["guest"] == 0] for _, _, o in res])
+    ko, kr = key64(owned), key64(ref)
+    assert len(ko) == len(kr) and len(np.unique(ko)) == len(ko)
+    a, b = owned[np.argsort(ko)], ref[np.argsort(kr)]
+    assert np.array_equal(a["key"], b["key"]) and np.array_equal(a["bc_type"], b["bc_type"])
+    for f in ("coords", "vel", "smoothed_v", "rho", "engr", "mass_frac", "pressure", "temperature", "smlen"):
+        e = relerr(a[f], b[f])
+        assert e <= 1e-12, (f, e)
+    wall = a["bc_type"] == 2
+    assert wall.any() and relerr(a["vel"][wall], b["vel"][wall]) <= 1e-12
+    for _, _, o in res:                                      # guests mirror their owners
+        g = o[o["guest"] != 0]
+        src = a[np.searchsorted(np.sort(ko), key64(g))]
+        assert np.array_equal(src["key"], g["key"])
+        for f in ("coords", "vel", "rho", "engr", "pressure"):
+            assert np.array_equal(src[f], g[f]), f

@@ -90,12 +90,16 @@ struct Comm
 Comm *comm_of(psph_ctx *ctx) { return (Comm *) ctx->comm; }
 
 // ---------------------------------------------------------------------------------------
-__global__ void k_owner(const int32_t *__restrict__ cell2rank, long long ncells, const int *__restrict__ cuts, int P,
+// A bucket of the mesh's bottom layer (k == 0: underground) always goes with the bucket above it: the reference sorts it
+// by the key of that bucket (PartiHead top_key, preprocess.cc:219-239, :264-275), so the two never part company.
+__device__ __forceinline__ long long partition_cell(long long c, int nz) { return (nz > 1 && c % nz == 0) ? c + 1 : c; }
+
+__global__ void k_owner(const int32_t *__restrict__ cell2rank, long long ncells, int nz, const int *__restrict__ cuts, int P,
                         int32_t *__restrict__ owner)
 {
   long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
-  const int r = cell2rank[c];
+  const int r = cell2rank[partition_cell(c, nz)];
   int q = 0;
   while (q + 1 < P && r >= cuts[q + 1]) q++;
   owner[c] = q;
@@ -193,11 +197,12 @@ __global__ void k_set_n(StepState *ss, int n) { ss->n = n; }
 
 // load weight of every cell in rank order, x100 so that the sums are exact integers
 // (real 2.0, wall ghost 0.75, erupt ghost 0.02, pressure ghost 0: repartition_BSFC.cc:128-143, parameters.h:1035-1038)
-__global__ void k_cell_weights(Tab V, const StepState *ss, const int32_t *__restrict__ cell2rank, unsigned long long *__restrict__ w)
+__global__ void k_cell_weights(Tab V, const StepState *ss, const int32_t *__restrict__ cell2rank, int nz, unsigned long long *__restrict__ w)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ss->n) return;
-  const int cell = V.i[I_CELL][p];
+  int cell = V.i[I_CELL][p];
+  if (cell >= 0) cell = (int) partition_cell(cell, nz);           // an underground bucket's load counts where it goes
   if (cell < 0 || V.i[I_GUEST][p]) return;
   const int bc = V.i[I_BC][p];
   const unsigned long long v = (bc == 100 || bc == 99) ? 200ull : bc == 2 ? 75ull : bc == 0 ? 2ull : 0ull;
@@ -315,7 +320,7 @@ int update_owner_tables(psph_ctx *ctx)
   Comm *C = comm_of(ctx);
   PSPH_CUDA(cudaMemcpyAsync(C->d_cuts, C->cuts.data(), (C->P + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   const unsigned grid = (unsigned) ((ctx->ncells + 255) / 256);
-  k_owner<<<grid, 256, 0, ctx->stream>>>(ctx->d_cell2rank, ctx->ncells, C->d_cuts, C->P, C->d_owner);
+  k_owner<<<grid, 256, 0, ctx->stream>>>(ctx->d_cell2rank, ctx->ncells, ctx->cfg.ncell[2], C->d_cuts, C->P, C->d_owner);
   PSPH_LAUNCH_CHECK();
   k_cellmask<<<grid, 256, 0, ctx->stream>>>(psph_grid_view(ctx), C->d_owner, C->me, C->d_cellmask);
   PSPH_LAUNCH_CHECK();
@@ -695,7 +700,7 @@ extern "C" int psph_repartition(psph_ctx *ctx)
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   PSPH_CUDA(cudaMemsetAsync(C->d_weights, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
   if (ctx->n > 0) {
-    k_cell_weights<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, ctx->d_ss, ctx->d_cell2rank, C->d_weights);
+    k_cell_weights<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, ctx->d_ss, ctx->d_cell2rank, ctx->cfg.ncell[2], C->d_weights);
     PSPH_LAUNCH_CHECK();
   }
   PSPH_NCCL(g_nccl.AllReduce(C->d_weights, C->d_weights, ctx->ncells, ncclUint64, ncclSum, C->comm, ctx->stream));

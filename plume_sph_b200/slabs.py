@@ -37,9 +37,25 @@ def plan_cuts(cell_weight_rank_order, nranks):
     return cuts
 
 
-def owners(cell2rank, cuts):
+def partition_cell(cell, nz):
+    """the cell whose key decides where `cell` goes: a bucket of the bottom layer (k == 0, underground) is sorted by the key
+    of the bucket above it (PartiHead top_key, preprocess.cc:219-239, :264-275), so the two always share a rank"""
+    cell = np.asarray(cell, np.int64)
+    return np.where((nz > 1) & (cell % nz == 0), cell + 1, cell)
+
+
+def cell_weights(cell, bc_type, cell2rank, nz):
+    """per-rank-position load (x100) from the particles' cells: what k_cell_weights accumulates"""
+    w = np.zeros(len(cell2rank), np.int64)
+    np.add.at(w, np.asarray(cell2rank)[partition_cell(cell, nz)], particle_weights(bc_type))
+    return w
+
+
+def owners(cell2rank, cuts, nz=1):
     """owner rank of every cell (linear cell index -> rank)"""
-    return (np.searchsorted(np.asarray(cuts[1:-1]), np.asarray(cell2rank), side="right")).astype(np.int32)
+    c2r = np.asarray(cell2rank)
+    r = c2r[partition_cell(np.arange(len(c2r)), nz)]
+    return (np.searchsorted(np.asarray(cuts[1:-1]), r, side="right")).astype(np.int32)
 
 
 def boundary_masks(owner, ncell):

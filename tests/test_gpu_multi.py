@@ -84,8 +84,7 @@ def test_slabs_match_single_gpu(P):
     mind = np.asarray([cfg.mindom[k] for k in range(3)])
     idx = np.floor((rows["coords"] - mind) / cfg.delta).astype(np.int64)
     cell = (idx[:, 0] * int(cfg.ncell[1]) + idx[:, 1]) * int(cfg.ncell[2]) + idx[:, 2]
-    w = np.zeros(cfg.ncells, np.int64)
-    np.add.at(w, ranks[cell], slabs.particle_weights(rows["bc_type"]))
+    w = slabs.cell_weights(cell, rows["bc_type"], ranks, int(cfg.ncell[2]))
     assert res[0][0] == slabs.plan_cuts(w, P)
     res = [x[:4] for x in res]
     for cuts, got, out, sent in res:
@@ -194,6 +193,17 @@ def test_plume_with_wall_ghosts_and_vent_across_slabs(P):
         assert e <= 1e-12, (f, e)
     wall = a["bc_type"] == 2
     assert wall.any() and relerr(a["vel"][wall], b["vel"][wall]) <= 1e-12
+    # an underground bucket (bottom layer of the mesh) sits on the rank of the bucket above it (preprocess.cc:264-275)
+    mind = np.asarray([cfg.mindom[k] for k in range(3)])
+    rank_of_cell = {}
+    for r, (_, _, o) in enumerate(res):
+        own = o[o["guest"] == 0]
+        idx = np.floor((own["coords"] * cfg.len_scale - mind) / cfg.delta).astype(np.int64)
+        for c in set(map(tuple, idx.tolist())):
+            rank_of_cell.setdefault(c, set()).add(r)
+    assert all(len(v) == 1 for v in rank_of_cell.values())
+    bottom = [c for c in rank_of_cell if c[2] == 0 and (c[0], c[1], 1) in rank_of_cell]
+    assert bottom and all(rank_of_cell[c] == rank_of_cell[(c[0], c[1], 1)] for c in bottom)
     for _, _, o in res:                                      # guests mirror their owners
         g = o[o["guest"] != 0]
         src = a[np.searchsorted(np.sort(ko), key64(g))]

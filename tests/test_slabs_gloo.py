@@ -47,10 +47,10 @@ def plan_single(cfg, rows, P):
     from plume_sph_b200 import slabs
     rank = hilbert_ranks(cfg)
     cell = cell_of(cfg, rows["coords"])
-    w = np.zeros(cfg.ncells, np.int64)
-    np.add.at(w, rank[cell], slabs.particle_weights(rows["bc_type"]))
+    nz = int(cfg.ncell[2])
+    w = slabs.cell_weights(cell, rows["bc_type"], rank, nz)
     cuts = slabs.plan_cuts(w, P)
-    owner = slabs.owners(rank, cuts)
+    owner = slabs.owners(rank, cuts, nz)
     mask = slabs.boundary_masks(owner, tuple(int(cfg.ncell[k]) for k in range(3)))
     return rank, cell, cuts, owner, mask
 
@@ -66,12 +66,12 @@ def worker(r, P, port, q):
     rank = hilbert_ranks(cfg)
     cell = cell_of(cfg, mine["coords"])
     # psph_repartition: local weights in rank order -> all-reduce -> exact prefix cut
-    w = np.zeros(cfg.ncells, np.int64)
-    np.add.at(w, rank[cell], slabs.particle_weights(mine["bc_type"]))
+    nz = int(cfg.ncell[2])
+    w = slabs.cell_weights(cell, mine["bc_type"], rank, nz)
     wt = torch.from_numpy(w)
     dist.all_reduce(wt)
     cuts = slabs.plan_cuts(wt.numpy(), P)
-    owner = slabs.owners(rank, cuts)
+    owner = slabs.owners(rank, cuts, nz)
     mask = slabs.boundary_masks(owner, tuple(int(cfg.ncell[k]) for k in range(3)))
     # migrate(): rows whose cell belongs to another rank go there
     dest = owner[cell]
@@ -138,3 +138,22 @@ def test_two_rank_slab_plan_matches_single_process():
     from plume_sph_b200 import slabs
     w = [int(slabs.particle_weights(rows["bc_type"][owner[cell] == r]).sum()) for r in range(P)]
     assert abs(w[0] - w[1]) <= 2 * 512 * 200
+
+
+
+def test_underground_bucket_goes_with_the_one_above():
+    """preprocess.cc:219-239, :264-275: a bucket of the mesh's bottom layer is sorted by the key of the bucket above it, so
+    both land on the same rank, and its load (wall ghosts: 0.75 each) is counted there"""
+    from plume_sph_b200 import slabs
+    n = (4, 3, 5)
+    ncells = n[0] * n[1] * n[2]
+    rng = np.random.default_rng(2)
+    rank = rng.permutation(ncells).astype(np.int32)
+    cell = rng.integers(0, ncells, 4000)
+    bc = rng.choice([100, 2, 1, 0], 4000)
+    w = slabs.cell_weights(cell, bc, rank, n[2])
+    bottom = np.arange(ncells) % n[2] == 0
+    assert w[rank[bottom]].sum() == 0 and w.sum() == slabs.particle_weights(bc).sum()
+    for P in (2, 3, 4):
+        owner = slabs.owners(rank, slabs.plan_cuts(w, P), n[2]).reshape(n)
+        assert np.array_equal(owner[:, :, 0], owner[:, :, 1])

@@ -193,6 +193,12 @@ int psph_download(psph_ctx *ctx, psph_particle *rows, size_t cap, size_t *n, int
 int psph_upload_rows(psph_ctx *ctx, const void *rows, size_t n, size_t row_bytes);
 int psph_append_rows(psph_ctx *ctx, const void *rows, size_t n, size_t row_bytes);
 int psph_download_rows(psph_ctx *ctx, void *rows, size_t cap, size_t *n, int order, size_t row_bytes);
+/* The output path as columns (write_h5part, h5part_writer.cc:40-269): the datasets of one "Step#k" group for the rows
+ * the writer emits — non-guest real particles (:88-91), or every particle when with_ghosts != 0 (a WRITE_GHOSTS build) —
+ * in THashTable iteration order (thashtab.cc:204-222, :86-134), selected, ordered and gathered on the device:
+ *   dcols[10] = x, y, z, Rho, Vx, Vy, Vz, engr, mssfrc, prss     icols[3] = phase, bctp, guest      (ID is 0 .. n-1)
+ * Each array holds `cap` entries (a NULL entry is skipped); *n = rows written.  dcols == NULL: count only. */
+int psph_download_h5part(psph_ctx *ctx, double *const *dcols, int32_t *const *icols, size_t cap, size_t *n, int with_ghosts);
 size_t psph_num_particles(const psph_ctx *ctx);
 /* rows the summation stages update on this rank (need_neigh, particle.h:555-558, and the list rule of
  * neighs.cc:65-82); builds the cell list if needed and synchronises */

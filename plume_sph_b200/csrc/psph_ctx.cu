@@ -403,7 +403,7 @@ __global__ void k_soa_to_aos(char *__restrict__ rows, size_t stride, int n, Tab 
     for (int k = 0; k < 15; k++) r.grad[k] = has_grad ? V.d[D_GRAD0 + k][p] : 0.0;
 }
 
-static int ensure_aos(psph_ctx *ctx, size_t n)
+int psph_ensure_aos(psph_ctx *ctx, size_t n)
 {
   if (n > ctx->aos_cap) {
     cudaFree(ctx->d_aos);
@@ -441,7 +441,7 @@ static int upload_at(psph_ctx *ctx, const void *rows, size_t n, size_t base, siz
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   if (psph_reserve(ctx, base + n)) return -1;
   if (n) {
-    if (ensure_aos(ctx, n)) return -1;
+    if (psph_ensure_aos(ctx, n)) return -1;
     PSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, rows, n * stride, cudaMemcpyHostToDevice, ctx->stream));
     k_aos_to_soa<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const char *>(ctx->d_aos), stride, (int) n,
                                                                          (int) base, ctx->cur.t, psph_grid_view(ctx), ctx->has_grad,
@@ -493,7 +493,7 @@ extern "C" int psph_download_rows(psph_ctx *ctx, void *rows_v, size_t cap, size_
   if (!rows) return 0;
   if (cap < n) { ctx->err = "psph_download: buffer too small"; return -2; }
   if (n == 0) return 0;
-  if (ensure_aos(ctx, n)) return -1;
+  if (psph_ensure_aos(ctx, n)) return -1;
   k_soa_to_aos<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<char *>(ctx->d_aos), stride, (int) n, ctx->cur.t,
                                                                        ctx->has_grad);
   PSPH_LAUNCH_CHECK();

@@ -116,14 +116,14 @@ __device__ __forceinline__ bool dev_in_support(double dx, double dy, double dz, 
 // line code, valid for the argument ranges that occur here (normal, finite operands), and
 // accurate to <= 2 ulp — inside the FP64 tolerance the parity tests state.
 
-// 1/x for normal finite x: hardware seed + two Newton steps
+// 1/x for normal finite x: hardware seed (MUFU.RCP64H: relative error 1e-6 measured) + two Newton steps.  Measured over
+// 2^24 operands in [2^-20, 2^20] (profiles/rcp_check.cu -> profiles/r02e_rcp_check.json): one step leaves 9.8e-13, two steps
+// return the correctly rounded quotient in every case — a third step buys nothing.
 __device__ __forceinline__ double dev_rcp(double x)
 {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   return fma(r, e, r);

@@ -211,7 +211,7 @@ k_mix_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__res
       const int lx = (int) (pk0 & 0xfffff) - cx * SUBDIV, ly = (int) ((pk0 >> 20) & 0xfffff) - cy * SUBDIV;
       const int q = lx >> 1;                                           // the block of the group
       float4 p32 = make_float4(0.f, 0.f, 0.f, 0.f);
-      int sz = 0, myself = -1;
+      int sz = 0, myself = -1, rsub = 0;
       bool bad = false;
       if (mine) {
         sz = (int) ((pk >> 40) & 0xfffff) - cz * SUBDIV;
@@ -220,7 +220,8 @@ k_mix_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__res
         // the neighbour-list / in_support limits (neighs.cc:84-92,130; sph_header.h:49-60) can bite: not a list row
         const bool nl = rmax > fmin(K.cutoff2 * hi, K.neigh_radius * V.t.d[D_HLIST][row]);
         // ... nor is one whose partners can sit beyond MR subcells, or that lies on a subcell face
-        bad = nl || (int) ceil(rmax * G.inv_subw - 1e-9) > MR || (pk >> 60) != 0 || row >= list_rows;
+        rsub = (int) ceil(rmax * G.inv_subw - 1e-9);          // subcells a partner can be away (rows on a subcell face are out)
+        bad = nl || rsub > MR || (pk >> 60) != 0 || row >= list_rows;
         if (cell_ok) {
           const int s = ((lx + MR) * MCY + ly + MR) * 3 + 1;
           myself = T.off[s] + (row - T.beg[s]);
@@ -235,6 +236,9 @@ k_mix_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__res
         continue;
       }
       const int zlo = __reduce_min_sync(FULL, mine ? sz : 0x7fffffff), zhi = __reduce_max_sync(FULL, mine ? sz : -1);
+      // the candidate box is as wide as THIS group's smoothing lengths need (h = 1.2 spacings: 4 subcells, not MR = 5:
+      // 9 x 9 instead of 11 x 11 columns)
+      const int R = min(max(__reduce_max_sync(FULL, mine ? rsub : 0), 1), MR);
       unsigned ovf = 0;
       int ig[GRP], selfslot[GRP], cnt[GRP], c0s[GRP], c1s[GRP];
       unsigned qa[GRP];
@@ -263,13 +267,14 @@ k_mix_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__res
         }
         __syncwarp();
       };
-      // the group's box in bucket-tile columns: x [lx, lx + 2 MR], y [ly, ly + 2 MR]; z levels [zlo, zhi + 2 MR]
-      const int lv0 = zlo, lv1 = zhi + 2 * MR + 1;
+      // the group's box in bucket-tile columns (the row's own column is (lx + MR, ly + MR), its level sz + MR):
+      // x [lx + MR - R, lx + MR + R], y likewise; z levels [zlo + MR - R, zhi + MR + R]
+      const int lv0 = zlo + MR - R, lv1 = zhi + MR + R + 1;
       for (int s = 0; s < MNSUB; s++) {
         const int xs0 = 2 * q + MSX * s;
-        const int xa = max(lx, xs0), xb = min(lx + 2 * MR, xs0 + MSX - 1);
+        const int xa = max(lx + MR - R, xs0), xb = min(lx + MR + R, xs0 + MSX - 1);
         const int subbase = T.off[xs0 * MCY * 3];                      // first slot of the sub-tile
-        const int ncy = 2 * MR + 1, ncol = max(xb - xa + 1, 0) * ncy;
+        const int ncy = 2 * R + 1, ncol = max(xb - xa + 1, 0) * ncy;
         int col_base = -32, c0 = 0, total = 0, slot = 0, len = 0;
 
         auto test = [&](unsigned sl, const float4 &p) {
@@ -328,7 +333,7 @@ k_mix_scan(DevView V, GridView G, KParams K, StepState *ss, unsigned char *__res
               const int c = col_base + lane;
               len = 0;
               if (c < ncol) {
-                const int ix = c / ncy, iy = c - ix * ncy, col = (xa + ix) * MCY + ly + iy;
+                const int ix = c / ncy, iy = c - ix * ncy, col = (xa + ix) * MCY + ly + MR - R + iy;
                 slot = T.colz[col][lv0];
                 len = (int) T.colz[col][lv1] - slot;
               }
@@ -426,14 +431,6 @@ __device__ __forceinline__ void mix_build(const GridView &G, int cx, int cy, int
   __syncthreads();
 }
 
-// slot of the sub-tile -> row (near partners: a few per row)
-__device__ __forceinline__ int mix_row_of(const MixTable &tab, int sl)
-{
-  int lo = 0, hi = MSEG;
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tab.off[mid] <= sl) lo = mid; else hi = mid; }
-  return tab.beg[lo] + (sl - tab.off[lo]);
-}
-
 // Stage interface on top of psph_gather.cuh / psph_stages.cu (S::I, S::init, S::R):
 //   kNCm          doubles per sub-tile row in shared memory
 //   kNAm          sums per row (4, or 6 when the stage forms the density sums on the side)
@@ -453,7 +450,9 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
   double *comp = reinterpret_cast<double *>(s_raw + sizeof(MixTable));                     // [kNCm][MCAP]
   double *acc = comp + (size_t) S::kNCm * MCAP;                                            // [MBR][NA]
   int *nnear = reinterpret_cast<int *>(acc + MBR * NA);                                    // [MBR]
-  int *tile_row = reinterpret_cast<int *>(comp);                                           // [MCAP] while a sub-tile is staged
+  // slot -> row of the staged sub-tile: kept next to the records when the stage lists near partners (NA == 6), else it
+  // only lives while the sub-tile is staged (in the first column's storage)
+  int *tile_row = NA == 6 ? nnear + MBR : reinterpret_cast<int *>(comp);                   // [MCAP]
   if (ss->pair_mode != 4) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short *__restrict__ lists = V.mlist;
@@ -482,7 +481,7 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
       int myrow[NPT];
 #pragma unroll
       for (int u = 0; u < NPT; u++) { const int t = threadIdx.x + u * WARPS * 32; myrow[u] = t < total ? tile_row[t] : -1; }
-      __syncthreads();                                              // the map shares its storage with the first column
+      if (NA != 6) __syncthreads();                                 // the map shares its storage with the first column
 #pragma unroll
       for (int u = 0; u < NPT; u++) {
         const int t = threadIdx.x + u * WARPS * 32;
@@ -517,7 +516,7 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
             const unsigned fb = __ballot_sync(FULL, near);
             if (fb) {                                                 // a partner inside the energy-smoothing kernel
               const int pos = nn + __popc(fb & ((1u << lane) - 1u));
-              if (near && pos < NEAR_MAX) V.near[NEARW * i + 1 + pos] = mix_row_of(tab, sl);
+              if (near && pos < NEAR_MAX) V.near[NEARW * i + 1 + pos] = tile_row[sl];
               nn += __popc(fb);
             }
           }
@@ -552,7 +551,8 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
 template <class S, int WARPS, int MINB>
 int launch_mix_gather(psph_ctx *ctx, int kid)
 {
-  constexpr size_t smem = sizeof(MixTable) + sizeof(double) * ((size_t) S::kNCm * MCAP + MBR * S::kNAm) + sizeof(int) * MBR;
+  constexpr size_t smem = sizeof(MixTable) + sizeof(double) * ((size_t) S::kNCm * MCAP + MBR * S::kNAm) + sizeof(int) * MBR +
+                          (S::kNAm == 6 ? sizeof(int) * MCAP : 0);
   static_assert((smem + 1024) * MINB <= 227 * 1024, "sub-tile does not fit in shared memory");
   PSPH_CUDA(cudaFuncSetAttribute(k_mix_gather<S, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   KernelTimer kt(ctx, kid);

@@ -91,6 +91,26 @@ class Solver:
                  "psph_download_rows")
         return out[:n.value]
 
+    H5PART_DOUBLE = ("x", "y", "z", "Rho", "Vx", "Vy", "Vz", "engr", "mssfrc", "prss")
+    H5PART_INT = ("phase", "bctp", "guest")
+
+    def download_h5part(self, with_ghosts=False):
+        """the datasets write_h5part (h5part_writer.cc:40-269) puts into one "Step#k" group, as a dict of arrays in the
+        writer's order (THashTable iteration, non-guest real particles unless with_ghosts): ID, x .. prss, phase, bctp,
+        guest — selected, ordered and gathered on the device (psph_download_h5part)"""
+        n = C.c_size_t(0)
+        self._ck(self.L.psph_download_h5part(self.h, None, None, 0, C.byref(n), int(with_ghosts)), "psph_download_h5part")
+        m = n.value
+        d = {k: np.zeros(m, np.float64) for k in self.H5PART_DOUBLE}
+        i = {k: np.zeros(m, np.int32) for k in self.H5PART_INT}
+        dp = (C.c_void_p * 10)(*[d[k].ctypes.data for k in self.H5PART_DOUBLE])
+        ip = (C.c_void_p * 3)(*[i[k].ctypes.data for k in self.H5PART_INT])
+        self._ck(self.L.psph_download_h5part(self.h, dp, ip, m, C.byref(n), int(with_ghosts)), "psph_download_h5part")
+        out = {"ID": np.arange(m, dtype=np.int32)}
+        out.update(d)
+        out.update(i)
+        return out
+
     def upload_device_soa(self, cols, bc=None, phase=None, n=0):
         """cols: list of PSPH_COL_COUNT device pointers (ints); bc/phase: device pointers or None."""
         arr = (C.c_void_p * len(cols))(*cols)

@@ -146,3 +146,37 @@ def test_sph_rows_round_trip():
     finally:
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("name", ["plume3d_small", "jpue3d"])
+def test_h5part_columns_match_the_writer(name):
+    """psph_download_h5part == what write_h5part (h5part_writer.cc:40-269) would put into a Step group from this table:
+    the reference's own dump is in THashTable iteration order (the writer's loop), the writer keeps the non-guest real
+    rows; and == the full-row download in reference order, filtered the same way, after a time step"""
+    z = golden(name)
+    ocfg = op.config_for(name, z)
+    s = psph.Solver(to_product_cfg(ocfg))
+    try:
+        attr, _ = cell_attrs(ocfg, z)
+        s.set_cells(attr)
+        pre = z["pre"]
+        rng = np.random.default_rng(3)
+        s.upload(dump_to_particles(pre)[rng.permutation(len(pre))])     # the table order must not depend on the upload order
+        cols = s.download_h5part()
+        w = (pre["bc_type"] == 100) & (pre["guest"] == 0)
+        assert len(cols["x"]) == int(w.sum()) and np.array_equal(cols["ID"], np.arange(int(w.sum())))
+        for k, (f, c) in dict(x=("coord", 0), y=("coord", 1), z=("coord", 2), Vx=("vel", 0), Vy=("vel", 1), Vz=("vel", 2)).items():
+            assert np.array_equal(cols[k], pre[f][w][:, c]), k
+        for k, f in dict(Rho="rho", engr="engr", mssfrc="mass_frac", prss="pressure", phase="phase", bctp="bc_type", guest="guest").items():
+            assert np.array_equal(cols[k], pre[f][w]), k
+        allc = s.download_h5part(with_ghosts=True)                      # a WRITE_GHOSTS build writes every particle
+        assert np.array_equal(allc["x"], pre["coord"][:, 0]) and np.array_equal(allc["bctp"], pre["bc_type"])
+        dt, lost, ierr = s.step(0.0, 1)
+        assert ierr == 0
+        rows = s.download(ORDER_REFERENCE)
+        w = (rows["bc_type"] == 100) & (rows["guest"] == 0)
+        cols = s.download_h5part()
+        assert np.array_equal(cols["z"], rows["coords"][w][:, 2]) and np.array_equal(cols["prss"], rows["pressure"][w])
+        assert np.array_equal(cols["Vy"], rows["vel"][w][:, 1]) and np.array_equal(cols["mssfrc"], rows["mass_frac"][w])
+    finally:
+        s.close()

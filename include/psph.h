@@ -80,7 +80,10 @@ typedef struct psph_config
   double c_smooth;           /* C_smooth_P = 2 */
   double thresh;             /* thresh_P = 1e-5 */
   int num_loop;              /* num_loop_P */
-  int pad0;
+  int gsph_reconstruct;      /* Riemann states of the GSPH variant (options.h:141-262, :544-663):
+                              *   0  piecewise constant: GSPH_SPECIFIC_VOL_APP 0, MINI_DERIVATIVE_COND 4 (the 1-D defaults)
+                              *   3  from the gradients of calc_gradients: GSPH_SPECIFIC_VOL_APP 3 (cubic interface position),
+                              *      MINI_DERIVATIVE_COND 10, GSPH_MODIFIED_MONOTONICITY 1, C_SHOCK = 3 (the 3-D defaults) */
   double ng0, Cvs, Cvg, Cva, Rg, Ra, rhoa0, pa0; /* EOS constants (particle.cc:528-604) */
   double erupt_top;          /* Ll_P[2]: erupt ghost turns real at z >= this (update_pos.cc:137) */
   double smlen_real;         /* matprops->smoothing_length, given to a particle that turns real */

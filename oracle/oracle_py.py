@@ -37,7 +37,7 @@ class Config(C.Structure):
         ("heat_trans_scale_ratio", C.c_double), ("e_smooth_ratio", C.c_double), ("tiny", C.c_double),
         ("alf", C.c_double), ("beta", C.c_double), ("ata", C.c_double), ("g", C.c_double),
         ("cfl", C.c_double), ("eta_smooth", C.c_double), ("c_smooth", C.c_double), ("thresh", C.c_double),
-        ("num_loop", C.c_int), ("pad0", C.c_int),
+        ("num_loop", C.c_int), ("gsph_reconstruct", C.c_int),
         ("ng0", C.c_double), ("Cvs", C.c_double), ("Cvg", C.c_double), ("Cva", C.c_double),
         ("Rg", C.c_double), ("Ra", C.c_double), ("rhoa0", C.c_double), ("pa0", C.c_double),
         ("erupt_top", C.c_double), ("smlen_real", C.c_double),
@@ -128,7 +128,16 @@ def config_jpue():
     return c
 
 
-CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue, "plume3d_sml": config_3d, "plume3d_grow": config_3d}
+def config_3d_gsph():
+    """the 3-D defaults with USE_GSPH 1 (options.h:544-663): Roe solver, Riemann states from the gradients
+    (GSPH_SPECIFIC_VOL_APP 3, MINI_DERIVATIVE_COND 10, GSPH_MODIFIED_MONOTONICITY 1)"""
+    c = config_3d()
+    c.use_gsph, c.riemann_solver, c.gsph_reconstruct = 1, 0, 3
+    return c
+
+
+CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue, "plume3d_sml": config_3d, "plume3d_grow": config_3d,
+              "plume3d_small_gsph": config_3d_gsph}
 
 
 def config_for(name, z=None):

@@ -412,10 +412,12 @@ static int mom_engr_sph(const psph_config *c, psph_oracle_state *st, double dt)
 }
 
 /* ---------------- GSPH: Riemann solvers, mom_engr_update, calc_gradients ---------------- */
-/* Option set restated: RP_MASS_WEIGHTED 0, SWITCH_OFF_AV_FOR_EXPAN 0, GSPH_SPECIFIC_VOL_APP 0,
- * MINI_DERIVATIVE_COND 4 (piecewise-constant Riemann states), SHEAR_VEL_APP 2, HLL_WAVE_SPEED_EVA 0,
- * FLUID_COMPRESSIBILITY 0 — the 1-D defaults (options.h:141-262).  With MINI_DERIVATIVE_COND 4 the
- * gradients do not enter the Riemann states (sph_lib.cc:2487-2493). */
+/* Option sets restated: RP_MASS_WEIGHTED 0, SWITCH_OFF_AV_FOR_EXPAN 0, SHEAR_VEL_APP 2, HLL_WAVE_SPEED_EVA 0,
+ * FLUID_COMPRESSIBILITY 0, and for the Riemann states (psph_config.gsph_reconstruct)
+ *   0: GSPH_SPECIFIC_VOL_APP 0, MINI_DERIVATIVE_COND 4 — the 1-D defaults (options.h:141-262): piecewise constant,
+ *      the gradients do not enter the states (sph_lib.cc:2487-2493);
+ *   3: GSPH_SPECIFIC_VOL_APP 3, MINI_DERIVATIVE_COND 10, GSPH_MODIFIED_MONOTONICITY 1 — the 3-D defaults
+ *      (options.h:544-663), normally with the Roe solver (RIEMANN_SOLVER 0). */
 static void hllc_rp_solver(double dl, double dr, double pl, double pr, double ul, double ur, double gj, double gi,
                            double *p_star, double *u_star)
 { /* sph_lib.cc:1753-1908, USE_GSPH==1 branch */
@@ -461,11 +463,34 @@ static void roe_rp_solver(double dl, double dr, double pl, double pr, double ul,
   *u_star = ulr - 0.5 * (pr - pl) / clr;
 }
 
+/* interface position, cubic in the specific volume (Compute_sij_star, sph_lib.cc:1667-1690) */
+static double compute_sij_star3(double hij, double Vi, double Vj, double Dri, double Drj, double dist)
+{
+  double DVi = -Vi * Vi * Dri;
+  double DVj = -Vj * Vj * Drj;
+  double dist_sq = dist * dist;
+  double dist_cub = dist_sq * dist;
+  double A = -2.0 * (Vi - Vj) / dist_cub + (DVi + DVj) / dist_sq;
+  double B = 0.5 * (DVi - DVj) / dist;
+  double C = 1.5 * (Vi - Vj) / dist - 0.25 * (DVi + DVj);
+  double D = 0.5 * (Vi + Vj) - 0.125 * (DVi - DVj) * dist;
+  double hsq = hij * hij;
+  double h4 = hsq * hsq;
+  double h6 = h4 * hsq;
+  double Vijsq = 0.234375 * h6 * A * A + 0.1875 * h4 * (2.0 * A * C + B * B) + 0.25 * hsq * (2.0 * B * D + C * C) + D * D;
+  return (0.46875 * h6 * A * B + 0.375 * h4 * (A * D + B * C) + 0.5 * hsq * C * D) / Vijsq;
+}
+
+/* gi/gj: the 15 gradient columns of i / j (d_rho, d_u, d_v, d_w, d_p; calc_gradients), used when
+ * c->gsph_reconstruct == 3: GSPH_SPECIFIC_VOL_APP 3, MINI_DERIVATIVE_COND 10, GSPH_MODIFIED_MONOTONICITY 1,
+ * C_SHOCK = 3 (constant.h:203) — the 3-D defaults (options.h:544-663) */
 static void riemann_solver(const psph_config *c, double rhoi, double rhoj, const double *vi, const double *vj, double pi,
-                           double pj, const double *xi, const double *xj, double gi, double gj, double *p_star,
+                           double pj, double hi, double hj, const double *xi, const double *xj, double CSi, double CSj,
+                           double gi, double gj, double dt_half, const double *Gi, const double *Gj, double *p_star,
                            double *v_star)
-{ /* sph_lib.cc:2247-2600 with the option set above */
+{ /* sph_lib.cc:2247-2600 */
   int dim = c->dim;
+  double hij = 0.5 * (hi + hj);
   double dx[3], e[3], dist = 0.0;
   for (int i = 0; i < dim; i++) dx[i] = xi[i] - xj[i];
   for (int i = 0; i < dim; i++) dist += dx[i] * dx[i];
@@ -473,8 +498,44 @@ static void riemann_solver(const psph_config *c, double rhoi, double rhoj, const
   for (int i = 0; i < dim; i++) e[i] = dx[i] / dist; /* Compute_eij, :1624-1631 */
   double ui = 0.0, uj = 0.0;
   for (int i = 0; i < dim; i++) { ui += vi[i] * e[i]; uj += vj[i] * e[i]; }
-  /* MINI_DERIVATIVE_COND == 4 */
-  double dr = rhoi, ur = ui, pr = pi, dl = rhoj, ul = uj, pl = pj;
+  double dr = rhoi, ur = ui, pr = pi, dl = rhoj, ul = uj, pl = pj; /* MINI_DERIVATIVE_COND == 4 */
+  if (c->gsph_reconstruct == 3) {
+    /* gradients projected on e (:2300-2355); the velocity gradient twice: (grad u_k . e) e_k */
+    double drhoi = 0.0, dpi = 0.0, drhoj = 0.0, dpj = 0.0, dvi[3] = { 0, 0, 0 }, dvj[3] = { 0, 0, 0 };
+    for (int i = 0; i < dim; i++) {
+      drhoi += Gi[i] * e[i];
+      drhoj += Gj[i] * e[i];
+      dpi += Gi[12 + i] * e[i];
+      dpj += Gj[12 + i] * e[i];
+      for (int k = 0; k < dim; k++) {
+        dvi[k] += Gi[3 * (k + 1) + i] * e[i];
+        dvj[k] += Gj[3 * (k + 1) + i] * e[i];
+      }
+    }
+    double ddui, dduj;
+    if (dim == 3) { ddui = dvi[0] * e[0] + dvi[1] * e[1] + dvi[2] * e[2]; dduj = dvj[0] * e[0] + dvj[1] * e[1] + dvj[2] * e[2]; }
+    else { ddui = dvi[0] * e[0]; dduj = dvj[0] * e[0]; }
+    if (ddui * dduj < 0) { ddui = 0.0; dduj = 0.0; }                 /* monotonicity (:2357-2363) */
+    if (3.0 * fabs(uj - ui) > fmin(CSi, CSj)) {                      /* GSPH_MODIFIED_MONOTONICITY 1 (:2364-2376) */
+      drhoi = 0.0; dpi = 0.0; ddui = 0.0;
+      drhoj = 0.0; dpj = 0.0; dduj = 0.0;
+    }
+    double Si = 0.5 * dist, Sj = -Si;
+    double sij_star = compute_sij_star3(hij, 1 / rhoi, 1 / rhoj, drhoi, drhoj, dist);
+    double delta_i = sij_star + CSi * dt_half - Si;
+    double delta_j = sij_star - CSj * dt_half - Sj;
+    dr = rhoi + drhoi * delta_i;
+    ur = ui + ddui * delta_i;
+    pr = pi + dpi * delta_i;
+    dl = rhoj + drhoj * delta_j;
+    ul = uj + dduj * delta_j;
+    pl = pj + dpj * delta_j;
+    if (dr < 0) dr = rhoi;                                           /* MINI_DERIVATIVE_COND 10 (:2467-2486) */
+    if (dl < 0) dl = rhoj;
+    if (pr < 0) pr = pi;
+    if (pl < 0) pl = pj;
+    if (3.0 * fabs(ul - ur) > fmin(CSi, CSj)) { ul = uj; ur = ui; }
+  }
   double u_star;
   if (c->riemann_solver == 0) roe_rp_solver(dl, dr, pl, pr, ul, ur, gj, gi, p_star, &u_star);
   else hllc_rp_solver(dl, dr, pl, pr, ul, ur, gj, gi, p_star, &u_star);
@@ -527,7 +588,8 @@ static int mom_engr_gsph(const psph_config *c, psph_oracle_state *st, double dt)
         if (!(max_dw > 0)) continue;
         for (int k = 0; k < dim; k++) velj[k] = lans ? D3(st->sv, j, k) : D3(st->v, j, k);
         double p_star, v_star[3];
-        riemann_solver(c, st->rho[i], st->rho[j], veli, velj, pressi, pressj, xi, xj, gammai, gammaj, &p_star, v_star);
+        riemann_solver(c, st->rho[i], st->rho[j], veli, velj, pressi, pressj, hi, hj, xi, xj, sndspdi, sndspdj, gammai, gammaj,
+                       0.5 * dt, st->grad + 15 * i, st->grad + 15 * j, &p_star, v_star);
         double turb_stress = 0.0;
         for (int k = 0; k < dim; k++) velij[k] = veli[k] - velj[k];
         if (lans) { /* SPH_epsilon_mom, sph_lib.cc:1331-1338 */

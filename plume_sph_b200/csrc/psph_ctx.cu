@@ -156,6 +156,11 @@ static void fill_kparams(psph_ctx *ctx)
   k.cutoff = c.cutoff; k.cutoff2 = c.cutoff2; k.neigh_radius = c.neigh_radius;
   k.msfrc_thresh = c.msfrc_thresh; k.epsilon_half = c.epsilon_half; k.prandtl = c.prandtl_num;
   k.heat_ratio = c.heat_trans_scale_ratio; k.e_ratio = c.e_smooth_ratio; k.tiny = c.tiny;
+  k.heat_c = 5.0 * c.epsilon_half / c.prandtl_num;
+  {
+    const double b1 = c.cutoff * (1.0 + 0x1p-40);
+    k.near_c = c.e_smooth_ratio * c.e_smooth_ratio / (c.dim * b1 * b1);
+  }
   k.alf = c.alf; k.beta = c.beta; k.ata = c.ata; k.g = c.g; k.cfl = c.cfl;
   k.eta_smooth = c.eta_smooth; k.c_smooth = c.c_smooth; k.thresh = c.thresh; k.num_loop = c.num_loop;
   k.ng0 = c.ng0; k.Cvs = c.Cvs; k.Cvg = c.Cvg; k.Cva = c.Cva; k.Rg = c.Rg; k.Ra = c.Ra;
@@ -199,6 +204,8 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
     ctx->scan_mode = sc ? atoi(sc) : 2;
     const char *dn = getenv("PSPH_DENSNEAR");
     ctx->dens_near = dn ? atoi(dn) : 1;
+    const char *mw = getenv("PSPH_MWARPS");
+    ctx->mix_warps = mw ? atoi(mw) : 16;
     const char *wc = getenv("PSPH_WCACHE");
     ctx->wcache = wc ? atoi(wc) : 1;
     ctx->has_erupt = false; ctx->d_erupt_boxes = nullptr; ctx->n_erupt_boxes = 0;

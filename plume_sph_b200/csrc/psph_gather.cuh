@@ -116,17 +116,17 @@ __device__ __forceinline__ bool dev_in_support(double dx, double dy, double dz, 
 // line code, valid for the argument ranges that occur here (normal, finite operands), and
 // accurate to <= 2 ulp — inside the FP64 tolerance the parity tests state.
 
-// 1/x for normal finite x: hardware seed (MUFU.RCP64H: relative error 1e-6 measured) + two Newton steps.  Measured over
-// 2^24 operands in [2^-20, 2^20] (profiles/rcp_check.cu -> profiles/r02e_rcp_check.json): one step leaves 9.8e-13, two steps
-// return the correctly rounded quotient in every case — a third step buys nothing.
+// 1/x for normal finite x: hardware seed (MUFU.RCP64H: relative error e0 <= 1e-6 measured) + ONE third-order step
+// r (1 + e + e^2), e = 1 - x r: the truncation error e0^3 = 1e-18 is below half an ulp by two orders of magnitude, so the
+// result is the correctly rounded quotient except where 1/x lies within 1e-18 of a rounding boundary.  Three dependent FMAs
+// where two Newton steps take four.  Measured over 2^24 operands in [2^-20, 2^20] (profiles/rcp_check.cu ->
+// profiles/r02f_rcp_check.json): "halley" column.
 __device__ __forceinline__ double dev_rcp(double x)
 {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
 }
 // polynomial coefficients as constant-bank operands (no per-use 64-bit immediate moves)
 __constant__ double c_exp[14] = { 1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01, -2.31904681384629956e-17,

@@ -337,7 +337,7 @@ struct MomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
   static constexpr int kRows = F_NEED, kWarps = 16, kWarpsGrp = 16, kPfGrp = 0, kWarpsScan = 24, kWarpsList = 16, kPfList = 0, kNRec = 3;
-  struct I { int i; double h, supp, hk, rho, Vi, pvsq, c, T, Cp, u[3], v0[3], e0, invh, ninvh2, norm, tin_e; };  // from invh on: init_uni / tile_uni
+  struct I { int i; double h, supp, hk, rho, hc, pvsq, c, T, Cp, u[3], v0[3], e0, invh, ninvh2, norm, tin_e; };  // from invh on: init_uni / tile_uni
   struct A { double rv[3], re; };
   static __device__ __forceinline__ double reach_h(const KParams &K, double h, double hmax)
   { return fmin(K.cutoff * 0.5 * (h + hmax), K.cutoff2 * h); }
@@ -347,8 +347,9 @@ struct MomStage
     s.h = V.t.d[D_H][i];
     s.supp = K.cutoff2 * s.h;
     s.rho = V.t.d[D_RHO][i];
-    s.Vi = 1.0 / s.rho;
-    s.pvsq = V.t.d[D_P][i] * s.Vi * s.Vi;
+    const double Vi = 1.0 / s.rho;
+    s.pvsq = V.t.d[D_P][i] * Vi * Vi;
+    s.hc = K.heat_c * Vi;
     s.c = V.t.d[D_C][i]; s.T = V.t.d[D_T][i]; s.Cp = V.t.d[D_CP][i];
     const int u = K.lans ? D_SVX : D_VX;
     s.u[0] = V.t.d[u][i]; s.u[1] = V.t.d[u + 1][i]; s.u[2] = V.t.d[u + 2][i];
@@ -400,7 +401,7 @@ struct MomStage
     load_old(V, i, s);
     s.i = i;
     const double2 p2 = tp(c, 2, t), p3 = tp(c, 3, t), p4 = tp(c, 4, t), p5 = tp(c, 5, t);
-    s.pvsq = p2.x; s.Vi = p2.y; s.rho = p3.x; s.c = p3.y; s.Cp = p4.x; s.T = p4.y;
+    s.pvsq = p2.x; s.hc = K.heat_c * p2.y; s.rho = p3.x; s.c = p3.y; s.Cp = p4.x; s.T = p4.y;
     s.u[0] = p5.x; s.u[1] = p5.y; s.u[2] = tp(c, 6, t).x;
   }
   static __device__ __forceinline__ void init_uni(const KParams &, I &s)
@@ -426,7 +427,7 @@ struct MomStage
   static __device__ __forceinline__ double pair_w(const KParams &K, const I &s, A &a, double dx, double dy, double dz, double hj,
                                                   const R &rec)
   {
-    const double h = UNI ? s.h : 0.5 * (s.h + hj);
+    const double h = UNI ? s.h : 0.5 * (s.h + hj), h2 = h * h;
     const double r2 = dx * dx + dy * dy + dz * dz;
     const double invh = UNI ? s.invh : dev_rcp(h);
     const double4 r0 = rec.r0, r1 = rec.r1, uj = rec.r2;
@@ -437,7 +438,7 @@ struct MomStage
     const double cab = 0.5 * (s.c + r1.x);
     // art_vis (sph_lib.cc:402-424): miu = h vr / (r2 + ata h^2); (beta miu - alf cab) miu / rho_ab if vr < 0.
     // One reciprocal serves both quotients; selected, not branched.
-    const double dA = r2 + K.ata * h * h, dB = s.rho + r0.w, rAB = dev_rcp(dA * dB);
+    const double dA = fma(K.ata, h2, r2), dB = s.rho + r0.w, rAB = dev_rcp(dA * dB);
     const double miu = h * vr * dB * rAB;
     double vis = (K.beta * miu - K.alf * cab) * miu * (2.0 * dA * rAB);
     vis = vr < 0 ? vis : 0.0;
@@ -447,9 +448,10 @@ struct MomStage
     if (K.lans && DIM == 3) {                                       // :307-314
       const double avr = fabs(vx * dx) + fabs(vy * dy) + fabs(vz * dz);
       const bool on = avr != 0. && r2 > 0.;
-      // k_ij = 10 eps Cp_ab r2 vv / (Pr avr) / (h cab)   (sph_lib.cc:1399-1439); F_ij = (gradW . dx) / r2 = g
-      const double kij = 10.0 * K.epsilon_half * (0.5 * (r1.y + s.Cp)) * r2 * vv * dev_rcp(on ? K.prandtl * avr * h * cab : 1.0);
-      heat = on ? r0.x * r0.z * s.Vi * kij * (s.T - r1.z) * g : 0.0;
+      // k_ij = 10 eps Cp_ab r2 vv / (Pr avr) / (h cab)   (sph_lib.cc:1399-1439); F_ij = (gradW . dx) / r2 = g;
+      // heat = m_j V_j V_i k_ij (T_i - T_j) F_ij, the constants and V_i gathered in the row's s.hc = (5 eps / Pr) V_i
+      const double num = s.hc * (s.Cp + r1.y) * (r2 * vv) * (r0.x * r0.z) * ((s.T - r1.z) * g);
+      heat = on ? num * dev_rcp(on ? avr * h * cab : 1.0) : 0.0;
     }
     const double mg = mpv * g;
     a.rv[0] -= mg * dx;
@@ -507,9 +509,10 @@ struct MomStage
     a[5] += md < 0.0 ? wm : 0.0;
     a[4] += md < 0.0 ? 0.0 : wm;
     if (K.energy_smooth == 1) {
-      const double h = 0.5 * (s.h + hj), q = K.e_ratio, b = K.cutoff * h * (1.0 + 0x1p-40);
-      // all |q dx_k / h| <= cutoff implies q^2 r2 <= DIM (cutoff h)^2: one compare clears most pairs
-      if ((dx * dx + dy * dy + dz * dz) * (q * q) <= DIM * b * b) near = !outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff);
+      const double h = 0.5 * (s.h + hj), q = K.e_ratio;
+      // all |q dx_k / h| <= cutoff implies q^2 r2 <= DIM (cutoff h)^2: one compare clears most pairs (K.near_c carries
+      // the constants and a 2^-39 margin)
+      if ((dx * dx + dy * dy + dz * dz) * K.near_c <= h * h) near = !outside_kernel<DIM>(q * dx, q * dy, q * dz, h, K.cutoff);
     }
   }
   static __device__ __forceinline__ void mix_finish(const DevView &V, const KParams &K, StepState *ss, int i, const I &s, const double *t)
@@ -764,7 +767,10 @@ static int launch_stage_gather(psph_ctx *ctx, int kid, bool writer)
       ctx->nbr_valid = true; ctx->nbr_kind = 2;
       KernelTimer kt(ctx, kid);
       if (launch_tile_gather_any<S<3> >(ctx, -1)) return -1;
-      if constexpr (S<3>::kNAm == 6) { if (launch_mix_gather<S<3>, 16, 1>(ctx, -1)) return -1; }   // (the writer is mom_engr_update)
+      if constexpr (S<3>::kNAm == 6) {                               // (the writer is mom_engr_update)
+        if (ctx->mix_warps == 24 ? launch_mix_gather<S<3>, 24, 1>(ctx, -1)
+            : ctx->mix_warps == 20 ? launch_mix_gather<S<3>, 20, 1>(ctx, -1) : launch_mix_gather<S<3>, 16, 1>(ctx, -1)) return -1;
+      }
       return launch_gather_grp<S<3> >(ctx, -1, 2);
     }
     if (ctx->nbr_mode == 3 && psph_nbr_prepare(ctx) == 1) { // general row lists: any smoothing lengths, tagged entries

@@ -28,7 +28,7 @@ class PsphConfig(C.Structure):
         ("heat_trans_scale_ratio", C.c_double), ("e_smooth_ratio", C.c_double), ("tiny", C.c_double),
         ("alf", C.c_double), ("beta", C.c_double), ("ata", C.c_double), ("g", C.c_double),
         ("cfl", C.c_double), ("eta_smooth", C.c_double), ("c_smooth", C.c_double), ("thresh", C.c_double),
-        ("num_loop", C.c_int), ("pad0", C.c_int),
+        ("num_loop", C.c_int), ("gsph_reconstruct", C.c_int),
         ("ng0", C.c_double), ("Cvs", C.c_double), ("Cvg", C.c_double), ("Cva", C.c_double),
         ("Rg", C.c_double), ("Ra", C.c_double), ("rhoa0", C.c_double), ("pa0", C.c_double),
         ("erupt_top", C.c_double), ("smlen_real", C.c_double),

@@ -1,4 +1,4 @@
-// rcp_check.cu — accuracy of the FP64 reciprocal seed (rcp.approx.ftz.f64 = MUFU.RCP64H) and of 1, 2, 3 Newton steps on it,
+// rcp_check.cu — accuracy of the FP64 reciprocal seed (rcp.approx.ftz.f64 = MUFU.RCP64H) and of 1, 2, 3 Newton steps / one third-order step on it,
 // over 2^24 operands spread across [2^-20, 2^20]: how many steps dev_rcp (psph_gather.cuh) needs.  Prints one JSON line.
 #include <cstdio>
 #include <cmath>
@@ -13,10 +13,15 @@ __global__ void k(double *err)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   const double exact = 1.0 / x;
-  double e[4];
+  double e[6];
   e[0] = fabs(r - exact) / exact;
+  {                                                                  // one third-order step r (1 + e + e^2): what dev_rcp does
+    const double t = fma(-x, r, 1.0), rh = fma(r, fma(t, t, t), r);
+    e[4] = fabs(rh - exact) / exact;
+    e[5] = rh != exact ? 1.0 : 0.0;                                  // (max -> 1 if any operand is not correctly rounded)
+  }
   for (int k = 1; k < 4; k++) { const double t = fma(-x, r, 1.0); r = fma(r, t, r); e[k] = fabs(r - exact) / exact; }
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < 6; k++) {
     double v = e[k];
     for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long *) &err[k], (unsigned long long) __double_as_longlong(v));
@@ -24,10 +29,10 @@ __global__ void k(double *err)
 }
 int main()
 {
-  double *d, h[4];
-  cudaMalloc(&d, 32); cudaMemset(d, 0, 32);
+  double *d, h[6];
+  cudaMalloc(&d, 48); cudaMemset(d, 0, 48);
   k<<<65536, 256>>>(d);
-  cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
-  printf("{\"seed_relerr\": %.3e, \"newton1\": %.3e, \"newton2\": %.3e, \"newton3\": %.3e, \"ulp\": %.3e}\n", h[0], h[1], h[2], h[3], 0x1p-53);
+  cudaMemcpy(h, d, 48, cudaMemcpyDeviceToHost);
+  printf("{\"seed_relerr\": %.3e, \"newton1\": %.3e, \"newton2\": %.3e, \"newton3\": %.3e, \"halley\": %.3e, \"halley_any_misrounded\": %d, \"ulp\": %.3e}\n", h[0], h[1], h[2], h[3], h[4], (int) h[5], 0x1p-53);
   return 0;
 }

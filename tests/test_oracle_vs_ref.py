@@ -16,10 +16,11 @@ def eq(a, b, what):
     assert np.array_equal(np.asarray(a), np.asarray(b)), what
 
 
-@pytest.mark.parametrize("name", ["plume3d_small", "jpue3d"])
+@pytest.mark.parametrize("name", ["plume3d_small", "jpue3d", "plume3d_small_gsph"])
 def test_plume3d_step1_bit_exact(name):
     """every stage of time step 1 of the reference's 3-D cases: the dusty-gas plume (ideal-gas mixture EOS,
-    gravity, Meteo atmosphere) and the JPUE jet (Tait EOS, g = 0)"""
+    gravity, Meteo atmosphere), the JPUE jet (Tait EOS, g = 0), and the plume built with USE_GSPH 1 (3-D gradients,
+    Riemann states reconstructed from them, Roe solver: options.h:544-663)"""
     z = golden(name)
     cfg = op.config_for(name, z)
     s = oracle_state_3d(cfg, z)
@@ -31,6 +32,9 @@ def test_plume3d_step1_bit_exact(name):
     loff, lidx = z["list_off"], z["list_idx"]
     for q, r in enumerate(z["list_rows"]):
         eq(np.sort(idx[off[r]:off[r + 1]]), lidx[loff[q]:loff[q + 1]], ("list", r))
+    if cfg.use_gsph:
+        assert s.calc_gradients() == 0
+        eq(s.a["grad"], z["s1_grad_grad"], "gradients")
     assert s.mom_engr_update(dt) == 0
     for f, o in (("vel", "v"), ("engr", "e"), ("pressure", "p"), ("sound_speed", "c"), ("temperature", "T"),
                  ("specific_heat_p", "Cp"), ("gamma", "gamma"), ("phase_density", "rho_ph")):

@@ -137,7 +137,7 @@ def config_3d_gsph():
 
 
 CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue, "plume3d_sml": config_3d, "plume3d_grow": config_3d,
-              "plume3d_small_gsph": config_3d_gsph}
+              "plume3d_small_gsph": config_3d_gsph, "plume3d_gsph2": config_3d_gsph}
 
 
 def config_for(name, z=None):

@@ -16,6 +16,7 @@ extern "C" void psph_config_default_3d(psph_config *c)
   c->dim = 3;
   c->use_gsph = 0;              // options.h:470
   c->riemann_solver = 0;        // options.h:544 (Roe)
+  c->gsph_reconstruct = 3;      // options.h:552-596 (used when use_gsph is switched on)
   c->have_turbulence_lans = 1;  // options.h:700
   c->have_energy_smooth = 1;    // options.h:730
   c->pghost_contribute_des = 1; // options.h:760
@@ -152,7 +153,7 @@ static void fill_kparams(psph_ctx *ctx)
   KParams &k = ctx->kp;
   k.dim = c.dim; k.use_gsph = c.use_gsph; k.riemann_solver = c.riemann_solver;
   k.lans = c.have_turbulence_lans; k.energy_smooth = c.have_energy_smooth;
-  k.pghost = c.pghost_contribute_des; k.compress = c.fluid_compressibility;
+  k.pghost = c.pghost_contribute_des; k.compress = c.fluid_compressibility; k.gsph_recon = c.gsph_reconstruct;
   k.cutoff = c.cutoff; k.cutoff2 = c.cutoff2; k.neigh_radius = c.neigh_radius;
   k.msfrc_thresh = c.msfrc_thresh; k.epsilon_half = c.epsilon_half; k.prandtl = c.prandtl_num;
   k.heat_ratio = c.heat_trans_scale_ratio; k.e_ratio = c.e_smooth_ratio; k.tiny = c.tiny;

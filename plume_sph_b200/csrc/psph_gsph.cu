@@ -3,11 +3,13 @@
 // Replaces  calc_gradients            src/plume/calculate_gradient.cc:22-209
 //           mom_engr_update (GSPH)    src/plume/mom_engr_update.cc:443-1145
 //           Riemann_Solver            src/plume/sph_lib.cc:2247-2600 (HLLC :1753-1908, Roe :1694-1749)
-// for the option set of the reference's 1-D GSPH defaults (options.h:141-262): RP_MASS_WEIGHTED 0,
-// SWITCH_OFF_AV_FOR_EXPAN 0, GSPH_SPECIFIC_VOL_APP 0, MINI_DERIVATIVE_COND 4 (piecewise-constant
-// Riemann states: the gradients are computed and stored like the reference does, but do not enter
-// the states, sph_lib.cc:2487-2493), SHEAR_VEL_APP 2 (Roe-averaged shear velocity),
-// HLL_WAVE_SPEED_EVA 0, ideal-gas sound speeds.  Both stages run on the warp gather of psph_gather.cuh.
+// for RP_MASS_WEIGHTED 0, SWITCH_OFF_AV_FOR_EXPAN 0, SHEAR_VEL_APP 2 (Roe-averaged shear velocity), HLL_WAVE_SPEED_EVA 0,
+// ideal-gas sound speeds, and both option sets of the Riemann states (psph_config.gsph_reconstruct):
+//   0  the 1-D defaults (options.h:141-262): GSPH_SPECIFIC_VOL_APP 0, MINI_DERIVATIVE_COND 4 — piecewise-constant states, the
+//      gradients are computed and stored like the reference does but do not enter them (sph_lib.cc:2487-2493);
+//   3  the 3-D defaults (options.h:544-663): states reconstructed from the gradients, GSPH_SPECIFIC_VOL_APP 3 (cubic interface
+//      position), MINI_DERIVATIVE_COND 10, GSPH_MODIFIED_MONOTONICITY 1 — normally with the Roe solver.
+// Both stages run on the warp gather of psph_gather.cuh.
 #include "psph_gather.cuh"
 
 // ---- stage records -----------------------------------------------------------------------
@@ -119,15 +121,58 @@ struct GradStage
 // =========================================================================================
 // Riemann problem between i ("right") and j ("left") along e = (x_i - x_j)/|x_i - x_j|
 // =========================================================================================
+// interface position, cubic in the specific volume (Compute_sij_star, sph_lib.cc:1667-1690)
+__device__ __forceinline__ double dev_sij_star3(double hij, double Vi, double Vj, double Dri, double Drj, double dist)
+{
+  const double DVi = -Vi * Vi * Dri, DVj = -Vj * Vj * Drj;
+  const double dist_sq = dist * dist, dist_cub = dist_sq * dist;
+  const double A = -2.0 * (Vi - Vj) / dist_cub + (DVi + DVj) / dist_sq;
+  const double B = 0.5 * (DVi - DVj) / dist;
+  const double C = 1.5 * (Vi - Vj) / dist - 0.25 * (DVi + DVj);
+  const double D = 0.5 * (Vi + Vj) - 0.125 * (DVi - DVj) * dist;
+  const double hsq = hij * hij, h4 = hsq * hsq, h6 = h4 * hsq;
+  const double Vijsq = 0.234375 * h6 * A * A + 0.1875 * h4 * (2.0 * A * C + B * B) + 0.25 * hsq * (2.0 * B * D + C * C) + D * D;
+  return (0.46875 * h6 * A * B + 0.375 * h4 * (A * D + B * C) + 0.5 * hsq * C * D) / Vijsq;
+}
+
+// Gi / Gj: the 15 gradient columns of i / j (d_rho, d_u, d_v, d_w, d_p), read only when K.gsph_recon == 3: the Riemann
+// states are then reconstructed from them (sph_lib.cc:2300-2486: GSPH_SPECIFIC_VOL_APP 3, MINI_DERIVATIVE_COND 10,
+// GSPH_MODIFIED_MONOTONICITY 1, C_SHOCK 3 — the 3-D defaults, options.h:544-663)
 template <int DIM>
 __device__ __forceinline__ void dev_riemann(const KParams &K, double rhoi, double rhoj, const double *vi, const double *vj,
                                             double pi, double pj, const double *dx, double dist, double gi, double gj,
+                                            double hij, double CSi, double CSj, double dt_half, const double *Gi, const double *Gj,
                                             double &p_star, double *v_star)
 {
   double e[3] = { 0, 0, 0 }, ui = 0.0, uj = 0.0;
   for (int k = 0; k < DIM; k++) e[k] = dx[k] / dist;                 // Compute_eij, sph_lib.cc:1624-1631
   for (int k = 0; k < DIM; k++) { ui += vi[k] * e[k]; uj += vj[k] * e[k]; }
-  const double dr = rhoi, ur = ui, pr = pi, dl = rhoj, ul = uj, pl = pj; // MINI_DERIVATIVE_COND 4
+  double dr = rhoi, ur = ui, pr = pi, dl = rhoj, ul = uj, pl = pj;   // MINI_DERIVATIVE_COND 4
+  if (K.gsph_recon == 3) {
+    double drhoi = 0.0, dpi = 0.0, drhoj = 0.0, dpj = 0.0, dvi[3] = { 0, 0, 0 }, dvj[3] = { 0, 0, 0 };
+    for (int a = 0; a < DIM; a++) {
+      drhoi += Gi[a] * e[a];
+      drhoj += Gj[a] * e[a];
+      dpi += Gi[12 + a] * e[a];
+      dpj += Gj[12 + a] * e[a];
+      for (int k = 0; k < DIM; k++) { dvi[k] += Gi[3 * (k + 1) + a] * e[a]; dvj[k] += Gj[3 * (k + 1) + a] * e[a]; }
+    }
+    double ddui = 0.0, dduj = 0.0;
+    for (int k = 0; k < DIM; k++) { ddui += dvi[k] * e[k]; dduj += dvj[k] * e[k]; }
+    if (ddui * dduj < 0) { ddui = 0.0; dduj = 0.0; }                // monotonicity (:2357-2363)
+    const double csmin = fmin(CSi, CSj);
+    if (3.0 * fabs(uj - ui) > csmin) { drhoi = dpi = ddui = drhoj = dpj = dduj = 0.0; }   // (:2364-2376)
+    const double Si = 0.5 * dist, Sj = -Si;
+    const double sij = dev_sij_star3(hij, 1 / rhoi, 1 / rhoj, drhoi, drhoj, dist);
+    const double delta_i = sij + CSi * dt_half - Si, delta_j = sij - CSj * dt_half - Sj;
+    dr = rhoi + drhoi * delta_i; ur = ui + ddui * delta_i; pr = pi + dpi * delta_i;
+    dl = rhoj + drhoj * delta_j; ul = uj + dduj * delta_j; pl = pj + dpj * delta_j;
+    if (dr < 0) dr = rhoi;                                          // MINI_DERIVATIVE_COND 10 (:2467-2486)
+    if (dl < 0) dl = rhoj;
+    if (pr < 0) pr = pi;
+    if (pl < 0) pl = pj;
+    if (3.0 * fabs(ul - ur) > csmin) { ul = uj; ur = ui; }
+  }
   const double rdl = sqrt(dl), rdr = sqrt(dr), den = 1.0 / (rdl + rdr);
   const double ulr = (ul * rdl + ur * rdr) * den;
   const double plr = (pl * rdl + pr * rdr) * den, gammalr = (gj * rdl + gi * rdr) * den, dlr = (dl * rdl + dr * rdr) * den;
@@ -168,12 +213,15 @@ template <int DIM>
 struct GsphMomStage
 {
   static constexpr bool kSymH = true, kSkipSelf = true, kCountSupport = false;
-  static constexpr int kRows = F_NEED, kWarps = 16;
-  struct I { int i, pass; double h, supp, hk, rho, Vi, p, c, gamma, T, Cp, u[3], rhs[3], xdot[3]; };
+  static constexpr int kRows = F_NEED, kWarps = DIM == 3 ? 8 : 16;   // 3-D: both gradient sets live in registers
+  struct I { int i, pass; double h, supp, hk, rho, Vi, p, c, gamma, T, Cp, u[3], rhs[3], xdot[3], dt_half, G[15]; };
   struct A { double rv[3], re; };
-  static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *, int i, I &s)
+  static __device__ __forceinline__ void init(const DevView &V, const KParams &K, StepState *ss, int i, I &s)
   {
     s.i = i;
+    s.dt_half = 0.5 * ss->dt;
+    if (K.gsph_recon == 3)
+      for (int k = 0; k < 15; k++) s.G[k] = V.t.d[D_GRAD0 + k][i];
     s.h = V.t.d[D_H][i]; s.supp = K.cutoff2 * s.h;
     s.rho = V.t.d[D_RHO][i]; s.Vi = 1.0 / s.rho; s.p = V.t.d[D_P][i];
     s.c = V.t.d[D_C][i]; s.gamma = V.t.d[D_GAMMA][i]; s.T = V.t.d[D_T][i]; s.Cp = V.t.d[D_CP][i];
@@ -196,7 +244,10 @@ struct GsphMomStage
     const double Vj = 1.0 / r0.y;
     const double d[3] = { dx, dy, dz }, uj[3] = { uj4.x, uj4.y, uj4.z };
     double p_star, v_star[3];
-    dev_riemann<DIM>(K, s.rho, r0.y, s.u, uj, s.p, r0.z, d, sqrt(r2), s.gamma, r1.x, p_star, v_star);
+    double Gj[15];
+    if (K.gsph_recon == 3)
+      for (int k = 0; k < 15; k++) Gj[k] = __ldg(&V.t.d[D_GRAD0 + k][j]);
+    dev_riemann<DIM>(K, s.rho, r0.y, s.u, uj, s.p, r0.z, d, sqrt(r2), s.gamma, r1.x, h, s.c, r0.w, s.dt_half, s.G, Gj, p_star, v_star);
     double vv = 0.0;
     for (int k = 0; k < DIM; k++) vv += (s.u[k] - uj[k]) * (s.u[k] - uj[k]);
     const double turb = K.lans ? K.epsilon_half * vv * Vj : 0.0;    // SPH_epsilon_mom

@@ -214,9 +214,9 @@ def golden_3d_sml(name="plume3d_sml", variant="3d_plume", edits=None, simdata="s
             out["pre%d" % st] = pre
             pack_buckets(out, "b%d" % st, os.path.join(dump, "s%04d_search_buckets.bin" % st))
             cur = {f: pre[f].copy() for f in pre.dtype.names}
-            for stage in ("sml", "mom", "dens", "svel", "pos"):
+            for stage in ("sml", "grad", "mom", "dens", "svel", "pos"):
                 fn = os.path.join(dump, "s%04d_%s_post.bin" % (st, stage))
-                if stage == "sml" and not sml_int:
+                if (stage == "sml" and not sml_int) or (stage == "grad" and "gsph" not in variant):
                     continue
                 assert os.path.exists(fn), fn
                 _, rows = refio.read_dump(fn)
@@ -312,8 +312,11 @@ if __name__ == "__main__":
         "erupt3d_jpue": lambda: golden_erupt("erupt3d_jpue", "3d_jpue", JPUE_3D, steps=(2, 3, 4),
                                              simdata="simulation_JPUE_incomp_back.data"),
         "plume3d_small": lambda: golden_3d("plume3d_small", "3d_plume", SMALL_3D),
-        "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D),
+        "plume3d_small_gsph": lambda: golden_3d("plume3d_small_gsph", "3d_plume_gsph", SMALL_3D, list_stride=16),
         "plume3d_sml": lambda: golden_3d_sml(),
+        # the USE_GSPH 1 build over two steps with adaptive_sml in each: step 2 has velocities, velocity gradients and
+        # per-particle smoothing lengths in the reconstructed Riemann states
+        "plume3d_gsph2": lambda: golden_3d_sml("plume3d_gsph2", "3d_plume_gsph"),
         # the same two steps with the reference's own SML_UPDATE_INT: uniform h, and a step (2) that follows a domain growth
         "plume3d_grow": lambda: golden_3d_sml("plume3d_grow", sml_int=0),
         # BASELINE config 2: JPUE weakly-compressible jet (Tait EOS, g = 0), the reference's own input file

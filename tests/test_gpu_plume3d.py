@@ -1,6 +1,7 @@
-"""-m gpu: CUDA path (through the C ABI) against the reference's own dumps of the 3-D plume
-case (tests/golden/plume3d_small.npz, produced by the unmodified reference — see
-tests/golden/make_golden.py): every stage of time step 1.
+"""-m gpu: CUDA path (through the C ABI) against the reference's own dumps of the 3-D cases
+(tests/golden/plume3d_small.npz, jpue3d.npz, and plume3d_small_gsph.npz = the plume built with USE_GSPH 1: 3-D gradients,
+reconstructed Riemann states, Roe solver; produced by the unmodified reference — see tests/golden/make_golden.py):
+every stage of time step 1.
 
 Bars: neighbour lists, particle ordering, re-binning, flags: bit-exact.  Fields: relative
 tolerance RTOL_STAGE (tests/common.py) per stage, stated against the field's max magnitude.
@@ -16,7 +17,7 @@ from plume_sph_b200.solver import ORDER_REFERENCE, ORDER_DEVICE
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["plume3d_small", "jpue3d"])
+@pytest.fixture(scope="module", params=["plume3d_small", "jpue3d", "plume3d_small_gsph"])
 def case(request):
     z = golden(request.param)
     ocfg = op.config_for(request.param, z)
@@ -70,7 +71,11 @@ def test_step1_all_stages(case):
         d = ref2dev[r]
         mine = np.sort(dev2ref[idx[off[d]:off[d + 1]]])
         assert np.array_equal(mine, lidx[loff[q]:loff[q + 1]]), r
-    # (3) the summation stages
+    # (3) the summation stages (a USE_GSPH build first forms the gradients the Riemann states are reconstructed from:
+    # calc_gradients, main.cc:341-350; every non-guest row, ghosts included)
+    if ocfg.use_gsph:
+        s.calc_gradients()
+        check_stage(s, z, "grad", ["grad"])
     s.mom_engr_update()
     check_stage(s, z, "mom", ["vel", "engr", "pressure", "sound_speed", "temperature", "specific_heat_p", "gamma",
                               "phase_density"])

@@ -20,6 +20,7 @@ from plume_sph_b200.solver import ORDER_REFERENCE
 pytestmark = pytest.mark.gpu
 
 STAGES = (("sml", ["smlen"], ()),
+          ("grad", ["grad"], ()),                      # USE_GSPH builds only (calc_gradients, main.cc:341-350)
           ("mom", ["vel", "engr", "pressure", "sound_speed", "temperature", "specific_heat_p", "gamma", "phase_density"], ()),
           ("dens", ["rho", "mass_frac", "engr", "pressure", "sound_speed", "temperature", "involved"], ("involved",)),
           ("svel", ["smoothed_v"], ()),
@@ -42,10 +43,10 @@ def run_step(z, step, name="plume3d_sml", sml_int=1):
         s.set_dt(dt, step, 1)
         s.search_neighs_consth()
         cur = {f: pre[f] for f in pre.dtype.names}
-        calls = dict(sml=s.adaptive_sml, mom=s.mom_engr_update, dens=s.smooth_density, svel=s.smooth_velocity, pos=s.update_pos)
+        calls = dict(sml=s.adaptive_sml, grad=s.calc_gradients, mom=s.mom_engr_update, dens=s.smooth_density, svel=s.smooth_velocity, pos=s.update_pos)
         worst = {}
         for stage, fields, exact in STAGES:
-            if stage == "sml" and sml_int != 1:
+            if (stage == "sml" and sml_int != 1) or (stage == "grad" and not ocfg.use_gsph):
                 continue
             calls[stage]()
             out = s.download(ORDER_REFERENCE)
@@ -72,6 +73,17 @@ def test_adaptive_sml_and_mixed_h_stages(step):
         pre = z["pre2"]
         assert len(np.unique(pre["smlen"][pre["bc_type"] == 100])) > 100     # the regime under test
     worst = run_step(z, step)
+    print("step", step, "worst relative errors:", {k: "%.1e" % v for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("step", [1, 2])
+def test_gsph_3d_two_steps(step):
+    """tests/golden/plume3d_gsph2.npz: the same two steps of the reference built with USE_GSPH 1 and its 3-D option set
+    (options.h:544-663: Riemann states reconstructed from the gradients of calc_gradients with the cubic interface position,
+    MINI_DERIVATIVE_COND 10, modified monotonicity, Roe solver; sph_lib.cc:2247-2600, :1667-1749).  Step 2 carries velocities,
+    velocity gradients and per-particle smoothing lengths into the reconstruction."""
+    z = golden("plume3d_gsph2")
+    worst = run_step(z, step, name="plume3d_gsph2")
     print("step", step, "worst relative errors:", {k: "%.1e" % v for k, v in worst.items()})
 
 

@@ -87,13 +87,15 @@ def test_plume3d_uniform_h_after_domain_growth_bit_exact(step):
     check("pos", [("coord", "x"), ("bc_type", "bc"), ("smlen", "h"), ("involved", "involved")])
 
 
+@pytest.mark.parametrize("name", ["plume3d_sml", "plume3d_gsph2"])
 @pytest.mark.parametrize("step", [1, 2])
-def test_plume3d_adaptive_sml_and_mixed_h_bit_exact(step):
+def test_plume3d_adaptive_sml_and_mixed_h_bit_exact(step, name):
     """adaptive_sml in 3-D (neighs.cc:479-693) and every summation stage with per-particle smoothing lengths: time steps
     1 and 2 of the small plume with adaptive_sml called every step (PSPH_SML_INT=1 on the reference's hook build).
-    Step 2 starts from mixed h (675 distinct values among the real particles)."""
-    z = golden("plume3d_sml")
-    cfg = op.config_for("plume3d_sml", z)
+    Step 2 starts from mixed h (675 distinct values among the real particles).  plume3d_gsph2: the same two steps of the
+    USE_GSPH 1 build — step 2 reconstructs the Riemann states from non-zero velocity gradients."""
+    z = golden(name)
+    cfg = op.config_for(name, z)
     pre = z["pre%d" % step]
     s = oracle_state_3d(cfg, z, "b%d" % step, rows="pre%d" % step)
     dt = float(z["dt"][step - 1])
@@ -113,6 +115,11 @@ def test_plume3d_adaptive_sml_and_mixed_h_bit_exact(step):
     s.adaptive_sml()
     check("sml", [("smlen", "h")])
     assert len(z["s%d_sml_smlen__rows" % step]) > 500
+    if cfg.use_gsph:
+        assert s.calc_gradients() == 0
+        check("grad", [("grad", "grad")])
+        if step == 2:
+            assert np.abs(s.a["grad"][:, 3:12]).max() > 0          # velocity gradients are in play
     assert s.mom_engr_update(dt) == 0
     check("mom", [("vel", "v"), ("engr", "e"), ("pressure", "p"), ("sound_speed", "c"), ("temperature", "T"),
                   ("specific_heat_p", "Cp"), ("gamma", "gamma"), ("phase_density", "rho_ph")])

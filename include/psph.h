@@ -129,9 +129,16 @@ typedef struct psph_cell_attr
   int32_t has_involved;      /* Bucket::get_has_involved() != 0 */
   int32_t active;
   int32_t bucket_index[6];   /* bucket.cc:434-452 */
-  int32_t pad;
+  int32_t flags;             /* bits 0-3: Bucket::particles_type (bit 0 real, 1 wall ghost, 2 pressure ghost, 3 erupt ghost
+                              * particles, bucket.h:364-399); bits 8-9: erupt_flag (1 erupt, 2 influx, :341-348).  Read by
+                              * the domain-growth calls (psph_scan_outside_layer ..) only */
   double bnd[6];
 } psph_cell_attr;
+#define PSPH_CELLF_REAL 1
+#define PSPH_CELLF_WALL 2
+#define PSPH_CELLF_PRESS 4
+#define PSPH_CELLF_ERUPT 8
+#define PSPH_CELLF_ERUPT_FLAG(flags) (((flags) >> 8) & 3)
 
 /* One wall-ghost image (BndImage, src/datstr/bnd_image.h:20-75): the mirror point of a wall ghost across the wall.
  * The driver keeps the table (search_bnd_images, main.cc:188,292,458) and hands it over whenever it changes. */
@@ -159,6 +166,23 @@ typedef struct psph_erupt
   double kmin[3], kmax[3];   /* THashTable::get_minDom() / get_maxDom(): the box the birth keys are normalised to */
 } psph_erupt;
 
+/* What add_pressure_ghost (src/plume/add_pressure_ghost.cc:36-316) reads besides the tables: the lattice
+ * constants, the key box of the particle table and the atmosphere its new particles are initialised from (initial_air,
+ * sph_lib.cc:831-872 -> air_prop :770-800). */
+typedef struct psph_growth
+{
+  double mass;               /* MatProps::particle_mass (overwritten by initial_air) */
+  double smlen;              /* MatProps::smoothing_length: lattice spacing dx */
+  double ratio_sml_dx;       /* RATIO_SML_DX (constant.h:190) */
+  double gamma_air;          /* gamma_P: e = p / (rho (gamma_P - 1)) */
+  double sndspd, gmm;        /* constructor values (add_pressure_ghost.cc:68-74): 340, 1.4 */
+  double Ta0;                /* Ta0_P (uniform atmosphere only) */
+  double kmin[3], kmax[3];   /* THashTable::get_minDom() / get_maxDom(): the box the birth keys are normalised to */
+  double Ll[3], Lu[3];       /* Ll_P, Lu_P: an on-ground MIXED bucket is filled above Ll[2] only (:139) */
+  int32_t atmosphere_type;   /* ATMOSPHERE_TYPE: 4 Meteo sounding (meteo.cc:64-110, linear in height), 2 uniform */
+  int32_t nmeteo;            /* rows of the sounding handed to psph_set_growth */
+} psph_growth;
+
 typedef struct psph_ctx psph_ctx;
 
 enum { PSPH_ORDER_DEVICE = 0, PSPH_ORDER_REFERENCE = 1 };
@@ -182,6 +206,24 @@ const char *psph_last_error(const psph_ctx *ctx);
 /* Bucket attributes: after Read_Grid and whenever the driver changes them
  * (adapt_domain.cc, mesh_update.cc).  attr == NULL: every cell OVERGROUND, involved, active. */
 int psph_set_cells(psph_ctx *ctx, const psph_cell_attr *attr, size_t ncells);
+/* ... and back: the domain-growth calls below change has_involved, active and flags on the device */
+int psph_get_cells(psph_ctx *ctx, psph_cell_attr *attr, size_t ncells);
+
+/* Domain growth on the device (main.cc:435 and the first half of the adapt block, :256-271).
+ * psph_scan_outside_layer (scan_outside_layer.cc:44-121), every step after the re-bin: a has_involved == 1 bucket that
+ *   holds an involved particle becomes has_involved = 3; *adapt = how many of them touch a non-empty, not-involved,
+ *   non-underground bucket (summed over the slabs).  No particle leaves the device for it.
+ * psph_adapt_domain (adapt_domain.cc:41-194), when adapt != 0: the not-involved, non-empty buckets next to a
+ *   has_involved >= 2 bucket become potential-involved and their pressure ghosts real (bc_type 100, involved 1).
+ * psph_set_growth + psph_add_pressure_ghost (add_pressure_ghost.cc:36-316): the exposed buckets are filled with a lattice
+ *   of static pressure ghosts (birth key = Hilbert index in the key box + add_step, state from the atmosphere);
+ *   *added = rows appended on this rank.  meteo_z [km], meteo_rho, meteo_p [hPa]: columns 0, 1, 2 of the sounding.
+ * The driver keeps shift_brief_buck, add_wall_ghost, update_bgmesh and the image search (they run on bucket attributes:
+ * psph_get_cells), and appends what they create with psph_append. */
+int psph_scan_outside_layer(psph_ctx *ctx, int *adapt);
+int psph_adapt_domain(psph_ctx *ctx, int *turned);
+int psph_set_growth(psph_ctx *ctx, const psph_growth *g, const double *meteo_z, const double *meteo_rho, const double *meteo_p);
+int psph_add_pressure_ghost(psph_ctx *ctx, uint32_t add_step, int *added);
 
 /* after initialisation (main.cc:199) / after add_new_erupt (:417) / ghost regeneration (:271-283) */
 int psph_upload(psph_ctx *ctx, const psph_particle *rows, size_t n);

@@ -50,7 +50,14 @@ class Config(C.Structure):
 
 class CellAttr(C.Structure):
     _fields_ = [("type", C.c_int32), ("has_involved", C.c_int32), ("active", C.c_int32),
-                ("bucket_index", C.c_int32 * 6), ("pad", C.c_int32), ("bnd", C.c_double * 6)]
+                ("bucket_index", C.c_int32 * 6), ("flags", C.c_int32), ("bnd", C.c_double * 6)]
+
+
+class Growth(C.Structure):
+    """Mirror of ``psph_growth`` (include/psph.h): what add_pressure_ghost reads (add_pressure_ghost.cc:36-316)."""
+    _fields_ = [("mass", C.c_double), ("smlen", C.c_double), ("ratio_sml_dx", C.c_double), ("gamma_air", C.c_double),
+                ("sndspd", C.c_double), ("gmm", C.c_double), ("Ta0", C.c_double), ("kmin", C.c_double * 3), ("kmax", C.c_double * 3),
+                ("Ll", C.c_double * 3), ("Lu", C.c_double * 3), ("atmosphere_type", C.c_int32), ("nmeteo", C.c_int32)]
 
 
 
@@ -71,7 +78,7 @@ PARTICLE_DTYPE = np.dtype([("key", "<u4", 3), ("bc_type", "<i4"), ("phase_num", 
 assert PARTICLE_DTYPE.itemsize == 328
 
 CELL_ATTR_DTYPE = np.dtype([("type", "<i4"), ("has_involved", "<i4"), ("active", "<i4"),
-                            ("bucket_index", "<i4", 6), ("pad", "<i4"), ("bnd", "<f8", 6)])
+                            ("bucket_index", "<i4", 6), ("flags", "<i4"), ("bnd", "<f8", 6)])
 assert CELL_ATTR_DTYPE.itemsize == C.sizeof(CellAttr)
 
 
@@ -137,7 +144,7 @@ def config_3d_gsph():
 
 
 CONFIGS_3D = {"plume3d_small": config_3d, "jpue3d": config_jpue, "plume3d_sml": config_3d, "plume3d_grow": config_3d,
-              "plume3d_small_gsph": config_3d_gsph, "plume3d_gsph2": config_3d_gsph}
+              "plume3d_small_gsph": config_3d_gsph, "plume3d_gsph2": config_3d_gsph, "grow3d": config_3d}
 
 
 def config_for(name, z=None):
@@ -248,6 +255,13 @@ def lib():
         L.psph_oracle_add_new_erupt.restype = C.c_int
         L.psph_oracle_hsfc3d.argtypes = [_P(C.c_double), _P(C.c_uint32)]
         L.psph_oracle_hsfc3d.restype = None
+        L.psph_oracle_scan_outside_layer.argtypes = [cp, sp, C.c_void_p]
+        L.psph_oracle_scan_outside_layer.restype = C.c_int
+        L.psph_oracle_adapt_domain.argtypes = [cp, sp, C.c_void_p]
+        L.psph_oracle_adapt_domain.restype = C.c_int
+        L.psph_oracle_add_pressure_ghost.argtypes = [cp, sp, C.c_void_p, C.POINTER(Growth), _P(C.c_double), _P(C.c_double),
+                                                     _P(C.c_double), C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        L.psph_oracle_add_pressure_ghost.restype = C.c_int
     return _lib
 
 
@@ -385,6 +399,25 @@ class OracleState:
         return lib().psph_oracle_apply_bcond(C.byref(self.cfg), C.byref(self.st), len(r), r.ctypes.data_as(_P(C.c_int32)),
                                              c.ctypes.data_as(_P(C.c_int64)), x.ctypes.data_as(_P(C.c_double)))
 
+    # domain growth: attr = CELL_ATTR_DTYPE array of the whole mesh, changed in place
+    def scan_outside_layer(self, attr):
+        return lib().psph_oracle_scan_outside_layer(C.byref(self.cfg), C.byref(self.st), attr.ctypes.data)
+
+    def adapt_domain(self, attr):
+        return lib().psph_oracle_adapt_domain(C.byref(self.cfg), C.byref(self.st), attr.ctypes.data)
+
+    def add_pressure_ghost(self, attr, growth, meteo_z, meteo_rho, meteo_p, add_step, cell_mincrd=None, cap=1 << 20):
+        out = np.zeros(cap, PARTICLE_DTYPE)
+        mc = None if cell_mincrd is None else np.ascontiguousarray(cell_mincrd, np.float64)
+        z, r, p = (np.ascontiguousarray(a, np.float64) for a in (meteo_z, meteo_rho, meteo_p))
+        n = lib().psph_oracle_add_pressure_ghost(C.byref(self.cfg), C.byref(self.st), attr.ctypes.data, C.byref(growth),
+                                                 z.ctypes.data_as(_P(C.c_double)), r.ctypes.data_as(_P(C.c_double)),
+                                                 p.ctypes.data_as(_P(C.c_double)), None if mc is None else mc.ctypes.data,
+                                                 int(add_step), out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError("psph_oracle_add_pressure_ghost: more than %d particles" % cap)
+        return out[:n]
+
     def rebin(self):
         lost = C.c_int(0)
         lib().psph_oracle_rebin(C.byref(self.cfg), C.byref(self.st), C.byref(lost))
@@ -399,6 +432,14 @@ class OracleState:
         lib().psph_oracle_free_lists(C.byref(self.st))
 
 
+def table_order(cfg, keys):
+    """permutation that puts rows with these keys ([n][3] uint32) into THashTable iteration order"""
+    k = np.ascontiguousarray(keys, np.uint32)
+    perm = np.zeros(len(k), np.int64)
+    lib().psph_oracle_table_order(C.byref(cfg), k.ctypes.data_as(_P(C.c_uint32)), len(k), perm.ctypes.data_as(_P(C.c_int64)))
+    return perm
+
+
 def add_new_erupt(cfg, erupt, boxes, time, dt, add_step, cap=65536):
     """psph_oracle_add_new_erupt: the rows (psph_particle layout) add_new_erupt adds at this time step"""
     boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 6)
@@ -408,6 +449,19 @@ def add_new_erupt(cfg, erupt, boxes, time, dt, add_step, cap=65536):
     if n < 0:
         raise RuntimeError("psph_oracle_add_new_erupt: more than %d particles" % cap)
     return out[:n]
+
+
+def growth_from_golden(z):
+    """Growth record + the sounding's columns from a domain-growth fixture (tests/golden/make_golden.py::golden_grow)"""
+    g = Growth()
+    g.mass, g.smlen, g.gamma_air = (float(x) for x in z["param_const"])
+    g.ratio_sml_dx, g.sndspd, g.gmm, g.Ta0 = 1.0, 340.0, 1.4, 0.0
+    for k in range(3):
+        g.kmin[k], g.kmax[k] = float(z["param_keybox"][k]), float(z["param_keybox"][3 + k])
+        g.Ll[k], g.Lu[k] = float(z["param_domain"][k]), float(z["param_domain"][3 + k])
+    g.atmosphere_type = int(z["param_step"][1])
+    g.nmeteo = len(z["meteo_z"])
+    return g, z["meteo_z"], z["meteo"][0], z["meteo"][1]
 
 
 def erupt_from_params(names, v):

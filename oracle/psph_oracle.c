@@ -1016,6 +1016,169 @@ int psph_oracle_add_new_erupt(const psph_config *c, const psph_erupt *er, const 
   return n;
 }
 
+/* ---------------- domain growth: scan_outside_layer, adapt_domain, add_pressure_ghost ---------------- */
+/* the 26 neighbours of a bucket that exist (neigh_proc > -1: inside the mesh) and are not brief */
+static int grow_neigh(const psph_config *c, const psph_cell_attr *attr, int64_t cl, int q, int64_t *nl)
+{
+  int ck = (int) (cl % c->ncell[2]), cj = (int) ((cl / c->ncell[2]) % c->ncell[1]);
+  int ci = (int) (cl / ((int64_t) c->ncell[2] * c->ncell[1]));
+  int ni = ci + q / 9 - 1, nj = cj + (q / 3) % 3 - 1, nk = ck + q % 3 - 1;
+  if (q == 13) return 0;
+  if (ni < 0 || nj < 0 || nk < 0 || ni >= c->ncell[0] || nj >= c->ncell[1] || nk >= c->ncell[2]) return 0;
+  *nl = cell_lin(c, ni, nj, nk);
+  return attr[*nl].type != PSPH_CELL_BRIEF;
+}
+
+int psph_oracle_scan_outside_layer(const psph_config *c, const psph_oracle_state *st, psph_cell_attr *attr)
+{ /* scan_outside_layer.cc:44-121 */
+  int adapt = 0;
+  int64_t nc = ncells_of(c);
+  for (int64_t cl = 0; cl < nc; cl++) {
+    psph_cell_attr *a = &attr[cl];
+    if (a->type == PSPH_CELL_BRIEF || a->has_involved != 1) continue;
+    int found = 0;
+    for (int64_t q = st->cell_off[cl]; q < st->cell_off[cl + 1] && !found; q++) found = st->involved[st->cell_rows[q]] == 2;
+    if (!found) continue;
+    a->has_involved = 3; /* HAS_BOTH */
+    for (int q = 0; q < 27; q++) {
+      int64_t nl;
+      if (!grow_neigh(c, attr, cl, q, &nl)) continue;
+      if (st->cell_off[nl + 1] > st->cell_off[nl] && !attr[nl].has_involved && attr[nl].type != PSPH_CELL_UNDERGROUND) { adapt++; break; }
+    }
+  }
+  return adapt;
+}
+
+int psph_oracle_adapt_domain(const psph_config *c, psph_oracle_state *st, psph_cell_attr *attr)
+{ /* adapt_domain.cc:41-194 */
+  int turned = 0;
+  int64_t nc = ncells_of(c);
+  for (int64_t cl = 0; cl < nc; cl++) {
+    psph_cell_attr *a = &attr[cl];
+    if (a->type == PSPH_CELL_BRIEF) continue;
+    if (!(!a->has_involved && st->cell_off[cl + 1] > st->cell_off[cl] && a->type != PSPH_CELL_UNDERGROUND && a->type != PSPH_CELL_PRESS_BC))
+      continue;
+    int hit = 0;
+    for (int q = 0; q < 27 && !hit; q++) {
+      int64_t nl;
+      if (grow_neigh(c, attr, cl, q, &nl) && (attr[nl].has_involved & 2)) hit = 1;
+    }
+    if (!hit) continue;
+    a->has_involved = (a->has_involved & 1) | 1; /* set_has_involved(false); set_has_potential_involved(true) */
+    a->flags |= PSPH_CELLF_REAL;
+    int mode = a->type == PSPH_CELL_MIXED ? (a->bucket_index[4] == -1 ? 1 : 2) : 3;
+    if (mode != 2) a->flags &= ~PSPH_CELLF_PRESS;
+    for (int64_t q = st->cell_off[cl]; q < st->cell_off[cl + 1]; q++) {
+      int32_t p = st->cell_rows[q];
+      int turn;
+      if (mode == 1) turn = st->bc[p] == 1;                            /* on-ground MIXED: its pressure ghosts (:113-118) */
+      else if (mode == 2) {                                            /* MIXED on a side or on top: rows inside the domain */
+        double pos[3];
+        for (int k = 0; k < 3; k++) pos[k] = D3(st->x, p, k);
+        turn = !determine_escape(c, a, pos);
+      } else turn = 1;                                                 /* OVERGROUND: every row (:163-170) */
+      if (turn) { st->bc[p] = 100; st->involved[p] = 1; turned++; }
+    }
+  }
+  return turned;
+}
+
+/* Meteo::interpolate (meteo.cc:64-147): the sample itself, the end values outside the range, else linear */
+static double meteo_interp(const double *z, const double *v, int n, double z0)
+{
+  for (int i = 0; i < n; i++) if (z[i] == z0) return v[i];
+  if (z0 < z[0]) return v[0];
+  if (z0 > z[n - 1]) return v[n - 1];
+  int lo = 0;
+  while (z[lo] < z0) lo++;            /* lower_bound: first z >= z0 (== upper_bound here: z0 is not a sample) */
+  int li = lo - 1, ui = lo;
+  return v[li] + (z0 - z[li]) / (z[ui] - z[li]) * (v[ui] - v[li]);
+}
+
+int psph_oracle_add_pressure_ghost(const psph_config *c, const psph_oracle_state *st, psph_cell_attr *attr, const psph_growth *g,
+                                   const double *mz, const double *mrho, const double *mp, const double *cell_mincrd, uint32_t add_step,
+                                   psph_particle *out, int cap)
+{ /* add_pressure_ghost.cc:36-316.  cell_mincrd [ncells][3]: Bucket::mincrd as the driver stores it (the lattice formula
+   * when NULL; the reference's stored bounds differ from it by a few float ulps in x: the new particles sit on them) */
+  int n_out = 0;
+  int64_t nc = ncells_of(c);
+  const double dx = g->smlen, dx2 = 0.5 * dx;
+  (void) st;
+  for (int64_t cl = 0; cl < nc; cl++) {
+    psph_cell_attr *a = &attr[cl];
+    if (a->type == PSPH_CELL_BRIEF) continue;
+    if (!(!a->has_involved && !(a->flags & PSPH_CELLF_PRESS) && PSPH_CELLF_ERUPT_FLAG(a->flags) == 0)) continue;
+    int hit = 0;
+    for (int q = 0; q < 27 && !hit; q++) {
+      int64_t nl;
+      if (grow_neigh(c, attr, cl, q, &nl) && attr[nl].has_involved) hit = 1;
+    }
+    if (!hit) continue;
+    a->active = 1;
+    if (!(a->type == PSPH_CELL_MIXED || a->type == PSPH_CELL_OVERGROUND || a->type == PSPH_CELL_PRESS_BC)) continue;
+    int ck = (int) (cl % c->ncell[2]), cj = (int) ((cl / c->ncell[2]) % c->ncell[1]);
+    int ci = (int) (cl / ((int64_t) c->ncell[2] * c->ncell[1]));
+    int idx[3] = { ci, cj, ck }, N[3];
+    double mincrd[3];
+    for (int k = 0; k < 3; k++) {
+      mincrd[k] = cell_mincrd ? cell_mincrd[3 * cl + k] : cell_min(c, k, idx[k]);
+      N[k] = (int) round(c->del / c->len_scale / dx);               /* (maxcrd - mincrd) / dx: one bucket edge */
+    }
+    const int ground = a->type == PSPH_CELL_MIXED && a->bucket_index[4] == -1;
+    for (int i = 0; i < N[0]; i++)
+      for (int j = 0; j < N[1]; j++)
+        for (int k = 0; k < N[2]; k++) {
+          double pcrd[3] = { mincrd[0] + dx2 + i * dx, mincrd[1] + dx2 + j * dx, mincrd[2] + dx2 + k * dx };
+          if (ground && !(pcrd[2] > g->Ll[2])) continue;             /* :139 */
+          if (n_out >= cap) return -1;
+          psph_particle *p = out + n_out++;
+          memset(p, 0, sizeof *p);
+          double normc[3];
+          for (int d = 0; d < 3; d++) normc[d] = (pcrd[d] - g->kmin[d]) / (g->kmax[d] - g->kmin[d]);
+          psph_oracle_hsfc3d(normc, p->key);
+          p->key[2] = add_step;
+          /* Particle ctor for initial air, particle.cc:116-190 */
+          p->bc_type = 1; p->phase_num = 1; p->involved = 0; p->guest = 0; p->myprocess = c->rank;
+          p->smlen = g->ratio_sml_dx * g->smlen;
+          for (int d = 0; d < 3; d++) p->coords[d] = pcrd[d];
+          p->mass_frac = 0.;
+          a->flags |= PSPH_CELLF_PRESS;
+          /* initial_air, sph_lib.cc:831-872 */
+          double sml2 = 0.5 * p->smlen, range[6];
+          for (int d = 0; d < 3; d++) { range[2 * d] = pcrd[d] - sml2; range[2 * d + 1] = pcrd[d] + sml2; }
+          double prss, dens, erg, mss;
+          if (g->atmosphere_type == 4) {                               /* air_prop_meteo_based, :737-766 */
+            prss = meteo_interp(mz, mp, g->nmeteo, pcrd[2] * 0.001) * 100;
+            dens = meteo_interp(mz, mrho, g->nmeteo, pcrd[2] * 0.001);
+            erg = prss / (dens * (g->gamma_air - 1));
+            double d1 = meteo_interp(mz, mrho, g->nmeteo, range[4] * 0.001), d2 = meteo_interp(mz, mrho, g->nmeteo, range[5] * 0.001);
+            mss = (range[1] - range[0]) * (range[3] - range[2]) * (range[5] - range[4]) * (0.1666667 * d1 + 0.6666666 * dens + 0.1666667 * d2);
+          } else {                                                     /* air_prop_uniform, :682-712 (ideal gas) */
+            prss = c->pa0;
+            dens = prss / (c->Ra * g->Ta0);
+            erg = prss / (dens * (g->gamma_air - 1));
+            mss = (range[1] - range[0]) * (range[3] - range[2]) * (range[5] - range[4]) * dens;
+          }
+          p->rho = dens; p->engr = erg; p->mass = mss;
+          { /* update_second_var (particle.cc:528-604) with ks = 0, ideal-gas branch; the ctor's gamma and sound speed are
+             * overwritten there */
+            double ks = 0., na = 1 - ks, ng = c->ng0 * ks, ns = ks - ng;
+            double Cvm = ns * c->Cvs + ng * c->Cvg + na * c->Cva;
+            double Rm = ng * c->Rg + na * c->Ra, Rmg = Rm / (ng + na);
+            p->gamma = 1 + Rm / Cvm;
+            double desmg = dens * (na + ng);
+            p->pressure = Rmg * desmg * erg / Cvm;
+            p->sound_speed = pow(p->gamma * p->pressure / desmg, 0.5);
+            p->phase_density[0] = dens * na;
+            p->phase_density[1] = dens * ks;
+            p->temperature = erg / Cvm;
+            p->specific_heat_p = c->have_turbulence_lans != 0 ? Cvm : 0.;
+          }
+        }
+  }
+  return n_out;
+}
+
 /* ---------------- Hilbert key ---------------- */
 void psph_oracle_hsfc3d(const double coord[3], uint32_t key[2])
 { /* HSFC3d + hsfc3d, hilbert.c:156-271,289-303 (Zoltan's 3-D Hilbert curve), restated as a

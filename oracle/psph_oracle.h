@@ -88,6 +88,16 @@ double psph_oracle_d_weight(int dim, const double *s, double h, double cutoff, i
  * maxcrd of the erupt buckets.  time = TimeProps::time after incrtime. */
 int psph_oracle_add_new_erupt(const psph_config *cfg, const psph_erupt *er, const double *boxes, int nbox, double time,
                               double dt, uint32_t add_step, psph_particle *out, int cap);
+/* Domain growth.  attr [ncells] is read AND written (has_involved, active, flags); the plists come from
+ * st->cell_off / cell_rows.  Single rank: no guest buckets.
+ * scan_outside_layer.cc:44-121 -> adapt;  adapt_domain.cc:41-194 -> rows turned real (st->bc, st->involved change);
+ * add_pressure_ghost.cc:36-316 + initial_air (sph_lib.cc:831-872): writes the new particles to out[] in bucket order
+ * (cells ascending, lattice i, j, k) and returns their number (-1: more than cap). */
+int psph_oracle_scan_outside_layer(const psph_config *cfg, const psph_oracle_state *st, psph_cell_attr *attr);
+int psph_oracle_adapt_domain(const psph_config *cfg, psph_oracle_state *st, psph_cell_attr *attr);
+int psph_oracle_add_pressure_ghost(const psph_config *cfg, const psph_oracle_state *st, psph_cell_attr *attr, const psph_growth *g,
+                                   const double *meteo_z, const double *meteo_rho, const double *meteo_p, const double *cell_mincrd,
+                                   uint32_t add_step, psph_particle *out, int cap);
 /* Hilbert key of a normalised position, hilbert.c:289-303 (HSFC3d) */
 void psph_oracle_hsfc3d(const double coord[3], uint32_t key[2]);
 

@@ -457,6 +457,122 @@ void psphhook_update_pos(THashTable *P, TimeProps *tp, MatProps *mp)
   dump_table(P, "pos", "post");
 }
 
+#if CODE_DIMENSION == 3
+/* ---- domain growth: scan_outside_layer (main.cc:435), adapt_domain and add_pressure_ghost (:265-271) ----
+ * Extended bucket file "<dir>/s<step>_<stage>_bucketsx.bin": i64 nb, then per non-brief bucket
+ *   u32 key[2], f64 mincrd[3], f64 maxcrd[3], i32 type, has_involved, active, guest, np, particles_type, erupt_flag,
+ *   i32 bucket_index[6], f64 bnd[6], i32 neigh_proc[27], i32 rows[np]
+ * (particles_type: bit 0 real, 1 wall ghost, 2 pressure ghost, 3 erupt ghost; bucket.h:364-399).
+ * "<dir>/s<step>_grow_params.bin": what add_pressure_ghost reads besides the tables: i32 step, nr, np, pad; f64 mass, smlen,
+ *   gamma_P, mindom[3], maxdom[3] (particle-table key box), Ll_P[3], Lu_P[3]; f64 z[nr]; f64 data[np][nr] (Meteo). */
+struct MeteoPeek : Meteo
+{
+  int rows() { return number_of_data; }
+  vector<double> &zz() { return z; }
+  vector<double> &col(int j) { return data[j]; }
+};
+
+void dump_bucketsx(THashTable *P, HashTable *BG, const char *stage)
+{
+  if (!dumping()) return;
+  map<TKey, int, KeyLess> idx;
+  {
+    THTIterator itr(P);
+    Particle *p; int i = 0;
+    while ((p = (Particle *) itr.next())) idx[p->getKey()] = i++;
+  }
+  char fn[512];
+  snprintf(fn, sizeof fn, "%s/s%04d_%s_bucketsx.bin", g_dir, g_step, stage);
+  FILE *f = fopen(fn, "wb");
+  long long nb = 0;
+  fwrite(&nb, 8, 1, f);
+  HTIterator it(BG);
+  void *t;
+  while ((t = it.next())) {
+    BriefBucket *bb = (BriefBucket *) t;
+    if (bb->check_brief()) continue;
+    Bucket *b = (Bucket *) t;
+    Key k = b->getKey();
+    fwrite(k.key, 4, 2, f);
+    fwrite(b->get_mincrd(), 8, 3, f);
+    fwrite(b->get_maxcrd(), 8, 3, f);
+    vector<TKey> pl = b->get_plist();
+    int ptype = (b->has_real_particles() ? 1 : 0) | (b->has_wall_ghost_particles() ? 2 : 0) |
+                (b->has_pressure_ghost_particles() ? 4 : 0) | (b->has_erupt_ghost_particles() ? 8 : 0);
+    int v[7] = { b->get_bucket_type(), (int) b->get_has_involved(), (int) b->is_active(), (int) b->is_guest(), (int) pl.size(),
+                 ptype, (int) b->get_erupt_flag() };
+    fwrite(v, 4, 7, f);
+    fwrite(b->get_bucket_index(), 4, 6, f);
+    fwrite(b->get_bnd(), 8, 6, f);
+    fwrite(b->get_neigh_proc(), 4, NEIGH_SIZE, f);
+    for (size_t j = 0; j < pl.size(); j++) {
+      map<TKey, int, KeyLess>::iterator q = idx.find(pl[j]);
+      int r = q == idx.end() ? -1 : q->second;
+      fwrite(&r, 4, 1, f);
+    }
+    nb++;
+  }
+  fseek(f, 0, SEEK_SET);
+  fwrite(&nb, 8, 1, f);
+  fclose(f);
+}
+
+int psphhook_scan_outside_layer(THashTable *P, HashTable *BG, int np, int myid)
+{
+  init_once();
+  dump_table(P, "scan", "pre");
+  dump_bucketsx(P, BG, "scan_pre");
+  int adapt = scan_outside_layer(P, BG, np, myid);
+  dump_bucketsx(P, BG, "scan_post");
+  if (dumping()) {
+    char fn[512];
+    snprintf(fn, sizeof fn, "%s/s%04d_scan_adapt.txt", g_dir, g_step);
+    FILE *f = fopen(fn, "w"); fprintf(f, "%d\n", adapt); fclose(f);
+  }
+  return adapt;
+}
+
+/* the adapt block (main.cc:256-304) follows timestep() (:220): its dumps carry the number of the step that has begun */
+void psphhook_adapt_domain(THashTable *P, HashTable *BG, MatProps *mp, int np, int myid)
+{
+  init_once();
+  dump_table(P, "adapt", "pre");
+  dump_bucketsx(P, BG, "adapt_pre");
+  adapt_domain(P, BG, mp, np, myid);
+  dump_table(P, "adapt", "post");
+  dump_bucketsx(P, BG, "adapt_post");
+}
+
+void psphhook_add_pressure_ghost(THashTable *P, HashTable *BG, SimProps *sp, MatProps *mp, TimeProps *tp, int np, int myid)
+{
+  init_once();
+  if (dumping()) {
+    char fn[512];
+    snprintf(fn, sizeof fn, "%s/s%04d_grow_params.bin", g_dir, g_step);
+    FILE *f = fopen(fn, "wb");
+    int nr = 0, npp = 0;
+#if ATMOSPHERE_TYPE == 4
+    MeteoPeek *m = static_cast<MeteoPeek *>(sp->meteo_data);
+    nr = m->rows(); npp = m->get_number_of_props();
+#endif
+    int hdr[4] = { (int) tp->step, nr, npp, ATMOSPHERE_TYPE };
+    fwrite(hdr, 4, 4, f);
+    double v[3] = { mp->particle_mass, mp->smoothing_length, gamma_P };
+    fwrite(v, 8, 3, f);
+    fwrite(P->get_minDom(), 8, 3, f); fwrite(P->get_maxDom(), 8, 3, f);
+    fwrite(Ll_P, 8, 3, f); fwrite(Lu_P, 8, 3, f);
+#if ATMOSPHERE_TYPE == 4
+    fwrite(&m->zz()[0], 8, nr, f);
+    for (int j = 0; j < npp; j++) fwrite(&m->col(j)[0], 8, nr, f);
+#endif
+    fclose(f);
+  }
+  add_pressure_ghost(P, BG, sp, mp, tp, np, myid);
+  dump_table(P, "pghost", "post");
+  dump_bucketsx(P, BG, "pghost_post");
+}
+#endif
+
 /* SML_UPDATE_INT (constant.h:189, a const int, not a macro) decides at main.cc:319-322 which steps call adaptive_sml.
  * PSPH_SML_INT overrides it for the text of main.cc that follows, so that a short run crosses adaptive_sml (goldens of
  * the regime after it: every particle with its own smoothing length); unset = the reference's value. */
@@ -482,5 +598,10 @@ int psphhook_sml_update_int()
 #define update_particles_in_bucket psphhook_update_particles_in_bucket
 #define add_new_erupt psphhook_add_new_erupt
 #define apply_bcond psphhook_apply_bcond
+#if CODE_DIMENSION == 3
+#define scan_outside_layer psphhook_scan_outside_layer
+#define adapt_domain psphhook_adapt_domain
+#define add_pressure_ghost psphhook_add_pressure_ghost
+#endif
 #include PSPH_REF_MAIN_CC
 #endif

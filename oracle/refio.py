@@ -67,6 +67,39 @@ def read_buckets(path):
     return out
 
 
+def read_bucketsx(path):
+    """extended bucket file of the domain-growth hooks -> list of dicts: read_buckets' fields + particles_type (bit 0 real,
+    1 wall ghost, 2 pressure ghost, 3 erupt ghost), erupt_flag, neigh_proc[27]"""
+    out = []
+    with open(path, "rb") as f:
+        nb, = struct.unpack("<q", f.read(8))
+        for _ in range(nb):
+            key = struct.unpack("<II", f.read(8))
+            mn = struct.unpack("<ddd", f.read(24))
+            mx = struct.unpack("<ddd", f.read(24))
+            typ, inv, act, guest, npart, ptype, erupt = struct.unpack("<7i", f.read(28))
+            bidx = struct.unpack("<6i", f.read(24))
+            bnd = struct.unpack("<6d", f.read(48))
+            nproc = struct.unpack("<27i", f.read(108))
+            rows = np.fromfile(f, dtype="<i4", count=npart)
+            out.append(dict(key=key, mincrd=mn, maxcrd=mx, type=typ, has_involved=inv, active=act, guest=guest,
+                            particles_type=ptype, erupt_flag=erupt, bucket_index=bidx, bnd=bnd, neigh_proc=nproc, rows=rows))
+    return out
+
+
+def read_grow_params(path):
+    """what add_pressure_ghost reads besides the tables (hook dump): step, constants, key box, Meteo table"""
+    with open(path, "rb") as f:
+        step, nr, npp, atm = struct.unpack("<4i", f.read(16))
+        mass, smlen, gamma = struct.unpack("<3d", f.read(24))
+        mindom = np.fromfile(f, "<f8", 3); maxdom = np.fromfile(f, "<f8", 3)
+        Ll = np.fromfile(f, "<f8", 3); Lu = np.fromfile(f, "<f8", 3)
+        z = np.fromfile(f, "<f8", nr)
+        data = np.fromfile(f, "<f8", nr * npp).reshape(npp, nr)
+    return dict(step=step, atmosphere_type=atm, mass=mass, smlen=smlen, gamma=gamma, mindom=mindom, maxdom=maxdom, Ll=Ll, Lu=Lu,
+                meteo_z=z, meteo=data)
+
+
 _TYPES = {1: "<i4", 2: "<u4", 3: "<f4", 4: "<f8", 5: "S1"}
 
 

@@ -79,7 +79,7 @@ assert PARTICLE_SPH_DTYPE.itemsize == 208 and all(
     PARTICLE_SPH_DTYPE.fields[n][1] == PARTICLE_DTYPE.fields[n][1] for n in PARTICLE_SPH_DTYPE.names)
 
 CELL_ATTR_DTYPE = np.dtype([("type", "<i4"), ("has_involved", "<i4"), ("active", "<i4"),
-                            ("bucket_index", "<i4", 6), ("pad", "<i4"), ("bnd", "<f8", 6)])
+                            ("bucket_index", "<i4", 6), ("flags", "<i4"), ("bnd", "<f8", 6)])
 assert CELL_ATTR_DTYPE.itemsize == 88
 # psph_image (include/psph.h): one wall-ghost image
 IMAGE_DTYPE = np.dtype([("ghost_key", "<u4", 3), ("cell", "<i4"), ("coord", "<f8", 3)])

@@ -114,6 +114,33 @@ def cell_attrs(cfg, z, tag="b0"):
     return attr, lin
 
 
+def grow_cell_attrs(cfg, z, tag):
+    """psph_cell_attr array of the whole mesh from a domain-growth fixture (tests/golden/grow3d.npz; absent = BRIEF), with
+    the flags word (particles_type, erupt_flag), and the linear index of every dumped bucket"""
+    n1, n2 = int(cfg.ncell[1]), int(cfg.ncell[2])
+    attr = np.zeros(int(cfg.ncell[0]) * n1 * n2, psph.CELL_ATTR_DTYPE)
+    mn = z[tag + "_mincrd"]
+    idx = np.rint((mn * cfg.len_scale - np.asarray([cfg.mindom[d] for d in range(3)])) / cfg.delta).astype(np.int64)
+    lin = (idx[:, 0] * n1 + idx[:, 1]) * n2 + idx[:, 2]
+    a = z[tag + "_attr"]
+    attr["type"][lin] = a[:, 0]
+    attr["has_involved"][lin] = a[:, 1]
+    attr["active"][lin] = a[:, 2]
+    attr["flags"][lin] = a[:, 4] | (a[:, 5] << 8)
+    attr["bucket_index"][lin] = z["bindex"]
+    attr["bnd"][lin] = z["bnd"]
+    return attr, lin
+
+
+def grow_cell_mincrd(cfg, z, lin):
+    """Bucket::mincrd of every cell as the reference stores it (the lattice formula for the cells the fixture does not hold)"""
+    n = [int(cfg.ncell[d]) for d in range(3)]
+    idx = np.stack(np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij"), axis=-1).reshape(-1, 3)
+    mc = (np.asarray([cfg.mindom[d] for d in range(3)]) + idx * cfg.delta) / cfg.len_scale
+    mc[lin] = z["scan_pre_mincrd"]
+    return mc
+
+
 def image_cells(cfg, z):
     """linear cell index of the bucket of every wall-ghost image of a golden 3-D fixture"""
     n1, n2 = int(cfg.ncell[1]), int(cfg.ncell[2])

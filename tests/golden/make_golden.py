@@ -237,6 +237,73 @@ def golden_3d_sml(name="plume3d_sml", variant="3d_plume", edits=None, simdata="s
         print(name, "->", os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
 
 
+def golden_grow(name="grow3d", variant="3d_plume", edits=None, simdata="simulation.data"):
+    """Domain growth in the small plume: scan_outside_layer at the end of step 1 raises `adapt`
+    (scan_outside_layer.cc:44-121), the adapt block at the start of step 2 (main.cc:256-304) turns the pressure ghosts of the
+    outer layer real (adapt_domain.cc:41-194) and fills the newly exposed buckets with pressure ghosts whose state comes from
+    the Meteo sounding (add_pressure_ghost.cc:36-316, sph_lib.cc:724-766,831-872).  Stored: the table the three calls start
+    from, the bucket attributes (with particles_type, erupt_flag) around each call, what adapt_domain changed, the rows
+    add_pressure_ghost added with their positions in the table's iteration order, and the call's parameters."""
+    edits = SMALL_3D if edits is None else edits
+    with tempfile.TemporaryDirectory() as top:
+        wd = os.path.join(top, "run")
+        os.makedirs(wd)
+        shutil.copytree(os.path.join(REF, "Meteo_data"), os.path.join(top, "Meteo_data"))
+        shutil.copy(os.path.join(REF, "bin", "scale.data"), wd)
+        txt = open(os.path.join(REF, "bin", simdata)).read()
+        for a, b in edits:
+            assert a in txt, a
+            txt = txt.replace(a, b)
+        open(os.path.join(wd, "simulation.data"), "w").write(txt)
+        smlen = [l for l in txt.splitlines() if l.startswith("smoothing length")][0].split(":")[1]
+        subprocess.run([os.path.join(REFBIN, variant, "preprocess"), "1", smlen, "0"], cwd=wd, check=True,
+                       stdout=subprocess.DEVNULL)
+        dump = os.path.join(wd, "dump")
+        os.makedirs(dump)
+        run_ref(variant, wd, dict(PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="1-2", PSPH_MAX_STEPS=2))
+        out = {}
+        out["adapt"] = np.asarray([int(open(os.path.join(dump, "s%04d_scan_adapt.txt" % k)).read()) for k in (1, 2)])
+        _, t0 = refio.read_dump(os.path.join(dump, "s0001_scan_pre.bin"))
+        _, t1 = refio.read_dump(os.path.join(dump, "s0002_adapt_pre.bin"))
+        _, t2 = refio.read_dump(os.path.join(dump, "s0002_adapt_post.bin"))
+        _, t3 = refio.read_dump(os.path.join(dump, "s0002_pghost_post.bin"))
+        for f in ("key", "bc_type", "involved", "guest", "coord"):   # (apply_bcond ran in between: wall-ghost states only)
+            assert np.array_equal(t0[f], t1[f]), f
+        out["table"] = t1
+        ch = (t1["bc_type"] != t2["bc_type"]) | (t1["involved"] != t2["involved"])
+        assert all(np.array_equal(t1[f], t2[f]) for f in t1.dtype.names if f not in ("bc_type", "involved"))
+        out["adapt_rows"] = np.nonzero(ch)[0].astype(np.int32)
+        out["adapt_bc_type"] = t2["bc_type"][ch]
+        out["adapt_involved"] = t2["involved"][ch]
+        old = {tuple(k) for k in t2["key"]}
+        isnew = np.asarray([tuple(k) not in old for k in t3["key"]])
+        assert np.array_equal(t3[~isnew], t2)                        # the old rows keep their relative order, untouched
+        out["pghost_pos"] = np.nonzero(isnew)[0].astype(np.int32)
+        out["pghost_rows"] = t3[isnew]
+        for tag, fn in (("scan_pre", "s0001_scan_pre"), ("scan_post", "s0001_scan_post"), ("adapt_pre", "s0002_adapt_pre"),
+                        ("adapt_post", "s0002_adapt_post"), ("pghost_post", "s0002_pghost_post")):
+            bk = refio.read_bucketsx(os.path.join(dump, fn + "_bucketsx.bin"))
+            out[tag + "_mincrd"] = np.asarray([b["mincrd"] for b in bk])
+            out[tag + "_attr"] = np.asarray([[b["type"], b["has_involved"], b["active"], b["guest"], b["particles_type"],
+                                             b["erupt_flag"]] for b in bk], np.int32)
+            if tag == "scan_pre":
+                out["bindex"] = np.asarray([b["bucket_index"] for b in bk], np.int32)
+                out["bnd"] = np.asarray([b["bnd"] for b in bk], np.float64)
+                out["neigh_proc"] = np.asarray([b["neigh_proc"] for b in bk], np.int32)
+                out["plist_off"] = np.cumsum([0] + [len(b["rows"]) for b in bk]).astype(np.int64)
+                out["plist_rows"] = np.concatenate([b["rows"] for b in bk]).astype(np.int32)
+        g = refio.read_grow_params(os.path.join(dump, "s0002_grow_params.bin"))
+        out["param_step"] = np.asarray([g["step"], g["atmosphere_type"]], np.int32)
+        out["param_const"] = np.asarray([g["mass"], g["smlen"], g["gamma"]])
+        out["param_keybox"] = np.concatenate([g["mindom"], g["maxdom"]])
+        out["param_domain"] = np.concatenate([g["Ll"], g["Lu"]])
+        out["meteo_z"] = g["meteo_z"]
+        out["meteo"] = g["meteo"]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "adapt", out["adapt"], "rows", len(t1), "turned", int(ch.sum()), "added", int(isnew.sum()), "->",
+              os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
+
+
 ERUPT_PARAMS = ("time", "dt", "step", "bot", "sml_of_phase2", "mass_of_phase2", "rv", "pos_v0", "pos_v1", "Vv0", "ev0", "rhov",
                 "pv0", "gamma_v", "sndspd", "vel_prof", "ratio_sml_dx", "kmin0", "kmin1", "kmin2", "kmax0", "kmax1", "kmax2",
                 "iferupt")
@@ -308,6 +375,7 @@ if __name__ == "__main__":
         "shu_gsph": lambda: golden_1d("shu_gsph", "1d_shu_gsph", "simulation_1D_shocktube_shu-Osher.data", 200),
         # (the reference's own plain-SPH build aborts on the strong blast at step 4: assert c>0, timestep.cc:167)
         "blast_gsph": lambda: golden_1d("blast_gsph", "1d_blast_gsph", "simulation_1D_shocktube_Strong-Blast.data", 300),
+        "grow3d": lambda: golden_grow(),
         "erupt3d": lambda: golden_erupt(),
         "erupt3d_jpue": lambda: golden_erupt("erupt3d_jpue", "3d_jpue", JPUE_3D, steps=(2, 3, 4),
                                              simdata="simulation_JPUE_incomp_back.data"),

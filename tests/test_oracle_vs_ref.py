@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_py as op
-from common import golden, oracle_state_3d, cell_attrs, image_cells, D2P, sparse_field
+from common import golden, oracle_state_3d, cell_attrs, image_cells, D2P, sparse_field, grow_cell_attrs, grow_cell_mincrd
 from plume_sph_b200.driver import TimeProps
 
 
@@ -149,6 +149,72 @@ def test_apply_bcond_bit_exact(name):
     other[w] = False
     for f, o in (("rho", "rho"), ("vel", "v"), ("engr", "e")):
         eq(s.a[o][other], z["bc_pre"][f][other], ("bcond leaves other rows alone", f))
+
+
+def grow_state(z, cfg):
+    """oracle state of the growth fixture: its table with the plists of the dumped buckets"""
+    s = op.OracleState.from_dump(cfg, z["table"])
+    attr, lin = grow_cell_attrs(cfg, z, "scan_pre")
+    counts = np.zeros(s.ncells, np.int64)
+    counts[lin] = np.diff(z["plist_off"])
+    s.cell_off[:] = 0
+    s.cell_off[1:] = np.cumsum(counts)
+    o = np.argsort(lin, kind="stable")
+    off = z["plist_off"]
+    s.cell_rows[:len(z["plist_rows"])] = np.concatenate([z["plist_rows"][off[b]:off[b + 1]] for b in o])
+    return s, attr, lin
+
+
+def test_domain_growth_bit_exact():
+    """SURVEY 8f N3 against the reference's own calls in the small plume (tests/golden/grow3d.npz): scan_outside_layer at
+    the end of step 1 (the bucket it marks, adapt = 1), adapt_domain at the start of step 2 (6144 pressure ghosts turned
+    real, bucket flags) and add_pressure_ghost (20480 new particles: keys, positions, mass, density, energy, EOS outputs
+    from the Meteo sounding; their places in the table's iteration order; bucket flags)"""
+    z = golden("grow3d")
+    cfg = op.config_for("grow3d")
+    s, attr, lin = grow_state(z, cfg)
+    # the mesh neighbourhood rule: neigh_proc > -1 exactly for the neighbours inside the lattice
+    n1, n2 = int(cfg.ncell[1]), int(cfg.ncell[2])
+    for b in (0, len(lin) // 2, len(lin) - 1):
+        ci, cj, ck = lin[b] // (n1 * n2), (lin[b] // n2) % n1, lin[b] % n2
+        for q in range(27):
+            ni, nj, nk = ci + q // 9 - 1, cj + (q // 3) % 3 - 1, ck + q % 3 - 1
+            inside = 0 <= ni < cfg.ncell[0] and 0 <= nj < n1 and 0 <= nk < n2
+            assert (z["neigh_proc"][b][q] > -1) == (inside and q != 13), (b, q)
+
+    def check(tag):
+        want, _ = grow_cell_attrs(cfg, z, tag)
+        for f in ("type", "has_involved", "flags"):
+            eq(attr[f], want[f], (tag, f))
+        eq(attr["active"][lin], want["active"][lin], (tag, "active"))
+
+    assert s.scan_outside_layer(attr) == int(z["adapt"][0]) == 1
+    check("scan_post")
+    attr["active"] = grow_cell_attrs(cfg, z, "adapt_pre")[0]["active"]     # (update_bgmesh ran in between)
+    check("adapt_pre")
+    bc0, inv0 = s.a["bc"].copy(), s.a["involved"].copy()
+    assert s.adapt_domain(attr) == len(z["adapt_rows"])
+    check("adapt_post")
+    bc0[z["adapt_rows"]] = z["adapt_bc_type"]
+    inv0[z["adapt_rows"]] = z["adapt_involved"]
+    eq(s.a["bc"], bc0, "bc_type after adapt_domain")
+    eq(s.a["involved"], inv0, "involved after adapt_domain")
+    g, mz, mrho, mp = op.growth_from_golden(z)
+    new = s.add_pressure_ghost(attr, g, mz, mrho, mp, int(z["param_step"][0]), grow_cell_mincrd(cfg, z, lin))
+    check("pghost_post")
+    want = z["pghost_rows"]
+    assert len(new) == len(want) == 20480
+    # the table's iteration order (thashtab.cc:204-222) puts the new rows where the reference's table has them
+    allkeys = np.concatenate([z["table"]["key"], new["key"]])
+    perm = op.table_order(cfg, allkeys)
+    isnew = perm >= len(z["table"])
+    eq(np.nonzero(isnew)[0], z["pghost_pos"], "positions of the new rows in the table order")
+    got = new[perm[isnew] - len(z["table"])]
+    for f in ("key", "bc_type", "involved", "guest", "mass", "smlen", "mass_frac", "pressure", "gamma", "sound_speed",
+              "temperature", "specific_heat_p", "phase_density", "vel", "smoothed_v", "rho", "engr", "smoothed_e"):
+        eq(got[f], want[f], ("new row", f))
+    eq(got["coords"], want["coord"], "new row coord")
+    eq(got["phase_num"], want["phase"], "new row phase")
 
 
 def test_table_order_matches_thashtable_iteration():

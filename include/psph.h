@@ -217,12 +217,15 @@ int psph_get_cells(psph_ctx *ctx, psph_cell_attr *attr, size_t ncells);
  *   has_involved >= 2 bucket become potential-involved and their pressure ghosts real (bc_type 100, involved 1).
  * psph_set_growth + psph_add_pressure_ghost (add_pressure_ghost.cc:36-316): the exposed buckets are filled with a lattice
  *   of static pressure ghosts (birth key = Hilbert index in the key box + add_step, state from the atmosphere);
- *   *added = rows appended on this rank.  meteo_z [km], meteo_rho, meteo_p [hPa]: columns 0, 1, 2 of the sounding.
+ *   *added = rows appended on this rank.  meteo_z [km], meteo_rho, meteo_p [hPa]: columns 0, 1, 2 of the sounding;
+ *   cell_mincrd [ncells][3]: Bucket::mincrd of every bucket as the driver stores it — the lattice points are
+ *   mincrd + dx / 2 + i dx (:161-163) — or NULL: (mindom + i del) / len_scale.
  * The driver keeps shift_brief_buck, add_wall_ghost, update_bgmesh and the image search (they run on bucket attributes:
  * psph_get_cells), and appends what they create with psph_append. */
 int psph_scan_outside_layer(psph_ctx *ctx, int *adapt);
 int psph_adapt_domain(psph_ctx *ctx, int *turned);
-int psph_set_growth(psph_ctx *ctx, const psph_growth *g, const double *meteo_z, const double *meteo_rho, const double *meteo_p);
+int psph_set_growth(psph_ctx *ctx, const psph_growth *g, const double *meteo_z, const double *meteo_rho, const double *meteo_p,
+                    const double *cell_mincrd);
 int psph_add_pressure_ghost(psph_ctx *ctx, uint32_t add_step, int *added);
 
 /* after initialisation (main.cc:199) / after add_new_erupt (:417) / ghost regeneration (:271-283) */

@@ -90,6 +90,7 @@ def config_3d(smlen=100.0, Ll=(-20800.0, -20800.0, 1666.0), Lu=(20800.0, 20800.0
     c.dim = 3
     c.use_gsph = 0
     c.riemann_solver = 0
+    c.gsph_reconstruct = 3
     c.have_turbulence_lans = 1
     c.have_energy_smooth = 1
     c.pghost_contribute_des = 1

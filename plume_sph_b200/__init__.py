@@ -10,9 +10,9 @@ hot path.  The product is the C-ABI library ``libpsph.so`` (include/psph.h, sour
 There is no CPU fallback: importing :mod:`lib` without a built ``libpsph.so`` raises, and
 ``psph_create`` fails when no CUDA device is visible.
 """
-from .lib import (PsphConfig, PsphErupt, PARTICLE_DTYPE, PARTICLE_SPH_DTYPE, CELL_ATTR_DTYPE, IMAGE_DTYPE, PsphError, load, config_default_3d,
+from .lib import (PsphConfig, PsphErupt, PsphGrowth, PARTICLE_DTYPE, PARTICLE_SPH_DTYPE, CELL_ATTR_DTYPE, IMAGE_DTYPE, PsphError, load, config_default_3d,
                   config_default_1d, LIB_PATH)
 from .solver import Solver
 
-__all__ = ["PsphConfig", "PsphErupt", "PARTICLE_DTYPE", "PARTICLE_SPH_DTYPE", "CELL_ATTR_DTYPE", "IMAGE_DTYPE", "PsphError", "load", "config_default_3d",
+__all__ = ["PsphConfig", "PsphErupt", "PsphGrowth", "PARTICLE_DTYPE", "PARTICLE_SPH_DTYPE", "CELL_ATTR_DTYPE", "IMAGE_DTYPE", "PsphError", "load", "config_default_3d",
            "config_default_1d", "Solver", "LIB_PATH"]

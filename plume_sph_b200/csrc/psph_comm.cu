@@ -733,6 +733,15 @@ int psph_comm_min_dt(psph_ctx *ctx)
   return 0;
 }
 
+// all-reduce of an int32 array over the slabs (op 0 sum, 1 max); no-op on one rank
+int psph_comm_allreduce_i32(psph_ctx *ctx, int32_t *d, size_t n, int op)
+{
+  Comm *C = comm_of(ctx);
+  if (!C || n == 0) return 0;
+  PSPH_NCCL(g_nccl.AllReduce(d, d, n, ncclInt32, op ? ncclMax : ncclSum, C->comm, ctx->stream));
+  return 0;
+}
+
 extern "C" int psph_slab_cuts(psph_ctx *ctx, int *cuts, size_t cap)
 {
   Comm *C = comm_of(ctx);

@@ -183,6 +183,7 @@ extern "C" int psph_create(const psph_config *cfg, psph_ctx **out)
   memset(&ctx->cur, 0, sizeof ctx->cur); memset(&ctx->alt, 0, sizeof ctx->alt);
   ctx->ncells = (long long) cfg->ncell[0] * cfg->ncell[1] * cfg->ncell[2];
   if (ctx->ncells <= 0 || ctx->ncells * SUBS >= 0x7fffffffLL) { delete ctx; return -2; }
+  ctx->grow = nullptr;
   ctx->d_attr = nullptr; ctx->d_sortkey = ctx->d_sortkey_alt = ctx->d_perm = ctx->d_perm_alt = nullptr;
   ctx->d_cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
   ctx->list_valid = false; ctx->n_dirty = false; ctx->step = 0; ctx->launches = 0;
@@ -262,6 +263,7 @@ extern "C" void psph_destroy(psph_ctx *ctx)
   for (int c = 0; c < NREC; c++) cudaFree(ctx->cur.rec[c]);
   cudaFree(ctx->cur.geo); cudaFree(ctx->cur.geo32); cudaFree(ctx->cur.nbr); cudaFree(ctx->cur.wts); cudaFree(ctx->cur.nbr_off); cudaFree(ctx->cur.nbr_cnt); cudaFree(ctx->cur.near); cudaFree(ctx->cur.mlist); cudaFree(ctx->cur.mseg); cudaFree(ctx->cur.flags); cudaFree(ctx->d_gspill);
   cudaFree(ctx->cur.gsub); cudaFree(ctx->cur.need_idx); cudaFree(ctx->cur.grad_idx);
+  psph_grow_free(ctx);
   cudaFree(ctx->d_cell2rank); cudaFree(ctx->d_rank2cell); cudaFree(ctx->d_sub_start); cudaFree(ctx->d_attr);
   cudaFree(ctx->d_cell_has_ghost); cudaFree(ctx->d_cell_hmax); cudaFree(ctx->d_blk_any);
   cudaFree(ctx->d_erupt_boxes);

@@ -20,34 +20,6 @@ struct EruptPar
   int base, cap, rank, has_grad, nbox;
 };
 
-// Hilbert key of a normalised position: HSFC3d + hsfc3d (hilbert.c:156-271,289-303), the 63-bit index walk of
-// psph_ctx.cu on the device
-__device__ void dev_hsfc3d(const double nc[3], uint32_t key[2])
-{
-  const unsigned char gray_inv[8] = { 0, 1, 3, 2, 7, 6, 4, 5 };
-  const unsigned char from[8][3] = { {2,1,0}, {0,2,1}, {0,1,2}, {2,0,1}, {2,0,1}, {0,1,2}, {0,2,1}, {2,1,0} };
-  const unsigned char refl[8][3] = { {0,0,0}, {0,0,0}, {0,0,0}, {1,1,0}, {0,1,1}, {0,0,0}, {0,1,1}, {1,0,1} };
-  uint32_t q[3];
-  for (int d = 0; d < 3; d++) {
-    const double v = nc[d] <= 0 ? 0.0 : __dmul_rn(4294967295.0, nc[d]);
-    q[d] = (uint32_t) (v > 4294967295.0 ? 4294967295.0 : v);
-  }
-  unsigned char ax[3] = { 0, 2, 4 };
-  unsigned long long H = 0;
-  for (int lvl = 1; lvl <= 21; lvl++) {
-    const unsigned s = 32 - lvl;
-    unsigned g = 0;
-    for (int a = 0; a < 3; a++) g |= (((q[ax[a] >> 1] >> s) ^ ax[a]) & 1u) << a;
-    const unsigned oct = gray_inv[g];
-    H = (H << 3) | oct;
-    const unsigned char o[3] = { ax[0], ax[1], ax[2] };
-    for (int a = 0; a < 3; a++) ax[a] = o[from[oct][a]] ^ refl[oct][a];
-  }
-  const unsigned long long K = H >> 1;        // the 2-word key drops the last bit
-  key[0] = (uint32_t) (K >> 32);
-  key[1] = (uint32_t) (K & 0xffffffffu);
-}
-
 // One block: the columns are few (tens to thousands) and the slots must not depend on scheduling — a row's place in
 // the table decides its place among the rows of its subcell after the (stable) sort, hence summation orders.  Columns
 // are taken 256 at a time; a block-wide exclusive scan of the per-column counts gives every column its slots.

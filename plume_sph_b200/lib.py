@@ -93,6 +93,13 @@ class PsphErupt(C.Structure):
                 ("gamma_v", C.c_double), ("sndspd", C.c_double), ("kmin", C.c_double * 3), ("kmax", C.c_double * 3)]
 
 
+class PsphGrowth(C.Structure):
+    """Mirror of ``psph_growth`` (include/psph.h): what add_pressure_ghost reads (add_pressure_ghost.cc:36-316)."""
+    _fields_ = [("mass", C.c_double), ("smlen", C.c_double), ("ratio_sml_dx", C.c_double), ("gamma_air", C.c_double),
+                ("sndspd", C.c_double), ("gmm", C.c_double), ("Ta0", C.c_double), ("kmin", C.c_double * 3), ("kmax", C.c_double * 3),
+                ("Ll", C.c_double * 3), ("Lu", C.c_double * 3), ("atmosphere_type", C.c_int32), ("nmeteo", C.c_int32)]
+
+
 # every symbol include/psph.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
 _CFG = C.POINTER(PsphConfig)
@@ -103,6 +110,11 @@ API = {
     "psph_destroy": (None, [_VP]),
     "psph_last_error": (C.c_char_p, [_VP]),
     "psph_set_cells": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "psph_get_cells": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "psph_scan_outside_layer": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+    "psph_adapt_domain": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+    "psph_set_growth": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "psph_add_pressure_ghost": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_int)]),
     "psph_upload": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_append": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_download": (C.c_int, [_VP, _VP, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),

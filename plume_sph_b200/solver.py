@@ -14,7 +14,7 @@ ORDER_DEVICE, ORDER_REFERENCE = 0, 1
 KERNELS = ("gather_mom_engr", "gather_density", "gather_velocity", "gather_adaptive_sml", "gather_gradients",
            "gather_gsph_mom_engr", "radix_sort", "reorder", "pair_scan")
 STAGES = ("timestep", "search", "adaptive_sml", "gradients", "mom_engr", "density", "velocity", "update_pos", "rebin",
-          "apply_bcond", "add_new_erupt")
+          "apply_bcond", "add_new_erupt", "domain_growth")
 
 
 class Solver:
@@ -54,6 +54,40 @@ class Solver:
             return self._ck(self.L.psph_set_cells(self.h, None, 0), "psph_set_cells")
         attr = np.ascontiguousarray(attr, dtype=_l.CELL_ATTR_DTYPE)
         return self._ck(self.L.psph_set_cells(self.h, attr.ctypes.data, attr.size), "psph_set_cells")
+
+    def get_cells(self):
+        """the bucket attributes as the device holds them (the domain-growth calls change has_involved, active, flags)"""
+        attr = np.zeros(int(self.cfg.ncell[0]) * int(self.cfg.ncell[1]) * int(self.cfg.ncell[2]), _l.CELL_ATTR_DTYPE)
+        self._ck(self.L.psph_get_cells(self.h, attr.ctypes.data, attr.size), "psph_get_cells")
+        return attr
+
+    # ---- domain growth on the device (SURVEY 8f N3) ----
+    def scan_outside_layer(self):
+        """scan_outside_layer (scan_outside_layer.cc:44-121) -> adapt"""
+        a = C.c_int(0)
+        self._ck(self.L.psph_scan_outside_layer(self.h, C.byref(a)), "psph_scan_outside_layer")
+        return a.value
+
+    def adapt_domain(self):
+        """adapt_domain (adapt_domain.cc:41-194) -> rows turned real on this rank"""
+        a = C.c_int(0)
+        self._ck(self.L.psph_adapt_domain(self.h, C.byref(a)), "psph_adapt_domain")
+        return a.value
+
+    def set_growth(self, growth, meteo_z=None, meteo_rho=None, meteo_p=None, cell_mincrd=None):
+        """growth record (lib.PsphGrowth), the sounding's columns (height [km], density, pressure [hPa]) and, optionally,
+        Bucket::mincrd of every bucket as the driver stores it"""
+        g = _l.PsphGrowth()
+        C.memmove(C.byref(g), C.byref(growth), C.sizeof(g))
+        keep = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (meteo_z, meteo_rho, meteo_p, cell_mincrd)]
+        ptr = [None if a is None else a.ctypes.data for a in keep]
+        return self._ck(self.L.psph_set_growth(self.h, C.byref(g), *ptr), "psph_set_growth")
+
+    def add_pressure_ghost(self, add_step):
+        """add_pressure_ghost (add_pressure_ghost.cc:36-316) on the device -> rows appended on this rank"""
+        a = C.c_int(0)
+        self._ck(self.L.psph_add_pressure_ghost(self.h, int(add_step), C.byref(a)), "psph_add_pressure_ghost")
+        return a.value
 
     def host_rows(self, n, dtype=None):
         """n rows (psph_particle, or lib.PARTICLE_SPH_DTYPE) in pinned host memory (psph_host_alloc); freed with the solver"""

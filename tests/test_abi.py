@@ -74,8 +74,8 @@ def test_header_compiles_as_c_and_cxx_with_the_mirrored_layouts(tmp_path):
     import oracle_py as op
     sizes = {"psph_config": C.sizeof(psph.PsphConfig), "psph_particle": psph.PARTICLE_DTYPE.itemsize,
              "psph_cell_attr": psph.CELL_ATTR_DTYPE.itemsize, "psph_image": psph.IMAGE_DTYPE.itemsize,
-             "psph_erupt": C.sizeof(psph.PsphErupt)}
-    assert C.sizeof(op.Erupt) == sizes["psph_erupt"]
+             "psph_erupt": C.sizeof(psph.PsphErupt), "psph_growth": C.sizeof(psph.PsphGrowth)}
+    assert C.sizeof(op.Erupt) == sizes["psph_erupt"] and C.sizeof(op.Growth) == sizes["psph_growth"]
     body = '#include "psph.h"\n' + "".join(
         "typedef char check_%s[sizeof(%s) == %d ? 1 : -1];\n" % (n, n, s) for n, s in sizes.items())
     body += "typedef char check_sph_row[PSPH_ROW_BYTES_SPH == %d ? 1 : -1];\n" % psph.PARTICLE_SPH_DTYPE.itemsize

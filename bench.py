@@ -305,6 +305,14 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_port(args.cpu_n)
+    s.close()
+    s = None
+    plume = None
+    if not args.no_plume:
+        try:
+            plume = run_plume(args, torch, dist, psph, rank, world, local, dev)
+        except Exception as ex:                            # the cube line must not die with the companion case
+            plume = {"error": "%s: %s" % (type(ex).__name__, ex)} if rank == 0 else None
 
     if rank == 0:
         other = {k: {kk: vv for kk, vv in v.items() if kk != "clocks"} for k, v in regimes.items()}
@@ -324,10 +332,193 @@ def run_b200(args):
                 "regimes": other, "invariant_violations": bad}
         if cpu:
             line["cpu_baseline"] = cpu
+        if plume:
+            line["plume"] = plume
         print(json.dumps(line), flush=True)
-    s.close()
+    if s is not None:
+        s.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own 3-D plume case, like for like (BASELINE.json config 3): the unmodified reference driver sets the case
+# up (input parsing, background mesh, Meteo atmosphere, air / pressure-ghost / wall-ghost / vent particles, image search —
+# everything north_star leaves with the driver) and is timed on the host cores; the state it starts its loop from is then
+# advanced by libpsph.so through the same per-step calls (psph_step, psph_add_new_erupt, psph_apply_bcond,
+# psph_scan_outside_layer), strong-scaled over the slabs when there are several GPUs.
+# ---------------------------------------------------------------------------------------------------------------------
+DUMP_ROW = [("key", "<u4", 3), ("bc_type", "<i4"), ("phase", "<i4"), ("involved", "<i4"), ("guest", "<i4"), ("pad", "<i4"),
+            ("mass", "<f8"), ("smlen", "<f8"), ("mass_frac", "<f8"), ("pressure", "<f8"), ("gamma", "<f8"), ("sound_speed", "<f8"),
+            ("temperature", "<f8"), ("specific_heat_p", "<f8"), ("phase_density", "<f8", 2), ("coord", "<f8", 3), ("vel", "<f8", 3),
+            ("smoothed_v", "<f8", 3), ("rho", "<f8"), ("engr", "<f8"), ("smoothed_e", "<f8"), ("grad", "<f8", 15)]
+
+
+def load_reference_setup(dump, psph, cfg):
+    """the state files the hooked reference driver wrote (oracle/ref_build/ref_hooks.cc formats) -> what the C ABI takes:
+    particle rows, bucket attributes, wall-ghost images, vent record + erupt buckets"""
+    import struct
+    import numpy as np
+    import ctypes as C
+    with open(os.path.join(dump, "s0000_init_post.bin"), "rb") as f:
+        f.read(12)
+        n, = struct.unpack("<q", f.read(8))
+        f.read(16)
+        d = np.fromfile(f, dtype=np.dtype(DUMP_ROW), count=n)
+    rows = np.zeros(n, psph.PARTICLE_DTYPE)
+    for a, b in (("key", "key"), ("bc_type", "bc_type"), ("phase_num", "phase"), ("involved", "involved"), ("guest", "guest"),
+                 ("mass", "mass"), ("smlen", "smlen"), ("mass_frac", "mass_frac"), ("pressure", "pressure"), ("gamma", "gamma"),
+                 ("sound_speed", "sound_speed"), ("temperature", "temperature"), ("specific_heat_p", "specific_heat_p"),
+                 ("phase_density", "phase_density"), ("coords", "coord"), ("vel", "vel"), ("smoothed_v", "smoothed_v"),
+                 ("rho", "rho"), ("engr", "engr"), ("smoothed_e", "smoothed_e")):
+        rows[a] = d[b]
+    n1, n2 = int(cfg.ncell[1]), int(cfg.ncell[2])
+    attr = np.zeros(int(cfg.ncell[0]) * n1 * n2, psph.CELL_ATTR_DTYPE)
+    key2cell = {}
+    mind = np.asarray([cfg.mindom[k] for k in range(3)])
+    with open(os.path.join(dump, "s0000_init_buckets.bin"), "rb") as f:
+        nb, = struct.unpack("<q", f.read(8))
+        for _ in range(nb):
+            key = struct.unpack("<II", f.read(8))
+            mn = np.asarray(struct.unpack("<ddd", f.read(24)))
+            f.read(24)
+            typ, inv, act, guest, npart = struct.unpack("<iiiii", f.read(20))
+            bidx = struct.unpack("<6i", f.read(24))
+            bnd = struct.unpack("<6d", f.read(48))
+            f.read(4 * npart)
+            idx = np.rint((mn * cfg.len_scale - mind) / cfg.delta).astype(np.int64)
+            lin = int((idx[0] * n1 + idx[1]) * n2 + idx[2])
+            key2cell[key] = lin
+            attr[lin] = (typ, inv, act, bidx, 0, bnd)
+    idt = np.dtype([("buckproc", "<i4"), ("partproc", "<i4"), ("bucket_key", "<u4", 2), ("ghost_key", "<u4", 3), ("coord", "<f8", 3)])
+    with open(os.path.join(dump, "s0001_images.bin"), "rb") as f:
+        ni, = struct.unpack("<q", f.read(8))
+        im = np.fromfile(f, dtype=idt, count=ni)
+    img = np.zeros(ni, psph.IMAGE_DTYPE)
+    img["ghost_key"] = im["ghost_key"]
+    img["cell"] = [key2cell[tuple(int(x) for x in k)] for k in im["bucket_key"]]
+    img["coord"] = im["coord"]
+    raw = open(os.path.join(dump, "s0001_erupt_params.bin"), "rb").read()
+    v = np.frombuffer(raw, np.float64, 24)
+    nbx = int(np.frombuffer(raw, np.int64, 1, 192)[0])
+    rec = np.frombuffer(raw, np.dtype([("mincrd", "<f8", 3), ("maxcrd", "<f8", 3), ("guest", "<i4"), ("pad", "<i4")]), nbx, 200)
+    e = psph.PsphErupt()
+    (_, _, _, e.bot, e.sml, e.mass, e.rv, e.pos_v[0], e.pos_v[1], e.Vv0, e.ev0, e.rhov, e.pv0, e.gamma_v, e.sndspd) = [float(x) for x in v[:15]]
+    e.vel_prof, e.ratio_sml_dx = int(v[15]), float(v[16])
+    for k in range(3):
+        e.kmin[k], e.kmax[k] = float(v[17 + k]), float(v[20 + k])
+    boxes = np.concatenate([rec["mincrd"], rec["maxcrd"]], axis=1)
+    return rows, attr, img, e, boxes
+
+
+def run_plume(args, torch, dist, psph, rank, world, local, dev):
+    """-> the "plume" object of the JSON line (rank 0), or None when the compiled reference is not there"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_build"))
+    import ref_run                                         # (the reference arm's runner: CPU baseline + set-up, rank 0 only)
+    if not ref_run.have_inputs():
+        return None
+    import tempfile
+    top = os.path.join(tempfile.gettempdir(), "psph_plume_case_%s" % os.environ.get("MASTER_PORT", "single"))   # same on every rank
+    dump = os.path.join(top, "dump")
+    ncpu = os.cpu_count() or 1
+    cpu = None
+    if rank == 0:
+        import shutil
+        shutil.rmtree(top, ignore_errors=True)
+        os.makedirs(top, exist_ok=True)
+        # set-up run (1 step, with the state files) — not timed
+        ref_run.time_plume3d(1, 0, replicas=1, edits=ref_run.MEDIUM, keep=os.path.join(top, "setup"), dump=dump)
+        if world == 1:
+            # CPU arm, bounded: 2 steps of the whole reference loop on every host core (single-rank replicas: no MPI here)
+            r = ref_run.time_plume3d(2, 0, replicas=ncpu, edits=ref_run.MEDIUM)
+            t = max(r["seconds"])
+            cpu = {"value": round(r["updates"] * ncpu / t, 1), "unit": UNIT, "cores": ncpu, "kind": "reference", "steps": 2,
+                   "one_replica_updates_per_s": round(r["updates"] / t, 1), "real": r["real"], "total": r["total"],
+                   "sample": "unmodified reference, whole loop, %d single-rank replicas side by side, 2 steps" % ncpu}
+    if world > 1:
+        dist.barrier()
+    cfg = psph.config_default_3d()                         # bin/simulation.data = the defaults: Eyjafjallajokull box, h = 100 m
+    cfg.device, cfg.rank, cfg.nranks = local, rank, world
+    rows, attr, img, er, boxes = load_reference_setup(dump, psph, cfg)
+    cfg.smlen_real = er.sml                                # sml_of_phase2 (setup_erupt.cc:95-101)
+    s = psph.Solver(cfg)
+    s.set_cells(attr)
+    part = np.array_split(np.argsort(rows["coords"][:, 0], kind="stable"), world)[rank]
+    s.upload(rows[part])
+    s.set_images(img)
+    s.set_erupt(er, boxes)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(psph.Solver.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        s.comm_init(bytes(idt.cpu().numpy().tobytes()))
+        s.repartition()
+    stream = torch.cuda.ExternalStream(s.stream(), device=dev)
+    warm, steps = 3, max(args.steps, 10)
+    t_sim, k, updates, adapt_at = 0.0, 0, 0, None
+
+    def one_step():
+        nonlocal t_sim, k
+        k += 1
+        dt, lost, ierr = s.step(0.0, 1)                    # main.cc:220-408 (dt comes back: TimeProps stays on the host)
+        t_sim += dt
+        s.add_new_erupt(t_sim, dt, k)                      # :414-417
+        adapt = s.scan_outside_layer()                     # :435
+        s.apply_bcond()                                    # :468
+        if world > 1:
+            s.exchange_ghosts()                            # :471
+        return adapt, ierr
+
+    for _ in range(warm):
+        one_step()
+    s.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    bad = 0
+    for _ in range(steps):
+        updates += s.num_updated
+        adapt, ierr = one_step()
+        bad += ierr
+        if adapt and adapt_at is None:
+            adapt_at = k
+    ev1.record(stream)
+    s.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    u = torch.tensor([float(updates), float(s.n)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    s.close()
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        return None
+    import shutil
+    shutil.rmtree(top, ignore_errors=True)
+    ms = float(t.item())
+    out = {"workload": "the reference's own 3-D dusty-gas plume (bin/simulation.data + Meteo sounding, initial domain +-1000 m), set up "
+                       "by the unmodified reference driver; per step: psph_step + psph_add_new_erupt + psph_scan_outside_layer + "
+                       "psph_apply_bcond" + (" + psph_exchange_ghosts" if world > 1 else ""),
+           "value": round(float(u[0].item()) / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms / steps, 4), "steps": steps,
+           "warmup": warm, "n_gpus": world, "scaling": "strong", "real_particles": int(float(u[0].item()) / steps),
+           "rows": int(u[1].item()) if world == 1 else None, "invariant_violations": bad,
+           "domain_growth_requested_at_step": adapt_at,
+           "note": "a step is launch-bound at this size (a few thousand real particles): the figure is the like-for-like companion "
+                   "of cpu_reference, not a throughput claim; the dt round trip per step is the drop-in's (TimeProps on the host)"}
+    if cpu:
+        out["cpu_reference"] = cpu
+        out["speedup_vs_all_host_cores"] = round(out["value"] / cpu["value"], 1)
+    return out
+
 
 
 def cpu_baseline_port(n):
@@ -406,6 +597,7 @@ def main():
     ap.add_argument("--strong", dest="weak", action="store_false", help="fixed total cube (default: weak, per-GPU cube)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-plume", action="store_true", help="skip the reference's own plume case (the like-for-like companion)")
     ap.add_argument("--cpu-n", type=int, default=32)
     ap.add_argument("--ref-replicas", type=int, default=0)
     ap.add_argument("--sml-int", type=int, default=0, help="run adaptive_sml every k-th step (default: the reference's 50)")

@@ -68,6 +68,9 @@ void psph_bind_collect_cells(HashTable *BG_mesh, const psph_config *cfg, vector<
     psph_cell_attr &a = attr[((size_t) idx[0] * cfg->ncell[1] + idx[1]) * cfg->ncell[2] + idx[2]];
     a.type = b->get_bucket_type(); a.has_involved = b->get_has_involved(); a.active = b->is_active();
     for (int k = 0; k < 6; k++) { a.bucket_index[k] = b->get_bucket_index()[k]; a.bnd[k] = b->get_bnd()[k]; }
+    a.flags = (b->has_real_particles() ? PSPH_CELLF_REAL : 0) | (b->has_wall_ghost_particles() ? PSPH_CELLF_WALL : 0) |
+              (b->has_pressure_ghost_particles() ? PSPH_CELLF_PRESS : 0) | (b->has_erupt_ghost_particles() ? PSPH_CELLF_ERUPT : 0) |
+              ((int) b->get_erupt_flag() << 8);                       /* read by the domain-growth calls */
   }
 }
 
@@ -115,6 +118,54 @@ void psph_bind_collect_erupt(THashTable *P_table, HashTable *BG_mesh, SimProps *
     for (int d = 0; d < 3; d++) boxes.push_back(*(b->get_mincrd() + d));
     for (int d = 0; d < 3; d++) boxes.push_back(*(b->get_maxcrd() + d));
   }
+}
+
+/* what add_pressure_ghost reads besides the tables (psph_set_growth): lattice constants, key box of the particle table,
+ * and the buckets' stored mincrd (the new particles sit on mincrd + dx / 2 + i dx, add_pressure_ghost.cc:161-163); the
+ * sounding's columns (height [km], density, pressure [hPa]) are the driver's own Meteo table (src/datstr/meteo.h) */
+void psph_bind_collect_growth(THashTable *P_table, HashTable *BG_mesh, MatProps *matprops, const psph_config *cfg, psph_growth *g,
+                              vector<double> &mincrd)
+{
+  g->mass = matprops->particle_mass; g->smlen = matprops->smoothing_length; g->ratio_sml_dx = RATIO_SML_DX;
+  g->gamma_air = gamma_P; g->sndspd = 340.; g->gmm = 1.4; g->Ta0 = Ta0_P;
+  for (int d = 0; d < 3; d++) {
+    g->kmin[d] = *(P_table->get_minDom() + d); g->kmax[d] = *(P_table->get_maxDom() + d);
+    g->Ll[d] = Ll_P[d]; g->Lu[d] = Lu_P[d];
+  }
+  g->atmosphere_type = ATMOSPHERE_TYPE; g->nmeteo = 0;                /* nmeteo: rows of the sounding the driver hands over */
+  mincrd.assign((size_t) cfg->ncell[0] * cfg->ncell[1] * cfg->ncell[2] * 3, 0.);
+  for (int i = 0; i < cfg->ncell[0]; i++)
+    for (int j = 0; j < cfg->ncell[1]; j++)
+      for (int k = 0; k < cfg->ncell[2]; k++) {
+        const int idx[3] = { i, j, k };
+        for (int d = 0; d < 3; d++)
+          mincrd[(((size_t) i * cfg->ncell[1] + j) * cfg->ncell[2] + k) * 3 + d] = (cfg->mindom[d] + idx[d] * cfg->del) / cfg->len_scale;
+      }
+  HTIterator it(BG_mesh);
+  void *t;
+  while ((t = it.next())) {
+    BriefBucket *bb = (BriefBucket *) t;
+    if (bb->check_brief()) continue;
+    Bucket *b = (Bucket *) t;
+    int idx[3];
+    for (int d = 0; d < 3; d++)
+      idx[d] = (int) floor((*(b->get_mincrd() + d) * cfg->len_scale - cfg->mindom[d]) / cfg->del + 0.5);
+    for (int d = 0; d < 3; d++)
+      mincrd[(((size_t) idx[0] * cfg->ncell[1] + idx[1]) * cfg->ncell[2] + idx[2]) * 3 + d] = *(b->get_mincrd() + d);
+  }
+}
+
+/* the end of a step and the first half of the adapt block (main.cc:435, :256-271) on the device */
+int psph_bind_grow(psph_ctx *gpu, TimeProps *timeprops, int *adapt_next)
+{
+  int turned = 0, added = 0;
+  if (*adapt_next) {                                                  /* :259: adapt of the previous step's scan */
+    if (psph_adapt_domain(gpu, &turned) < 0) return -1;               /* :265 */
+    if (psph_add_pressure_ghost(gpu, (uint32_t) timeprops->step, &added) < 0) return -1; /* :271 */
+    /* shift_brief_buck, add_wall_ghost, update_bgmesh, search_bnd_images (:274-292) stay with the driver: psph_get_cells
+     * brings the attributes back, psph_append / psph_set_cells / psph_set_images take what they create */
+  }
+  return psph_scan_outside_layer(gpu, adapt_next);                    /* :435 */
 }
 
 /* one time step of main.cc:217-471 with the stage calls forwarded (single rank) */

@@ -70,8 +70,10 @@ def _parse(log):
     return stamps, real, total, stages, reals, totals
 
 
-def time_plume3d(steps, warmup=0, replicas=1, edits=SMALL, variant="3d_plume", keep=None):
-    """-> dict(seconds=[per replica time of the `steps` timed steps], real=, total=, stages=)"""
+def time_plume3d(steps, warmup=0, replicas=1, edits=SMALL, variant="3d_plume", keep=None, dump=None):
+    """-> dict(seconds=[per replica time of the `steps` timed steps], real=, total=, stages=).
+    dump: directory that receives the hook dumps of steps 0-1 of replica 0 (the state after the reference's own
+    initialisation, its bucket attributes, image table and vent record: the set-up a drop-in run starts from)"""
     top = keep or tempfile.mkdtemp(prefix="psph_ref_")
     try:
         shutil.copytree(os.path.join(INPUTS, "Meteo_data"), os.path.join(top, "Meteo_data"), dirs_exist_ok=True)
@@ -96,6 +98,9 @@ def time_plume3d(steps, warmup=0, replicas=1, edits=SMALL, variant="3d_plume", k
         env = dict(os.environ, PSPH_STAGE_TIMES="1", PSPH_MAX_STEPS=str(steps + warmup))
         for r in range(replicas):
             wd = os.path.join(top, "run%d" % r)
+            if dump and r == 0:
+                os.makedirs(dump, exist_ok=True)
+                env = dict(env, PSPH_DUMP_DIR=dump, PSPH_DUMP_STEPS="0-1")
             procs.append(subprocess.Popen([os.path.join(OUT, variant, "particler_hooked")], cwd=wd, env=env,
                                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
         secs, stages, updates, total = [], {}, 0, 0

@@ -674,6 +674,8 @@ extern "C" int psph_exchange_ghosts(psph_ctx *ctx)
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
   const unsigned dirty = C->dirty;
   C->dirty = 0;
+  if (!dirty) return 0;
+  StageTimer tm(ctx, ST_COMM);                // (timing pass only) migration + ghost layer / column refresh, host waits included
   if (dirty & DIRTY_LAYOUT) { // positions / membership / population changed: migrate, then mirror the boundary cells anew
     if (migrate(ctx)) return -1;
     return rebuild_ghosts(ctx);

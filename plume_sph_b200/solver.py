@@ -14,7 +14,7 @@ ORDER_DEVICE, ORDER_REFERENCE = 0, 1
 KERNELS = ("gather_mom_engr", "gather_density", "gather_velocity", "gather_adaptive_sml", "gather_gradients",
            "gather_gsph_mom_engr", "radix_sort", "reorder", "pair_scan")
 STAGES = ("timestep", "search", "adaptive_sml", "gradients", "mom_engr", "density", "velocity", "update_pos", "rebin",
-          "apply_bcond", "add_new_erupt", "domain_growth")
+          "apply_bcond", "add_new_erupt", "domain_growth", "halo_exchange")
 
 
 class Solver:

@@ -210,3 +210,78 @@ def test_plume_with_wall_ghosts_and_vent_across_slabs(P):
         assert np.array_equal(src["key"], g["key"])
         for f in ("coords", "vel", "rho", "engr", "pressure"):
             assert np.array_equal(src[f], g[f]), f
+
+
+@pytest.mark.skipif(ndev() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("P", [2, 4])
+def test_domain_growth_across_slabs(P):
+    """psph_scan_outside_layer / psph_adapt_domain / psph_add_pressure_ghost on P key-range slabs == the reference's calls
+    (tests/golden/grow3d.npz; the single-GPU comparison is tests/test_gpu_grow.py): the per-bucket facts are summed over the
+    slabs, every rank takes the same decision for every bucket (the attribute tables stay identical without being
+    exchanged), flips the rows it holds and fills the buckets it owns — every new particle exists on exactly one rank"""
+    if ndev() < P:
+        pytest.skip("needs %d GPUs" % P)
+    from common import grow_cell_attrs, grow_cell_mincrd
+    from test_gpu_grow import growth_record
+    z = golden("grow3d")
+    ocfg = op.config_for("grow3d")
+    cfg = to_product_cfg(ocfg)
+    attr0, lin = grow_cell_attrs(ocfg, z, "scan_pre")
+    table = z["table"]
+    rows = dump_to_particles(table)
+    g, mz, mrho, mp = growth_record(z)
+    mincrd = grow_cell_mincrd(ocfg, z, lin)
+    uid = psph.Solver.comm_unique_id()
+    parts = np.array_split(np.argsort(rows["coords"][:, 0], kind="stable"), P)
+
+    def rank(r):
+        c = cfg.copy()
+        c.device, c.rank, c.nranks = r, r, P
+        s = psph.Solver(c)
+        s.set_cells(attr0); s.upload(rows[parts[r]])
+        s.comm_init(uid)
+        s.repartition()
+        s.search_neighs_consth()
+        adapt = s.scan_outside_layer()
+        a = s.get_cells()
+        a["active"] = grow_cell_attrs(ocfg, z, "adapt_pre")[0]["active"]
+        s.set_cells(a)
+        turned = s.adapt_domain()
+        s.set_growth(g, mz, mrho, mp, mincrd)
+        added = s.add_pressure_ghost(int(z["param_step"][0]))
+        s.exchange_ghosts()
+        attr = s.get_cells()
+        out = s.download(ORDER_DEVICE)
+        dt, lost, ierr = s.step(0.0, 1)                   # the grown, re-balanced table steps
+        s.close()
+        return adapt, turned, added, attr, out, ierr
+
+    res = run_ranks(P, rank)
+    want, _ = grow_cell_attrs(ocfg, z, "pghost_post")
+    assert all(r[0] == 1 for r in res)                                   # the global count on every rank (main.cc:226-258)
+    assert sum(r[1] for r in res) == len(z["adapt_rows"])
+    assert sum(r[2] for r in res) == len(z["pghost_rows"])
+    for r in res:
+        assert r[5] == 0
+        for f in ("type", "has_involved", "flags"):
+            assert np.array_equal(r[3][f], want[f]), f
+    owned = np.concatenate([r[4][r[4]["guest"] == 0] for r in res])
+    ko = key96(owned)
+    assert len(np.unique(ko, axis=0)) == len(ko) == len(table) + len(z["pghost_rows"])
+    # same rows as the reference's table after the three calls
+    bc, inv = table["bc_type"].copy(), table["involved"].copy()
+    bc[z["adapt_rows"]] = z["adapt_bc_type"]
+    inv[z["adapt_rows"]] = z["adapt_involved"]
+    ref_keys = np.concatenate([table["key"], z["pghost_rows"]["key"]])
+    ref_bc = np.concatenate([bc, z["pghost_rows"]["bc_type"]])
+    ref_inv = np.concatenate([inv, z["pghost_rows"]["involved"]])
+    ref_x = np.concatenate([table["coord"], z["pghost_rows"]["coord"]])
+    ref_rho = np.concatenate([table["rho"], z["pghost_rows"]["rho"]])
+    oa = np.lexsort(owned["key"].T[::-1]); ob = np.lexsort(ref_keys.T[::-1])
+    assert np.array_equal(owned["key"][oa], ref_keys[ob])
+    assert np.array_equal(owned["bc_type"][oa], ref_bc[ob]) and np.array_equal(owned["involved"][oa], ref_inv[ob])
+    assert np.array_equal(owned["coords"][oa], ref_x[ob]) and np.array_equal(owned["rho"][oa], ref_rho[ob])
+
+
+def key96(rows):
+    return rows["key"].astype(np.uint64)

@@ -224,6 +224,7 @@ def run_b200(args):
         s.sync()
         kms, sms = s.kernel_ms(), s.stage_ms()
         s.set_timing(False)
+        pstats = s.pair_stats()
         dom = max(ALG_BYTES, key=lambda k: kms[k][0])
         dom_ms = kms[dom][0] / max(kms[dom][1], 1)
         achieved = ALG_BYTES[dom] * n_real_local / (dom_ms * 1e-3) / 1e9
@@ -237,7 +238,8 @@ def run_b200(args):
                 "stage_ms_per_step": {k: round(v / ksteps, 4) for k, v in sms.items() if v > 0},
                 "kernel_ms_per_launch": {k: round(v[0] / max(v[1], 1), 4) for k, v in kms.items() if v[1] > 0}}
         return {"value": round(n_real * steps / (ms * 1e-3), 1), "ms_per_step": round(ms / steps, 4), "steps": steps,
-                "warmup": warmup, "n_real": n_real, "gpu_launches": int(cnt[1].item()), "clocks": clk, "roofline": roof}
+                "warmup": warmup, "n_real": n_real, "gpu_launches": int(cnt[1].item()), "clocks": clk, "roofline": roof,
+                "pair_path_rank0": pstats}
 
     regimes = {}
     # ---- regime 1: uniform h (time steps 1-49 of a default run: before the first adaptive_sml call, main.cc:319-322)
@@ -269,6 +271,19 @@ def run_b200(args):
         roofline["from_profile"] = json.load(open(PROFILE_FIGURES))
     except Exception:
         roofline["from_profile"] = None
+    # the roofline that does bind the pair sums: the FP64 pipe.  Peak = the DFMA micro-benchmark of this pool's B200
+    # (profiles/r02d_dfma_peak.json); the kernel's share of it is an ncu figure (a profile run, not this run) and says so.
+    fp = roofline["from_profile"] or {}
+    kname = roofline["kernel"].replace(", WM=1>", ",WM=1>").replace(", WM=2>", ",WM=2>")
+    kfig = fp.get(kname) or {}
+    pk = fp.get("_fp64_peak") or {}
+    if kfig.get("fp64_pipe_pct") is not None and pk:
+        roofline["fp64"] = {"bound": "fp64 pipe", "peak_dfma_per_s": pk["dfma_per_s"], "peak_tflops": pk["fp64_fma_tflops"],
+                            "peak_source": pk["source"], "kernel": roofline["kernel"],
+                            "pipe_busy_pct_from_profile": kfig["fp64_pipe_pct"], "profile_source": kfig.get("fp64_source"),
+                            "what": "share of the FP64 pipe's issue capacity the dominant kernel uses (ncu "
+                                    "sm__inst_executed_pipe_fp64, committed capture at the size named in profile_source); the "
+                                    "time of THIS run's launch is roofline.ms_per_launch"}
     bad = s.errors()
 
     # ---- end to end through the C ABI with host rows (pinned): upload + step + download per step

@@ -320,6 +320,10 @@ int psph_emit_neighbours(psph_ctx *ctx, int64_t *offsets, int32_t *idx, size_t i
 /* Invariant violations the reference assert()s on (rho <= 0, empty normalisation sums),
  * counted on the device since the last reset; synchronises the stream. */
 int psph_errors(psph_ctx *ctx, int reset);
+/* diagnostics of the last step's pair path: out = { pair_mode (2 block tiles, 4 sub-tiled mixed-h lists, else legacy), rows
+ * the summation stages update, rows among them that got no pair list (summed by the fused gather), rows whose
+ * near-partner list overflowed (smooth_density sums those by itself) }; synchronises */
+int psph_pair_stats(psph_ctx *ctx, int32_t out[4]);
 
 /* diagnostic: linear background-cell index (x-major, z-minor) of every row, in the row order
  * psph_download(order = PSPH_ORDER_DEVICE) returns right afterwards; replaces walking the

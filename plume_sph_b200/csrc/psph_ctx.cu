@@ -157,6 +157,10 @@ static void fill_kparams(psph_ctx *ctx)
   k.cutoff = c.cutoff; k.cutoff2 = c.cutoff2; k.neigh_radius = c.neigh_radius;
   k.msfrc_thresh = c.msfrc_thresh; k.epsilon_half = c.epsilon_half; k.prandtl = c.prandtl_num;
   k.heat_ratio = c.heat_trans_scale_ratio; k.e_ratio = c.e_smooth_ratio; k.tiny = c.tiny;
+  {
+    const double ce[14] = PSPH_EXP_COEF;
+    for (int q = 0; q < 14; q++) k.cexp[q] = ce[q];
+  }
   k.heat_c = 5.0 * c.epsilon_half / c.prandtl_num;
   {
     const double b1 = c.cutoff * (1.0 + 0x1p-40);

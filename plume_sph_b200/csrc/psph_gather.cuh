@@ -128,32 +128,32 @@ __device__ __forceinline__ double dev_rcp(double x)
   const double e = fma(-x, r, 1.0);
   return fma(r, fma(e, e, e), r);
 }
-// polynomial coefficients as constant-bank operands (no per-use 64-bit immediate moves)
-__constant__ double c_exp[14] = { 1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01, -2.31904681384629956e-17,
-                                  1.66666666666664770e-01, 5.00000000000001221e-01, 8.33333333345504315e-03,
-                                  4.16666666665197541e-02, 1.98412695891154973e-04, 1.38888889459163798e-03,
-                                  2.75575145458824386e-06, 2.48014910390991645e-05, 2.50223225365029900e-08,
-                                  2.76309034881731077e-07 };
+// polynomial coefficients as constant-bank operands (no per-use 64-bit immediate moves).  The same 14 values also travel in
+// KParams::cexp: kernel parameters live in constant bank 0, which FP64 instructions read as a direct operand, whereas a
+// user __constant__ array (bank 3) costs one LDC per coefficient and pair round — 10 of ~150 instructions in the
+// mom_engr_update body.  The hot pair bodies use the K.cexp overloads below.
+__constant__ double c_exp[14] = PSPH_EXP_COEF;
 // exp(x) for -700 < x <= 0 (the kernel exponent is >= -27): k = rint(x*log2 e), r = x - k ln 2,
 // degree-11 polynomial in Estrin form, scaled by 2^k through the exponent field
-__device__ __forceinline__ double dev_exp_neg(double x)
+__device__ __forceinline__ double dev_exp_neg(double x, const double *__restrict__ ce)
 {
-  const double kd0 = fma(x, c_exp[0], c_exp[1]);
+  const double kd0 = fma(x, ce[0], ce[1]);
   const int k = __double2loint(kd0);
-  const double kd = kd0 - c_exp[1];
-  double r = fma(kd, c_exp[2], x);   // ln 2 split hi + lo
-  r = fma(kd, c_exp[3], r);
+  const double kd = kd0 - ce[1];
+  double r = fma(kd, ce[2], x);   // ln 2 split hi + lo
+  r = fma(kd, ce[3], r);
   const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
   const double p01 = r + 1.0;
-  const double p23 = fma(r, c_exp[4], c_exp[5]);
-  const double p45 = fma(r, c_exp[6], c_exp[7]);
-  const double p67 = fma(r, c_exp[8], c_exp[9]);
-  const double p89 = fma(r, c_exp[10], c_exp[11]);
-  const double pab = fma(r, c_exp[12], c_exp[13]);
+  const double p23 = fma(r, ce[4], ce[5]);
+  const double p45 = fma(r, ce[6], ce[7]);
+  const double p67 = fma(r, ce[8], ce[9]);
+  const double p89 = fma(r, ce[10], ce[11]);
+  const double pab = fma(r, ce[12], ce[13]);
   const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
   const double p = fma(r8, q2, fma(r4, q1, q0));
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
+__device__ __forceinline__ double dev_exp_neg(double x) { return dev_exp_neg(x, c_exp); }
 // SPH kernel (sph_lib.cc:207-230) for a pair already known to be inside the cutoff:
 // w = (pi^-1/2 / h)^DIM * exp(-|dx|^2/h^2)
 template <int DIM>
@@ -172,6 +172,16 @@ __device__ __forceinline__ double dev_weight_norm(double invh)
   return DIM == 3 ? t * t * t : t;
 }
 __device__ __forceinline__ double dev_weight_pre(double r2, double ninvh2, double norm) { return norm * dev_exp_neg(r2 * ninvh2); }
+// the same two with the coefficients taken from the kernel parameters (K.cexp)
+template <int DIM>
+__device__ __forceinline__ double dev_weight_in(double r2, double invh, const double *__restrict__ ce)
+{
+  const double t = 0.564189583547756 * invh;
+  const double norm = DIM == 3 ? t * t * t : t;
+  return norm * dev_exp_neg(-(r2 * invh * invh), ce);
+}
+__device__ __forceinline__ double dev_weight_pre(double r2, double ninvh2, double norm, const double *__restrict__ ce)
+{ return norm * dev_exp_neg(r2 * ninvh2, ce); }
 
 // Stage interface (static members):
 //   kSymH         pair smoothing length is 0.5*(h_i+h_j) (true) or S::I::hk (false)

@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
 k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict__ spill)
 {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  constexpr int CHUNK = WARPS * RPWG;
+  // LM 2 (rows the list paths left over): they come in clusters — a plume's hot core, rows on subcell faces — so a warp takes
+  // 4 consecutive list entries per chunk instead of 32 and the cluster spreads over 8 times as many warps
+  constexpr int RPW_ = LM == 2 ? GRP : RPWG;
+  constexpr int CHUNK = WARPS * RPW_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   GrpScratch<QC> *scr = reinterpret_cast<GrpScratch<QC> *>(s_raw) + warp;
@@ -126,8 +129,8 @@ k_gather_grp(DevView V, GridView G, KParams K, StepState *ss, double *__restrict
   const int nsubx = G.ncell[0] * SUBDIV - 1, nsuby = G.ncell[1] * SUBDIV - 1, nsubz = G.ncell[2] * SUBDIV - 1;
 
   for (int chunk = blockIdx.x; chunk * CHUNK < cnt; chunk += gridDim.x) {
-    int e = chunk * CHUNK + warp * RPWG;
-    const int eend = min(e + RPWG, cnt);
+    int e = chunk * CHUNK + warp * RPW_;
+    const int eend = min(e + RPW_, cnt);
     while (e < eend) {
       // ---- form the group: the leading run of list entries in the same subcell column of one bucket
       int row = -1, cell = -1;
@@ -431,7 +434,8 @@ int launch_gather_grp_w(psph_ctx *ctx, int kid)
   const size_t spill_rows = (size_t) ctx->sms * 32 * GRP * GNA * 32; // up to 32 warps per CTA, one CTA per SM
   if (!ctx->d_gspill) PSPH_CUDA(cudaMalloc(&ctx->d_gspill, spill_rows * sizeof(double)));
   KernelTimer kt(ctx, kid);
-  const int nchunks = (ctx->n + WARPS * RPWG - 1) / (WARPS * RPWG);
+  constexpr int RPW_ = LM == 2 ? GRP : RPWG;
+  const int nchunks = (ctx->n + WARPS * RPW_ - 1) / (WARPS * RPW_);
   const int grid = min(max(nchunks, 1), ctx->sms);
   k_gather_grp<S, WARPS, PF, LM, QC><<<grid, threads, smem, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, ctx->d_gspill);
   PSPH_LAUNCH_CHECK();

@@ -431,7 +431,7 @@ struct MomStage
     const double r2 = dx * dx + dy * dy + dz * dz;
     const double invh = UNI ? s.invh : dev_rcp(h);
     const double4 r0 = rec.r0, r1 = rec.r1, uj = rec.r2;
-    const double w = UNI ? dev_weight_pre(r2, s.ninvh2, s.norm) : dev_weight_in<DIM>(r2, invh);
+    const double w = UNI ? dev_weight_pre(r2, s.ninvh2, s.norm, K.cexp) : dev_weight_in<DIM>(r2, invh, K.cexp);
     const double g = -2.0 * invh * invh * w;                        // dW/dx_k = g * dx_k
     const double vx = s.u[0] - uj.x, vy = s.u[1] - uj.y, vz = s.u[2] - uj.z;
     const double vr = dx * vx + dy * vy + dz * vz, vv = vx * vx + vy * vy + vz * vz;
@@ -611,7 +611,7 @@ struct VelStage
                                                 const R &rec)
   {
     const double4 rj = rec.r0;
-    const double mvw = dev_weight_pre(dx * dx + dy * dy + dz * dz, s.ninvh2, s.norm) * rj.x;
+    const double mvw = dev_weight_pre(dx * dx + dy * dy + dz * dz, s.ninvh2, s.norm, K.cexp) * rj.x;
     a.dv[0] += mvw * (rj.y - s.v[0]);
     if (DIM == 3) { a.dv[1] += mvw * (rj.z - s.v[1]); a.dv[2] += mvw * (rj.w - s.v[2]); }
     a.wn += mvw;
@@ -1096,6 +1096,16 @@ extern "C" int psph_errors(psph_ctx *ctx, int reset)
     PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return bad;
+}
+
+// pair path of the last step as the device saw it (diagnostics of bench.py / the tests); synchronises
+extern "C" int psph_pair_stats(psph_ctx *ctx, int32_t out[4])
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  PSPH_CUDA(cudaMemcpyAsync(ctx->h_ss, ctx->d_ss, sizeof(StepState), cudaMemcpyDeviceToHost, ctx->stream));
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  out[0] = ctx->h_ss->pair_mode; out[1] = ctx->h_ss->n_need; out[2] = ctx->h_ss->n_uncached; out[3] = ctx->h_ss->n_near_ovf;
+  return 0;
 }
 
 // rows the gathers update (need_neigh and the list rule), exact after a list build; synchronises

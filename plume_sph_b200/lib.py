@@ -140,6 +140,7 @@ API = {
     "psph_append_rows": (C.c_int, [_VP, _VP, C.c_size_t, C.c_size_t]),
     "psph_download_rows": (C.c_int, [_VP, _VP, C.c_size_t, C.POINTER(C.c_size_t), C.c_int, C.c_size_t]),
     "psph_download_h5part": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
+    "psph_pair_stats": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
     "psph_step": (C.c_int, [_VP, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "psph_run": (C.c_int, [_VP, C.c_int, C.c_int]),
     "psph_comm_unique_id": (C.c_int, [_VP, C.c_size_t]),

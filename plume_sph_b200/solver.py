@@ -307,6 +307,12 @@ class Solver:
     def num_updated(self):
         return int(self._ck(self.L.psph_num_updated(self.h), "psph_num_updated"))
 
+    def pair_stats(self):
+        """pair path of the last step: dict(pair_mode, rows_updated, rows_without_list, near_overflow_rows)"""
+        o = (C.c_int32 * 4)()
+        self._ck(self.L.psph_pair_stats(self.h, o), "psph_pair_stats")
+        return dict(pair_mode=int(o[0]), rows_updated=int(o[1]), rows_without_list=int(o[2]), near_overflow_rows=int(o[3]))
+
     def exchange_ghosts(self):
         return self._ck(self.L.psph_exchange_ghosts(self.h), "psph_exchange_ghosts")
 

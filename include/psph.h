@@ -220,13 +220,18 @@ int psph_get_cells(psph_ctx *ctx, psph_cell_attr *attr, size_t ncells);
  *   *added = rows appended on this rank.  meteo_z [km], meteo_rho, meteo_p [hPa]: columns 0, 1, 2 of the sounding;
  *   cell_mincrd [ncells][3]: Bucket::mincrd of every bucket as the driver stores it — the lattice points are
  *   mincrd + dx / 2 + i dx (:161-163) — or NULL: (mindom + i del) / len_scale.
- * The driver keeps shift_brief_buck, add_wall_ghost, update_bgmesh and the image search (they run on bucket attributes:
- * psph_get_cells), and appends what they create with psph_append. */
+ * The driver keeps shift_brief_buck, update_bgmesh and the image search (they run on bucket attributes: psph_get_cells). */
 int psph_scan_outside_layer(psph_ctx *ctx, int *adapt);
 int psph_adapt_domain(psph_ctx *ctx, int *turned);
 int psph_set_growth(psph_ctx *ctx, const psph_growth *g, const double *meteo_z, const double *meteo_rho, const double *meteo_p,
                     const double *cell_mincrd);
 int psph_add_pressure_ghost(psph_ctx *ctx, uint32_t add_step, int *added);
+/* add_wall_ghost (add_wall_ghost.cc:44-293, main.cc:277), after the driver's shift_brief_buck (psph_set_cells with the new
+ * buckets): every non-empty on-ground MIXED bucket without wall ghosts, outside the vent, gets the lattice layers below
+ * Ll[2] as wall ghosts (bc_type 2, state of initial_air), and the bucket under it — marked active — a full lattice.
+ * -2 when such a bucket has no bucket below it (the reference asserts).  The image search for the new ghosts stays with the
+ * driver (search_bnd_images, main.cc:292; plume_sph_b200.mesh.wall_ghost_images for a flat ground). */
+int psph_add_wall_ghost(psph_ctx *ctx, uint32_t add_step, int *added);
 
 /* after initialisation (main.cc:199) / after add_new_erupt (:417) / ghost regeneration (:271-283) */
 int psph_upload(psph_ctx *ctx, const psph_particle *rows, size_t n);

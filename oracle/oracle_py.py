@@ -263,6 +263,9 @@ def lib():
         L.psph_oracle_add_pressure_ghost.argtypes = [cp, sp, C.c_void_p, C.POINTER(Growth), _P(C.c_double), _P(C.c_double),
                                                      _P(C.c_double), C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
         L.psph_oracle_add_pressure_ghost.restype = C.c_int
+        L.psph_oracle_add_wall_ghost.argtypes = [cp, C.c_void_p, _P(C.c_int32), C.POINTER(Growth), _P(C.c_double), _P(C.c_double),
+                                                 _P(C.c_double), C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        L.psph_oracle_add_wall_ghost.restype = C.c_int
     return _lib
 
 
@@ -449,6 +452,21 @@ def add_new_erupt(cfg, erupt, boxes, time, dt, add_step, cap=65536):
                                         float(time), float(dt), int(add_step), out.ctypes.data, cap)
     if n < 0:
         raise RuntimeError("psph_oracle_add_new_erupt: more than %d particles" % cap)
+    return out[:n]
+
+
+def add_wall_ghost(cfg, attr, cell_count, growth, meteo_z, meteo_rho, meteo_p, add_step, cell_mincrd=None, cap=1 << 20):
+    """psph_oracle_add_wall_ghost (add_wall_ghost.cc:44-293): attr changed in place, returns the new rows"""
+    out = np.zeros(cap, PARTICLE_DTYPE)
+    cnt = np.ascontiguousarray(cell_count, np.int32)
+    z, r, p = (np.ascontiguousarray(a, np.float64) for a in (meteo_z, meteo_rho, meteo_p))
+    mc = None if cell_mincrd is None else np.ascontiguousarray(cell_mincrd, np.float64)
+    n = lib().psph_oracle_add_wall_ghost(C.byref(cfg), attr.ctypes.data, cnt.ctypes.data_as(_P(C.c_int32)), C.byref(growth),
+                                         z.ctypes.data_as(_P(C.c_double)), r.ctypes.data_as(_P(C.c_double)),
+                                         p.ctypes.data_as(_P(C.c_double)), None if mc is None else mc.ctypes.data, int(add_step),
+                                         out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("psph_oracle_add_wall_ghost: %d" % n)
     return out[:n]
 
 

@@ -1095,6 +1095,52 @@ static double meteo_interp(const double *z, const double *v, int n, double z0)
   return v[li] + (z0 - z[li]) / (z[ui] - z[li]) * (v[ui] - v[li]);
 }
 
+/* one new air particle of a growth step: Particle ctor for initial air (particle.cc:116-190) + initial_air
+ * (sph_lib.cc:831-872); bc = 1 pressure ghost, 2 wall ghost */
+static void grow_new_air(const psph_config *c, const psph_growth *g, const double *mz, const double *mrho, const double *mp,
+                         uint32_t add_step, const double *pcrd, int bc, psph_particle *p)
+{
+  memset(p, 0, sizeof *p);
+  double normc[3];
+  for (int d = 0; d < 3; d++) normc[d] = (pcrd[d] - g->kmin[d]) / (g->kmax[d] - g->kmin[d]);
+  psph_oracle_hsfc3d(normc, p->key);
+  p->key[2] = add_step;
+  p->bc_type = bc; p->phase_num = 1; p->involved = 0; p->guest = 0; p->myprocess = c->rank;
+  p->smlen = g->ratio_sml_dx * g->smlen;
+  for (int d = 0; d < 3; d++) p->coords[d] = pcrd[d];
+  p->mass_frac = 0.;
+  double sml2 = 0.5 * p->smlen, range[6];
+  for (int d = 0; d < 3; d++) { range[2 * d] = pcrd[d] - sml2; range[2 * d + 1] = pcrd[d] + sml2; }
+  double prss, dens, erg, mss;
+  if (g->atmosphere_type == 4) {                               /* air_prop_meteo_based, :737-766 */
+    prss = meteo_interp(mz, mp, g->nmeteo, pcrd[2] * 0.001) * 100;
+    dens = meteo_interp(mz, mrho, g->nmeteo, pcrd[2] * 0.001);
+    erg = prss / (dens * (g->gamma_air - 1));
+    double d1 = meteo_interp(mz, mrho, g->nmeteo, range[4] * 0.001), d2 = meteo_interp(mz, mrho, g->nmeteo, range[5] * 0.001);
+    mss = (range[1] - range[0]) * (range[3] - range[2]) * (range[5] - range[4]) * (0.1666667 * d1 + 0.6666666 * dens + 0.1666667 * d2);
+  } else {                                                     /* air_prop_uniform, :682-712 (ideal gas) */
+    prss = c->pa0;
+    dens = prss / (c->Ra * g->Ta0);
+    erg = prss / (dens * (g->gamma_air - 1));
+    mss = (range[1] - range[0]) * (range[3] - range[2]) * (range[5] - range[4]) * dens;
+  }
+  p->rho = dens; p->engr = erg; p->mass = mss;
+  { /* update_second_var (particle.cc:528-604) with ks = 0, ideal-gas branch; the ctor's gamma and sound speed are
+     * overwritten there */
+    double ks = 0., na = 1 - ks, ng = c->ng0 * ks, ns = ks - ng;
+    double Cvm = ns * c->Cvs + ng * c->Cvg + na * c->Cva;
+    double Rm = ng * c->Rg + na * c->Ra, Rmg = Rm / (ng + na);
+    p->gamma = 1 + Rm / Cvm;
+    double desmg = dens * (na + ng);
+    p->pressure = Rmg * desmg * erg / Cvm;
+    p->sound_speed = pow(p->gamma * p->pressure / desmg, 0.5);
+    p->phase_density[0] = dens * na;
+    p->phase_density[1] = dens * ks;
+    p->temperature = erg / Cvm;
+    p->specific_heat_p = c->have_turbulence_lans != 0 ? Cvm : 0.;
+  }
+}
+
 int psph_oracle_add_pressure_ghost(const psph_config *c, const psph_oracle_state *st, psph_cell_attr *attr, const psph_growth *g,
                                    const double *mz, const double *mrho, const double *mp, const double *cell_mincrd, uint32_t add_step,
                                    psph_particle *out, int cap)
@@ -1131,50 +1177,48 @@ int psph_oracle_add_pressure_ghost(const psph_config *c, const psph_oracle_state
           double pcrd[3] = { mincrd[0] + dx2 + i * dx, mincrd[1] + dx2 + j * dx, mincrd[2] + dx2 + k * dx };
           if (ground && !(pcrd[2] > g->Ll[2])) continue;             /* :139 */
           if (n_out >= cap) return -1;
-          psph_particle *p = out + n_out++;
-          memset(p, 0, sizeof *p);
-          double normc[3];
-          for (int d = 0; d < 3; d++) normc[d] = (pcrd[d] - g->kmin[d]) / (g->kmax[d] - g->kmin[d]);
-          psph_oracle_hsfc3d(normc, p->key);
-          p->key[2] = add_step;
-          /* Particle ctor for initial air, particle.cc:116-190 */
-          p->bc_type = 1; p->phase_num = 1; p->involved = 0; p->guest = 0; p->myprocess = c->rank;
-          p->smlen = g->ratio_sml_dx * g->smlen;
-          for (int d = 0; d < 3; d++) p->coords[d] = pcrd[d];
-          p->mass_frac = 0.;
+          grow_new_air(c, g, mz, mrho, mp, add_step, pcrd, 1, out + n_out++);
           a->flags |= PSPH_CELLF_PRESS;
-          /* initial_air, sph_lib.cc:831-872 */
-          double sml2 = 0.5 * p->smlen, range[6];
-          for (int d = 0; d < 3; d++) { range[2 * d] = pcrd[d] - sml2; range[2 * d + 1] = pcrd[d] + sml2; }
-          double prss, dens, erg, mss;
-          if (g->atmosphere_type == 4) {                               /* air_prop_meteo_based, :737-766 */
-            prss = meteo_interp(mz, mp, g->nmeteo, pcrd[2] * 0.001) * 100;
-            dens = meteo_interp(mz, mrho, g->nmeteo, pcrd[2] * 0.001);
-            erg = prss / (dens * (g->gamma_air - 1));
-            double d1 = meteo_interp(mz, mrho, g->nmeteo, range[4] * 0.001), d2 = meteo_interp(mz, mrho, g->nmeteo, range[5] * 0.001);
-            mss = (range[1] - range[0]) * (range[3] - range[2]) * (range[5] - range[4]) * (0.1666667 * d1 + 0.6666666 * dens + 0.1666667 * d2);
-          } else {                                                     /* air_prop_uniform, :682-712 (ideal gas) */
-            prss = c->pa0;
-            dens = prss / (c->Ra * g->Ta0);
-            erg = prss / (dens * (g->gamma_air - 1));
-            mss = (range[1] - range[0]) * (range[3] - range[2]) * (range[5] - range[4]) * dens;
-          }
-          p->rho = dens; p->engr = erg; p->mass = mss;
-          { /* update_second_var (particle.cc:528-604) with ks = 0, ideal-gas branch; the ctor's gamma and sound speed are
-             * overwritten there */
-            double ks = 0., na = 1 - ks, ng = c->ng0 * ks, ns = ks - ng;
-            double Cvm = ns * c->Cvs + ng * c->Cvg + na * c->Cva;
-            double Rm = ng * c->Rg + na * c->Ra, Rmg = Rm / (ng + na);
-            p->gamma = 1 + Rm / Cvm;
-            double desmg = dens * (na + ng);
-            p->pressure = Rmg * desmg * erg / Cvm;
-            p->sound_speed = pow(p->gamma * p->pressure / desmg, 0.5);
-            p->phase_density[0] = dens * na;
-            p->phase_density[1] = dens * ks;
-            p->temperature = erg / Cvm;
-            p->specific_heat_p = c->have_turbulence_lans != 0 ? Cvm : 0.;
-          }
         }
+  }
+  return n_out;
+}
+
+int psph_oracle_add_wall_ghost(const psph_config *c, psph_cell_attr *attr, const int32_t *cell_count, const psph_growth *g,
+                               const double *mz, const double *mrho, const double *mp, const double *cell_mincrd, uint32_t add_step,
+                               psph_particle *out, int cap)
+{ /* add_wall_ghost.cc:44-293: every non-empty on-ground MIXED bucket without wall ghosts (and outside the vent) gets the
+   * lattice points below the ground, and the bucket under it — marked active — a full lattice; all bc_type 2 */
+  int n_out = 0;
+  int64_t nc = ncells_of(c);
+  const double dx = g->smlen, dx2 = 0.5 * dx;
+  const int N = (int) round(c->del / c->len_scale / dx);
+  for (int64_t cl = 0; cl < nc; cl++) {
+    psph_cell_attr *a = &attr[cl];
+    if (a->type == PSPH_CELL_BRIEF) continue;
+    if (!(a->bucket_index[4] == -1 && a->type == PSPH_CELL_MIXED && cell_count[cl] > 0 && !(a->flags & PSPH_CELLF_WALL) &&
+          PSPH_CELLF_ERUPT_FLAG(a->flags) == 0))
+      continue;
+    int ck = (int) (cl % c->ncell[2]), cj = (int) ((cl / c->ncell[2]) % c->ncell[1]);
+    int ci = (int) (cl / ((int64_t) c->ncell[2] * c->ncell[1]));
+    for (int pass = 0; pass < 2; pass++) {                           /* the bucket itself, then the one below (:219-283) */
+      if (pass == 1 && ck == 0) return -2;                           /* assert(Down_buck) */
+      int64_t tl = pass == 0 ? cl : cell_lin(c, ci, cj, ck - 1);
+      psph_cell_attr *ta = &attr[tl];
+      if (pass == 1) { if (ta->type == PSPH_CELL_BRIEF) return -2; ta->active = 1; }
+      int idx[3] = { ci, cj, pass == 0 ? ck : ck - 1 };
+      double mincrd[3];
+      for (int k = 0; k < 3; k++) mincrd[k] = cell_mincrd ? cell_mincrd[3 * tl + k] : cell_min(c, k, idx[k]);
+      for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)
+          for (int k = 0; k < N; k++) {
+            double pcrd[3] = { mincrd[0] + dx2 + i * dx, mincrd[1] + dx2 + j * dx, mincrd[2] + dx2 + k * dx };
+            if (pass == 0 && !(pcrd[2] < g->Ll[2])) continue;        /* :163: below the ground only */
+            if (n_out >= cap) return -1;
+            grow_new_air(c, g, mz, mrho, mp, add_step, pcrd, 2, out + n_out++);
+            ta->flags |= PSPH_CELLF_WALL; ta->active = 1;            /* add_wall_ghost_particle, bucket.h:656-661 */
+          }
+    }
   }
   return n_out;
 }

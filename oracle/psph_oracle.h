@@ -98,6 +98,11 @@ int psph_oracle_adapt_domain(const psph_config *cfg, psph_oracle_state *st, psph
 int psph_oracle_add_pressure_ghost(const psph_config *cfg, const psph_oracle_state *st, psph_cell_attr *attr, const psph_growth *g,
                                    const double *meteo_z, const double *meteo_rho, const double *meteo_p, const double *cell_mincrd,
                                    uint32_t add_step, psph_particle *out, int cap);
+/* add_wall_ghost.cc:44-293; cell_count [ncells] = plist sizes at the time of the call (after add_pressure_ghost and
+ * shift_brief_buck); -2: a bucket to fill has no bucket below it (the reference asserts) */
+int psph_oracle_add_wall_ghost(const psph_config *cfg, psph_cell_attr *attr, const int32_t *cell_count, const psph_growth *g,
+                               const double *meteo_z, const double *meteo_rho, const double *meteo_p, const double *cell_mincrd,
+                               uint32_t add_step, psph_particle *out, int cap);
 /* Hilbert key of a normalised position, hilbert.c:289-303 (HSFC3d) */
 void psph_oracle_hsfc3d(const double coord[3], uint32_t key[2]);
 

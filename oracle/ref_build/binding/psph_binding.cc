@@ -162,8 +162,10 @@ int psph_bind_grow(psph_ctx *gpu, TimeProps *timeprops, int *adapt_next)
   if (*adapt_next) {                                                  /* :259: adapt of the previous step's scan */
     if (psph_adapt_domain(gpu, &turned) < 0) return -1;               /* :265 */
     if (psph_add_pressure_ghost(gpu, (uint32_t) timeprops->step, &added) < 0) return -1; /* :271 */
-    /* shift_brief_buck, add_wall_ghost, update_bgmesh, search_bnd_images (:274-292) stay with the driver: psph_get_cells
-     * brings the attributes back, psph_append / psph_set_cells / psph_set_images take what they create */
+    /* shift_brief_buck (:274) stays with the driver: psph_get_cells brings the attributes back, psph_set_cells takes the new
+     * buckets down; then */
+    if (psph_add_wall_ghost(gpu, (uint32_t) timeprops->step, &added) < 0) return -1;     /* :277 */
+    /* update_bgmesh, search_bnd_images (:283-292) on the host again -> psph_set_cells / psph_set_images */
   }
   return psph_scan_outside_layer(gpu, adapt_next);                    /* :435 */
 }

@@ -571,6 +571,15 @@ void psphhook_add_pressure_ghost(THashTable *P, HashTable *BG, SimProps *sp, Mat
   dump_table(P, "pghost", "post");
   dump_bucketsx(P, BG, "pghost_post");
 }
+
+void psphhook_add_wall_ghost(THashTable *P, HashTable *BG, SimProps *sp, MatProps *mp, TimeProps *tp, int np, int myid)
+{
+  init_once();
+  dump_bucketsx(P, BG, "wghost_pre");       /* (shift_brief_buck ran since add_pressure_ghost: more buckets exist) */
+  add_wall_ghost(P, BG, sp, mp, tp, np, myid);
+  dump_table(P, "wghost", "post");
+  dump_bucketsx(P, BG, "wghost_post");
+}
 #endif
 
 /* SML_UPDATE_INT (constant.h:189, a const int, not a macro) decides at main.cc:319-322 which steps call adaptive_sml.
@@ -602,6 +611,7 @@ int psphhook_sml_update_int()
 #define scan_outside_layer psphhook_scan_outside_layer
 #define adapt_domain psphhook_adapt_domain
 #define add_pressure_ghost psphhook_add_pressure_ghost
+#define add_wall_ghost psphhook_add_wall_ghost
 #endif
 #include PSPH_REF_MAIN_CC
 #endif

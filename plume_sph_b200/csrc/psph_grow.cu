@@ -131,11 +131,27 @@ struct GrowPar
   const double *mincrd;            // [ncells][3] Bucket::mincrd as the driver stores it, or nullptr: the lattice formula
   uint32_t add_step;
   int base, cap, rank, has_grad, nper;
+  int bc;                          // bc_type of the new rows: 1 pressure ghost, 2 wall ghost
 };
 
 // fill[cell] = lattice points the call puts into the bucket (0: none); the bucket is marked active either way when a
 // neighbour is involved (:108)
-__global__ void k_pghost_mark(GridView G, psph_cell_attr *attr, const int32_t *__restrict__ owner, GrowPar P, int32_t *__restrict__ fill)
+// layers of a bucket's lattice whose z lies above (mode 1) / below (mode 2) Ll[2]; every layer for mode 0
+__device__ __forceinline__ int grow_layers(const GridView &G, const GrowPar &P, int cell, int mode)
+{
+  if (mode == 0) return P.nper;
+  const int ck = cell % G.ncell[2];
+  const double z0 = P.mincrd ? P.mincrd[3 * cell + 2] : (G.mindom[2] + ck * G.del) / G.len_scale;
+  int n = 0;
+  for (int k = 0; k < P.nper; k++) {
+    const double z = __dadd_rn(__dadd_rn(z0, __dmul_rn(0.5, P.g.smlen)), __dmul_rn((double) k, P.g.smlen));
+    n += mode == 1 ? z > P.g.Ll[2] : z < P.g.Ll[2];
+  }
+  return n;
+}
+
+__global__ void k_pghost_mark(GridView G, psph_cell_attr *attr, const int32_t *__restrict__ owner, GrowPar P, int32_t *__restrict__ fill,
+                              int32_t *__restrict__ zmode)
 {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= G.ncells) return;
@@ -150,16 +166,45 @@ __global__ void k_pghost_mark(GridView G, psph_cell_attr *attr, const int32_t *_
   if (!hit) return;
   a.active = 1;
   if (!(a.type == PSPH_CELL_MIXED || a.type == PSPH_CELL_OVERGROUND || a.type == PSPH_CELL_PRESS_BC)) return;
-  int n = P.nper * P.nper * P.nper;
-  if (a.type == PSPH_CELL_MIXED && a.bucket_index[4] == -1) {         // on the ground: the layers above Ll[2] only (:139)
-    const int ck = cell % G.ncell[2];
-    const double z0 = P.mincrd ? P.mincrd[3 * cell + 2] : (G.mindom[2] + ck * G.del) / G.len_scale;
-    int above = 0;
-    for (int k = 0; k < P.nper; k++) above += __dadd_rn(__dadd_rn(z0, __dmul_rn(0.5, P.g.smlen)), __dmul_rn((double) k, P.g.smlen)) > P.g.Ll[2];
-    n = P.nper * P.nper * above;
-  }
+  const int mode = (a.type == PSPH_CELL_MIXED && a.bucket_index[4] == -1) ? 1 : 0;   // on the ground: the layers above Ll[2] only (:139)
+  zmode[cell] = mode;
+  const int n = P.nper * P.nper * grow_layers(G, P, cell, mode);
   if (n > 0) a.flags |= PSPH_CELLF_PRESS;                             // add_pressure_ghost_particle (bucket.h:664-669)
   if (owner && owner[cell] != P.rank) return;                         // slabs: every rank fills the buckets it owns (!is_guest())
+  fill[cell] = n;
+}
+
+// ---- add_wall_ghost (add_wall_ghost.cc:44-293) ---------------------------------------------------
+// mark[cell] = 1: a non-empty on-ground MIXED bucket without wall ghosts, outside the vent (:136)
+__global__ void k_wghost_pick(GridView G, const psph_cell_attr *attr, const int32_t *__restrict__ cnt, int32_t *__restrict__ mark)
+{
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= G.ncells) return;
+  const psph_cell_attr &a = attr[cell];
+  mark[cell] = a.type == PSPH_CELL_MIXED && a.bucket_index[4] == -1 && cnt[cell] > 0 && !(a.flags & PSPH_CELLF_WALL) &&
+               PSPH_CELLF_ERUPT_FLAG(a.flags) == 0;
+}
+// a picked bucket gets the lattice layers below Ll[2]; the bucket UNDER a picked bucket is marked active and gets the full
+// lattice (:219-283).  bad: a picked bucket with no bucket below it (the reference asserts)
+__global__ void k_wghost_mark(GridView G, psph_cell_attr *attr, const int32_t *__restrict__ owner, GrowPar P, const int32_t *__restrict__ mark,
+                              int32_t *__restrict__ fill, int32_t *__restrict__ zmode, int *bad)
+{
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= G.ncells) return;
+  psph_cell_attr &a = attr[cell];
+  const int ck = cell % G.ncell[2];
+  const bool self = mark[cell] != 0, under = ck + 1 < G.ncell[2] && mark[cell + 1] != 0;   // (z-minor: cell + 1 is the bucket above)
+  fill[cell] = 0; zmode[cell] = 0;
+  if (self && (ck == 0 || attr[cell - 1].type == PSPH_CELL_BRIEF)) atomicAdd(bad, 1);
+  if (!self && !under) return;
+  if (under && a.type == PSPH_CELL_BRIEF) return;                     // (counted as bad by the bucket above)
+  const int mode = under ? 0 : 2;                                     // (a bucket that is both would be filled twice: the reference exits)
+  const int n = P.nper * P.nper * grow_layers(G, P, cell, mode);
+  if (under) a.active = 1;
+  if (n > 0) { a.flags |= PSPH_CELLF_WALL; a.active = 1; }            // add_wall_ghost_particle (bucket.h:656-661)
+  const int own_cell = under ? cell + 1 : cell;                       // filled by the rank that owns the on-ground bucket (:136, :219)
+  if (owner && owner[own_cell] != P.rank) return;
+  zmode[cell] = mode;
   fill[cell] = n;
 }
 
@@ -177,7 +222,7 @@ __device__ double dev_meteo(const double *__restrict__ z, const double *__restri
 }
 
 // one thread per lattice point of a bucket that is filled; off[cell] = first new row of the bucket (exclusive scan of fill)
-__global__ void k_pghost_fill(Tab V, GridView G, KParams K, const psph_cell_attr *attr, GrowPar P, const int32_t *__restrict__ fill,
+__global__ void k_pghost_fill(Tab V, GridView G, KParams K, GrowPar P, const int32_t *__restrict__ zmode,
                               const int32_t *__restrict__ off, const int32_t *__restrict__ cells, int ncell_fill)
 {
   const int per = P.nper * P.nper * P.nper;
@@ -185,7 +230,6 @@ __global__ void k_pghost_fill(Tab V, GridView G, KParams K, const psph_cell_attr
   if (t >= (long long) ncell_fill * per) return;
   const int cell = cells[t / per], l = (int) (t % per);
   const int i = l / (P.nper * P.nper), j = (l / P.nper) % P.nper, k = l % P.nper;
-  const psph_cell_attr &a = attr[cell];
   const psph_growth &g = P.g;
   const int ck = cell % G.ncell[2], cj = (cell / G.ncell[2]) % G.ncell[1], ci = cell / (G.ncell[2] * G.ncell[1]);
   const int idx[3] = { ci, cj, ck }, ijk[3] = { i, j, k };
@@ -196,15 +240,18 @@ __global__ void k_pghost_fill(Tab V, GridView G, KParams K, const psph_cell_attr
     crd[d] = __dadd_rn(__dadd_rn(mn, dx2), __dmul_rn((double) ijk[d], dx));
   }
   int slot = l;
-  if (a.type == PSPH_CELL_MIXED && a.bucket_index[4] == -1) {         // on the ground: the layers above Ll[2], densely numbered
-    if (!(crd[2] > g.Ll[2])) return;
-    int below = 0;
+  const int mode = zmode[cell];
+  if (mode) {                                                         // an on-ground bucket: the layers above (pressure ghosts) or
+    if (!(mode == 1 ? crd[2] > g.Ll[2] : crd[2] < g.Ll[2])) return;   // below (wall ghosts) Ll[2], densely numbered
+    const double z00 = __dadd_rn(P.mincrd ? P.mincrd[3 * cell + 2] : (G.mindom[2] + ck * G.del) / G.len_scale, dx2);
+    int skipped = 0, nz = 0;
     for (int kk = 0; kk < P.nper; kk++) {
-      const double z = __dadd_rn(__dadd_rn(P.mincrd ? P.mincrd[3 * cell + 2] : (G.mindom[2] + ck * G.del) / G.len_scale, dx2), __dmul_rn((double) kk, dx));
-      below += !(z > g.Ll[2]);
+      const double z = __dadd_rn(z00, __dmul_rn((double) kk, dx));
+      const bool in = mode == 1 ? z > g.Ll[2] : z < g.Ll[2];
+      nz += in;
+      skipped += (!in && kk < k);
     }
-    const int nz = P.nper - below;
-    slot = (i * P.nper + j) * nz + (k - below);
+    slot = (i * P.nper + j) * nz + (k - skipped);
   }
   const int p = P.base + off[cell] + slot;
   if (p >= P.cap) return;
@@ -250,7 +297,7 @@ __global__ void k_pghost_fill(Tab V, GridView G, KParams K, const psph_cell_attr
   V.d[D_RPH0][p] = __dmul_rn(dens, na); V.d[D_RPH1][p] = __dmul_rn(dens, ks);
   if (P.has_grad)
     for (int q = 0; q < 15; q++) V.d[D_GRAD0 + q][p] = 0.0;
-  V.i[I_BC][p] = 1; V.i[I_PHASE][p] = 1; V.i[I_INVOLVED][p] = 0; V.i[I_GUEST][p] = 0; V.i[I_MYPROC][p] = P.rank;
+  V.i[I_BC][p] = P.bc; V.i[I_PHASE][p] = 1; V.i[I_INVOLVED][p] = 0; V.i[I_GUEST][p] = 0; V.i[I_MYPROC][p] = P.rank;
   V.i[I_KEY0][p] = (int32_t) key[0]; V.i[I_KEY1][p] = (int32_t) key[1]; V.i[I_KEY2][p] = (int32_t) P.add_step;
   V.i[I_CELL][p] = cell;
 }
@@ -369,6 +416,41 @@ extern "C" int psph_adapt_domain(psph_ctx *ctx, int *turned)
   return turned ? grow_read_counter(ctx, S, turned) : 0;
 }
 
+static int grow_fill_host(psph_ctx *ctx, GrowState *S, GrowPar &P, int *added)
+{
+  // the buckets to fill and their first rows: the list is short (one shell of buckets) and the call rare — scanned on the host
+  S->h_fill.resize((size_t) ctx->ncells);
+  PSPH_CUDA(cudaMemcpyAsync(S->h_fill.data(), S->d_mark, (size_t) ctx->ncells * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (psph_sync_n(ctx)) return -1;
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> cells, off((size_t) ctx->ncells, 0);
+  long long total = 0;
+  for (long long c = 0; c < ctx->ncells; c++)
+    if (S->h_fill[c] > 0) { cells.push_back((int32_t) c); off[c] = (int32_t) total; total += S->h_fill[c]; }
+  if (total == 0) return 0;
+  if ((long long) ctx->n + total > 0x7fffffffLL) { ctx->err = "psph_grow: table would exceed 2^31 rows"; return -2; }
+  const int base = ctx->n;
+  if (psph_reserve(ctx, (size_t) base + (size_t) total)) return -1;
+  PSPH_CUDA(cudaMemcpyAsync(S->d_off, off.data(), (size_t) ctx->ncells * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  PSPH_CUDA(cudaMemcpyAsync(S->d_cells, cells.data(), cells.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  P.base = base; P.cap = (int) std::min<size_t>(ctx->cap, 0x7fffffff);
+  const long long nthreads = (long long) cells.size() * P.nper * P.nper * P.nper;
+  k_pghost_fill<<<(unsigned) ((nthreads + 255) / 256), 256, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), ctx->kp, P, S->d_inv, S->d_off,
+                                                                             S->d_cells, (int) cells.size());
+  PSPH_LAUNCH_CHECK();
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));                      // (off / cells are host vectors of this call)
+  ctx->n = base + (int) total;
+  ctx->h_ss->n = ctx->n;
+  PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->n, &ctx->h_ss->n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->n_dirty = false;
+  ctx->h_unknown = true;
+  ctx->list_valid = false;
+  psph_comm_mark(ctx, DIRTY_LAYOUT);
+  if (added) *added = (int) total;
+  return 0;
+}
+
 extern "C" int psph_set_growth(psph_ctx *ctx, const psph_growth *g, const double *mz, const double *mrho, const double *mp,
                                const double *cell_mincrd)
 {
@@ -416,38 +498,39 @@ extern "C" int psph_add_pressure_ghost(psph_ctx *ctx, uint32_t add_step, int *ad
   P.add_step = add_step; P.rank = ctx->cfg.rank; P.has_grad = ctx->has_grad;
   P.nper = (int) llround(ctx->cfg.del / ctx->cfg.len_scale / S->g.smlen);   // round((maxcrd - mincrd) / dx), :148-150
   if (P.nper < 1 || P.nper > 64) { ctx->err = "psph_add_pressure_ghost: bucket edge / smlen out of range"; return -2; }
-  P.base = 0; P.cap = 0;
-  k_pghost_mark<<<GRID(ctx->ncells)>>>(psph_grid_view(ctx), ctx->d_attr, owner, P, S->d_mark);
+  P.base = 0; P.cap = 0; P.bc = 1;
+  k_pghost_mark<<<GRID(ctx->ncells)>>>(psph_grid_view(ctx), ctx->d_attr, owner, P, S->d_mark, S->d_inv);   // (d_inv: z mode per bucket)
   PSPH_LAUNCH_CHECK();
-  // the buckets to fill and their first rows: the list is short (one shell of buckets) and the call rare — scanned on the host
-  S->h_fill.resize((size_t) ctx->ncells);
-  PSPH_CUDA(cudaMemcpyAsync(S->h_fill.data(), S->d_mark, (size_t) ctx->ncells * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (psph_sync_n(ctx)) return -1;
-  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
-  std::vector<int32_t> cells, off((size_t) ctx->ncells, 0);
-  long long total = 0;
-  for (long long c = 0; c < ctx->ncells; c++)
-    if (S->h_fill[c] > 0) { cells.push_back((int32_t) c); off[c] = (int32_t) total; total += S->h_fill[c]; }
-  if (total == 0) return 0;
-  if ((long long) ctx->n + total > 0x7fffffffLL) { ctx->err = "psph_add_pressure_ghost: table would exceed 2^31 rows"; return -2; }
-  const int base = ctx->n;
-  if (psph_reserve(ctx, (size_t) base + (size_t) total)) return -1;
-  PSPH_CUDA(cudaMemcpyAsync(S->d_off, off.data(), (size_t) ctx->ncells * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-  PSPH_CUDA(cudaMemcpyAsync(S->d_cells, cells.data(), cells.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-  P.base = base; P.cap = (int) std::min<size_t>(ctx->cap, 0x7fffffff);
-  const long long nthreads = (long long) cells.size() * P.nper * P.nper * P.nper;
-  k_pghost_fill<<<(unsigned) ((nthreads + 255) / 256), 256, 0, ctx->stream>>>(ctx->cur.t, psph_grid_view(ctx), ctx->kp, ctx->d_attr, P, S->d_mark,
-                                                                             S->d_off, S->d_cells, (int) cells.size());
+  return grow_fill_host(ctx, S, P, added);
+}
+
+
+extern "C" int psph_add_wall_ghost(psph_ctx *ctx, uint32_t add_step, int *added)
+{
+  PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (added) *added = 0;
+  if (ctx->cfg.dim != 3) return 0;
+  if (!ctx->d_attr) { ctx->err = "psph_add_wall_ghost: psph_set_cells has not been called"; return -2; }
+  GrowState *S = grow_of(ctx);
+  if (!S) return -1;
+  if (!S->has_growth) { ctx->err = "psph_add_wall_ghost: psph_set_growth has not been called"; return -2; }
+  const int32_t *owner = nullptr;
+  if (ctx->cfg.nranks > 1 && !(owner = psph_comm_owner_table(ctx))) { ctx->err = "psph_add_wall_ghost: psph_comm_init was not called"; return -2; }
+  StageTimer tm(ctx, ST_GROW);
+  if (grow_facts(ctx, S)) return -1;                                  // rows per bucket (the pressure ghosts just added count)
+  GrowPar P;
+  P.g = S->g; P.mz = S->d_mz; P.mrho = S->d_mrho; P.mp = S->d_mp; P.mincrd = S->d_mincrd;
+  P.add_step = add_step; P.rank = ctx->cfg.rank; P.has_grad = ctx->has_grad;
+  P.nper = (int) llround(ctx->cfg.del / ctx->cfg.len_scale / S->g.smlen);
+  if (P.nper < 1 || P.nper > 64) { ctx->err = "psph_add_wall_ghost: bucket edge / smlen out of range"; return -2; }
+  P.base = 0; P.cap = 0; P.bc = 2;
+  PSPH_CUDA(cudaMemsetAsync(S->d_counter, 0, sizeof(int), ctx->stream));
+  k_wghost_pick<<<GRID(ctx->ncells)>>>(psph_grid_view(ctx), ctx->d_attr, S->d_cnt, S->d_off);          // (d_off: picked buckets)
   PSPH_LAUNCH_CHECK();
-  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));                      // (off / cells are host vectors of this call)
-  ctx->n = base + (int) total;
-  ctx->h_ss->n = ctx->n;
-  PSPH_CUDA(cudaMemcpyAsync(&ctx->d_ss->n, &ctx->h_ss->n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  PSPH_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->n_dirty = false;
-  ctx->h_unknown = true;
-  ctx->list_valid = false;
-  psph_comm_mark(ctx, DIRTY_LAYOUT);
-  if (added) *added = (int) total;
-  return 0;
+  k_wghost_mark<<<GRID(ctx->ncells)>>>(psph_grid_view(ctx), ctx->d_attr, owner, P, S->d_off, S->d_mark, S->d_inv, S->d_counter);
+  PSPH_LAUNCH_CHECK();
+  int bad = 0;
+  if (grow_read_counter(ctx, S, &bad)) return -1;
+  if (bad) { ctx->err = "psph_add_wall_ghost: an on-ground bucket has no bucket below it (the reference asserts, add_wall_ghost.cc:222)"; return -2; }
+  return grow_fill_host(ctx, S, P, added);
 }

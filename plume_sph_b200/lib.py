@@ -115,6 +115,7 @@ API = {
     "psph_adapt_domain": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "psph_set_growth": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "psph_add_pressure_ghost": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_int)]),
+    "psph_add_wall_ghost": (C.c_int, [_VP, C.c_uint32, C.POINTER(C.c_int)]),
     "psph_upload": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_append": (C.c_int, [_VP, _VP, C.c_size_t]),
     "psph_download": (C.c_int, [_VP, _VP, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),

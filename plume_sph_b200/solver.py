@@ -89,6 +89,12 @@ class Solver:
         self._ck(self.L.psph_add_pressure_ghost(self.h, int(add_step), C.byref(a)), "psph_add_pressure_ghost")
         return a.value
 
+    def add_wall_ghost(self, add_step):
+        """add_wall_ghost (add_wall_ghost.cc:44-293) on the device -> rows appended on this rank"""
+        a = C.c_int(0)
+        self._ck(self.L.psph_add_wall_ghost(self.h, int(add_step), C.byref(a)), "psph_add_wall_ghost")
+        return a.value
+
     def host_rows(self, n, dtype=None):
         """n rows (psph_particle, or lib.PARTICLE_SPH_DTYPE) in pinned host memory (psph_host_alloc); freed with the solver"""
         dtype = dtype or _l.PARTICLE_DTYPE

@@ -127,17 +127,17 @@ def grow_cell_attrs(cfg, z, tag):
     attr["has_involved"][lin] = a[:, 1]
     attr["active"][lin] = a[:, 2]
     attr["flags"][lin] = a[:, 4] | (a[:, 5] << 8)
-    attr["bucket_index"][lin] = z["bindex"]
-    attr["bnd"][lin] = z["bnd"]
+    attr["bucket_index"][lin] = z[tag + "_bindex"] if tag + "_bindex" in z else z["bindex"]
+    attr["bnd"][lin] = z[tag + "_bnd"] if tag + "_bnd" in z else z["bnd"]
     return attr, lin
 
 
-def grow_cell_mincrd(cfg, z, lin):
+def grow_cell_mincrd(cfg, z, lin, tag="scan_pre"):
     """Bucket::mincrd of every cell as the reference stores it (the lattice formula for the cells the fixture does not hold)"""
     n = [int(cfg.ncell[d]) for d in range(3)]
     idx = np.stack(np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij"), axis=-1).reshape(-1, 3)
     mc = (np.asarray([cfg.mindom[d] for d in range(3)]) + idx * cfg.delta) / cfg.len_scale
-    mc[lin] = z["scan_pre_mincrd"]
+    mc[lin] = z[tag + "_mincrd"]
     return mc
 
 

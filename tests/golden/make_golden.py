@@ -280,6 +280,21 @@ def golden_grow(name="grow3d", variant="3d_plume", edits=None, simdata="simulati
         assert np.array_equal(t3[~isnew], t2)                        # the old rows keep their relative order, untouched
         out["pghost_pos"] = np.nonzero(isnew)[0].astype(np.int32)
         out["pghost_rows"] = t3[isnew]
+        # add_wall_ghost (add_wall_ghost.cc:44-293), after shift_brief_buck: the rows it added and where they sit
+        _, t4 = refio.read_dump(os.path.join(dump, "s0002_wghost_post.bin"))
+        old3 = {tuple(k) for k in t3["key"]}
+        isnew4 = np.asarray([tuple(k) not in old3 for k in t4["key"]])
+        assert np.array_equal(t4[~isnew4], t3)
+        out["wghost_pos"] = np.nonzero(isnew4)[0].astype(np.int32)
+        out["wghost_rows"] = t4[isnew4]
+        for tag in ("wghost_pre", "wghost_post"):
+            bk = refio.read_bucketsx(os.path.join(dump, "s0002_" + tag + "_bucketsx.bin"))
+            out[tag + "_mincrd"] = np.asarray([b["mincrd"] for b in bk])
+            out[tag + "_attr"] = np.asarray([[b["type"], b["has_involved"], b["active"], b["guest"], b["particles_type"],
+                                             b["erupt_flag"]] for b in bk], np.int32)
+            out[tag + "_bindex"] = np.asarray([b["bucket_index"] for b in bk], np.int32)
+            out[tag + "_bnd"] = np.asarray([b["bnd"] for b in bk], np.float64)
+            out[tag + "_count"] = np.asarray([len(b["rows"]) for b in bk], np.int32)
         for tag, fn in (("scan_pre", "s0001_scan_pre"), ("scan_post", "s0001_scan_post"), ("adapt_pre", "s0002_adapt_pre"),
                         ("adapt_post", "s0002_adapt_post"), ("pghost_post", "s0002_pghost_post")):
             bk = refio.read_bucketsx(os.path.join(dump, fn + "_bucketsx.bin"))
@@ -300,7 +315,8 @@ def golden_grow(name="grow3d", variant="3d_plume", edits=None, simdata="simulati
         out["meteo_z"] = g["meteo_z"]
         out["meteo"] = g["meteo"]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-        print(name, "adapt", out["adapt"], "rows", len(t1), "turned", int(ch.sum()), "added", int(isnew.sum()), "->",
+        print(name, "adapt", out["adapt"], "rows", len(t1), "turned", int(ch.sum()), "added", int(isnew.sum()), "wall ghosts",
+              int(isnew4.sum()), "buckets", len(out["wghost_pre_mincrd"]), "->",
               os.path.getsize(os.path.join(HERE, name + ".npz")), "B")
 
 

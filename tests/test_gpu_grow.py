@@ -4,6 +4,7 @@
   psph_scan_outside_layer   scan_outside_layer.cc:44-121  (end of step 1: the vent's bucket becomes has_involved = 3, adapt = 1)
   psph_adapt_domain         adapt_domain.cc:41-194        (start of step 2: 6144 pressure ghosts turn real, bucket flags)
   psph_add_pressure_ghost   add_pressure_ghost.cc:36-316  (20480 new pressure ghosts whose state comes from the Meteo sounding)
+  psph_add_wall_ghost       add_wall_ghost.cc:44-293      (12288 new wall ghosts under the grown domain, after shift_brief_buck)
 
 Everything here is integer / flag work or explicit IEEE arithmetic in the reference's order: the bar is BIT-EXACT — bucket
 attributes, bc_type / involved of every row, and for the new rows keys, positions, mass, density, energy and every EOS output,
@@ -100,6 +101,33 @@ def test_domain_growth_matches_reference(with_bounds):
             b = want[np.lexsort(np.rint(want["coord"]).T[::-1])]
             assert np.abs(a["coords"] - b["coord"]).max() < 1e-3
             assert np.array_equal(a["rho"], b["rho"]) and np.array_equal(a["engr"], b["engr"])   # functions of z only
+        # ---- add_wall_ghost, after the driver's shift_brief_buck (the fixture's bucket set at that point)
+        attr_w, lin_w = grow_cell_attrs(ocfg, z, "wghost_pre")
+        s.set_cells(attr_w)
+        if with_bounds:
+            s.set_growth(g, mz, mrho, mp, grow_cell_mincrd(ocfg, z, lin_w, "wghost_pre"))
+        nwall = s.add_wall_ghost(int(z["param_step"][0]))
+        wantw = z["wghost_rows"]
+        assert nwall == len(wantw) == 12288
+        want_a, _ = grow_cell_attrs(ocfg, z, "wghost_post")
+        got_a = s.get_cells()
+        for f in ("type", "has_involved", "flags", "active"):
+            assert np.array_equal(got_a[f], want_a[f]), ("wghost_post", f)
+        rows2 = s.download(ORDER_REFERENCE)
+        assert len(rows2) == len(rows) + nwall
+        if with_bounds:
+            posw = z["wghost_pos"]
+            oldw = np.ones(len(rows2), bool)
+            oldw[posw] = False
+            assert np.array_equal(rows2["key"][oldw], rows["key"])
+            got = rows2[posw]
+            for f, d in (("key", "key"), ("bc_type", "bc_type"), ("phase_num", "phase"), ("involved", "involved"), ("coords", "coord"),
+                         ("mass", "mass"), ("smlen", "smlen"), ("rho", "rho"), ("engr", "engr"), ("pressure", "pressure"),
+                         ("gamma", "gamma"), ("sound_speed", "sound_speed"), ("temperature", "temperature"),
+                         ("specific_heat_p", "specific_heat_p"), ("phase_density", "phase_density"), ("vel", "vel")):
+                assert np.array_equal(got[f], wantw[d]), ("wall ghost", f)
+        else:
+            assert int((rows2["bc_type"] == 2).sum()) == int((rows["bc_type"] == 2).sum()) + nwall
         # the grown table steps: new ghosts are binned, real rows see them
         dt, lost, ierr = s.step(0.0, 1)
         assert ierr == 0 and dt > 0

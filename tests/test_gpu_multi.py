@@ -231,6 +231,8 @@ def test_domain_growth_across_slabs(P):
     rows = dump_to_particles(table)
     g, mz, mrho, mp = growth_record(z)
     mincrd = grow_cell_mincrd(ocfg, z, lin)
+    attr_w, lin_w = grow_cell_attrs(ocfg, z, "wghost_pre")
+    mincrd_w = grow_cell_mincrd(ocfg, z, lin_w, "wghost_pre")
     uid = psph.Solver.comm_unique_id()
     parts = np.array_split(np.argsort(rows["coords"][:, 0], kind="stable"), P)
 
@@ -252,11 +254,27 @@ def test_domain_growth_across_slabs(P):
         s.exchange_ghosts()
         attr = s.get_cells()
         out = s.download(ORDER_DEVICE)
+        # add_wall_ghost after the driver's shift_brief_buck (the fixture's bucket set at that point)
+        s.set_cells(attr_w)
+        s.set_growth(g, mz, mrho, mp, mincrd_w)
+        nwall = s.add_wall_ghost(int(z["param_step"][0]))
+        s.exchange_ghosts()
+        outw = s.download(ORDER_DEVICE)
+        attrw = s.get_cells()
         dt, lost, ierr = s.step(0.0, 1)                   # the grown, re-balanced table steps
         s.close()
-        return adapt, turned, added, attr, out, ierr
+        return adapt, turned, added, attr, out, ierr, nwall, outw, attrw
 
     res = run_ranks(P, rank)
+    want_w, _ = grow_cell_attrs(ocfg, z, "wghost_post")
+    assert sum(r[6] for r in res) == len(z["wghost_rows"])
+    ownw = np.concatenate([r[7][r[7]["guest"] == 0] for r in res])
+    wk = ownw[ownw["bc_type"] == 2]
+    refw = np.concatenate([table[table["bc_type"] == 2]["key"], z["wghost_rows"]["key"]])
+    assert np.array_equal(wk["key"][np.lexsort(wk["key"].T[::-1])], refw[np.lexsort(refw.T[::-1])])   # every wall ghost on exactly one rank
+    for r in res:
+        for f in ("type", "has_involved", "flags", "active"):
+            assert np.array_equal(r[8][f], want_w[f]), ("wghost_post", f)
     want, _ = grow_cell_attrs(ocfg, z, "pghost_post")
     assert all(r[0] == 1 for r in res)                                   # the global count on every rank (main.cc:226-258)
     assert sum(r[1] for r in res) == len(z["adapt_rows"])

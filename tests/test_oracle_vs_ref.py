@@ -215,6 +215,25 @@ def test_domain_growth_bit_exact():
         eq(got[f], want[f], ("new row", f))
     eq(got["coords"], want["coord"], "new row coord")
     eq(got["phase_num"], want["phase"], "new row phase")
+    # ---- add_wall_ghost (add_wall_ghost.cc:44-293), after shift_brief_buck turned the adhered brief buckets into buckets
+    attr_w, lin_w = grow_cell_attrs(cfg, z, "wghost_pre")
+    cnt = np.zeros(len(attr_w), np.int32)
+    cnt[lin_w] = z["wghost_pre_count"]
+    wall = op.add_wall_ghost(cfg, attr_w, cnt, g, mz, mrho, mp, int(z["param_step"][0]), grow_cell_mincrd(cfg, z, lin_w, "wghost_pre"))
+    want_a, _ = grow_cell_attrs(cfg, z, "wghost_post")
+    for f in ("type", "has_involved", "flags", "active"):
+        eq(attr_w[f], want_a[f], ("wghost_post", f))
+    want = z["wghost_rows"]
+    assert len(wall) == len(want) == 12288
+    allkeys = np.concatenate([z["table"]["key"], new["key"], wall["key"]])
+    perm = op.table_order(cfg, allkeys)
+    n_old = len(z["table"]) + len(new)
+    eq(np.nonzero(perm >= n_old)[0], z["wghost_pos"], "positions of the wall ghosts in the table order")
+    got = wall[perm[perm >= n_old] - n_old]
+    for f in ("key", "bc_type", "involved", "guest", "mass", "smlen", "mass_frac", "pressure", "gamma", "sound_speed",
+              "temperature", "specific_heat_p", "phase_density", "vel", "smoothed_v", "rho", "engr", "smoothed_e"):
+        eq(got[f], want[f], ("wall ghost", f))
+    eq(got["coords"], want["coord"], "wall ghost coord")
 
 
 def test_table_order_matches_thashtable_iteration():

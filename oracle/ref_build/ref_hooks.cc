@@ -78,6 +78,7 @@ double g_time = 0, g_dt = 0;
 map<string, double> g_stage_time;
 double g_loop_t0 = 0, g_excluded = 0;
 THashTable *g_P = NULL;
+THashTable *hook_table() { return g_P; }   /* (parameters.h has a g_P of its own: unqualified use outside this namespace is ambiguous) */
 
 double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
@@ -572,6 +573,15 @@ void psphhook_add_pressure_ghost(THashTable *P, HashTable *BG, SimProps *sp, Mat
   dump_bucketsx(P, BG, "pghost_post");
 }
 
+/* update_bgmesh (mesh_update.cc:32-245; main.cc:283 in the adapt block): bucket attributes after it */
+int psphhook_update_bgmesh(HashTable *BG, int myid, int np, int *my_comm)
+{
+  init_once();
+  int rc = update_bgmesh(BG, myid, np, my_comm);
+  if (hook_table() && g_step >= 1) dump_bucketsx(hook_table(), BG, "bgmesh_post");
+  return rc;
+}
+
 void psphhook_add_wall_ghost(THashTable *P, HashTable *BG, SimProps *sp, MatProps *mp, TimeProps *tp, int np, int myid)
 {
   init_once();
@@ -612,6 +622,7 @@ int psphhook_sml_update_int()
 #define adapt_domain psphhook_adapt_domain
 #define add_pressure_ghost psphhook_add_pressure_ghost
 #define add_wall_ghost psphhook_add_wall_ghost
+#define update_bgmesh psphhook_update_bgmesh
 #endif
 #include PSPH_REF_MAIN_CC
 #endif

@@ -120,6 +120,15 @@ __global__ void __launch_bounds__(256) k_apply_bcond(DevView V, GridView G, KPar
   }
 }
 
+// an image whose wall ghost is not in the table: the reference stops with "ghost particle missing" (bcond.cc:59-66, return 3);
+// here it is counted into the invariant-violation counter psph_errors() / psph_step() report (single rank: on slabs the ghost
+// of an image this rank computes may legitimately live on another rank only)
+__global__ void k_bc_unmatched(const int32_t *__restrict__ img_row, int n_img, StepState *ss)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_img && img_row[i] < 0) atomicAdd(&ss->bad, 1);
+}
+
 extern "C" int psph_set_images(psph_ctx *ctx, const psph_image *img, size_t n)
 {
   PSPH_CUDA(cudaSetDevice(ctx->cfg.device));
@@ -174,6 +183,7 @@ extern "C" int psph_apply_bcond(psph_ctx *ctx)
     k_bc_match<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->cur.t, ctx->d_ss, (const ImgKey *) ctx->d_img_keys, ctx->n_img,
                                                             ctx->d_img_row, list, count, ctx->d_img_cell, owner, ctx->cfg.rank);
     PSPH_LAUNCH_CHECK();
+    if (!slabs) { k_bc_unmatched<<<(ctx->n_img + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_img_row, ctx->n_img, ctx->d_ss); PSPH_LAUNCH_CHECK(); }
     const int grid = std::min((ctx->n_img + 7) / 8, ctx->sms * 8);
     k_apply_bcond<<<grid, 256, 0, ctx->stream>>>(ctx->cur, psph_grid_view(ctx), ctx->kp, ctx->d_ss, list, count, ctx->d_img_row,
                                                  ctx->d_img_coord, ctx->d_img_cell);

@@ -287,7 +287,9 @@ def golden_grow(name="grow3d", variant="3d_plume", edits=None, simdata="simulati
         assert np.array_equal(t4[~isnew4], t3)
         out["wghost_pos"] = np.nonzero(isnew4)[0].astype(np.int32)
         out["wghost_rows"] = t4[isnew4]
-        for tag in ("wghost_pre", "wghost_post"):
+        # (wghost_pre = the buckets after shift_brief_buck, shift_brief_buck.cc:33-129; bgmesh_post = after update_bgmesh,
+        # mesh_update.cc:32-245, which follows add_wall_ghost at main.cc:286)
+        for tag in ("wghost_pre", "wghost_post", "bgmesh_post"):
             bk = refio.read_bucketsx(os.path.join(dump, "s0002_" + tag + "_bucketsx.bin"))
             out[tag + "_mincrd"] = np.asarray([b["mincrd"] for b in bk])
             out[tag + "_attr"] = np.asarray([[b["type"], b["has_involved"], b["active"], b["guest"], b["particles_type"],

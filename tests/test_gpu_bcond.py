@@ -78,3 +78,23 @@ def test_no_images_is_a_no_op():
         assert np.array_equal(out["rho"], z["bc_pre"]["rho"])
     finally:
         s.close()
+
+
+def test_an_image_without_its_ghost_is_reported():
+    """the reference stops with "ghost particle missing" (bcond.cc:59-66, return 3); here every such image counts into the
+    invariant-violation counter, and the other images are applied as usual"""
+    z = golden("plume3d_small")
+    ocfg = op.config_for("plume3d_small", z)
+    s = psph.Solver(to_product_cfg(ocfg))
+    try:
+        attr, _ = cell_attrs(ocfg, z, "b2")
+        s.set_cells(attr)
+        s.upload(dump_to_particles(z["bc_pre"]))
+        img = images_of(ocfg, z)
+        img["ghost_key"][:3, 2] += 12345                    # three images point at ghosts that do not exist
+        s.set_images(img)
+        assert s.apply_bcond() == 0
+        assert s.errors() == 3
+        assert s.errors() == 0                              # (read and reset)
+    finally:
+        s.close()

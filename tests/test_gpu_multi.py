@@ -233,6 +233,9 @@ def test_domain_growth_across_slabs(P):
     mincrd = grow_cell_mincrd(ocfg, z, lin)
     attr_w, lin_w = grow_cell_attrs(ocfg, z, "wghost_pre")
     mincrd_w = grow_cell_mincrd(ocfg, z, lin_w, "wghost_pre")
+    # (everything the rank threads need is read off the fixture HERE: an NpzFile is not safe to read from several threads)
+    add_step = int(z["param_step"][0])
+    active_pre = grow_cell_attrs(ocfg, z, "adapt_pre")[0]["active"]
     uid = psph.Solver.comm_unique_id()
     parts = np.array_split(np.argsort(rows["coords"][:, 0], kind="stable"), P)
 
@@ -246,18 +249,18 @@ def test_domain_growth_across_slabs(P):
         s.search_neighs_consth()
         adapt = s.scan_outside_layer()
         a = s.get_cells()
-        a["active"] = grow_cell_attrs(ocfg, z, "adapt_pre")[0]["active"]
+        a["active"] = active_pre
         s.set_cells(a)
         turned = s.adapt_domain()
         s.set_growth(g, mz, mrho, mp, mincrd)
-        added = s.add_pressure_ghost(int(z["param_step"][0]))
+        added = s.add_pressure_ghost(add_step)
         s.exchange_ghosts()
         attr = s.get_cells()
         out = s.download(ORDER_DEVICE)
         # add_wall_ghost after the driver's shift_brief_buck (the fixture's bucket set at that point)
         s.set_cells(attr_w)
         s.set_growth(g, mz, mrho, mp, mincrd_w)
-        nwall = s.add_wall_ghost(int(z["param_step"][0]))
+        nwall = s.add_wall_ghost(add_step)
         s.exchange_ghosts()
         outw = s.download(ORDER_DEVICE)
         attrw = s.get_cells()

@@ -439,6 +439,12 @@ __device__ __forceinline__ void mix_build(const GridView &G, int cx, int cy, int
 //   mix_pair(K, st, a[], c, sl, gx, gy, gz, near&)   one listed pair: adds to a[0 .. kNAm); near = partner inside the
 //                                                    energy-smoothing kernel (kNAm == 6 only)
 //   mix_finish(V, K, ss, i, st, tot[])               the row's totals (own / self term added here) -> outputs
+// PSPH_MIX_DYN 1: the warps of a CTA take the block's rows from a shared cursor (one per sub-tile) instead of a fixed share of
+// WARPS-th each: rows differ in list length by sub-tile, and a fixed split leaves warps waiting at the sub-tile barriers.  A
+// row's arithmetic does not depend on which warp sums it, so results are bit-identical either way.
+#ifndef PSPH_MIX_DYN
+#define PSPH_MIX_DYN 0
+#endif
 template <class S, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned char *__restrict__ blk_any)
@@ -453,6 +459,7 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
   // slot -> row of the staged sub-tile: kept next to the records when the stage lists near partners (NA == 6), else it
   // only lives while the sub-tile is staged (in the first column's storage)
   int *tile_row = NA == 6 ? nnear + MBR : reinterpret_cast<int *>(comp);                   // [MCAP]
+  __shared__ int s_next;                                                                  // PSPH_MIX_DYN: next row of the sub-tile
   if (ss->pair_mode != 4) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned short *__restrict__ lists = V.mlist;
@@ -471,6 +478,7 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
     const int w0 = rb0 + warp * per, w1 = min(w0 + per, rb1);       // this warp's rows
     for (int s = 0; s < MNSUB; s++) {
       mix_build(G, cx, cy, cz, q, s, tab);                          // (two barriers inside: the previous sub-tile is done with)
+      if (PSPH_MIX_DYN && threadIdx.x == 0) s_next = 0;             // (read after the staging barrier below)
       const int total = tab.off[MSEG];
       if (threadIdx.x < MSEG) {
         const int sg = threadIdx.x, beg = tab.beg[sg], o = tab.off[sg], len = tab.off[sg + 1] - o;
@@ -489,7 +497,16 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
       }
       __syncthreads();
       // ---- this warp's rows: the entries of sub-tile s of every listed row
+#if PSPH_MIX_DYN
+      for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&s_next, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= nrow) break;
+        i += rb0;
+#else
       for (int i = w0; i < w1; i++) {
+#endif
         int n = -1, sg = 0;
         if (lane == 0 && (V.flags[i] & F_NEED)) { n = V.nbr_cnt[i]; sg = V.mseg[i]; }
         n = __shfl_sync(FULL, n, 0); sg = __shfl_sync(FULL, sg, 0);
@@ -532,9 +549,14 @@ k_mix_gather(DevView V, GridView G, KParams K, StepState *ss, const unsigned cha
         }
       }
     }
+#if PSPH_MIX_DYN
+    __syncthreads();                                                // every row of every sub-tile is summed
+    for (int i = rb0 + (int) threadIdx.x; i < rb1; i += WARPS * 32) {
+#else
     __syncwarp();
     // ---- finish this warp's rows (its own accumulators: no barrier needed)
     for (int i = w0 + lane; i < w1; i += 32) {
+#endif
       if (!(V.flags[i] & F_NEED) || V.nbr_cnt[i] < 0) continue;
       typename S::I st;
       S::init(V, K, ss, i, st);

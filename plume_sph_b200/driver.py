@@ -71,15 +71,44 @@ def timeprops_from(d, time_scale=1.0):
     return TimeProps(d["max_time"], d["max_steps"], d["timeoutput"], d["stat_erupt"], d["end_erupt"], time_scale)
 
 
-def run_loop(solver, tp, on_output=None, max_steps=None, erupt=False):
+def grow_domain(solver, tp, growth):
+    """The adapt block of main.cc:256-304 for a flat ground: the particle work on the device (adapt_domain, add_pressure_ghost,
+    add_wall_ghost, apply_bcond), the bucket bookkeeping on the host on the attribute array (shift_brief_buck, update_bgmesh,
+    the image search).  growth: dict(latent=attr array of mesh.background_mesh with every cell a bucket, mindom, ncell, delta,
+    len_scale); the Solver must have been given psph_set_growth."""
+    from . import mesh
+    n = [int(x) for x in growth["ncell"]]
+    solver.adapt_domain()                                             # :265
+    solver.add_pressure_ghost(tp.step)                                # :271
+    attr = solver.get_cells()
+    mesh.shift_brief_buck(attr, growth["latent"], n)                  # :274
+    solver.set_cells(attr)
+    solver.add_wall_ghost(tp.step)                                    # :277
+    attr = solver.get_cells()
+    cells, rows = solver.cells()                                      # bucket of every row + the rows (a growth step is rare:
+    cnt = np.bincount(np.asarray(cells)[np.asarray(cells) >= 0], minlength=len(attr))   # one read-back for the host's bookkeeping)
+    mesh.update_bgmesh(attr, cnt, n)                                  # :286
+    solver.set_cells(attr)
+    img, _ = mesh.wall_ghost_images(rows, growth["mindom"], n, growth["delta"], attr, growth.get("len_scale", 1.0))   # :292
+    solver.set_images(img)
+    return solver.apply_bcond()                                       # :298
+
+
+def run_loop(solver, tp, on_output=None, max_steps=None, erupt=False, growth=None):
     """The reference time loop with the stage calls on the GPU.  One host round trip per step
     (the CFL dt comes back, is clipped by TimeProps.incrtime and goes down again) exactly as
-    main.cc:220-231 does; ``Solver.run`` is the variant without it."""
+    main.cc:220-231 does; ``Solver.run`` is the variant without it.  growth (see grow_domain): the domain follows the
+    plume as in an ADJUST_DOMAIN build — psph_scan_outside_layer every step (:435), the adapt block at the start of the
+    step after it raised `adapt` (:256-304)."""
     cfg = solver.cfg
     nsteps = 0
+    adapt = 0
     while not tp.ifend() and (max_steps is None or nsteps < max_steps):
         dt = solver.timestep()                       # main.cc:220 / :679
         dt = tp.incrtime(dt)                         # :231 / :682
+        if growth is not None and adapt:
+            grow_domain(solver, tp, growth)          # :256-304
+        adapt = 0
         solver.set_dt(dt, tp.step, tp.iferupt())
         solver.search_neighs_consth()                # :318 (3-D; a geometry refresh in 1-D)
         if cfg.adaptive_sml and (cfg.dim == 1 or tp.step % cfg.sml_update_int == 0):
@@ -95,6 +124,8 @@ def run_loop(solver, tp, on_output=None, max_steps=None, erupt=False):
             solver.update_particles_in_bucket()      # :408
             if erupt and tp.iferupt():
                 solver.add_new_erupt(tp.time, dt, tp.step)   # :414-417 (after Solver.set_erupt)
+            if growth is not None:
+                adapt = solver.scan_outside_layer()  # :435
             solver.apply_bcond()                     # :468 (no-op until the driver hands over its Image_table)
         nsteps += 1
         if tp.ifoutput() and on_output is not None:  # :474 / :746

@@ -75,6 +75,43 @@ def background_mesh(Ll, Lu, smlen, idom_min, idom_max, particle_density=8, ext=1
     return mindom, n, d, attr
 
 
+def _neigh_sum(flag, n):
+    """for every cell: how many of its 26 lattice neighbours carry `flag` (cells outside the mesh do not exist)"""
+    f = np.pad(np.asarray(flag, np.int32).reshape(n), 1)
+    s = np.zeros(n, np.int32)
+    for di in range(3):
+        for dj in range(3):
+            for dk in range(3):
+                if (di, dj, dk) != (1, 1, 1):
+                    s += f[di:di + n[0], dj:dj + n[1], dk:dk + n[2]]
+    return s.reshape(-1)
+
+
+def shift_brief_buck(attr, latent, ncell):
+    """shift_brief_buck (src/plume/shift_brief_buck.cc:33-129): every brief bucket (type 0) next to a bucket that is not involved,
+    holds pressure ghosts and lies outside the vent becomes a bucket — with the attributes `switch_brief` computes
+    (sph_lib.cc:1442-1560), which are the closed-form ones of `background_mesh` (`latent` = its attr array built with an
+    initial domain that covers the whole mesh).  attr is changed in place; returns the linear indices of the new buckets."""
+    n = [int(x) for x in ncell]
+    src = (attr["type"] != 0) & (attr["has_involved"] == 0) & ((attr["flags"] & 4) != 0) & (((attr["flags"] >> 8) & 3) == 0)
+    new = np.flatnonzero((attr["type"] == 0) & (_neigh_sum(src, n) > 0))
+    for f in ("type", "bucket_index", "bnd"):
+        attr[f][new] = latent[f][new]
+    attr["has_involved"][new] = 0
+    attr["flags"][new] = 0
+    attr["active"][new] = 1                                  # (Bucket ctor: active until update_bgmesh says otherwise)
+    return new
+
+
+def update_bgmesh(attr, rows_per_cell, ncell):
+    """update_bgmesh (src/datstr/mesh_update.cc:32-245): a bucket is active when one of its neighbour buckets holds a
+    particle (rows_per_cell: plist sizes over the whole lattice, all ranks).  attr["active"] is rewritten."""
+    n = [int(x) for x in ncell]
+    occ = (attr["type"] != 0) & (np.asarray(rows_per_cell) > 0)
+    attr["active"] = ((attr["type"] != 0) & (_neigh_sum(occ, n) > 0)).astype(np.int32)
+    return attr
+
+
 def wall_ghost_images(rows, mindom, ncell, d, attr, len_scale=1.0):
     """search_bnd_images (src/datstr/bnd_image.cc:27-270) for a FLAT ground, in closed form: every wall ghost (bc_type 2,
     not a guest) of an on-ground MIXED bucket (bucket_index[4] == -1, [5] == 0) gets the mirror point across the ground

@@ -84,6 +84,60 @@ def test_run_loop_calls_the_stages_in_the_reference_order():
     assert "add_new_erupt" not in s2.calls                     # outside the eruption window (properties.h iferupt)
 
 
+def test_run_loop_grows_the_domain_in_the_reference_order():
+    """with growth on, run_loop scans the outer layer every step (main.cc:435) and runs the adapt block at the start of the
+    step after the scan raised `adapt` (:256-304), in the reference's order: adapt_domain, add_pressure_ghost,
+    [shift_brief_buck], add_wall_ghost, [update_bgmesh, image search], apply_bcond"""
+    from plume_sph_b200 import driver, mesh
+    import plume_sph_b200 as psph
+
+    class Cfg:
+        adaptive_sml, dim, sml_update_int, use_gsph, have_turbulence_lans = 1, 3, 50, 0, 1
+
+    n = [3, 3, 3]
+
+    class Rec:
+        cfg = Cfg()
+
+        def __init__(self):
+            self.calls, self.scans = [], 0
+
+        def get_cells(self):
+            self.calls.append("get_cells")
+            a = np.zeros(27, psph.CELL_ATTR_DTYPE)
+            a["type"] = 12
+            return a
+
+        def cells(self):
+            self.calls.append("cells")
+            return np.zeros(4, np.int32), np.zeros(4, psph.PARTICLE_DTYPE)
+
+        def download(self):
+            self.calls.append("download")
+            return np.zeros(4, psph.PARTICLE_DTYPE)
+
+        def scan_outside_layer(self):
+            self.calls.append("scan_outside_layer")
+            self.scans += 1
+            return 1 if self.scans == 1 else 0
+
+        def __getattr__(self, name):
+            def f(*a):
+                self.calls.append(name)
+                return 0.25 if name == "timestep" else 0
+            return f
+
+    _, _, _, latent = mesh.background_mesh((0., 0., 0.), (24., 24., 24.), 1.0, (-1e9,) * 3, (1e9,) * 3)
+    growth = dict(latent=np.resize(latent, 27), mindom=[0., 0., 0.], ncell=n, delta=8.0)
+    s = Rec()
+    assert driver.run_loop(s, driver.TimeProps(max_time=10.0, max_steps=100, timeoutput=100.0), max_steps=2, growth=growth) == 2
+    stages = ["set_dt", "search_neighs_consth", "mom_engr_update", "smooth_density", "smooth_velocity", "update_pos",
+              "update_particles_in_bucket", "scan_outside_layer", "apply_bcond"]
+    block = ["adapt_domain", "add_pressure_ghost", "get_cells", "set_cells", "add_wall_ghost", "get_cells", "cells", "set_cells",
+             "set_images", "apply_bcond"]
+    assert s.calls == ["timestep"] + stages + ["timestep"] + block + stages
+
+
 @pytest.mark.parametrize("name,Ll,Lu,smlen,imin,imax", [
     ("plume3d_small", (-20800., -20800., 1666.), (20800., 20800., 24000.), 100.0, (-350., -350., 1666.), (350., 350., 2400.)),
     ("jpue3d", (-576., -576., 0.), (576., 576., 6000.), 8.0, (-60., -60., 0.), (60., 60., 100.))])
@@ -123,6 +177,44 @@ def test_wall_ghost_images_match_the_reference_table(name):
     assert np.array_equal(img["coord"], z["bc_img_coord"][o])
     assert np.array_equal(img["cell"], image_cells(cfg, z)[o])
     assert np.array_equal(img["ghost_key"], z["bc_pre"]["key"][sel])
+
+
+def test_shift_brief_buck_matches_the_reference():
+    """mesh.shift_brief_buck against the buckets the unmodified reference created in the growth step of the small plume
+    (tests/golden/grow3d.npz: bucket dumps before and after shift_brief_buck): the same 120 cells, with bit-identical
+    type, bucket_index and bnd (the closed-form attributes of mesh.background_mesh), not involved, no particle flags"""
+    import oracle_py as op
+    from common import golden, grow_cell_attrs
+    from plume_sph_b200 import mesh
+    z = golden("grow3d")
+    cfg = op.config_for("grow3d")
+    n = [cfg.ncell[k] for k in range(3)]
+    before, l0 = grow_cell_attrs(cfg, z, "pghost_post")
+    after, l1 = grow_cell_attrs(cfg, z, "wghost_pre")
+    Ll, Lu = z["param_domain"][:3], z["param_domain"][3:]
+    _, _, _, latent = mesh.background_mesh(Ll, Lu, float(z["param_const"][1]), Ll - 1e9, Lu + 1e9)   # every cell as a bucket
+    new = mesh.shift_brief_buck(before, latent, n)
+    assert np.array_equal(np.sort(new), np.setdiff1d(l1, l0)) and len(new) == 120
+    for f in ("type", "has_involved", "flags", "bucket_index", "bnd", "active"):
+        assert np.array_equal(before[f], after[f]), f
+
+
+def test_update_bgmesh_rule():
+    """mesh.update_bgmesh: active = a neighbour bucket holds a particle (mesh_update.cc:50-63).  (No reference pin: in the
+    small-plume fixture the reference's own call stops half way with "neigh-bucket missing")"""
+    from plume_sph_b200 import mesh
+    import plume_sph_b200 as psph
+    n = [4, 4, 3]
+    attr = np.zeros(48, psph.CELL_ATTR_DTYPE)
+    attr["type"] = 12
+    attr["type"][0] = 0                                       # a brief bucket is never active
+    cnt = np.zeros(48, np.int64)
+    cnt[(1 * 4 + 1) * 3 + 1] = 5                              # one occupied bucket at (1, 1, 1)
+    mesh.update_bgmesh(attr, cnt, n)
+    idx = np.stack(np.meshgrid(np.arange(4), np.arange(4), np.arange(3), indexing="ij"), -1).reshape(-1, 3)
+    near = (np.abs(idx - 1).max(axis=1) <= 1) & ~((idx == 1).all(axis=1))
+    want = near & (attr["type"] != 0)
+    assert np.array_equal(attr["active"].astype(bool), want)
 
 
 def test_default_lattice_has_the_bucket_count_of_the_reference_run():

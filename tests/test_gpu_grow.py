@@ -133,3 +133,56 @@ def test_domain_growth_matches_reference(with_bounds):
         assert ierr == 0 and dt > 0
     finally:
         s.close()
+
+
+def test_whole_adapt_block_matches_the_reference():
+    """The adapt block of main.cc:256-304 end to end — psph_adapt_domain, psph_add_pressure_ghost, [shift_brief_buck on the host],
+    psph_add_wall_ghost, [update_bgmesh and the image search on the host], psph_apply_bcond — as plume_sph_b200.driver.grow_domain
+    runs it, from the reference's table at the end of step 1 (grow3d) to the table the reference starts the stages of step 2 from
+    (plume3d_grow `pre2`): the same 52 112 particles in the reference's table order; flags, positions and every field of the
+    non-wall rows bit for bit; the wall ghosts' interpolated states (apply_bcond over old AND new ghosts) within RTOL_STAGE."""
+    from common import relerr, RTOL_STAGE
+    from plume_sph_b200 import mesh, driver
+    z, g2 = golden("grow3d"), golden("plume3d_grow")
+    ocfg = op.config_for("grow3d")
+    cfg = to_product_cfg(ocfg)
+    attr0, lin = grow_cell_attrs(ocfg, z, "scan_pre")
+    _, lin_w = grow_cell_attrs(ocfg, z, "wghost_pre")
+    s = psph.Solver(cfg)
+    try:
+        s.set_cells(attr0)
+        s.upload(dump_to_particles(z["table"]))
+        s.search_neighs_consth()
+        assert s.scan_outside_layer() == 1                                   # main.cc:435 at the end of step 1
+        a = s.get_cells()
+        a["active"] = grow_cell_attrs(ocfg, z, "adapt_pre")[0]["active"]
+        s.set_cells(a)
+        Ll, Lu = z["param_domain"][:3], z["param_domain"][3:]
+        mindom, n, d, latent = mesh.background_mesh(Ll, Lu, float(z["param_const"][1]), Ll - 1e9, Lu + 1e9)
+        assert [int(x) for x in n] == [ocfg.ncell[k] for k in range(3)]
+        g, mz, mrho, mp = growth_record(z)
+        s.set_growth(g, mz, mrho, mp, grow_cell_mincrd(ocfg, z, lin_w, "wghost_pre"))
+        tp = driver.TimeProps()
+        tp.step = int(z["param_step"][0])
+        assert driver.grow_domain(s, tp, dict(latent=latent, mindom=[float(x) for x in mindom], ncell=n, delta=d)) == 0
+        assert s.errors() == 0
+        rows = s.download(ORDER_REFERENCE)
+        want = g2["pre2"]
+        assert len(rows) == len(want) == 52112
+        assert np.array_equal(rows["key"], want["key"])
+        for f, w in (("bc_type", "bc_type"), ("involved", "involved"), ("phase_num", "phase"), ("coords", "coord"), ("mass", "mass"),
+                     ("smlen", "smlen"), ("mass_frac", "mass_frac")):
+            assert np.array_equal(rows[f], want[w]), f
+        wall = want["bc_type"] == 2
+        for f, w in (("rho", "rho"), ("engr", "engr"), ("pressure", "pressure"), ("vel", "vel"), ("sound_speed", "sound_speed"),
+                     ("temperature", "temperature")):
+            assert np.array_equal(rows[f][~wall], want[w][~wall]), f
+            e = relerr(rows[f][wall], want[w][wall])
+            assert e <= RTOL_STAGE, (f, e)
+        # the host's bucket bookkeeping: the buckets of the reference after shift_brief_buck, with their attributes
+        got_a = s.get_cells()
+        want_a, _ = grow_cell_attrs(ocfg, z, "wghost_post")
+        for f in ("type", "has_involved", "flags"):
+            assert np.array_equal(got_a[f], want_a[f]), f
+    finally:
+        s.close()

@@ -224,3 +224,27 @@ def test_default_lattice_has_the_bucket_count_of_the_reference_run():
     mindom, n, d = mesh.lattice((-20800., -20800., 1666.), (20800., 20800., 24000.), 100.0)
     assert [int(x) for x in n] == [55, 55, 31] and int(np.prod(n)) == 93775 and d == 800.0
     assert [float(x) for x in mindom] == [-22000.0, -22000.0, 466.0]
+
+
+def test_bench_plume_setup_loader(tmp_path):
+    """bench.py's plume leg: the state files the hooked reference driver writes (its own set-up of bin/simulation.data with a
+    +-1000 m initial domain, 1 step) load into what the C ABI takes — rows, bucket attributes over the default lattice, the
+    wall-ghost image table (every image points at an existing wall ghost, inside a bucket that exists) and the vent record"""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle", "ref_build"))
+    import ref_run
+    if not ref_run.have_inputs():
+        pytest.skip("oracle/_ref is not built in this checkout (python -c 'import __graft_entry__ as g; g.build()')")
+    import bench
+    import plume_sph_b200 as psph
+    dump = str(tmp_path / "dump")
+    ref_run.time_plume3d(1, 0, replicas=1, edits=ref_run.MEDIUM, keep=str(tmp_path / "setup"), dump=dump)
+    cfg = psph.config_default_3d()
+    rows, attr, img, er, boxes = bench.load_reference_setup(dump, psph, cfg)
+    assert len(rows) == 52112 and int((rows["bc_type"] == 100).sum()) == 6912
+    assert len(attr) == 55 * 55 * 31 and int((attr["type"] != 0).sum()) == 245
+    keys = {tuple(k) for k in rows["key"][rows["bc_type"] == 2]}
+    assert len(img) > 0 and all(tuple(k) in keys for k in img["ghost_key"])
+    assert (attr["type"][img["cell"]] != 0).all()
+    assert er.sml == 40.0 and er.rv == 120.0 and boxes.shape == (2, 6) and er.kmax[2] > er.kmin[2]

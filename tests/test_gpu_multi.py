@@ -34,7 +34,9 @@ def run_ranks(P, fn):
         except Exception as e:  # surface in the main thread
             err[r] = e
 
-    th = [threading.Thread(target=work, args=(r,)) for r in range(P)]
+    # daemon threads: when one rank fails, the others sit in an NCCL call that never returns — they must not keep the
+    # interpreter alive after pytest has reported (profiles/r02m_*: a 15-minute hang on an 8-GPU box)
+    th = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(P)]
     for t in th:
         t.start()
     for t in th:
